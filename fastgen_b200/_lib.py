@@ -1,0 +1,114 @@
+"""ctypes binding of ``libfastgen_b200.so`` (the C ABI declared in ``include/fastgen_b200.h``).
+
+There is NO fallback: if the shared library is missing the import of any compute path raises.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or ``make -C fastgen_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfastgen_b200.so")
+
+FG_MAX_SEG = 6
+FG_F32, FG_BF16, FG_F64 = 0, 1, 2
+FG_RES_NONE, FG_RES_SAME, FG_RES_UP2, FG_RES_DOWN2 = 0, 1, 2, 3
+
+# every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
+SYMBOLS = (
+    "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
+    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention",
+    "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16",
+)
+
+
+class ConvSeg(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a_ld", C.c_int64), ("w", C.c_void_p), ("cin", C.c_int32), ("taps", C.c_int32)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cout", C.c_int32), ("nseg", C.c_int32),
+        ("seg", ConvSeg * FG_MAX_SEG),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int64),
+        ("res", C.c_void_p), ("res_dtype", C.c_int32), ("res_mode", C.c_int32), ("res_ld", C.c_int64),
+        ("out_scale", C.c_float),
+        ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_ld", C.c_int64),
+    ]
+
+
+class GnApplyParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int32), ("x_ld", C.c_int64),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("groups", C.c_int32),
+        ("stats", C.c_void_p), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("mod_ld", C.c_int64),
+        ("silu", C.c_int32), ("resample", C.c_int32),
+        ("y", C.c_void_p), ("y_ld", C.c_int64), ("y_lo", C.c_void_p),
+        ("raw", C.c_void_p), ("raw_ld", C.c_int64), ("raw_lo", C.c_void_p),
+    ]
+
+
+class EdmStepParams(C.Structure):
+    _fields_ = [
+        ("f", C.c_void_p), ("f_ld", C.c_int64),
+        ("x_t", C.c_void_p), ("eps", C.c_void_p), ("x_dtype", C.c_int32),
+        ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
+        ("c_skip", C.c_void_p), ("c_out", C.c_void_p),
+        ("ode", C.c_int32),
+        ("alpha_cur", C.c_void_p), ("sigma_cur", C.c_void_p),
+        ("alpha_next", C.c_void_p), ("sigma_next", C.c_void_p),
+        ("x0", C.c_void_p), ("x_next", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class FastGenB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FastGenB200Error(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is not built. There is no CPU/PyTorch fallback; "
+            "run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root."
+        )
+    l = C.CDLL(LIB_PATH)
+    l.fg_last_error.restype = C.c_char_p
+    l.fg_version.restype = C.c_int
+    l.fg_launch_count.restype = C.c_int64
+    l.fg_launch_count_reset.restype = None
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    l.fg_conv_gemm.argtypes = [C.POINTER(ConvParams), vp]
+    l.fg_gn_stats.argtypes = [vp, i32, i64, i32, i32, i32, i32, vp, vp]
+    l.fg_gn_apply.argtypes = [C.POINTER(GnApplyParams), vp]
+    l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
+    l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
+    l.fg_axpby.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
+    l.fg_sub_div.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
+    l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
+    l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
+    for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",
+                 "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16"):
+        getattr(l, name).restype = C.c_int
+    _lib = l
+    return l
+
+
+def check(status: int, what: str) -> None:
+    """Map a negative fg_status to a Python exception (ValueError for bad arguments, RuntimeError otherwise)."""
+    if status == 0:
+        return
+    msg = lib().fg_last_error().decode("utf-8", "replace")
+    if status == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise FastGenB200Error(f"{what}: status {status}: {msg}")

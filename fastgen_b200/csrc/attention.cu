@@ -1,0 +1,317 @@
+// Fused UNet self-attention for sm_100a: softmax(q.k^T / sqrt(d)) v per (sample, head), flash style.
+//   TMA stages Q once and K/V tiles in a 2-deep ring; S = Q.K^T and O += P.V run on tcgen05 with S (double
+//   buffered) and O accumulators in TMEM; the softmax warps own one query row per thread (tcgen05.ld 32x32b),
+//   keep running max / sum in fp32, write P as the bf16 A operand into 128B-swizzled shared memory, and only
+//   rescale O when the running max grew by more than 2^8 (lazy rescale).
+//   V is consumed straight from the channels-last qkv tensor as an MN-major B operand - no transpose pass.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = softmax/epilogue.
+//
+// Replaces: fastgen/networks/EDM/network.py:160-168 (AttentionOp.forward) and :290-296 (the qkv unbind and the
+// two einsums), which materialise the [N*heads, T, T] weight tensor in fp32.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fg {
+
+constexpr int kAttnThreads = 192;
+constexpr int kQRows = 128;
+
+template <int DP, int BKV>
+struct AttnCfg {
+  static constexpr int DC = DP / 64;                    // 64-wide head-dim chunks
+  static constexpr int Q_BYTES = DC * kQRows * 128;
+  static constexpr int KV_TILE_BYTES = DC * BKV * 128;  // K (or V) of one stage
+  static constexpr int STAGES = 2;
+  static constexpr int P_BYTES = (BKV / 64) * kQRows * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_TILE_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int TMEM_O = 2 * BKV;
+  static constexpr int TMEM_COLS_RAW = 2 * BKV + DP;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static_assert(TMEM_COLS_RAW <= 512, "TMEM budget");
+};
+
+struct AttnKParams {
+  CUtensorMap tmQ;   // box (64, 1, 128, 1)
+  CUtensorMap tmKV;  // box (64, 1, BKV, 1)
+  int32_t N, T, H, d;
+  float scale_log2;  // log2(e) / sqrt(d)
+  __nv_bfloat16* out;
+  int64_t out_ld;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int DP, int BKV>
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<DP, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;  // stage s: K at s*2*KV_TILE_BYTES, V right after
+  uint8_t* sP = sKV + Cfg::STAGES * 2 * Cfg::KV_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (p.T + kQRows - 1) / kQRows;
+  const int qt = blockIdx.x % q_tiles;
+  const int head = (blockIdx.x / q_tiles) % p.H;
+  const int img = blockIdx.x / (q_tiles * p.H);
+  const int q0 = qt * kQRows;
+  const int nkv = (p.T + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmKV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+      }
+      mbar_init(p_full, 4);
+      mbar_init(pv_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+      for (int dc = 0; dc < Cfg::DC; ++dc) tma_load_4d(sQ + dc * kQRows * 128, &p.tmQ, q_full, dc * 64, head, q0, img);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1u);
+        uint8_t* sk = sKV + s * 2 * Cfg::KV_TILE_BYTES;
+        uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_TILE_BYTES);
+        for (int dc = 0; dc < Cfg::DC; ++dc) {
+          tma_load_4d(sk + dc * BKV * 128, &p.tmKV, &kv_full[s], dc * 64, p.H + head, j * BKV, img);
+          tma_load_4d(sv + dc * BKV * 128, &p.tmKV, &kv_full[s], dc * 64, 2 * p.H + head, j * BKV, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kQRows, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kQRows, DP, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + s * 2 * Cfg::KV_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(s * BKV);
+#pragma unroll
+        for (int dc = 0; dc < Cfg::DC; ++dc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + dc * kQRows * 128 + k * 32),
+                         umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk, (dc | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_qk(j + 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const int s = j & 1;
+        const uint32_t v_addr = smem_u32(sKV + s * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_bf16_ss(tmem_base + Cfg::TMEM_O, umma_desc_sw128(p_addr + (kk >> 2) * kQRows * 128 + (kk & 3) * 32),
+                       umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    float m_run = -INFINITY;  // running max in scaled (log2) units
+    float l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c]);
+        tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(b * BKV + c), chunk);
+      }
+      tmem_ld_wait();
+      const int kv_valid = p.T - j * BKV;  // columns >= kv_valid are padding
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        float s = __uint_as_float(sv[c]) * p.scale_log2;
+        s = (c < kv_valid) ? s : -INFINITY;
+        sv[c] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // P buffer consumed, O stable
+        tc_fence_after();
+        const bool need = mx > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_run;
+          const float alpha = exp2f(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < DP; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + c), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + c), o);
+          }
+          tmem_st_wait();
+        }
+      } else {
+        m_run = mx;
+      }
+      float lsum = 0.f;
+      uint8_t* prow = sP + row * 128;
+#pragma unroll
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pv[i] = exp2f(__uint_as_float(sv[c8 * 8 + i]) - m_run);
+          lsum += pv[i];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(pv[0], pv[1]), u.y = pack_bf16x2(pv[2], pv[3]);
+        u.z = pack_bf16x2(pv[4], pv[5]), u.w = pack_bf16x2(pv[6], pv[7]);
+        const int sub = c8 >> 3, chunk = c8 & 7;
+        *reinterpret_cast<uint4*>(prow + sub * (kQRows * 128) + ((chunk ^ (row & 7)) << 4)) = u;
+      }
+      l_run += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 ----
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int tok = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(img) * p.T + tok) * p.out_ld + head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < DP; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + c), o);
+      tmem_ld_wait();
+      if (tok < p.T) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          if (c + i < p.d) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + i) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int DP, int BKV>
+static int launch_attention(AttnKParams& kp, const void* qkv, int64_t qkv_ld, cudaStream_t stream) {
+  using Cfg = AttnCfg<DP, BKV>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return FG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const uint64_t ldb = static_cast<uint64_t>(qkv_ld) * 2;
+  const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)(3 * kp.H), (uint64_t)kp.T, (uint64_t)kp.N};
+  const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, ldb, ldb * kp.T};
+  const uint32_t boxq[4] = {64, 1, (uint32_t)kQRows, 1};
+  const uint32_t boxkv[4] = {64, 1, (uint32_t)BKV, 1};
+  int r = encode_tmap_bf16(&kp.tmQ, qkv, 4, dims, strides, boxq);
+  if (r != FG_OK) return r;
+  r = encode_tmap_bf16(&kp.tmKV, qkv, 4, dims, strides, boxkv);
+  if (r != FG_OK) return r;
+  const int q_tiles = (kp.T + kQRows - 1) / kQRows;
+  const int grid = kp.N * kp.H * q_tiles;
+  attention_kernel<DP, BKV><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  FG_CHECK_LAUNCH("attention");
+  return FG_OK;
+}
+
+}  // namespace fg
+
+extern "C" int fg_attention(const void* qkv, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
+                            void* out, int64_t out_ld, fg_stream_t stream_) {
+  using namespace fg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FG_CHECK_ARG(qkv && out, "attention: null pointer");
+  FG_CHECK_ARG(n > 0 && tokens > 0 && heads > 0 && d > 0, "attention: empty problem");
+  FG_CHECK_ARG(d % 8 == 0 && d <= 256, "attention: head dim %d must be a multiple of 8 and <= 256", d);
+  FG_CHECK_ARG(qkv_ld >= 3 * heads * d && qkv_ld % 8 == 0, "attention: qkv_ld %lld too small / unaligned",
+               (long long)qkv_ld);
+  FG_CHECK_ARG(out_ld >= heads * d && out_ld % 8 == 0, "attention: out_ld %lld too small / unaligned",
+               (long long)out_ld);
+  FG_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+               "attention: pointers must be 16-byte aligned");
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = n, kp.T = tokens, kp.H = heads, kp.d = d;
+  kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(d));
+  kp.out = static_cast<__nv_bfloat16*>(out);
+  kp.out_ld = out_ld;
+  if (d <= 64) return launch_attention<64, 128>(kp, qkv, qkv_ld, stream);
+  if (d <= 128) return launch_attention<128, 128>(kp, qkv, qkv_ld, stream);
+  return launch_attention<256, 64>(kp, qkv, qkv_ld, stream);
+}

@@ -1,0 +1,345 @@
+// GroupNorm for channels-last activations, split into a statistics pass and a fused apply pass.
+//   fg_gn_stats : per (sample, group) sum / sum-of-squares, fp32 per-thread partials merged in fp64.
+//   fg_gn_apply : y = [silu]( (x-mean)*rstd*gamma+beta ) * (1+scale) + shift ), written as the bf16 operand
+//                 of the next convolution, optionally 2x up/down-sampled on the fly, optionally with a bf16
+//                 low part (split precision) and a bf16 copy of the raw input for the 1x1 skip projection.
+// Both kernels are HBM-bound streaming kernels: 16-byte vector accesses, a warp covers 512 contiguous bytes.
+//
+// Replaces: fastgen/networks/EDM/network.py:141-149 (GroupNorm.forward), silu/addcmul at :276-283 and the
+// depthwise resample convolutions at :114-121.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fg {
+
+constexpr int kGnThreads = 256;
+
+template <typename T>
+struct Vec;  // 16-byte vector of T
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 f;
+    f = unpack_bf16x2(a.x), v[0] = f.x, v[1] = f.y;
+    f = unpack_bf16x2(a.y), v[2] = f.x, v[3] = f.y;
+    f = unpack_bf16x2(a.z), v[4] = f.x, v[5] = f.y;
+    f = unpack_bf16x2(a.w), v[6] = f.x, v[7] = f.y;
+  }
+};
+
+// grid (slabs, n).  A warp owns a pixel row subset; lane l handles channel vectors l, l+32, ...
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restrict__ x, int64_t ld, int hw, int c,
+                                                              int cg, int groups, int pix_per_slab,
+                                                              double* __restrict__ stats) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ double s_acc[];  // [groups][2]
+  for (int i = threadIdx.x; i < groups * 2; i += kGnThreads) s_acc[i] = 0.0;
+  __syncthreads();
+
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_slab;
+  const int p1 = min(hw, p0 + pix_per_slab);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kGnThreads / 32;
+  const int nvec = c / V;
+  const T* base = x + static_cast<int64_t>(n) * hw * ld;
+
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float s[V], ss[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = 0.f, ss[k] = 0.f;
+    int pix = p0 + warp;
+    // 4 independent loads in flight per thread
+    for (; pix + 3 * kWarps < p1; pix += 4 * kWarps) {
+      float v0[V], v1[V], v2[V], v3[V];
+      Vec<T>::load(base + static_cast<int64_t>(pix) * ld + vi * V, v0);
+      Vec<T>::load(base + static_cast<int64_t>(pix + kWarps) * ld + vi * V, v1);
+      Vec<T>::load(base + static_cast<int64_t>(pix + 2 * kWarps) * ld + vi * V, v2);
+      Vec<T>::load(base + static_cast<int64_t>(pix + 3 * kWarps) * ld + vi * V, v3);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        s[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+        ss[k] += (v0[k] * v0[k] + v1[k] * v1[k]) + (v2[k] * v2[k] + v3[k] * v3[k]);
+      }
+    }
+    for (; pix < p1; pix += kWarps) {
+      float v0[V];
+      Vec<T>::load(base + static_cast<int64_t>(pix) * ld + vi * V, v0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) s[k] += v0[k], ss[k] += v0[k] * v0[k];
+    }
+    // fold the V channels of this thread into their groups (a vector may straddle a group boundary)
+    int g_prev = (vi * V) / cg;
+    double ds = 0.0, dss = 0.0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int g = (vi * V + k) / cg;
+      if (g != g_prev) {
+        atomicAdd(&s_acc[2 * g_prev], ds);
+        atomicAdd(&s_acc[2 * g_prev + 1], dss);
+        ds = 0.0, dss = 0.0, g_prev = g;
+      }
+      ds += static_cast<double>(s[k]);
+      dss += static_cast<double>(ss[k]);
+    }
+    atomicAdd(&s_acc[2 * g_prev], ds);
+    atomicAdd(&s_acc[2 * g_prev + 1], dss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += kGnThreads)
+    atomicAdd(&stats[static_cast<int64_t>(n) * groups * 2 + i], s_acc[i]);
+}
+
+struct GnApplyK {
+  const void* x;
+  int64_t x_ld;
+  int n, h, w, c, groups, cg;
+  const double* stats;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* scale;
+  const float* shift;
+  int64_t mod_ld;
+  int silu, resample;
+  __nv_bfloat16* y;
+  int64_t y_ld;
+  __nv_bfloat16* y_lo;
+  __nv_bfloat16* raw;
+  int64_t raw_ld;
+  __nv_bfloat16* raw_lo;
+  int pix_per_slab;  // in OUTPUT pixels for DOWN2, input pixels otherwise
+};
+
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void split8(const float (&v)[8], float (&lo)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) lo[k] = v[k] - __bfloat162float(__float2bfloat16_rn(v[k]));
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  Vec<__nv_bfloat16>::load(p, v);
+}
+
+// grid (slabs, n): coefficients a[c], b[c] with y = a*x + b are built once per CTA in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyK p) {
+  extern __shared__ float s_coef[];  // a[c] | b[c]
+  float* s_a = s_coef;
+  float* s_b = s_coef + p.c;
+  const int n = blockIdx.y;
+  const int hw = p.h * p.w;
+  {
+    const double cnt = static_cast<double>(hw) * p.cg;
+    for (int ch = threadIdx.x; ch < p.c; ch += kGnThreads) {
+      const int g = ch / p.cg;
+      const double s = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2];
+      const double ss = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2 + 1];
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+      const float meanf = static_cast<float>(mean);
+      float a = rstd * __ldg(p.gamma + ch);
+      float b = __ldg(p.beta + ch) - meanf * a;
+      if (p.scale) {
+        const float sc = 1.0f + __ldg(p.scale + n * p.mod_ld + ch);
+        a *= sc;
+        b *= sc;
+      }
+      if (p.shift) b += __ldg(p.shift + n * p.mod_ld + ch);
+      s_a[ch] = a;
+      s_b[ch] = b;
+    }
+  }
+  __syncthreads();
+
+  const T* xb = static_cast<const T*>(p.x) + static_cast<int64_t>(n) * hw * p.x_ld;
+  const int nvec = p.c >> 3;
+
+  if (p.resample == FG_RES_DOWN2) {
+    const int ow = p.w >> 1, ohw = (p.h >> 1) * ow;
+    const int q0 = blockIdx.x * p.pix_per_slab;
+    const int q1 = min(ohw, q0 + p.pix_per_slab);
+    const int64_t total = static_cast<int64_t>(q1 - q0) * nvec;
+    for (int64_t idx = threadIdx.x; idx < total; idx += kGnThreads) {
+      const int vi = static_cast<int>(idx % nvec);
+      const int opix = q0 + static_cast<int>(idx / nvec);
+      const int oy = opix / ow, ox = opix % ow;
+      float a8[8], b8[8], acc[8], racc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a8[k] = s_a[vi * 8 + k], b8[k] = s_b[vi * 8 + k], acc[k] = 0.f, racc[k] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int ipix = (2 * oy + (d >> 1)) * p.w + 2 * ox + (d & 1);
+        float v[8];
+        load8<T>(xb + static_cast<int64_t>(ipix) * p.x_ld + vi * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float yv = fmaf(a8[k], v[k], b8[k]);
+          if (p.silu) yv = silu_f(yv);
+          acc[k] += yv;
+          racc[k] += v[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= 0.25f, racc[k] *= 0.25f;
+      const int64_t o = (static_cast<int64_t>(n) * ohw + opix);
+      store8_bf16(p.y + o * p.y_ld + vi * 8, acc);
+      if (p.y_lo) {
+        float lo[8];
+        split8(acc, lo);
+        store8_bf16(p.y_lo + o * p.y_ld + vi * 8, lo);
+      }
+      if (p.raw) {
+        store8_bf16(p.raw + o * p.raw_ld + vi * 8, racc);
+        if (p.raw_lo) {
+          float lo[8];
+          split8(racc, lo);
+          store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, lo);
+        }
+      }
+    }
+    return;
+  }
+
+  const int p0 = blockIdx.x * p.pix_per_slab;
+  const int p1 = min(hw, p0 + p.pix_per_slab);
+  const int64_t total = static_cast<int64_t>(p1 - p0) * nvec;
+  for (int64_t idx = threadIdx.x; idx < total; idx += kGnThreads) {
+    const int vi = static_cast<int>(idx % nvec);
+    const int pix = p0 + static_cast<int>(idx / nvec);
+    float v[8], yv[8];
+    load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + vi * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = fmaf(s_a[vi * 8 + k], v[k], s_b[vi * 8 + k]);
+      yv[k] = p.silu ? silu_f(t) : t;
+    }
+    float ylo[8], rlo[8];
+    if (p.y_lo) split8(yv, ylo);
+    if (p.raw_lo) split8(v, rlo);
+    if (p.resample == FG_RES_UP2) {
+      const int iy = pix / p.w, ix = pix % p.w;
+      const int W2 = p.w * 2;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t o = static_cast<int64_t>(n) * hw * 4 + static_cast<int64_t>(2 * iy + (d >> 1)) * W2 + 2 * ix + (d & 1);
+        store8_bf16(p.y + o * p.y_ld + vi * 8, yv);
+        if (p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + vi * 8, ylo);
+        if (p.raw) store8_bf16(p.raw + o * p.raw_ld + vi * 8, v);
+        if (p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, rlo);
+      }
+    } else {
+      const int64_t o = static_cast<int64_t>(n) * hw + pix;
+      store8_bf16(p.y + o * p.y_ld + vi * 8, yv);
+      if (p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + vi * 8, ylo);
+      if (p.raw) store8_bf16(p.raw + o * p.raw_ld + vi * 8, v);
+      if (p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, rlo);
+    }
+  }
+}
+
+static int pick_slab(int n, int pixels, int c, int* pix_per_slab) {
+  // ~64K elements per CTA, but at least ~4 CTAs per SM in total when the batch is small
+  int64_t slabs = (static_cast<int64_t>(pixels) * c + 65535) / 65536;
+  const int64_t want = (592 + n - 1) / n;
+  if (slabs < want) slabs = want;
+  if (slabs > pixels) slabs = pixels;
+  if (slabs < 1) slabs = 1;
+  *pix_per_slab = static_cast<int>((pixels + slabs - 1) / slabs);
+  return static_cast<int>((pixels + *pix_per_slab - 1) / *pix_per_slab);
+}
+
+}  // namespace fg
+
+extern "C" int fg_gn_stats(const void* x, int32_t x_dtype, int64_t x_ld, int32_t n, int32_t hw, int32_t c,
+                           int32_t groups, double* stats, fg_stream_t stream_) {
+  using namespace fg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FG_CHECK_ARG(x && stats, "gn_stats: null pointer");
+  FG_CHECK_ARG(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0, "gn_stats: bad shape n=%d hw=%d c=%d g=%d", n,
+               hw, c, groups);
+  FG_CHECK_ARG(x_dtype == FG_F32 || x_dtype == FG_BF16, "gn_stats: bad dtype %d", x_dtype);
+  const int v = x_dtype == FG_F32 ? 4 : 8;
+  FG_CHECK_ARG(c % v == 0 && x_ld % v == 0 && x_ld >= c, "gn_stats: c=%d / ld=%lld must be multiples of %d", c,
+               (long long)x_ld, v);
+  FG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "gn_stats: x must be 16-byte aligned");
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * groups, stream) != cudaSuccess) {
+    set_error("gn_stats: memset failed");
+    return FG_ERR_CUDA;
+  }
+  int pps = 0;
+  const int slabs = pick_slab(n, hw, c, &pps);
+  const dim3 grid(slabs, n);
+  const size_t smem = sizeof(double) * 2 * groups;
+  if (x_dtype == FG_F32)
+    gn_stats_kernel<float><<<grid, kGnThreads, smem, stream>>>(static_cast<const float*>(x), x_ld, hw, c, c / groups,
+                                                               groups, pps, stats);
+  else
+    gn_stats_kernel<__nv_bfloat16><<<grid, kGnThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ld, hw,
+                                                                       c, c / groups, groups, pps, stats);
+  FG_CHECK_LAUNCH("gn_stats");
+  return FG_OK;
+}
+
+extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
+  using namespace fg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FG_CHECK_ARG(p && p->x && p->stats && p->gamma && p->beta && p->y, "gn_apply: null pointer");
+  FG_CHECK_ARG(p->n > 0 && p->h > 0 && p->w > 0 && p->c > 0 && p->groups > 0 && p->c % p->groups == 0,
+               "gn_apply: bad shape");
+  FG_CHECK_ARG(p->x_dtype == FG_F32 || p->x_dtype == FG_BF16, "gn_apply: bad dtype %d", p->x_dtype);
+  FG_CHECK_ARG(p->c % 8 == 0 && p->x_ld % 8 == 0 && p->y_ld % 8 == 0 && p->x_ld >= p->c && p->y_ld >= p->c,
+               "gn_apply: c=%d, x_ld=%lld, y_ld=%lld must be multiples of 8 and ld >= c", p->c, (long long)p->x_ld,
+               (long long)p->y_ld);
+  FG_CHECK_ARG(p->resample >= FG_RES_NONE && p->resample <= FG_RES_DOWN2 && p->resample != FG_RES_SAME,
+               "gn_apply: bad resample %d", p->resample);
+  if (p->resample == FG_RES_DOWN2) FG_CHECK_ARG(p->h % 2 == 0 && p->w % 2 == 0, "gn_apply: DOWN2 needs even h,w");
+  if (p->raw) FG_CHECK_ARG(p->raw_ld % 8 == 0 && p->raw_ld >= p->c, "gn_apply: bad raw_ld");
+  if (p->scale || p->shift) FG_CHECK_ARG(p->mod_ld >= p->c, "gn_apply: mod_ld < c");
+  GnApplyK k;
+  k.x = p->x, k.x_ld = p->x_ld, k.n = p->n, k.h = p->h, k.w = p->w, k.c = p->c, k.groups = p->groups;
+  k.cg = p->c / p->groups;
+  k.stats = p->stats, k.eps = p->eps, k.gamma = p->gamma, k.beta = p->beta;
+  k.scale = p->scale, k.shift = p->shift, k.mod_ld = p->mod_ld, k.silu = p->silu, k.resample = p->resample;
+  k.y = static_cast<__nv_bfloat16*>(p->y), k.y_ld = p->y_ld, k.y_lo = static_cast<__nv_bfloat16*>(p->y_lo);
+  k.raw = static_cast<__nv_bfloat16*>(p->raw), k.raw_ld = p->raw_ld, k.raw_lo = static_cast<__nv_bfloat16*>(p->raw_lo);
+  const int pixels = p->resample == FG_RES_DOWN2 ? (p->h / 2) * (p->w / 2) : p->h * p->w;
+  const int slabs = pick_slab(p->n, pixels, p->c, &k.pix_per_slab);
+  const dim3 grid(slabs, p->n);
+  const size_t smem = sizeof(float) * 2 * p->c;
+  if (p->x_dtype == FG_F32)
+    gn_apply_kernel<float><<<grid, kGnThreads, smem, stream>>>(k);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid, kGnThreads, smem, stream>>>(k);
+  FG_CHECK_LAUNCH("gn_apply");
+  return FG_OK;
+}

@@ -1,0 +1,184 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/fastgen_b200.h``).
+
+PyTorch is used for device memory and streams only: every function here passes raw device
+pointers and sizes to ``libfastgen_b200.so`` on the current CUDA stream (so the calls are
+CUDA-graph capturable) and raises if the library reports an error.  No function has a
+PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.FG_F32, torch.bfloat16: L.FG_BF16, torch.float64: L.FG_F64}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.FastGenB200Error("fastgen_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+class Seg:
+    """One K segment of :func:`conv_gemm`: bf16 activation view [N,H,W,cin] (pixel stride ``ld``) and its weight."""
+
+    __slots__ = ("a", "ld", "w", "cin", "taps")
+
+    def __init__(self, a: torch.Tensor, ld: int, w: torch.Tensor, cin: int, taps: int):
+        self.a, self.ld, self.w, self.cin, self.taps = a, ld, w, cin, taps
+
+
+def conv_gemm(
+    segs: Sequence[Seg],
+    n: int, h: int, w: int, cout: int,
+    out: torch.Tensor, out_ld: int,
+    bias: Optional[torch.Tensor] = None,
+    rowvec: Optional[torch.Tensor] = None, rowvec_ld: int = 0,
+    res: Optional[torch.Tensor] = None, res_ld: int = 0, res_mode: int = L.FG_RES_NONE,
+    out_scale: float = 1.0,
+) -> None:
+    """out = out_scale * (sum_s conv(A_s, W_s) + bias + rowvec[n] + resample(res)) -- see ``fg_conv_gemm``."""
+    _need_cuda(out, bias, rowvec, res, *[s.a for s in segs], *[s.w for s in segs])
+    p = L.ConvParams()
+    p.n, p.h, p.w, p.cout, p.nseg = n, h, w, cout, len(segs)
+    if len(segs) > L.FG_MAX_SEG:
+        raise ValueError(f"conv_gemm: {len(segs)} segments > FG_MAX_SEG={L.FG_MAX_SEG}")
+    for i, s in enumerate(segs):
+        if s.a.dtype != torch.bfloat16 or s.w.dtype != torch.bfloat16:
+            raise ValueError("conv_gemm: operands must be bfloat16")
+        p.seg[i].a, p.seg[i].a_ld, p.seg[i].w, p.seg[i].cin, p.seg[i].taps = s.a.data_ptr(), s.ld, s.w.data_ptr(), s.cin, s.taps
+    p.bias = _ptr(bias)
+    p.rowvec, p.rowvec_ld = _ptr(rowvec), rowvec_ld
+    p.res, p.res_ld, p.res_mode = _ptr(res), res_ld, (res_mode if res is not None else L.FG_RES_NONE)
+    p.res_dtype = _DT[res.dtype] if res is not None else 0
+    p.out_scale = out_scale
+    p.out, p.out_dtype, p.out_ld = out.data_ptr(), _DT[out.dtype], out_ld
+    L.check(L.lib().fg_conv_gemm(C.byref(p), _stream()), "fg_conv_gemm")
+
+
+def gn_stats(x: torch.Tensor, x_ld: int, n: int, hw: int, c: int, groups: int, stats: torch.Tensor) -> None:
+    _need_cuda(x, stats)
+    assert stats.dtype == torch.float64 and stats.numel() >= 2 * n * groups
+    L.check(L.lib().fg_gn_stats(x.data_ptr(), _DT[x.dtype], x_ld, n, hw, c, groups, stats.data_ptr(), _stream()),
+            "fg_gn_stats")
+
+
+def gn_apply(
+    x: torch.Tensor, x_ld: int, n: int, h: int, w: int, c: int, groups: int,
+    stats: torch.Tensor, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+    y: torch.Tensor, y_ld: int,
+    scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, mod_ld: int = 0,
+    silu: bool = True, resample: int = L.FG_RES_NONE,
+    y_lo: Optional[torch.Tensor] = None,
+    raw: Optional[torch.Tensor] = None, raw_ld: int = 0, raw_lo: Optional[torch.Tensor] = None,
+) -> None:
+    _need_cuda(x, stats, gamma, beta, y, scale, shift, y_lo, raw, raw_lo)
+    p = L.GnApplyParams()
+    p.x, p.x_dtype, p.x_ld = x.data_ptr(), _DT[x.dtype], x_ld
+    p.n, p.h, p.w, p.c, p.groups = n, h, w, c, groups
+    p.stats, p.eps = stats.data_ptr(), eps
+    p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    p.scale, p.shift, p.mod_ld = _ptr(scale), _ptr(shift), mod_ld
+    p.silu, p.resample = int(silu), resample
+    p.y, p.y_ld, p.y_lo = y.data_ptr(), y_ld, _ptr(y_lo)
+    p.raw, p.raw_ld, p.raw_lo = _ptr(raw), raw_ld, _ptr(raw_lo)
+    L.check(L.lib().fg_gn_apply(C.byref(p), _stream()), "fg_gn_apply")
+
+
+def attention(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d: int,
+              out: torch.Tensor, out_ld: int) -> None:
+    _need_cuda(qkv, out)
+    L.check(L.lib().fg_attention(qkv.data_ptr(), qkv_ld, n, tokens, heads, d, out.data_ptr(), out_ld, _stream()),
+            "fg_attention")
+
+
+def edm_input(x: torch.Tensor, c_in: Optional[torch.Tensor], xin: torch.Tensor, c_pad: int,
+              xin_lo: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(x, c_in, xin, xin_lo)
+    n, c = x.shape[0], x.shape[1]
+    hw = x[0, 0].numel()
+    assert x.is_contiguous()
+    L.check(L.lib().fg_edm_input(x.data_ptr(), _DT[x.dtype], n, c, hw, _ptr(c_in), xin.data_ptr(), _ptr(xin_lo), c_pad,
+                                 _stream()), "fg_edm_input")
+
+
+def edm_step(
+    f: torch.Tensor, f_ld: int, x_t: torch.Tensor, x0: torch.Tensor,
+    c_skip: Optional[torch.Tensor], c_out: Optional[torch.Tensor],
+    x_next: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
+    alpha_next: Optional[torch.Tensor] = None, sigma_next: Optional[torch.Tensor] = None,
+    ode: bool = False, alpha_cur: Optional[torch.Tensor] = None, sigma_cur: Optional[torch.Tensor] = None,
+) -> None:
+    _need_cuda(f, x_t, x0, c_skip, c_out, x_next, eps, alpha_next, sigma_next, alpha_cur, sigma_cur)
+    assert x_t.is_contiguous() and x0.is_contiguous() and f.dtype == torch.float32
+    p = L.EdmStepParams()
+    p.f, p.f_ld = f.data_ptr(), f_ld
+    p.x_t, p.eps, p.x_dtype = x_t.data_ptr(), _ptr(eps), _DT[x_t.dtype]
+    p.n, p.c, p.hw = x_t.shape[0], x_t.shape[1], x_t[0, 0].numel()
+    p.c_skip, p.c_out = _ptr(c_skip), _ptr(c_out)
+    p.ode = int(ode)
+    p.alpha_cur, p.sigma_cur = _ptr(alpha_cur), _ptr(sigma_cur)
+    p.alpha_next, p.sigma_next = _ptr(alpha_next), _ptr(sigma_next)
+    p.x0, p.x_next = x0.data_ptr(), _ptr(x_next)
+    L.check(L.lib().fg_edm_step(C.byref(p), _stream()), "fg_edm_step")
+
+
+def axpby(a: torch.Tensor, ca: torch.Tensor, b: Optional[torch.Tensor] = None, cb: Optional[torch.Tensor] = None,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = cast(double(a)*ca[n] + double(b)*cb[n]) with per-sample fp64 coefficients (one rounding)."""
+    _need_cuda(a, b, ca, cb)
+    assert a.is_contiguous() and (b is None or b.is_contiguous())
+    assert ca.dtype == torch.float64 and (cb is None or cb.dtype == torch.float64)
+    out = torch.empty_like(a) if out is None else out
+    n = a.shape[0]
+    L.check(L.lib().fg_axpby(a.data_ptr(), _ptr(b), _DT[a.dtype], n, a.numel() // n, ca.data_ptr(), _ptr(cb),
+                             out.data_ptr(), _stream()), "fg_axpby")
+    return out
+
+
+def sub_div(a: torch.Tensor, b: torch.Tensor, cb: torch.Tensor, cd: torch.Tensor,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = cast((double(a) - double(b)*cb[n]) / cd[n])."""
+    _need_cuda(a, b, cb, cd)
+    assert a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a) if out is None else out
+    n = a.shape[0]
+    L.check(L.lib().fg_sub_div(a.data_ptr(), b.data_ptr(), _DT[a.dtype], n, a.numel() // n, cb.data_ptr(),
+                               cd.data_ptr(), out.data_ptr(), _stream()), "fg_sub_div")
+    return out
+
+
+def pos_embedding(t: torch.Tensor, channels: int, max_positions: int, endpoint: bool, swap: bool,
+                  out: torch.Tensor, out_ld: int) -> None:
+    _need_cuda(t, out)
+    assert t.dtype == torch.float32 and out.dtype == torch.float32
+    L.check(L.lib().fg_pos_embedding(t.data_ptr(), t.numel(), channels, max_positions, int(endpoint), int(swap),
+                                     out.data_ptr(), out_ld, _stream()), "fg_pos_embedding")
+
+
+def split_bf16(x: torch.Tensor, x_ld: int, n: int, c: int, hi: torch.Tensor, out_ld: int,
+               lo: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None, add_ld: int = 0,
+               act: int = 0, y: Optional[torch.Tensor] = None, y_ld: int = 0) -> None:
+    _need_cuda(x, hi, lo, add, y)
+    L.check(L.lib().fg_split_bf16(x.data_ptr(), x_ld, _ptr(add), add_ld, n, c, act, hi.data_ptr(), _ptr(lo), out_ld,
+                                  _ptr(y), y_ld, _stream()), "fg_split_bf16")
+
+
+def launch_count() -> int:
+    return int(L.lib().fg_launch_count())
+
+
+def launch_count_reset() -> None:
+    L.lib().fg_launch_count_reset()

@@ -1,0 +1,177 @@
+/*
+ * fastgen_b200 -- C ABI of the B200 (sm_100a) kernels behind the FastGen few-step student sampler.
+ *
+ * The reference (linnanwang/FastGen) is pure Python/PyTorch and has no FFI of its own; the "operator
+ * API" of its hot path is two Python contracts: the network forward
+ * `FastGenNetwork.forward(x_t, t, condition, ..., fwd_pred_type)` (fastgen/networks/network.py:156-208)
+ * and the sampler `FastGenModel.generator_fn / _student_sample_loop` (fastgen/methods/model.py:315-420).
+ * Every entry point below replaces the PyTorch/ATen/cuDNN call(s) the reference makes at the cited lines;
+ * `fastgen_b200/` (Python) re-assembles them behind those two contracts and binds this file with ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - activations are channels-last: a "pixel row" is `C` contiguous elements, consecutive pixels of a
+ *     [N,H,W,C] tensor are `ld` elements apart (ld >= C lets a tensor live inside a wider concat buffer);
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, keeps no global state
+ *     besides a cached driver entry point, and is CUDA-graph capturable;
+ *   - return value: FG_OK (0) or a negative fg_status; fg_last_error() gives a thread-local message.
+ */
+#ifndef FASTGEN_B200_H_
+#define FASTGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fg_stream_t; /* cudaStream_t */
+
+typedef enum { FG_OK = 0, FG_ERR_INVALID = -1, FG_ERR_CUDA = -2, FG_ERR_UNSUPPORTED = -3 } fg_status;
+typedef enum { FG_F32 = 0, FG_BF16 = 1, FG_F64 = 2 } fg_dtype;
+typedef enum { FG_RES_NONE = 0, FG_RES_SAME = 1, FG_RES_UP2 = 2, FG_RES_DOWN2 = 3 } fg_resample;
+
+const char* fg_last_error(void);
+int fg_version(void);
+/* number of kernels this library has launched on the calling thread since the last reset (bench bookkeeping) */
+int64_t fg_launch_count(void);
+void fg_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-staged, TMEM accumulators).
+ * Replaces F.conv2d 3x3/1x1 (fastgen/networks/EDM/network.py:109-123), Linear (:47-51) and the
+ * bias / embedding / skip-add / skip_scale elementwise tail of UNetBlock.forward (:276-298).
+ *
+ *   out[p, co] = out_scale * ( sum_s sum_tap sum_ci  A_s[p + tap, ci] * W_s[co, tap, ci]
+ *                              + bias[co] + rowvec[n(p), co] + resample(res)[p, co] )
+ *
+ * Each K segment s has its own bf16 activation A_s (same N,H,W; zero padding 1 for 3x3) and bf16 weight
+ * W_s laid out [cout][taps][cin]; several segments accumulate into one TMEM tile, which is how a block's
+ * conv1 + 1x1 skip projection, and the bf16x3 split-precision ("fp32 path") products, become ONE launch.
+ * H=W=1 turns it into a plain row-major GEMM  out[n, co] = A[n, :] . W[co, :].
+ * ---------------------------------------------------------------------------------------------------- */
+#define FG_MAX_SEG 6
+
+typedef struct {
+  const void* a;  /* bf16 [N,H,W,cin], pixel stride a_ld elements (a_ld % 8 == 0, 16-byte aligned base) */
+  int64_t a_ld;
+  const void* w;  /* bf16 [cout][taps][cin] contiguous */
+  int32_t cin;    /* % 8 == 0 */
+  int32_t taps;   /* 1 (1x1 / linear) or 9 (3x3, pad 1, tap = kh*3+kw) */
+} fg_conv_seg;
+
+typedef struct {
+  int32_t n, h, w;      /* output == input spatial size (stride-1 conv); w, h powers of two or multiples of 128 */
+  int32_t cout;
+  int32_t nseg;
+  fg_conv_seg seg[FG_MAX_SEG];
+  const float* bias;    /* [cout] fp32 or NULL */
+  const float* rowvec;  /* [n][rowvec_ld] fp32 per-sample additive vector or NULL (UNetBlock `x.add_(params)`) */
+  int64_t rowvec_ld;
+  const void* res;      /* residual input or NULL; FG_RES_UP2 reads a (h/2,w/2) tensor (nearest), FG_RES_DOWN2 */
+  int32_t res_dtype;    /* averages 2x2 of a (2h,2w) tensor: the kernel-0 skip of up/down blocks (:253-262)     */
+  int32_t res_mode;
+  int64_t res_ld;
+  float out_scale;      /* skip_scale (:287,298) */
+  void* out;            /* [N,H,W,cout] fp32 or bf16, pixel stride out_ld */
+  int32_t out_dtype;
+  int64_t out_ld;
+} fg_conv_params;
+
+int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GroupNorm (+ per-sample scale/shift, + SiLU, + 2x resample) -- replaces torch group_norm + silu +
+ * addcmul + the depthwise resample convs (fastgen/networks/EDM/network.py:141-149, 114-121, 276-283).
+ * ---------------------------------------------------------------------------------------------------- */
+/* stats[n][g] = {sum, sum of squares} (fp64) over the hw * (c/groups) elements of group g of sample n. */
+int fg_gn_stats(const void* x, int32_t x_dtype, int64_t x_ld, int32_t n, int32_t hw, int32_t c, int32_t groups,
+                double* stats, fg_stream_t stream);
+
+typedef struct {
+  const void* x;        /* [N,H,W,C] fp32 or bf16 */
+  int32_t x_dtype;
+  int64_t x_ld;
+  int32_t n, h, w, c, groups;
+  const double* stats;  /* from fg_gn_stats */
+  float eps;
+  const float* gamma;   /* [c] */
+  const float* beta;    /* [c] */
+  const float* scale;   /* [n][mod_ld] or NULL: y = shift + gn(x) * (1 + scale)  (adaptive_scale, :279-281) */
+  const float* shift;   /* [n][mod_ld] or NULL */
+  int64_t mod_ld;
+  int32_t silu;         /* apply SiLU after the affine */
+  int32_t resample;     /* FG_RES_NONE / FG_RES_UP2 (nearest, output 2h x 2w) / FG_RES_DOWN2 (2x2 mean, h/2 x w/2) */
+  void* y;              /* bf16 normalised output (the next conv's A operand), pixel stride y_ld */
+  int64_t y_ld;
+  void* y_lo;           /* optional bf16 low part: y + y_lo carries ~16 mantissa bits (fp32 path) or NULL */
+  void* raw;            /* optional bf16 copy of x itself under the same resample (skip 1x1 operand) or NULL */
+  int64_t raw_ld;
+  void* raw_lo;         /* optional low part of raw or NULL */
+} fg_gn_apply_params;
+
+int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * UNet self-attention (softmax(q.k/sqrt(d)) v per head, fp32 softmax) -- replaces AttentionOp + the two
+ * einsums (fastgen/networks/EDM/network.py:160-168, 290-296).  qkv is the 1x1-conv output in channels-last
+ * form [N, T, 3*heads*d] with channel order (q|k|v, head, d) (the wrapper permutes the conv's rows once).
+ * ---------------------------------------------------------------------------------------------------- */
+int fg_attention(const void* qkv /* bf16 */, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
+                 void* out /* bf16 [N,T,heads*d] */, int64_t out_ld, fg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Sampler-step kernels (fastgen/methods/model.py:346-370, noise_schedule.py:72-88,425-449,544-574,
+ * EDM/network.py:755-805).  x tensors are the caller's NCHW latents; `f` is the network's raw output in
+ * channels-last fp32 with pixel stride f_ld.  Per-sample coefficients are fp64 [n] device arrays computed
+ * by the host mirror of the noise schedule, so they are bit-identical to the reference's.
+ * ---------------------------------------------------------------------------------------------------- */
+/* xin[n,h,w,c_pad] (bf16, zero padded channels; optional low part) = cast(c_in[n]) * x[n,c,h,w]  (:771-773) */
+int fg_edm_input(const void* x, int32_t x_dtype, int32_t n, int32_t c, int32_t hw, const double* c_in,
+                 void* xin, void* xin_lo, int32_t c_pad, fg_stream_t stream);
+
+/* x0 = cast(c_skip)*x_t + cast(c_out)*F in x dtype (:800-805);  if eps != NULL also
+ * x_next = cast_x( double(x0)*alpha_next + double(eps)*sigma_next )  (noise_schedule.py:441-449).
+ * eps == NULL and ode != 0: eps is derived as (x_t - x0*alpha_cur)/clamp(sigma_cur) (:544-574) first. */
+typedef struct {
+  const void* f;        /* fp32 [N,H,W,f_ld] raw network output */
+  int64_t f_ld;
+  const void* x_t;      /* NCHW, x_dtype */
+  const void* eps;      /* NCHW, x_dtype, or NULL */
+  int32_t x_dtype;
+  int32_t n, c, hw;
+  const double* c_skip; /* [n] or NULL (drop_precond output): x0 = F */
+  const double* c_out;  /* [n] */
+  int32_t ode;
+  const double* alpha_cur;  /* [n], ode only */
+  const double* sigma_cur;  /* [n], ode only (already non-zero-clamped by the host) */
+  const double* alpha_next; /* [n] or NULL: no re-noising (last step) */
+  const double* sigma_next; /* [n] */
+  void* x0;             /* NCHW out */
+  void* x_next;         /* NCHW out or NULL */
+} fg_edm_step_params;
+
+int fg_edm_step(const fg_edm_step_params* p, fg_stream_t stream);
+
+/* out = cast( double(a)*ca[n] + double(b)*cb[n] ) elementwise over [n][inner]; b may be NULL.
+ * Covers latents() (noise*sigma), forward_process (x*alpha + eps*sigma), flow_to_x0 (x - v*t), the
+ * MeanFlow update (x - dt*u) -- all "fp64 arithmetic, one rounding" in the reference. */
+int fg_axpby(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* ca,
+             const double* cb, void* out, fg_stream_t stream);
+
+/* (a - b*cb[n]) / cd[n] in fp64, one rounding: x0_to_eps / eps_to_x0 (noise_schedule.py:544-608). */
+int fg_sub_div(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* cb,
+               const double* cd, void* out, fg_stream_t stream);
+
+/* small helpers used by the embedding path */
+/* PositionalEmbedding (:306-319): out[n, :] = [cos(t*f) | sin(t*f)] (optionally swapped), fp32 */
+int fg_pos_embedding(const float* t, int32_t n, int32_t channels, int32_t max_positions, int32_t endpoint,
+                     int32_t swap_sin_cos, float* out, int64_t out_ld, fg_stream_t stream);
+/* y = act(x + add) split into bf16 hi/lo;  act: 0 none, 1 SiLU.  x fp32 [n][c] */
+int fg_split_bf16(const float* x, int64_t x_ld, const float* add, int64_t add_ld, int32_t n, int32_t c, int32_t act,
+                  void* hi, void* lo, int64_t out_ld, float* y_f32, int64_t y_ld, fg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTGEN_B200_H_ */
