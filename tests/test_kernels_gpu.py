@@ -316,3 +316,60 @@ def test_pos_embedding_and_split():
     ref = F.silu(x + add)
     assert torch.allclose(y, ref, atol=1e-6)
     assert _rel(hi.float() + lo.float(), ref) < 1e-5
+
+
+ATTN_CASES = [
+    # n, tokens, heads, d
+    (2, 1024, 6, 64),
+    (3, 256, 9, 64),
+    (2, 64, 12, 64),
+    (2, 256, 1, 256),
+    (2, 64, 1, 256),
+    (1, 16, 2, 32),     # tiny nets: d < 64 (TMA zero fill), T < one tile
+    (2, 4, 1, 64),
+    (1, 384, 2, 128),
+    (1, 4096, 2, 64),   # SDXL-like token count
+]
+
+
+@pytest.mark.parametrize("n,tokens,heads,d", ATTN_CASES)
+def test_attention_matches_torch(n, tokens, heads, d):
+    from fastgen_b200 import ops
+
+    torch.manual_seed(8)
+    dev = "cuda"
+    c = heads * d
+    ld = 3 * c + 8
+    buf = (torch.randn(n, tokens, ld, device=dev) * 1.5).bfloat16()
+    qkv = buf[..., :3 * c].float().reshape(n, tokens, 3, heads, d)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # [n, T, H, d]
+    w = torch.einsum("nqhd,nkhd->nhqk", q, k / math.sqrt(d)).softmax(dim=-1)
+    ref = torch.einsum("nhqk,nkhd->nqhd", w, v).reshape(n, tokens, c)
+    out = torch.zeros(n, tokens, c + 8, device=dev, dtype=torch.bfloat16)
+    ops.attention(buf, ld, n, tokens, heads, d, out, c + 8)
+    torch.cuda.synchronize()
+    assert out[..., c:].abs().max().item() == 0
+    assert _rel(out[..., :c], ref) < 1e-2, _rel(out[..., :c], ref)
+
+
+def test_attention_large_logits_rescale():
+    """running-max growth across KV tiles exercises the lazy O rescale"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(9)
+    dev = "cuda"
+    n, tokens, heads, d = 1, 512, 2, 64
+    c = heads * d
+    x = torch.randn(n, tokens, 3 * c, device=dev)
+    x[:, :, :2 * c] *= 4.0                      # sharp softmax
+    x[:, 384:, c:2 * c] *= 2.5                  # later keys carry much larger logits
+    buf = x.bfloat16()
+    qkv = buf.float().reshape(n, tokens, 3, heads, d)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    w = torch.einsum("nqhd,nkhd->nhqk", q, k / math.sqrt(d)).softmax(dim=-1)
+    ref = torch.einsum("nhqk,nkhd->nqhd", w, v).reshape(n, tokens, c)
+    out = torch.zeros(n, tokens, c, device=dev, dtype=torch.bfloat16)
+    ops.attention(buf, 3 * c, n, tokens, heads, d, out, c)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 1.5e-2, _rel(out, ref)
