@@ -93,8 +93,8 @@ def lib() -> C.CDLL:
     l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
     l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
-    l.fg_axpby.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
-    l.fg_sub_div.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
+    l.fg_axpby.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
+    l.fg_sub_div.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
     l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",

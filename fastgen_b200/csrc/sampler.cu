@@ -163,13 +163,13 @@ __global__ void __launch_bounds__(kEwThreads) edm_step_kernel(const EdmStepK p) 
 // generic fp64 helpers over [n][inner] tensors with per-sample fp64 coefficients
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int MODE>  // MODE 0: a*ca + b*cb ; MODE 1: (a - b*cb)/cd
-__global__ void __launch_bounds__(kEwThreads) coef_kernel(const T* __restrict__ a, const T* __restrict__ b, int n,
-                                                          int64_t inner, const double* __restrict__ c0,
-                                                          const double* __restrict__ c1, T* __restrict__ out) {
-  const int64_t total = static_cast<int64_t>(n) * inner;
+__global__ void __launch_bounds__(kEwThreads) coef_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                          int64_t total, int64_t outer, int64_t mid, int64_t inner,
+                                                          const double* __restrict__ c0, const double* __restrict__ c1,
+                                                          T* __restrict__ out) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kEwThreads) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * kEwThreads) {
-    const int img = static_cast<int>(i / inner);
+    const int64_t img = (i / outer) * mid + (i / inner) % mid;
     double r;
     if (MODE == 0) {
       r = __dmul_rn(to_double<T>(a[i]), c0[img]);
@@ -281,38 +281,44 @@ extern "C" int fg_edm_step(const fg_edm_step_params* p, fg_stream_t stream_) {
 }
 
 template <int MODE>
-static int launch_coef(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* c0,
-                       const double* c1, void* out, cudaStream_t stream, const char* name) {
+static int launch_coef(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid,
+                       int64_t inner, const double* c0, const double* c1, void* out, cudaStream_t stream,
+                       const char* name) {
   using namespace fg;
   FG_CHECK_ARG(a && out && c0, "%s: null pointer", name);
-  FG_CHECK_ARG(n > 0 && inner > 0, "%s: empty tensor", name);
+  FG_CHECK_ARG(total > 0 && outer > 0 && mid > 0 && inner > 0 && total % outer == 0 && outer % (mid * inner) == 0,
+               "%s: bad extents total=%lld outer=%lld mid=%lld inner=%lld", name, (long long)total, (long long)outer,
+               (long long)mid, (long long)inner);
   if (MODE == 0) FG_CHECK_ARG((b == nullptr) || c1, "%s: b given without its coefficient", name);
   if (MODE == 1) FG_CHECK_ARG(b && c1, "%s: null pointer", name);
-  const int grid = ew_grid(static_cast<int64_t>(n) * inner);
+  const int grid = ew_grid(total);
   if (dtype == FG_F32)
     coef_kernel<float, MODE><<<grid, kEwThreads, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b),
-                                                              n, inner, c0, c1, static_cast<float*>(out));
+                                                              total, outer, mid, inner, c0, c1,
+                                                              static_cast<float*>(out));
   else if (dtype == FG_BF16)
     coef_kernel<__nv_bfloat16, MODE><<<grid, kEwThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
-                                                                      static_cast<const __nv_bfloat16*>(b), n, inner, c0,
-                                                                      c1, static_cast<__nv_bfloat16*>(out));
+                                                                      static_cast<const __nv_bfloat16*>(b), total, outer,
+                                                                      mid, inner, c0, c1,
+                                                                      static_cast<__nv_bfloat16*>(out));
   else if (dtype == FG_F64)
     coef_kernel<double, MODE><<<grid, kEwThreads, 0, stream>>>(static_cast<const double*>(a),
-                                                               static_cast<const double*>(b), n, inner, c0, c1,
-                                                               static_cast<double*>(out));
+                                                               static_cast<const double*>(b), total, outer, mid, inner,
+                                                               c0, c1, static_cast<double*>(out));
   else
     FG_CHECK_ARG(false, "%s: unsupported dtype %d", name, dtype);
   FG_CHECK_LAUNCH(name);
   return FG_OK;
 }
 
-extern "C" int fg_axpby(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* ca,
-                        const double* cb, void* out, fg_stream_t stream) {
-  return launch_coef<0>(a, b, dtype, n, inner, ca, cb, out, static_cast<cudaStream_t>(stream), "axpby");
+extern "C" int fg_axpby(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid,
+                        int64_t inner, const double* ca, const double* cb, void* out, fg_stream_t stream) {
+  return launch_coef<0>(a, b, dtype, total, outer, mid, inner, ca, cb, out, static_cast<cudaStream_t>(stream), "axpby");
 }
-extern "C" int fg_sub_div(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* cb,
-                          const double* cd, void* out, fg_stream_t stream) {
-  return launch_coef<1>(a, b, dtype, n, inner, cb, cd, out, static_cast<cudaStream_t>(stream), "sub_div");
+extern "C" int fg_sub_div(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid,
+                          int64_t inner, const double* cb, const double* cd, void* out, fg_stream_t stream) {
+  return launch_coef<1>(a, b, dtype, total, outer, mid, inner, cb, cd, out, static_cast<cudaStream_t>(stream),
+                        "sub_div");
 }
 
 extern "C" int fg_pos_embedding(const float* t, int32_t n, int32_t channels, int32_t max_positions, int32_t endpoint,

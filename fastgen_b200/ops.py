@@ -40,7 +40,7 @@ class Seg:
         self.a, self.ld, self.w, self.cin, self.taps = a, ld, w, cin, taps
 
 
-def conv_gemm(
+def conv_gemm_params(
     segs: Sequence[Seg],
     n: int, h: int, w: int, cout: int,
     out: torch.Tensor, out_ld: int,
@@ -48,8 +48,8 @@ def conv_gemm(
     rowvec: Optional[torch.Tensor] = None, rowvec_ld: int = 0,
     res: Optional[torch.Tensor] = None, res_ld: int = 0, res_mode: int = L.FG_RES_NONE,
     out_scale: float = 1.0,
-) -> None:
-    """out = out_scale * (sum_s conv(A_s, W_s) + bias + rowvec[n] + resample(res)) -- see ``fg_conv_gemm``."""
+) -> "L.ConvParams":
+    """Fill an ``fg_conv_params`` (the tensors must stay alive and in place while the struct is used)."""
     _need_cuda(out, bias, rowvec, res, *[s.a for s in segs], *[s.w for s in segs])
     p = L.ConvParams()
     p.n, p.h, p.w, p.cout, p.nseg = n, h, w, cout, len(segs)
@@ -65,6 +65,12 @@ def conv_gemm(
     p.res_dtype = _DT[res.dtype] if res is not None else 0
     p.out_scale = out_scale
     p.out, p.out_dtype, p.out_ld = out.data_ptr(), _DT[out.dtype], out_ld
+    return p
+
+
+def conv_gemm(*args, **kwargs) -> None:
+    """out = out_scale * (sum_s conv(A_s, W_s) + bias + rowvec[n] + resample(res)) -- see ``fg_conv_gemm``."""
+    p = conv_gemm_params(*args, **kwargs)
     L.check(L.lib().fg_conv_gemm(C.byref(p), _stream()), "fg_conv_gemm")
 
 
@@ -75,7 +81,7 @@ def gn_stats(x: torch.Tensor, x_ld: int, n: int, hw: int, c: int, groups: int, s
             "fg_gn_stats")
 
 
-def gn_apply(
+def gn_apply_params(
     x: torch.Tensor, x_ld: int, n: int, h: int, w: int, c: int, groups: int,
     stats: torch.Tensor, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
     y: torch.Tensor, y_ld: int,
@@ -83,7 +89,7 @@ def gn_apply(
     silu: bool = True, resample: int = L.FG_RES_NONE,
     y_lo: Optional[torch.Tensor] = None,
     raw: Optional[torch.Tensor] = None, raw_ld: int = 0, raw_lo: Optional[torch.Tensor] = None,
-) -> None:
+) -> "L.GnApplyParams":
     _need_cuda(x, stats, gamma, beta, y, scale, shift, y_lo, raw, raw_lo)
     p = L.GnApplyParams()
     p.x, p.x_dtype, p.x_ld = x.data_ptr(), _DT[x.dtype], x_ld
@@ -94,6 +100,11 @@ def gn_apply(
     p.silu, p.resample = int(silu), resample
     p.y, p.y_ld, p.y_lo = y.data_ptr(), y_ld, _ptr(y_lo)
     p.raw, p.raw_ld, p.raw_lo = _ptr(raw), raw_ld, _ptr(raw_lo)
+    return p
+
+
+def gn_apply(*args, **kwargs) -> None:
+    p = gn_apply_params(*args, **kwargs)
     L.check(L.lib().fg_gn_apply(C.byref(p), _stream()), "fg_gn_apply")
 
 
@@ -135,27 +146,43 @@ def edm_step(
     L.check(L.lib().fg_edm_step(C.byref(p), _stream()), "fg_edm_step")
 
 
+def _coef_extents(a: torch.Tensor, coef: torch.Tensor) -> Tuple[int, int, int, int]:
+    """(total, outer, mid, inner) for a coefficient tensor that broadcasts against ``a`` like the reference's
+    ``expand_like``: a scalar, one value per sample ([B]), or one per (sample, frame) ([B,1,T,1,1] for 5-D ``a``)."""
+    total = a.numel()
+    k = coef.numel()
+    b = a.shape[0]
+    if k == 1:
+        return total, total, 1, total
+    if k == b:
+        return total, total // b, 1, total // b
+    if a.dim() == 5 and k == b * a.shape[2]:
+        hw = a.shape[3] * a.shape[4]
+        return total, total // b, a.shape[2], hw
+    raise ValueError(f"coefficient of {k} elements does not broadcast against tensor {tuple(a.shape)}")
+
+
 def axpby(a: torch.Tensor, ca: torch.Tensor, b: Optional[torch.Tensor] = None, cb: Optional[torch.Tensor] = None,
           out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = cast(double(a)*ca[n] + double(b)*cb[n]) with per-sample fp64 coefficients (one rounding)."""
+    """out = cast(double(a)*ca + double(b)*cb) with fp64 coefficients broadcast per sample / per frame (one rounding)."""
     _need_cuda(a, b, ca, cb)
     assert a.is_contiguous() and (b is None or b.is_contiguous())
     assert ca.dtype == torch.float64 and (cb is None or cb.dtype == torch.float64)
     out = torch.empty_like(a) if out is None else out
-    n = a.shape[0]
-    L.check(L.lib().fg_axpby(a.data_ptr(), _ptr(b), _DT[a.dtype], n, a.numel() // n, ca.data_ptr(), _ptr(cb),
+    total, outer, mid, inner = _coef_extents(a, ca)
+    L.check(L.lib().fg_axpby(a.data_ptr(), _ptr(b), _DT[a.dtype], total, outer, mid, inner, ca.data_ptr(), _ptr(cb),
                              out.data_ptr(), _stream()), "fg_axpby")
     return out
 
 
 def sub_div(a: torch.Tensor, b: torch.Tensor, cb: torch.Tensor, cd: torch.Tensor,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = cast((double(a) - double(b)*cb[n]) / cd[n])."""
+    """out = cast((double(a) - double(b)*cb) / cd)."""
     _need_cuda(a, b, cb, cd)
     assert a.is_contiguous() and b.is_contiguous()
     out = torch.empty_like(a) if out is None else out
-    n = a.shape[0]
-    L.check(L.lib().fg_sub_div(a.data_ptr(), b.data_ptr(), _DT[a.dtype], n, a.numel() // n, cb.data_ptr(),
+    total, outer, mid, inner = _coef_extents(a, cb)
+    L.check(L.lib().fg_sub_div(a.data_ptr(), b.data_ptr(), _DT[a.dtype], total, outer, mid, inner, cb.data_ptr(),
                                cd.data_ptr(), out.data_ptr(), _stream()), "fg_sub_div")
     return out
 

@@ -153,15 +153,17 @@ typedef struct {
 
 int fg_edm_step(const fg_edm_step_params* p, fg_stream_t stream);
 
-/* out = cast( double(a)*ca[n] + double(b)*cb[n] ) elementwise over [n][inner]; b may be NULL.
+/* out[i] = cast( double(a[i])*ca[k] + double(b[i])*cb[k] ), k = (i / outer) * mid + (i / inner) % mid; b may be NULL.
+ * Per-sample coefficients: outer = elements per sample, mid = 1, inner = outer.  Per-frame coefficients of a
+ * [B,C,T,H,W] latent (t of shape [B,1,T,1,1], causvid.py:55-56): outer = C*T*H*W, mid = T, inner = H*W.
  * Covers latents() (noise*sigma), forward_process (x*alpha + eps*sigma), flow_to_x0 (x - v*t), the
  * MeanFlow update (x - dt*u) -- all "fp64 arithmetic, one rounding" in the reference. */
-int fg_axpby(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* ca,
-             const double* cb, void* out, fg_stream_t stream);
+int fg_axpby(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid, int64_t inner,
+             const double* ca, const double* cb, void* out, fg_stream_t stream);
 
-/* (a - b*cb[n]) / cd[n] in fp64, one rounding: x0_to_eps / eps_to_x0 (noise_schedule.py:544-608). */
-int fg_sub_div(const void* a, const void* b, int32_t dtype, int32_t n, int64_t inner, const double* cb,
-               const double* cd, void* out, fg_stream_t stream);
+/* (a - b*cb[k]) / cd[k] in fp64, one rounding: x0_to_eps / eps_to_x0 (noise_schedule.py:544-608). */
+int fg_sub_div(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid, int64_t inner,
+               const double* cb, const double* cd, void* out, fg_stream_t stream);
 
 /* small helpers used by the embedding path */
 /* PositionalEmbedding (:306-319): out[n, :] = [cos(t*f) | sin(t*f)] (optionally swapped), fp32 */

@@ -1,0 +1,242 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference on CPU.
+
+Run in the build container (where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+TEST INFRASTRUCTURE ONLY.  The reference's own tests hold no golden tensors for this path (shapes
+and schedule identities only), so the oracle is pinned against outputs of the reference itself generated here:
+weights come from ``oracle.edm_oracle.make_state_dict`` (numpy PCG64, platform independent), inputs from seeded
+torch CPU generators and are stored in the fixture, the random draws of the sampler are recorded.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import edm_oracle as EO  # noqa: E402
+from oracle.ref_shims import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CONFIGS = {
+    "song_tiny": dict(img_resolution=16, img_channels=3, label_dim=10, sigma_shift=0.0, sigma_data=0.5,
+                      model_type="SongUNet", augment_dim=9, model_channels=32, channel_mult=[1, 2], num_blocks=1,
+                      attn_resolutions=[8], channel_mult_noise=1, embedding_type="positional",
+                      encoder_type="standard", decoder_type="standard", resample_filter=[1, 1], dropout=0.0,
+                      label_dropout=0, r_timestep=False, drop_precond=None),
+    "dhariwal_tiny": dict(img_resolution=16, img_channels=3, label_dim=12, sigma_shift=0.0, sigma_data=0.5,
+                          model_type="DhariwalUNet", augment_dim=0, model_channels=64, channel_mult=[1, 2],
+                          channel_mult_emb=4, num_blocks=1, attn_resolutions=[8], dropout=0.0, label_dropout=0,
+                          r_timestep=False, drop_precond=None),
+    "meanflow_tiny": dict(img_resolution=16, img_channels=3, label_dim=10, sigma_shift=0.0, sigma_data=0.5,
+                          model_type="SongUNet", augment_dim=0, model_channels=32, channel_mult=[1, 2], num_blocks=1,
+                          attn_resolutions=[8], dropout=0.0, label_dropout=0, r_timestep=True, drop_precond="both",
+                          net_pred_type="flow", schedule_type="rf"),
+}
+SEED = 20251018
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy()
+    return t.detach().numpy()
+
+
+class _Recorder:
+    """records torch.randn_like draws and the network outputs during a reference sampler call"""
+
+    def __init__(self, net):
+        self.eps, self.outs = [], []
+        self._orig = torch.randn_like
+        self._net = net
+
+    def __enter__(self):
+        def rl(*a, **k):
+            v = self._orig(*a, **k)
+            self.eps.append(v.clone())
+            return v
+
+        torch.randn_like = rl
+        self._hook = self._net.register_forward_hook(lambda m, i, o: self.outs.append(o.detach().clone()))
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self._orig
+        self._hook.remove()
+
+
+def build_reference_net(cfg, seed):
+    from fastgen.networks.EDM.network import EDMPrecond
+
+    net = EDMPrecond(**cfg)
+    sd = EO.make_state_dict(cfg, seed)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("resample_filter" in k for k in missing), missing  # buffers only
+    return net.eval(), sd
+
+
+def edm_fixture(name: str):
+    from fastgen.methods.model import FastGenModel
+
+    cfg = CONFIGS[name]
+    net, _ = build_reference_net(cfg, SEED)
+    g = torch.Generator().manual_seed(SEED + 1)
+    B, R = 4, cfg["img_resolution"]
+    noise = torch.randn(B, 3, R, R, generator=g)
+    labels = torch.eye(cfg["label_dim"])[torch.randint(cfg["label_dim"], (B,), generator=g)]
+    t = torch.tensor([80.0, 2.5265068484381206, 0.17256643947993575, 1.1], dtype=torch.float64)
+    x_t = noise * t.float().reshape(B, 1, 1, 1)
+    fx = dict(cfg=json.dumps(cfg), seed=SEED, noise=_np(noise), labels=_np(labels), t=_np(t), x_t=_np(x_t))
+    with torch.no_grad():
+        fx["fwd_x0"] = _np(net(x_t, t, condition=labels, fwd_pred_type="x0"))
+        fx["fwd_x0_nolabel"] = _np(net(x_t, t, condition=None, fwd_pred_type="x0"))
+        fx["fwd_eps"] = _np(net(x_t, t, condition=labels, fwd_pred_type="eps"))
+        net64 = net.double()
+        fx["fwd_x0_f64"] = _np(net64(x_t.double(), t, condition=labels.double(), fwd_pred_type="x0"))
+        net = net.float()
+    for steps, stype, tl in [(1, "sde", None), (2, "sde", None), (2, "ode", None), (2, "sde", [80.0, 1.1, 0.0]),
+                             (4, "sde", None)]:
+        tag = f"gen{steps}_{stype}" + ("_tl" if tl else "")
+        torch.manual_seed(SEED + 7)
+        with _Recorder(net) as rec:
+            out = FastGenModel.generator_fn(net, noise, condition=labels, student_sample_steps=steps,
+                                            student_sample_type=stype, t_list=tl)
+        fx[tag + "_out"] = _np(out)
+        for i, e in enumerate(rec.eps):
+            fx[f"{tag}_eps{i}"] = _np(e)
+        for i, o in enumerate(rec.outs):
+            fx[f"{tag}_x0_{i}"] = _np(o)
+    np.savez_compressed(os.path.join(OUT, f"edm_{name}.npz"), **fx)
+    print("wrote", name, {k: v.shape for k, v in fx.items() if hasattr(v, "shape") and v.ndim > 1 and "gen" not in k})
+
+
+def meanflow_fixture():
+    from fastgen.methods.consistency_model.mean_flow import MeanFlowModel
+
+    name = "meanflow_tiny"
+    cfg = CONFIGS[name]
+    net, _ = build_reference_net(cfg, SEED)
+    g = torch.Generator().manual_seed(SEED + 2)
+    B, R = 4, cfg["img_resolution"]
+    noise = torch.randn(B, 3, R, R, generator=g)
+    labels = torch.eye(cfg["label_dim"])[torch.randint(cfg["label_dim"], (B,), generator=g)]
+    fx = dict(cfg=json.dumps(cfg), seed=SEED, noise=_np(noise), labels=_np(labels))
+    t = torch.tensor([0.999, 0.7, 0.3, 0.05], dtype=torch.float64)
+    r = torch.tensor([0.5, 0.0, 0.1, 0.0], dtype=torch.float64)
+    with torch.no_grad():
+        fx["t"], fx["r"] = _np(t), _np(r)
+        fx["fwd_flow"] = _np(net(noise, t, condition=labels, r=r, fwd_pred_type="flow"))
+        fx["fwd_x0"] = _np(net(noise, t, condition=labels, r=r, fwd_pred_type="x0"))
+    for steps, stype in [(1, "sde"), (2, "sde"), (2, "ode"), (4, "ode")]:
+        tag = f"gen{steps}_{stype}"
+        torch.manual_seed(SEED + 9)
+        with _Recorder(net) as rec:
+            out = MeanFlowModel.generator_fn(net, noise, condition=labels, student_sample_steps=steps,
+                                             student_sample_type=stype)
+        fx[tag + "_out"] = _np(out)
+        for i, e in enumerate(rec.eps):
+            fx[f"{tag}_eps{i}"] = _np(e)
+    np.savez_compressed(os.path.join(OUT, f"edm_{name}.npz"), **fx)
+    print("wrote", name)
+
+
+def schedule_fixture():
+    from fastgen.networks.noise_schedule import get_noise_schedule
+
+    fx = {}
+    edm = get_noise_schedule("edm")
+    rf = get_noise_schedule("rf")
+    fx["edm_sigmas"] = _np(edm.sigmas)
+    for s in (1, 2, 3, 4, 7, 8):
+        fx[f"edm_t_list_{s}"] = _np(edm.get_t_list(s))
+        fx[f"edm_idx_{s}"] = _np(torch.linspace(edm._max_step, edm._min_step, s + 1).long())
+        fx[f"rf_t_list_{s}"] = _np(rf.get_t_list(s))
+    fx["rf_rescale"] = _np(rf.rescale_t(rf.get_t_list(4)))
+    abar = torch.cumprod(1 - torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2, 0)
+    al = get_noise_schedule("alphas", alphas_cumprod=abar)
+    fx["alphas_cumprod"] = _np(abar)
+    tt = torch.tensor([0.999, 0.74925, 0.4995, 0.24975, 0.0], dtype=torch.float64)
+    fx["alphas_t"] = _np(tt)
+    fx["alphas_alpha"] = _np(al.alpha(tt))
+    fx["alphas_sigma"] = _np(al.sigma(tt))
+    fx["alphas_idx"] = _np(al._t_to_idx(tt))
+    g = torch.Generator().manual_seed(SEED + 3)
+    for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        x = torch.randn(3, 4, 8, 8, generator=g).to(dt)
+        e = torch.randn(3, 4, 8, 8, generator=g).to(dt)
+        fx[f"x_{dt_name}"], fx[f"e_{dt_name}"] = _np(x), _np(e)
+        for sname, sch, t in (("edm", edm, torch.tensor([80.0, 1.1, 0.002], dtype=torch.float64)),
+                              ("rf", rf, torch.tensor([0.999, 0.5, 0.0], dtype=torch.float64)),
+                              ("alphas", al, torch.tensor([0.999, 0.5, 0.0], dtype=torch.float64))):
+            fx[f"{sname}_t3"] = _np(t)
+            fx[f"{sname}_latents_{dt_name}"] = _np(sch.latents(x, t[1]))
+            fx[f"{sname}_fwd_{dt_name}"] = _np(sch.forward_process(x, e, t))
+            fx[f"{sname}_x0_to_eps_{dt_name}"] = _np(sch.x0_to_eps(x, e, t))
+            fx[f"{sname}_eps_to_x0_{dt_name}"] = _np(sch.eps_to_x0(x, e, t))
+            if sname != "alphas":
+                fx[f"{sname}_flow_to_x0_{dt_name}"] = _np(sch.flow_to_x0(x, e, t))
+                fx[f"{sname}_x0_to_flow_{dt_name}"] = _np(sch.x0_to_flow(x, e, t))
+            else:
+                fx[f"{sname}_v_to_x0_{dt_name}"] = _np(sch.v_to_x0(x, e, t))
+    # per-frame t ([B,1,T,1,1]) on a video latent (causvid.py:55-56)
+    xv = torch.randn(2, 4, 6, 4, 4, generator=g)
+    ev = torch.randn(2, 4, 6, 4, 4, generator=g)
+    tv = torch.rand(2, 6, generator=g, dtype=torch.float64) * 0.999
+    fx["video_x"], fx["video_e"], fx["video_t"] = _np(xv), _np(ev), _np(tv)
+    fx["video_fwd"] = _np(rf.forward_process(xv, ev, tv[:, None, :, None, None]))
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **fx)
+    print("wrote schedules")
+
+
+def causal_trace_fixture():
+    """call trace of CausVidModel._student_sample_loop against a stub causal network"""
+    from fastgen.methods.distribution_matching.causvid import CausVidModel
+    from fastgen.networks.network import CausalFastGenNetwork
+
+    trace = []
+
+    class Stub(CausalFastGenNetwork):
+        def __init__(self):
+            super().__init__(net_pred_type="flow", schedule_type="rf", chunk_size=3, total_num_frames=7)
+
+        def clear_caches(self):
+            trace.append(["clear_caches"])
+
+        def forward(self, x_t, t, condition=None, r=None, return_features_early=False, feature_indices=None,
+                    return_logvar=False, fwd_pred_type=None, **kw):
+            trace.append(["net", list(x_t.shape), float(t[0]), fwd_pred_type, kw.get("cache_tag"),
+                          int(kw.get("cur_start_frame")), bool(kw.get("store_kv")), bool(kw.get("is_ar")),
+                          sorted(k for k in kw if k not in ("cache_tag", "cur_start_frame", "store_kv", "is_ar"))])
+            return 0.5 * x_t
+
+    net = Stub()
+    torch.manual_seed(SEED + 11)
+    noise = torch.randn(2, 4, 7, 4, 4)
+    with _Recorder(net) as rec:
+        out = CausVidModel.generator_fn(net, noise, condition=None, neg_condition="neg", student_sample_steps=4,
+                                        student_sample_type="sde", t_list=[0.999, 0.937, 0.833, 0.624, 0.0])
+    fx = dict(trace=json.dumps(trace), noise=_np(noise), out=_np(out))
+    for i, e in enumerate(rec.eps):
+        fx[f"eps{i}"] = _np(e)
+    np.savez_compressed(os.path.join(OUT, "causal_trace.npz"), **fx)
+    print("wrote causal trace:", len(trace), "calls")
+
+
+if __name__ == "__main__":
+    load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    schedule_fixture()
+    edm_fixture("song_tiny")
+    edm_fixture("dhariwal_tiny")
+    meanflow_fixture()
+    causal_trace_fixture()

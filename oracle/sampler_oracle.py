@@ -1,0 +1,156 @@
+"""CPU oracle for the sampler and the noise schedules (float64 torch / numpy arithmetic).
+
+TEST INFRASTRUCTURE ONLY (see oracle/edm_oracle.py).  Restates, with the random draws passed in explicitly:
+  fastgen/methods/model.py:315-420          FastGenModel._student_sample_loop / generator_fn
+  fastgen/methods/consistency_model/mean_flow.py:336-381   MeanFlowModel._student_sample_loop
+  fastgen/methods/distribution_matching/causvid.py:87-185  CausVidModel._student_sample_loop (call trace)
+  fastgen/networks/noise_schedule.py:72-88, 259-272, 425-449, 544-608, 752-759, 940-1004, 1337-1341, 1426-1486
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def _bc(v: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    v = torch.atleast_1d(v)
+    return v.reshape(tuple(v.shape) + (1,) * (like.dim() - v.dim()))
+
+
+class Schedule:
+    """alpha / sigma of the three schedules the sampler path uses, float64."""
+
+    def __init__(self, kind: str, alphas_cumprod: Optional[torch.Tensor] = None):
+        self.kind = kind
+        if kind == "edm":
+            self.min_t, self.max_t = 0.002, 80.0
+            # ascending Karras rho = 7 table (:752-759); torch float64 ops so the table (and hence every t list)
+            # is bit-identical to the reference's on the same host
+            ramp = torch.linspace(0, 1, 1000, dtype=torch.float64)
+            lo, hi = 0.002 ** (1 / 7.0), 80.0 ** (1 / 7.0)
+            self.sigmas = torch.flip((hi + ramp * (lo - hi)) ** 7.0, [0]).numpy().copy()
+        elif kind == "rf":
+            self.min_t, self.max_t = 0.0, 0.999
+        elif kind == "alphas":
+            self.min_t, self.max_t = 0.0, 0.999
+            self.abar = alphas_cumprod.double()
+        else:
+            raise KeyError(kind)
+
+    def alpha(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.double()
+        if self.kind == "edm":
+            return torch.ones_like(t)
+        if self.kind == "rf":
+            return 1 - t
+        return self.abar[(1000 * t).long().clamp(0, 999)].sqrt()
+
+    def sigma(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.double()
+        if self.kind in ("edm", "rf"):
+            return t
+        return (1 - self.abar[(1000 * t).long().clamp(0, 999)]).sqrt()
+
+    def t_list_indices(self, steps: int) -> np.ndarray:
+        """int64 sigma-table indices of the EDM t list: linspace(998, 2, steps+1) truncated (:957-962)."""
+        return np.linspace(998.0, 2.0, steps + 1, dtype=np.float32).astype(np.int64)
+
+    def get_t_list(self, steps: int) -> torch.Tensor:
+        if self.kind == "edm":
+            t = self.sigmas[self.t_list_indices(steps)].copy()
+            t[-1] = 0.0
+            return torch.from_numpy(t).clamp(max=self.max_t)
+        return torch.linspace(self.max_t, 0, steps + 1, dtype=torch.float64).clamp(max=self.max_t)
+
+    # latent arithmetic: float64, one rounding to the input dtype
+    def latents(self, noise: torch.Tensor, t0: torch.Tensor) -> torch.Tensor:
+        return (noise.double() * _bc(self.sigma(t0), noise)).to(noise.dtype)
+
+    def forward_process(self, x: torch.Tensor, eps: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        return (x.double() * _bc(self.alpha(t), x) + eps.double() * _bc(self.sigma(t), x)).to(x.dtype)
+
+    @staticmethod
+    def _nz(v: torch.Tensor, c: float = 1e-6) -> torch.Tensor:
+        return torch.where(v >= 0, v.clamp(min=c), v.clamp(max=-c))
+
+    def x0_to_eps(self, xt, x0, t):
+        return ((xt.double() - x0.double() * _bc(self.alpha(t), xt)) / _bc(self._nz(self.sigma(t)), xt)).to(xt.dtype)
+
+    def eps_to_x0(self, xt, eps, t):
+        return ((xt.double() - eps.double() * _bc(self.sigma(t), xt)) / _bc(self._nz(self.alpha(t)), xt)).to(xt.dtype)
+
+    def flow_to_x0(self, xt, v, t):  # EDM and RF: x0 = xt - t v
+        return (xt.double() - v.double() * _bc(t.double(), xt)).to(xt.dtype)
+
+    def x0_to_flow(self, xt, x0, t):
+        return ((xt.double() - x0.double()) / _bc(self._nz(t.double()), xt)).to(xt.dtype)
+
+
+NetFn = Callable[..., torch.Tensor]  # net(x, t_batch, **kw) -> prediction
+
+
+def student_sample_loop(net: NetFn, sched: Schedule, x: torch.Tensor, t_list: torch.Tensor,
+                        eps_list: Sequence[torch.Tensor], sample_type: str = "sde",
+                        trace: Optional[List[Tuple[str, torch.Tensor]]] = None) -> torch.Tensor:
+    """model.py:315-372 with the `randn_like` draws supplied in call order."""
+    b = x.shape[0]
+    draws = iter(eps_list)
+    x_pred = x
+    for t_cur, t_next in zip(t_list[:-1], t_list[1:]):
+        tb = t_cur.expand(b)
+        x_pred = net(x, tb)
+        if trace is not None:
+            trace.append(("x0", x_pred))
+        if t_next > 0:
+            if sample_type == "sde":
+                eps = next(draws)
+            elif sample_type == "ode":
+                eps = sched.x0_to_eps(x, x_pred, tb)
+            else:
+                raise NotImplementedError(f"student_sample_type must be one of 'sde', 'ode' but got {sample_type}")
+            x = sched.forward_process(x_pred, eps, t_next.expand(b))
+            if trace is not None:
+                trace.append(("x_next", x))
+    return x_pred
+
+
+def generator_fn(net: NetFn, sched: Schedule, noise: torch.Tensor, steps: int = 1,
+                 t_list: Optional[Sequence[float]] = None, eps_list: Sequence[torch.Tensor] = (),
+                 sample_type: str = "sde", trace=None) -> torch.Tensor:
+    """model.py:374-420."""
+    if t_list is None:
+        tl = sched.get_t_list(steps)
+    else:
+        assert len(t_list) - 1 == steps
+        tl = torch.tensor(list(t_list), dtype=torch.float64)
+    assert tl[-1].item() == 0, "t_list[-1] must be zero"
+    lat = sched.latents(noise, tl[0])
+    return student_sample_loop(net, sched, lat, tl, eps_list, sample_type, trace).to(noise.dtype)
+
+
+def meanflow_sample_loop(net: NetFn, sched: Schedule, x: torch.Tensor, t_list: torch.Tensor,
+                         eps_list: Sequence[torch.Tensor], sample_type: str = "sde") -> torch.Tensor:
+    """mean_flow.py:336-381: net(x, t, r=...) returns the average velocity u (fwd_pred_type='flow')."""
+    b = x.shape[0]
+    draws = iter(eps_list)
+    for t_cur, t_next in zip(t_list[:-1], t_list[1:]):
+        tb, nb = t_cur.expand(b), t_next.expand(b)
+        if sample_type == "sde":
+            x = x - _bc(t_cur, x).to(x.dtype) * net(x, tb, r=torch.zeros_like(nb))
+            if t_next > 0:
+                x = sched.forward_process(x, next(draws), nb)
+        elif sample_type == "ode":
+            x = x - _bc(t_cur - t_next, x).to(x.dtype) * net(x, tb, r=nb)
+        else:
+            raise NotImplementedError(f"student_sample_type must be one of 'sde', 'ode' but got {sample_type}")
+    return x
+
+
+def causal_chunks(num_frames: int, chunk_size: int) -> List[Tuple[int, int]]:
+    """causvid.py:117-129: remainder frames are absorbed by the first chunk."""
+    nchunks, rem = num_frames // chunk_size, num_frames % chunk_size
+    if nchunks == 0:
+        return [(0, rem)]
+    return [(0 if i == 0 else chunk_size * i + rem, chunk_size * (i + 1) + rem) for i in range(nchunks)]

@@ -1,0 +1,150 @@
+"""Pin the CPU oracle (oracle/) against fixtures produced by the real reference (oracle/make_golden.py).
+
+Runs on CPU (`-m "not gpu"`).  Integer / index tensors and everything the reference evaluates in float64 must be
+bit-exact; fp32 network forwards agree to op-ordering noise."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import edm_oracle as EO
+from oracle import sampler_oracle as SO
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def _t(a, bf16=False):
+    t = torch.from_numpy(np.asarray(a))
+    return t.view(torch.bfloat16) if bf16 else t
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def test_edm_t_list_and_indices_bit_exact():
+    g = _load("schedules.npz")
+    s = SO.Schedule("edm")
+    assert np.array_equal(s.sigmas, g["edm_sigmas"])
+    for k in (1, 2, 3, 4, 7, 8):
+        assert np.array_equal(s.t_list_indices(k), g[f"edm_idx_{k}"])
+        assert np.array_equal(s.get_t_list(k).numpy(), g[f"edm_t_list_{k}"])
+        assert np.array_equal(SO.Schedule("rf").get_t_list(k).numpy(), g[f"rf_t_list_{k}"])
+    # SURVEY.md A.2 known answers
+    assert s.t_list_indices(4).tolist() == [998, 749, 500, 251, 2]
+    assert s.get_t_list(4).tolist() == [79.56382521581216, 17.49810610061577, 2.5265068484381206,
+                                        0.17256643947993575, 0.0]
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("kind", ["edm", "rf", "alphas"])
+def test_schedule_arithmetic_bit_exact(kind, dt):
+    g = _load("schedules.npz")
+    bf = dt == "bf16"
+    s = SO.Schedule(kind, alphas_cumprod=_t(g["alphas_cumprod"]) if kind == "alphas" else None)
+    x, e, t = _t(g[f"x_{dt}"], bf), _t(g[f"e_{dt}"], bf), _t(g[f"{kind}_t3"])
+    assert torch.equal(s.latents(x, t[1]), _t(g[f"{kind}_latents_{dt}"], bf))
+    assert torch.equal(s.forward_process(x, e, t), _t(g[f"{kind}_fwd_{dt}"], bf))
+    assert torch.equal(s.x0_to_eps(x, e, t), _t(g[f"{kind}_x0_to_eps_{dt}"], bf))
+    assert torch.equal(s.eps_to_x0(x, e, t), _t(g[f"{kind}_eps_to_x0_{dt}"], bf))
+    if kind != "alphas":
+        assert torch.equal(s.flow_to_x0(x, e, t), _t(g[f"{kind}_flow_to_x0_{dt}"], bf))
+        assert torch.equal(s.x0_to_flow(x, e, t), _t(g[f"{kind}_x0_to_flow_{dt}"], bf))
+
+
+def test_alphas_table_lookup_bit_exact():
+    g = _load("schedules.npz")
+    s = SO.Schedule("alphas", alphas_cumprod=_t(g["alphas_cumprod"]))
+    t = _t(g["alphas_t"])
+    assert np.array_equal((1000 * t).long().clamp(0, 999).numpy(), g["alphas_idx"])
+    assert np.array_equal(s.alpha(t).numpy(), g["alphas_alpha"])
+    assert np.array_equal(s.sigma(t).numpy(), g["alphas_sigma"])
+
+
+def test_per_frame_forward_process_bit_exact():
+    g = _load("schedules.npz")
+    s = SO.Schedule("rf")
+    out = s.forward_process(_t(g["video_x"]), _t(g["video_e"]), _t(g["video_t"])[:, None, :, None, None])
+    assert torch.equal(out, _t(g["video_fwd"]))
+
+
+@pytest.mark.parametrize("name", ["song_tiny", "dhariwal_tiny"])
+def test_edm_forward_matches_reference(name):
+    g = _load(f"edm_{name}.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = EO.make_state_dict(cfg, int(g["seed"]))
+    x_t, t, labels = _t(g["x_t"]), _t(g["t"]), _t(g["labels"])
+    with torch.no_grad():
+        out = EO.edm_precond_forward(sd, cfg, x_t, t, labels)
+        out_nl = EO.edm_precond_forward(sd, cfg, x_t, t, None)
+        sd64 = {k: v.double() for k, v in sd.items()}
+        out64 = EO.edm_precond_forward(sd64, cfg, x_t.double(), t, labels.double())
+    assert _rel(out, _t(g["fwd_x0"])) < 2e-6
+    assert _rel(out_nl, _t(g["fwd_x0_nolabel"])) < 2e-6
+    assert _rel(out64, _t(g["fwd_x0_f64"])) < 1e-12
+    # the raw network output is NOT degenerate with the parity weights (SURVEY.md 0.6 trap)
+    raw = EO.edm_precond_forward(sd, cfg, x_t, t, labels, return_raw=True)
+    assert raw.std().item() > 0.1
+
+
+@pytest.mark.parametrize("name", ["song_tiny", "dhariwal_tiny"])
+@pytest.mark.parametrize("tag,steps,stype,tl", [("gen1_sde", 1, "sde", None), ("gen2_sde", 2, "sde", None),
+                                                ("gen2_ode", 2, "ode", None), ("gen2_sde_tl", 2, "sde", [80.0, 1.1, 0.0]),
+                                                ("gen4_sde", 4, "sde", None)])
+def test_edm_sampler_matches_reference(name, tag, steps, stype, tl):
+    g = _load(f"edm_{name}.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = EO.make_state_dict(cfg, int(g["seed"]))
+    noise, labels = _t(g["noise"]), _t(g["labels"])
+    eps = [_t(g[f"{tag}_eps{i}"]) for i in range(steps) if f"{tag}_eps{i}" in g]
+    trace = []
+    with torch.no_grad():
+        out = SO.generator_fn(lambda x, t, **kw: EO.edm_precond_forward(sd, cfg, x, t, labels), SO.Schedule("edm"),
+                              noise, steps, tl, eps, stype, trace)
+    x0s = [v for k, v in trace if k == "x0"]
+    for i, v in enumerate(x0s):
+        assert _rel(v, _t(g[f"{tag}_x0_{i}"])) < 1e-5, (i, _rel(v, _t(g[f"{tag}_x0_{i}"])))
+    assert _rel(out, _t(g[f"{tag}_out"])) < 1e-5
+
+
+@pytest.mark.parametrize("tag,steps,stype", [("gen1_sde", 1, "sde"), ("gen2_sde", 2, "sde"), ("gen2_ode", 2, "ode"),
+                                             ("gen4_ode", 4, "ode")])
+def test_meanflow_sampler_matches_reference(tag, steps, stype):
+    g = _load("edm_meanflow_tiny.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = EO.make_state_dict(cfg, int(g["seed"]))
+    noise, labels = _t(g["noise"]), _t(g["labels"])
+    sched = SO.Schedule("rf")
+    with torch.no_grad():
+        flow = EO.edm_precond_forward(sd, cfg, noise, _t(g["t"]), labels, r=_t(g["r"]))
+        assert _rel(flow, _t(g["fwd_flow"])) < 2e-6
+        eps = [_t(g[f"{tag}_eps{i}"]) for i in range(steps) if f"{tag}_eps{i}" in g]
+        tl = sched.get_t_list(steps)
+        lat = sched.latents(noise, tl[0])
+        out = SO.meanflow_sample_loop(lambda x, t, r: EO.edm_precond_forward(sd, cfg, x, t, labels, r=r), sched, lat, tl,
+                                      eps, stype)
+    assert _rel(out, _t(g[f"{tag}_out"])) < 1e-5
+
+
+def test_causal_chunking_matches_reference_trace():
+    g = _load("causal_trace.npz")
+    trace = json.loads(str(g["trace"]))
+    calls = [c for c in trace if c[0] == "net"]
+    chunks = SO.causal_chunks(7, 3)
+    assert chunks == [(0, 4), (4, 7)]
+    # per chunk: 4 denoise calls (store_kv False) + 1 cache-fill call at t=0 (store_kv True)
+    assert trace[0] == ["clear_caches"] and trace[-1] == ["clear_caches"]
+    exp_t = [0.999, 0.937, 0.833, 0.624, 0.0]
+    for ci, (s, e) in enumerate(chunks):
+        for k in range(5):
+            c = calls[ci * 5 + k]
+            assert c[1][2] == e - s and c[5] == s
+            assert abs(c[2] - exp_t[k]) < 1e-12
+            assert c[6] == (k == 4) and c[7] is True and c[3] == "x0" and c[4] == "pos"
+            assert c[8] == ["neg_condition"]
