@@ -268,10 +268,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyK p) 
 }
 
 static int pick_slab(int n, int pixels, int c, int* pix_per_slab) {
-  // ~64K elements per CTA, but at least ~4 CTAs per SM in total when the batch is small
-  int64_t slabs = (static_cast<int64_t>(pixels) * c + 65535) / 65536;
-  const int64_t want = (592 + n - 1) / n;
-  if (slabs < want) slabs = want;
+  // ~32K elements per CTA.  Deliberately independent of the batch size: a sample's partial sums are then
+  // accumulated in the same order whatever batch it is part of.
+  (void)n;
+  int64_t slabs = (static_cast<int64_t>(pixels) * c + 32767) / 32768;
   if (slabs > pixels) slabs = pixels;
   if (slabs < 1) slabs = 1;
   *pix_per_slab = static_cast<int>((pixels + slabs - 1) / slabs);

@@ -66,8 +66,9 @@ class FastGenModel:
         t_host = t_list.detach().cpu()
         t_dev = t_list.to(x.device)
         sched = net.noise_scheduler
-        # validate every t once on the host (reference asserts inside each schedule call, with a sync each time)
-        assert sched.is_t_valid(t_host), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
+        # validate every t that reaches a schedule call once, on the host (the reference asserts inside each call,
+        # paying a device sync each time; the trailing 0 is never passed to the schedule)
+        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
         fused = isinstance(net, EDMPrecond) and net.net_pred_type == "x0" and not has_preserve_hook
         x_pred = x
         for i in range(len(t_host) - 1):
@@ -139,8 +140,7 @@ class MeanFlowModel(FastGenModel):
         t_host = t_list.detach().cpu()
         t_dev = t_list.to(x.device)
         sched = net.noise_scheduler
-        assert sched.is_t_valid(t_host), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
-        one = torch.ones(1, device=x.device, dtype=torch.float64)
+        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
         for i in range(len(t_host) - 1):
             t_cur_batch = t_dev[i].expand(batch_size)
             t_next_batch = t_dev[i + 1].expand(batch_size)
@@ -175,7 +175,7 @@ class CausVidModel(FastGenModel):
         t_host = t_list.detach().cpu()
         t_dev = t_list.to(x.device)
         sched = net.noise_scheduler
-        assert sched.is_t_valid(t_host), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
+        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
         for i in range(max(1, num_chunks)):
             if num_chunks == 0:
                 start, end = 0, remaining
