@@ -265,6 +265,7 @@ class _Plan:
         self.dev = next(net.parameters()).device
         self.x3 = net.compute == "bf16x3"
         self.steps: List[Tuple[Any, tuple]] = []
+        self.step_flops: List[float] = []
         self.keep: List[Any] = []
         self._build()
 
@@ -316,13 +317,15 @@ class _Plan:
         return self._scratch_buf[name][:numel].view(*shape)
 
     # ---- launch helpers (append to the list; tensors referenced by structs are kept alive) ----
-    def _launch(self, fn, *args):
+    def _launch(self, fn, *args, flops: float = 0.0):
         self.steps.append((fn, args))
+        self.step_flops.append(flops)
 
     def conv(self, segs, n, h, w, cout, out: torch.Tensor, out_ld: int, **kw):
         p = ops.conv_gemm_params(segs, n, h, w, cout, out, out_ld, **kw)
         self.keep.append((p, segs, out, kw))
-        self._launch(L.lib().fg_conv_gemm, C.byref(p))
+        flops = 2.0 * n * h * w * cout * sum(s.cin * s.taps for s in segs if s.alg)
+        self._launch(L.lib().fg_conv_gemm, C.byref(p), flops=flops)
 
     def gn(self, x: _Act, norm: _GroupNorm, pk: Dict[str, torch.Tensor], y: torch.Tensor, silu: bool, resample: int = 0,
            scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None):
@@ -340,12 +343,13 @@ class _Plan:
     def segs3(self, a_hi, a_lo, ld, w_hi, w_lo, cin, taps) -> List[ops.Seg]:
         s = [ops.Seg(a_hi, ld, w_hi, cin, taps)]
         if self.x3:
-            s += [ops.Seg(a_lo, ld, w_hi, cin, taps), ops.Seg(a_hi, ld, w_lo, cin, taps)]
+            s += [ops.Seg(a_lo, ld, w_hi, cin, taps, alg=False), ops.Seg(a_hi, ld, w_lo, cin, taps, alg=False)]
         return s
 
     def linear(self, a_hi, a_lo, k: int, wpk, cout: int, out: torch.Tensor, out_ld: int, **kw):
         """small fp32-accurate GEMM of the embedding path: always split precision (3 segments)."""
-        segs = [ops.Seg(a_hi, k, wpk["hi"], k, 1), ops.Seg(a_lo, k, wpk["hi"], k, 1), ops.Seg(a_hi, k, wpk["lo"], k, 1)]
+        segs = [ops.Seg(a_hi, k, wpk["hi"], k, 1), ops.Seg(a_lo, k, wpk["hi"], k, 1, alg=False),
+                ops.Seg(a_hi, k, wpk["lo"], k, 1, alg=False)]
         self.conv(segs, self.n, 1, 1, cout, out, out_ld, bias=wpk.get("bias"), **kw)
 
     def split(self, x: torch.Tensor, x_ld: int, c: int, act: int = 0):
@@ -556,11 +560,11 @@ class _Plan:
                   bias=wq["bias"])
         att = self._scratch("att", [n, ho, wo, cout])
         self._launch(L.lib().fg_attention, qkv.data_ptr(), 3 * cout, n, ho * wo, b.num_heads, cout // b.num_heads,
-                     att.data_ptr(), cout)
+                     att.data_ptr(), cout, flops=4.0 * n * (ho * wo) ** 2 * cout)
         wp = pk[key + ".proj"]
         segs = [ops.Seg(att, cout, wp["hi"], cout, 1)]
         if self.x3:
-            segs.append(ops.Seg(att, cout, wp["lo"], cout, 1))
+            segs.append(ops.Seg(att, cout, wp["lo"], cout, 1, alg=False))
         self.conv(segs, n, ho, wo, cout, dst.t, dst.ld, bias=wp["bias"], res=mid.t, res_ld=mid.ld,
                   res_mode=L.FG_RES_SAME, out_scale=float(b.skip_scale))
 
@@ -570,6 +574,27 @@ class _Plan:
             st = fn(*args, stream)
             if st:
                 check(st, fn.__name__)
+
+    def run_timed(self, stream: int) -> Dict[str, Dict[str, float]]:
+        """Same launches with a CUDA event pair around each one (measurement pass of bench.py): returns, per entry
+        point, the launch count, the summed device time in ms and the summed algorithmic FLOPs."""
+        evs = []
+        for (fn, args), fl in zip(self.steps, self.step_flops):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            st = fn(*args, stream)
+            b.record()
+            if st:
+                L.check(st, fn.__name__)
+            evs.append((fn.__name__, a, b, fl))
+        torch.cuda.synchronize()
+        out: Dict[str, Dict[str, float]] = {}
+        for name, a, b, fl in evs:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += fl
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -593,6 +618,7 @@ class EDMPrecond(FastGenNetwork):
                            out_channels=img_channels, label_dim=label_dim, **model_kwargs)
         self._packed: Optional[Dict[str, Any]] = None
         self._plans: Dict[int, _Plan] = {}
+        self.profile: Optional[Dict[str, Dict[str, float]]] = None  # set to {} to time every launch (bench.py)
 
     # ---- weight packing ---------------------------------------------------------------------------------
     def _invalidate(self):
@@ -771,7 +797,14 @@ class EDMPrecond(FastGenNetwork):
                 plan.augment.zero_()
             else:
                 plan.augment[:, :m.augment_dim].copy_(augment.reshape(-1, m.augment_dim).to(torch.float32).expand(n, -1))
-        plan.run(torch.cuda.current_stream().cuda_stream)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.profile is None:
+            plan.run(stream)
+        else:  # measurement pass: per entry point launch count / device ms / algorithmic FLOPs, accumulated
+            for name, d in plan.run_timed(stream).items():
+                acc = self.profile.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+                for k in acc:
+                    acc[k] += d[k]
         return plan, c_skip, c_out
 
     def forward(self, x_t: torch.Tensor, t: torch.Tensor, condition: Any = None, r: Optional[torch.Tensor] = None,

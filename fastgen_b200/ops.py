@@ -34,10 +34,11 @@ def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
 class Seg:
     """One K segment of :func:`conv_gemm`: bf16 activation view [N,H,W,cin] (pixel stride ``ld``) and its weight."""
 
-    __slots__ = ("a", "ld", "w", "cin", "taps")
+    __slots__ = ("a", "ld", "w", "cin", "taps", "alg")
 
-    def __init__(self, a: torch.Tensor, ld: int, w: torch.Tensor, cin: int, taps: int):
+    def __init__(self, a: torch.Tensor, ld: int, w: torch.Tensor, cin: int, taps: int, alg: bool = True):
         self.a, self.ld, self.w, self.cin, self.taps = a, ld, w, cin, taps
+        self.alg = alg  # False for the extra hi*lo / lo*hi products of split precision (not algorithmic FLOPs)
 
 
 def conv_gemm_params(
