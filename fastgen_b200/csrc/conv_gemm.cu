@@ -26,20 +26,25 @@ struct ConvCfg {
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
   static constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int OUT_SLAB_BYTES = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 B (TMA store box)
+  static constexpr int OUT_SLABS = 2;
+  static constexpr int STAGES_RAW = (196 * 1024 - OUT_SLABS * OUT_SLAB_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
                                    : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + OUT_SLABS * OUT_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
 };
 
 struct ConvKParams {
   CUtensorMap tmA[FG_MAX_SEG];
   CUtensorMap tmW[FG_MAX_SEG];
+  CUtensorMap tmOut;  // output tile store: box (32 fp32 | 64 bf16 channels, BW, BH, BNI)
+  int32_t tma_store;  // 1: epilogue stages 128B-row slabs in smem and stores them with TMA
   int32_t seg_taps[FG_MAX_SEG];
   int32_t seg_kchunks[FG_MAX_SEG];
   int32_t nseg;
@@ -170,12 +175,59 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint3
   }
 }
 
+// Fused tail evaluated into registers (vector path only): a[j] = out_scale * (acc + bias + rowvec + residual).
+template <int CH>
+__device__ __forceinline__ void epilogue_values(const ConvKParams& p, const uint32_t (&v)[CH], int c_base, int img,
+                                                int h, int w, bool valid, float (&a)[CH]) {
+  const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
+  int64_t rpix = pix;
+  int64_t rstep_w = 0, rstep_h = 0;
+  if (p.res_mode == FG_RES_UP2) {
+    rpix = (static_cast<int64_t>(img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+  } else if (p.res_mode == FG_RES_DOWN2) {
+    const int64_t W2 = static_cast<int64_t>(p.W) * 2;
+    rpix = (static_cast<int64_t>(img) * (p.H * 2) + 2 * h) * W2 + 2 * w;
+    rstep_w = p.res_ld;
+    rstep_h = W2 * p.res_ld;
+  }
+#pragma unroll
+  for (int j = 0; j < CH; j += 4) {
+    const int c = c_base + j;
+    float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                           __uint_as_float(v[j + 3]));
+    if (valid && c < p.Cout) {
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
+      }
+      if (p.rowvec) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowvec + img * p.rowvec_ld + c));
+        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
+      }
+      if (p.res_mode == FG_RES_SAME || p.res_mode == FG_RES_UP2) {
+        const float4 b = ld4(p.res, p.res_dtype, rpix * p.res_ld + c);
+        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
+      } else if (p.res_mode == FG_RES_DOWN2) {
+        const int64_t o = rpix * p.res_ld + c;
+        const float4 b0 = ld4(p.res, p.res_dtype, o), b1 = ld4(p.res, p.res_dtype, o + rstep_w);
+        const float4 b2 = ld4(p.res, p.res_dtype, o + rstep_h), b3 = ld4(p.res, p.res_dtype, o + rstep_h + rstep_w);
+        r.x += 0.25f * ((b0.x + b1.x) + (b2.x + b3.x));
+        r.y += 0.25f * ((b0.y + b1.y) + (b2.y + b3.y));
+        r.z += 0.25f * ((b0.z + b1.z) + (b2.z + b3.z));
+        r.w += 0.25f * ((b0.w + b1.w) + (b2.w + b3.w));
+      }
+    }
+    a[j] = r.x * p.out_scale, a[j + 1] = r.y * p.out_scale, a[j + 2] = r.z * p.out_scale, a[j + 3] = r.w * p.out_scale;
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* out_slabs = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_slabs + Cfg::OUT_SLABS * Cfg::OUT_SLAB_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -189,6 +241,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       tma_prefetch_desc(&p.tmA[s]);
       tma_prefetch_desc(&p.tmW[s]);
     }
+    if (p.tma_store) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -282,6 +335,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int il = row / (p.BW * p.BH);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t slab_idx = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int img = t.img0 + il, h = t.h0 + hl, w = t.w0 + wl;
@@ -289,7 +343,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-      if constexpr (BLOCK_N >= 32) {
+      if (p.tma_store) {
+        // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem slab -> TMA store (full-line writes,
+        //      out-of-range rows / channels clipped by the tensor map) ----
+        if constexpr (BLOCK_N >= 32) {
+          const bool is_store_thread = (warp == 2 && lane == 0);
+          const int slab_cols = (p.out_dtype == FG_F32) ? 32 : 64;
+          uint8_t* my_row_base = out_slabs + row * 128;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BLOCK_N; c0 += slab_cols) {
+            if (t.co0 + c0 >= p.Cout) break;  // warp-uniform: nothing left to store in this tile
+            uint8_t* slab = my_row_base + (slab_idx & 1) * Cfg::OUT_SLAB_BYTES;
+            if (is_store_thread) tma_store_wait_read<1>();  // the store that used this slab two slabs ago is done
+            named_bar_sync(1, 128);
+#pragma unroll 1
+            for (int cc = 0; cc < slab_cols; cc += 32) {
+              uint32_t v[32];
+              float a[32];
+              tmem_ld_32x32(taddr + c0 + cc, v);
+              tmem_ld_wait();
+              epilogue_values<32>(p, v, t.co0 + c0 + cc, img, h, w, valid, a);
+              if (p.out_dtype == FG_F32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(slab + ((j ^ (row & 7)) << 4)) =
+                      make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 u;
+                  u.x = pack_bf16x2(a[8 * j], a[8 * j + 1]), u.y = pack_bf16x2(a[8 * j + 2], a[8 * j + 3]);
+                  u.z = pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), u.w = pack_bf16x2(a[8 * j + 6], a[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(slab + ((((cc >> 3) + j) ^ (row & 7)) << 4)) = u;
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (is_store_thread) {
+              tma_store_4d(&p.tmOut, out_slabs + (slab_idx & 1) * Cfg::OUT_SLAB_BYTES, t.co0 + c0, t.w0, t.h0, t.img0);
+              tma_store_commit();
+            }
+            ++slab_idx;
+          }
+        }
+      } else if constexpr (BLOCK_N >= 32) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t v[32];
@@ -309,6 +407,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -448,6 +547,21 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.vec = (p->cout % 4 == 0) && (p->out_ld % 4 == 0) && aligned16(p->out) && (!p->bias || aligned16(p->bias)) &&
            (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
            (kp.res_mode == FG_RES_NONE || (aligned16(p->res) && p->res_ld % 4 == 0));
+
+  // TMA-store epilogue whenever the output rows are 16-byte addressable and the tile is at least 32 wide
+  kp.tma_store = 0;
+  {
+    const int esz = p->out_dtype == FG_F32 ? 4 : 2;
+    if (kp.vec && block_n >= 64 && (p->out_ld * esz) % 16 == 0) {
+      const uint64_t dims[4] = {(uint64_t)p->cout, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
+      const uint64_t ldb = (uint64_t)p->out_ld * esz;
+      const uint64_t strides[4] = {(uint64_t)esz, ldb, ldb * p->w, ldb * p->w * p->h};
+      const uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
+      int r = encode_tmap(&kp.tmOut, p->out, p->out_dtype, 4, dims, strides, box);
+      if (r != FG_OK) return r;
+      kp.tma_store = 1;
+    }
+  }
 
   int dev = 0, num_sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||

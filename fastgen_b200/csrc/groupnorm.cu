@@ -149,8 +149,8 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
 }
 
 // grid (slabs, n): coefficients a[c], b[c] with y = a*x + b are built once per CTA in shared memory.
-template <typename T>
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyK p) {
+template <typename T, int MODE, bool LO>  // MODE: FG_RES_NONE / FG_RES_UP2 / FG_RES_DOWN2; LO: split-precision outputs
+__global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK p) {
   extern __shared__ float s_coef[];  // a[c] | b[c]
   float* s_a = s_coef;
   float* s_b = s_coef + p.c;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyK p) 
   const int hw = p.h * p.w;
   {
     const double cnt = static_cast<double>(hw) * p.cg;
-    for (int ch = threadIdx.x; ch < p.c; ch += kGnThreads) {
+    for (int ch = threadIdx.x; ch < p.c; ch += blockDim.x) {
       const int g = ch / p.cg;
       const double s = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2];
       const double ss = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2 + 1];
@@ -183,86 +183,107 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyK p) 
 
   const T* xb = static_cast<const T*>(p.x) + static_cast<int64_t>(n) * hw * p.x_ld;
   const int nvec = p.c >> 3;
+  // thread -> (8-channel vector, pixel row): the vector index is FIXED per thread, so its 16 coefficients live
+  // in registers and the pixel loop has no div/mod; 4 pixels are in flight per thread.
+  const int vpp = min(nvec, static_cast<int>(blockDim.x));  // vectors per pass
+  const int ppi = blockDim.x / vpp;                         // pixels per iteration of the block
+  const int prow = threadIdx.x / vpp;
+  if (prow >= ppi) return;
+  constexpr bool up = MODE == FG_RES_UP2;
+  constexpr bool down = MODE == FG_RES_DOWN2;
+  const int ow = down ? (p.w >> 1) : p.w;
+  const int npix = down ? (p.h >> 1) * ow : hw;  // pixels this kernel iterates over (output pixels for DOWN2)
+  const int p0 = blockIdx.x * p.pix_per_slab;
+  const int p1 = min(npix, p0 + p.pix_per_slab);
 
-  if (p.resample == FG_RES_DOWN2) {
-    const int ow = p.w >> 1, ohw = (p.h >> 1) * ow;
-    const int q0 = blockIdx.x * p.pix_per_slab;
-    const int q1 = min(ohw, q0 + p.pix_per_slab);
-    const int64_t total = static_cast<int64_t>(q1 - q0) * nvec;
-    for (int64_t idx = threadIdx.x; idx < total; idx += kGnThreads) {
-      const int vi = static_cast<int>(idx % nvec);
-      const int opix = q0 + static_cast<int>(idx / nvec);
-      const int oy = opix / ow, ox = opix % ow;
-      float a8[8], b8[8], acc[8], racc[8];
+  for (int vi = threadIdx.x % vpp; vi < nvec; vi += vpp) {
+    float a8[8], b8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a8[k] = s_a[vi * 8 + k], b8[k] = s_b[vi * 8 + k], acc[k] = 0.f, racc[k] = 0.f;
+    for (int k = 0; k < 8; ++k) a8[k] = s_a[vi * 8 + k], b8[k] = s_b[vi * 8 + k];
+    const int co = vi * 8;
+
+    if constexpr (down) {
+      for (int opix = p0 + prow; opix < p1; opix += ppi) {
+        const int oy = opix / ow, ox = opix % ow;
+        float v[4][8];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int ipix = (2 * oy + (d >> 1)) * p.w + 2 * ox + (d & 1);
-        float v[8];
-        load8<T>(xb + static_cast<int64_t>(ipix) * p.x_ld + vi * 8, v);
+        for (int d = 0; d < 4; ++d)
+          load8<T>(xb + static_cast<int64_t>((2 * oy + (d >> 1)) * p.w + 2 * ox + (d & 1)) * p.x_ld + co, v[d]);
+        float acc[8], racc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float yv = fmaf(a8[k], v[k], b8[k]);
-          if (p.silu) yv = silu_f(yv);
-          acc[k] += yv;
-          racc[k] += v[k];
+          float y0 = fmaf(a8[k], v[0][k], b8[k]), y1 = fmaf(a8[k], v[1][k], b8[k]);
+          float y2 = fmaf(a8[k], v[2][k], b8[k]), y3 = fmaf(a8[k], v[3][k], b8[k]);
+          if (p.silu) y0 = silu_f(y0), y1 = silu_f(y1), y2 = silu_f(y2), y3 = silu_f(y3);
+          acc[k] = 0.25f * ((y0 + y1) + (y2 + y3));
+          racc[k] = 0.25f * ((v[0][k] + v[1][k]) + (v[2][k] + v[3][k]));
         }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] *= 0.25f, racc[k] *= 0.25f;
-      const int64_t o = (static_cast<int64_t>(n) * ohw + opix);
-      store8_bf16(p.y + o * p.y_ld + vi * 8, acc);
-      if (p.y_lo) {
-        float lo[8];
-        split8(acc, lo);
-        store8_bf16(p.y_lo + o * p.y_ld + vi * 8, lo);
-      }
-      if (p.raw) {
-        store8_bf16(p.raw + o * p.raw_ld + vi * 8, racc);
-        if (p.raw_lo) {
+        const int64_t o = static_cast<int64_t>(n) * npix + opix;
+        store8_bf16(p.y + o * p.y_ld + co, acc);
+        if (LO && p.y_lo) {
           float lo[8];
-          split8(racc, lo);
-          store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, lo);
+          split8(acc, lo);
+          store8_bf16(p.y_lo + o * p.y_ld + co, lo);
+        }
+        if (p.raw) {
+          store8_bf16(p.raw + o * p.raw_ld + co, racc);
+          if (LO && p.raw_lo) {
+            float lo[8];
+            split8(racc, lo);
+            store8_bf16(p.raw_lo + o * p.raw_ld + co, lo);
+          }
         }
       }
+      continue;
     }
-    return;
-  }
 
-  const int p0 = blockIdx.x * p.pix_per_slab;
-  const int p1 = min(hw, p0 + p.pix_per_slab);
-  const int64_t total = static_cast<int64_t>(p1 - p0) * nvec;
-  for (int64_t idx = threadIdx.x; idx < total; idx += kGnThreads) {
-    const int vi = static_cast<int>(idx % nvec);
-    const int pix = p0 + static_cast<int>(idx / nvec);
-    float v[8], yv[8];
-    load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + vi * 8, v);
+    auto emit = [&](int pix, const float (&v)[8]) {
+      float yv[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float t = fmaf(s_a[vi * 8 + k], v[k], s_b[vi * 8 + k]);
-      yv[k] = p.silu ? silu_f(t) : t;
-    }
-    float ylo[8], rlo[8];
-    if (p.y_lo) split8(yv, ylo);
-    if (p.raw_lo) split8(v, rlo);
-    if (p.resample == FG_RES_UP2) {
-      const int iy = pix / p.w, ix = pix % p.w;
-      const int W2 = p.w * 2;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int64_t o = static_cast<int64_t>(n) * hw * 4 + static_cast<int64_t>(2 * iy + (d >> 1)) * W2 + 2 * ix + (d & 1);
-        store8_bf16(p.y + o * p.y_ld + vi * 8, yv);
-        if (p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + vi * 8, ylo);
-        if (p.raw) store8_bf16(p.raw + o * p.raw_ld + vi * 8, v);
-        if (p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, rlo);
+      for (int k = 0; k < 8; ++k) {
+        const float t = fmaf(a8[k], v[k], b8[k]);
+        yv[k] = p.silu ? silu_f(t) : t;
       }
-    } else {
-      const int64_t o = static_cast<int64_t>(n) * hw + pix;
-      store8_bf16(p.y + o * p.y_ld + vi * 8, yv);
-      if (p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + vi * 8, ylo);
-      if (p.raw) store8_bf16(p.raw + o * p.raw_ld + vi * 8, v);
-      if (p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + vi * 8, rlo);
+      float ylo[8], rlo[8];
+      if (LO && p.y_lo) split8(yv, ylo);
+      if (LO && p.raw_lo) split8(v, rlo);
+      if constexpr (up) {
+        const int iy = pix / p.w, ix = pix % p.w;
+        const int W2 = p.w * 2;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int64_t o =
+              static_cast<int64_t>(n) * hw * 4 + static_cast<int64_t>(2 * iy + (d >> 1)) * W2 + 2 * ix + (d & 1);
+          store8_bf16(p.y + o * p.y_ld + co, yv);
+          if (LO && p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + co, ylo);
+          if (p.raw) store8_bf16(p.raw + o * p.raw_ld + co, v);
+          if (LO && p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
+        }
+      } else {
+        const int64_t o = static_cast<int64_t>(n) * hw + pix;
+        store8_bf16(p.y + o * p.y_ld + co, yv);
+        if (LO && p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + co, ylo);
+        if (p.raw) store8_bf16(p.raw + o * p.raw_ld + co, v);
+        if (LO && p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
+      }
+    };
+
+    int pix = p0 + prow;
+    for (; pix + 3 * ppi < p1; pix += 4 * ppi) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
+      load8<T>(xb + static_cast<int64_t>(pix + ppi) * p.x_ld + co, v1);
+      load8<T>(xb + static_cast<int64_t>(pix + 2 * ppi) * p.x_ld + co, v2);
+      load8<T>(xb + static_cast<int64_t>(pix + 3 * ppi) * p.x_ld + co, v3);
+      emit(pix, v0);
+      emit(pix + ppi, v1);
+      emit(pix + 2 * ppi, v2);
+      emit(pix + 3 * ppi, v3);
+    }
+    for (; pix < p1; pix += ppi) {
+      float v0[8];
+      load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
+      emit(pix, v0);
     }
   }
 }
@@ -336,10 +357,31 @@ extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
   const int slabs = pick_slab(p->n, pixels, p->c, &k.pix_per_slab);
   const dim3 grid(slabs, p->n);
   const size_t smem = sizeof(float) * 2 * p->c;
+  const int nvec = p->c / 8;
+  const int threads = nvec >= kGnThreads ? kGnThreads : nvec * (kGnThreads / nvec);
+  const bool lo = p->y_lo || p->raw_lo;
+#define FG_GN_LAUNCH(T, MODE)                                             \
+  do {                                                                    \
+    if (lo)                                                               \
+      gn_apply_kernel<T, MODE, true><<<grid, threads, smem, stream>>>(k); \
+    else                                                                  \
+      gn_apply_kernel<T, MODE, false><<<grid, threads, smem, stream>>>(k); \
+  } while (0)
+#define FG_GN_DISPATCH(T)                                        \
+  do {                                                           \
+    if (p->resample == FG_RES_UP2)                               \
+      FG_GN_LAUNCH(T, FG_RES_UP2);                               \
+    else if (p->resample == FG_RES_DOWN2)                        \
+      FG_GN_LAUNCH(T, FG_RES_DOWN2);                             \
+    else                                                         \
+      FG_GN_LAUNCH(T, FG_RES_NONE);                              \
+  } while (0)
   if (p->x_dtype == FG_F32)
-    gn_apply_kernel<float><<<grid, kGnThreads, smem, stream>>>(k);
+    FG_GN_DISPATCH(float);
   else
-    gn_apply_kernel<__nv_bfloat16><<<grid, kGnThreads, smem, stream>>>(k);
+    FG_GN_DISPATCH(__nv_bfloat16);
+#undef FG_GN_DISPATCH
+#undef FG_GN_LAUNCH
   FG_CHECK_LAUNCH("gn_apply");
   return FG_OK;
 }

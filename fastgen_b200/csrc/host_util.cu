@@ -37,6 +37,12 @@ static EncodeTiledFn get_encode() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(map, base, FG_BF16, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap(CUtensorMap* map, const void* base, int fg_dtype_, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box) {
+  const CUtensorMapDataType dt = fg_dtype_ == FG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   EncodeTiledFn fn = get_encode();
   if (!fn) return FG_ERR_CUDA;
   cuuint64_t gdim[5];
@@ -49,7 +55,7 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

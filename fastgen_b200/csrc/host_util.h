@@ -17,6 +17,9 @@ void count_launch(int n = 1);
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1; bf16 elements, 128B swizzle.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box);
+// same for an FG_F32 / FG_BF16 tensor (fg_dtype)
+int encode_tmap(CUtensorMap* map, const void* base, int fg_dtype_, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box);
 
 #define FG_CHECK_ARG(cond, ...)      \
   do {                               \
