@@ -12,6 +12,8 @@
 //
 // Replaces: fastgen/networks/EDM/network.py:93-126 (Conv2d.forward), :47-51 (Linear.forward) and the
 // elementwise tail of UNetBlock.forward (:283, :286-287, :297-298).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -552,7 +554,8 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.tma_store = 0;
   {
     const int esz = p->out_dtype == FG_F32 ? 4 : 2;
-    if (kp.vec && block_n >= 64 && (p->out_ld * esz) % 16 == 0) {
+    static const bool allow_tma_store = !(getenv("FG_CONV_TMA_STORE") && getenv("FG_CONV_TMA_STORE")[0] == '0');
+    if (allow_tma_store && kp.vec && block_n >= 64 && (p->out_ld * esz) % 16 == 0) {
       const uint64_t dims[4] = {(uint64_t)p->cout, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
       const uint64_t ldb = (uint64_t)p->out_ld * esz;
       const uint64_t strides[4] = {(uint64_t)esz, ldb, ldb * p->w, ldb * p->w * p->h};

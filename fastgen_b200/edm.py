@@ -266,6 +266,7 @@ class _Plan:
         self.x3 = net.compute == "bf16x3"
         self.steps: List[Tuple[Any, tuple]] = []
         self.step_flops: List[float] = []
+        self.step_desc: List[Tuple[str, float]] = []
         self.keep: List[Any] = []
         self._build()
 
@@ -317,15 +318,21 @@ class _Plan:
         return self._scratch_buf[name][:numel].view(*shape)
 
     # ---- launch helpers (append to the list; tensors referenced by structs are kept alive) ----
-    def _launch(self, fn, *args, flops: float = 0.0):
+    def _launch(self, fn, *args, flops: float = 0.0, desc: str = "", nbytes: float = 0.0):
         self.steps.append((fn, args))
         self.step_flops.append(flops)
+        self.step_desc.append((desc, nbytes))
 
     def conv(self, segs, n, h, w, cout, out: torch.Tensor, out_ld: int, **kw):
         p = ops.conv_gemm_params(segs, n, h, w, cout, out, out_ld, **kw)
         self.keep.append((p, segs, out, kw))
         flops = 2.0 * n * h * w * cout * sum(s.cin * s.taps for s in segs if s.alg)
-        self._launch(L.lib().fg_conv_gemm, C.byref(p), flops=flops)
+        ktot = sum(s.cin * s.taps for s in segs if s.alg)
+        res = kw.get("res")
+        nbytes = n * h * w * (sum(2 * s.cin for s in segs if s.alg) + cout * out.element_size()
+                              + (cout * res.element_size() if res is not None else 0))
+        self._launch(L.lib().fg_conv_gemm, C.byref(p), flops=flops, nbytes=nbytes,
+                     desc=f"conv {h}x{w} K={ktot} N={cout} out={str(out.dtype)[6:]} res={kw.get('res_mode', 0)}")
 
     def gn(self, x: _Act, norm: _GroupNorm, pk: Dict[str, torch.Tensor], y: torch.Tensor, silu: bool, resample: int = 0,
            scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None):
@@ -333,12 +340,15 @@ class _Plan:
         groups = norm.num_groups
         xv = x.t
         self._launch(L.lib().fg_gn_stats, xv.data_ptr(), ops._DT[xv.dtype], x.ld, n, h * w, c, groups,
-                     self.stats.data_ptr())
+                     self.stats.data_ptr(), desc=f"gn_stats {h}x{w} c={c}", nbytes=n * h * w * c * xv.element_size())
         p = ops.gn_apply_params(xv, x.ld, n, h, w, c, groups, self.stats, norm.eps, pk["gamma"], pk["beta"], y, c,
                                 scale=scale, shift=shift, mod_ld=mod_ld, silu=silu, resample=resample, y_lo=y_lo,
                                 raw=raw, raw_ld=c, raw_lo=raw_lo)
         self.keep.append((p, xv, y, y_lo, raw, raw_lo, scale, shift))
-        self._launch(L.lib().fg_gn_apply, C.byref(p))
+        outs = 1 + (y_lo is not None) + (raw is not None) + (raw_lo is not None)
+        opix = h * w * (4 if resample == L.FG_RES_UP2 else 1) // (4 if resample == L.FG_RES_DOWN2 else 1)
+        self._launch(L.lib().fg_gn_apply, C.byref(p), desc=f"gn_apply {h}x{w} c={c} outs={outs} rs={resample}",
+                     nbytes=n * c * (h * w * xv.element_size() + opix * 2 * outs))
 
     def segs3(self, a_hi, a_lo, ld, w_hi, w_lo, cin, taps) -> List[ops.Seg]:
         s = [ops.Seg(a_hi, ld, w_hi, cin, taps)]
@@ -589,11 +599,15 @@ class _Plan:
             evs.append((fn.__name__, a, b, fl))
         torch.cuda.synchronize()
         out: Dict[str, Dict[str, float]] = {}
-        for name, a, b, fl in evs:
+        detail = getattr(self.net, "profile_detail", None)
+        for (name, a, b, fl), (desc, nbytes) in zip(evs, self.step_desc):
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            ms = a.elapsed_time(b)
             d["launches"] += 1
-            d["ms"] += a.elapsed_time(b)
+            d["ms"] += ms
             d["flops"] += fl
+            if detail is not None:
+                detail.append((name, desc, ms, fl, nbytes))
         return out
 
 

@@ -1,0 +1,56 @@
+"""Micro-benchmark of fg_conv_gemm on single layer shapes (CUDA events, L2 flushed between runs by the sheer
+tensor sizes).  usage (GPU box): python profiles/conv_micro.py"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fastgen_b200 import ops  # noqa: E402
+
+dev = "cuda"
+
+
+def run(tag, n, h, w, cin, cout, taps, out_dtype, res=False, bias=True, iters=5):
+    a = torch.randn(n, h, w, cin, device=dev).bfloat16()
+    wt = (torch.randn(cout, taps, cin, device=dev) / math.sqrt(cin * taps)).bfloat16()
+    b = torch.randn(cout, device=dev) if bias else None
+    out = torch.empty(n, h, w, cout, device=dev, dtype=out_dtype)
+    r = torch.randn(n, h, w, cout, device=dev) if res else None
+    kw = dict(bias=b)
+    if res:
+        kw.update(res=r, res_ld=cout, res_mode=1)
+    f = lambda: ops.conv_gemm([ops.Seg(a, cin, wt, cin, taps)], n, h, w, cout, out, cout, **kw)  # noqa: E731
+    f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * n * h * w * cout * cin * taps
+    by = n * h * w * (cin * 2 + cout * out.element_size() + (cout * 4 if res else 0))
+    print(f"{tag:34s} {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s {by / ms / 1e6:8.1f} GB/s", flush=True)
+
+
+B = 256
+if len(sys.argv) > 1:
+    run("proj 32x32 K384 N384 f32", B, 32, 32, 384, 384, 1, torch.float32, iters=1)
+    run("proj 32x32 K384 N384 f32 +res", B, 32, 32, 384, 384, 1, torch.float32, res=True, iters=1)
+    sys.exit(0)
+run("qkv 32x32 K384 N1152 bf16", B, 32, 32, 384, 1152, 1, torch.bfloat16)
+run("qkv 32x32 K384 N1152 f32", B, 32, 32, 384, 1152, 1, torch.float32)
+run("qkv nobias bf16", B, 32, 32, 384, 1152, 1, torch.bfloat16, bias=False)
+run("proj 32x32 K384 N384 f32 +res", B, 32, 32, 384, 384, 1, torch.float32, res=True)
+run("proj 32x32 K384 N384 f32", B, 32, 32, 384, 384, 1, torch.float32)
+run("proj 32x32 K384 N384 bf16", B, 32, 32, 384, 384, 1, torch.bfloat16)
+run("3x3 32x32 K3456 N384 f32", B, 32, 32, 384, 384, 9, torch.float32)
+run("3x3 32x32 K3456 N384 f32 +res", B, 32, 32, 384, 384, 9, torch.float32, res=True)
+run("3x3 64x64 K1728 N192 f32", B, 64, 64, 192, 192, 9, torch.float32)
+run("3x3 64x64 K1728 N192 f32 +res", B, 64, 64, 192, 192, 9, torch.float32, res=True)
+run("3x3 64x64 K1728 N192 bf16", B, 64, 64, 192, 192, 9, torch.bfloat16)
+run("1x1 64x64 K192 N192 bf16", B, 64, 64, 192, 192, 1, torch.bfloat16)
+run("1x1 8x8 K768 N2304 bf16", B, 8, 8, 768, 2304, 1, torch.bfloat16)
