@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfastgen_b200.so")
 FG_MAX_SEG = 6
 FG_F32, FG_BF16, FG_F64 = 0, 1, 2
 FG_RES_NONE, FG_RES_SAME, FG_RES_UP2, FG_RES_DOWN2 = 0, 1, 2, 3
+FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU = 0, 1, 2
 
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
@@ -32,6 +33,7 @@ class ConvParams(C.Structure):
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cout", C.c_int32), ("nseg", C.c_int32),
         ("seg", ConvSeg * FG_MAX_SEG),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int64),
+        ("act", C.c_int32), ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("gate_rows", C.c_int32),
         ("res", C.c_void_p), ("res_dtype", C.c_int32), ("res_mode", C.c_int32), ("res_ld", C.c_int64),
         ("out_scale", C.c_float),
         ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_ld", C.c_int64),

@@ -1,6 +1,7 @@
 // Implicit-GEMM convolution / linear layer for sm_100a:
 //   TMA (tile mode, 128B swizzle) -> shared memory ring -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM)
-//   -> tcgen05.ld epilogue with the fused bias / per-sample vector / residual(+resample) / scale tail.
+//   -> tcgen05.ld epilogue with the fused bias / per-sample vector / activation / gate / residual(+resample) / scale
+//   tail -> 128B-swizzled shared-memory slab -> TMA store.
 //
 // GEMM view: M = N*H*W output pixels (128 per tile = one TMA box of BW x BH x BNI pixels),
 //            N = cout (BLOCK_N per tile), K = sum over segments of taps * cin (64 per pipeline stage).
@@ -10,8 +11,15 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  Two TMEM accumulator stages let the epilogue of
 // tile i overlap the main loop of tile i+1.
 //
-// Replaces: fastgen/networks/EDM/network.py:93-126 (Conv2d.forward), :47-51 (Linear.forward) and the
-// elementwise tail of UNetBlock.forward (:283, :286-287, :297-298).
+// Epilogue: a ring of four 16 KB slabs (128 rows x 128 B).  The residual of a slab is prefetched into the ring by
+// TMA two slabs ahead (FG_RES_SAME: into the slab itself, added in place; FG_RES_UP2: the quarter-size source box),
+// the 128 epilogue threads add their accumulator row and the slab leaves through a TMA store: every global access
+// of the tail is a full 128-byte line.  The hot loop is specialised at compile time on (output type, residual
+// kind); measured on B200 the runtime-generic version of the same loop was 3x slower (instruction issue bound).
+//
+// Replaces: fastgen/networks/EDM/network.py:93-126 (Conv2d.forward), :47-51 (Linear.forward), the elementwise tail
+// of UNetBlock.forward (:283, :286-287, :297-298); and, for the transformer networks, the Linear + bias + GELU /
+// gate * x + residual tails of the Wan / DiT blocks (fastgen/networks/Wan/network.py:116-151, DiT/network.py:184-201).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -23,14 +31,23 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kConvThreads = 192;
 
+// epilogue specialisations
+constexpr int kEpiGeneric = -1;  // no TMA store: direct (vector or scalar) global accesses, every feature at run time
+constexpr int kResNone = 0;      // no residual, or one the TMA path cannot take (read with plain loads)
+constexpr int kResSame = 1;
+constexpr int kResUp2 = 2;
+__host__ __device__ constexpr int epi_mode(bool out_bf16, int res) { return (out_bf16 ? 1 : 0) | (res << 1); }
+
 template <int BLOCK_N>
 struct ConvCfg {
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
   static constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_SLAB_BYTES = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 B (TMA store box)
-  static constexpr int OUT_SLABS = 2;
-  static constexpr int STAGES_RAW = (196 * 1024 - OUT_SLABS * OUT_SLAB_BYTES) / STAGE_BYTES;
+  static constexpr int OUT_SLAB_BYTES = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 B (TMA box)
+  static constexpr int OUT_SLABS = 4;                   // ring: residual prefetch (TMA load) -> in-place add -> TMA store
+  static constexpr int RES_UP_BYTES = OUT_SLAB_BYTES / 4;  // FG_RES_UP2: the (BW/2 x BH/2) source box of a slab
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - 256 - OUT_SLABS * OUT_SLAB_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
@@ -46,7 +63,7 @@ struct ConvKParams {
   CUtensorMap tmA[FG_MAX_SEG];
   CUtensorMap tmW[FG_MAX_SEG];
   CUtensorMap tmOut;  // output tile store: box (32 fp32 | 64 bf16 channels, BW, BH, BNI)
-  int32_t tma_store;  // 1: epilogue stages 128B-row slabs in smem and stores them with TMA
+  CUtensorMap tmRes;  // residual prefetch: same box (FG_RES_SAME) or (.., BW/2, BH/2, BNI) of the half-size tensor (UP2)
   int32_t seg_taps[FG_MAX_SEG];
   int32_t seg_kchunks[FG_MAX_SEG];
   int32_t nseg;
@@ -54,10 +71,15 @@ struct ConvKParams {
   int32_t BW, BH, BNI;  // TMA box in pixels, BW*BH*BNI == 128
   int32_t tiles_w, tiles_h, tiles_img, tiles_n, total_tiles;
   int32_t k_iters;
-  int32_t vec;  // 1: every epilogue access may use 4-element vectors
+  int32_t vec;  // generic epilogue: every access may use 4-element vectors
+  int32_t dbg;  // FG_CONV_DBG bit mask (profiling experiments only; results are wrong when non-zero)
   const float* bias;
   const float* rowvec;
   int64_t rowvec_ld;
+  int32_t act;
+  const float* gate;
+  int64_t gate_ld;
+  int32_t gate_rows;
   const void* res;
   int32_t res_dtype, res_mode;
   int64_t res_ld;
@@ -97,22 +119,61 @@ __device__ __forceinline__ float ld1(const void* base, int dtype, int64_t idx) {
   return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[idx]);
 }
 
-// Fused tail for CH accumulator columns of one output pixel.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == FG_ACT_GELU_TANH) {
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    return 0.5f * x * (1.0f + tanh_fast(u));
+  }
+  if (act == FG_ACT_SILU) return silu_f(x);
+  return x;
+}
+
+// residual source of one output pixel, for plain-load access
+struct ResAddr {
+  int64_t rpix, step_w, step_h;
+};
+__device__ __forceinline__ ResAddr res_addr(const ConvKParams& p, int img, int h, int w) {
+  ResAddr r;
+  r.rpix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
+  r.step_w = 0, r.step_h = 0;
+  if (p.res_mode == FG_RES_UP2) {
+    r.rpix = (static_cast<int64_t>(img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+  } else if (p.res_mode == FG_RES_DOWN2) {
+    const int64_t W2 = static_cast<int64_t>(p.W) * 2;
+    r.rpix = (static_cast<int64_t>(img) * (p.H * 2) + 2 * h) * W2 + 2 * w;
+    r.step_w = p.res_ld;
+    r.step_h = W2 * p.res_ld;
+  }
+  return r;
+}
+__device__ __forceinline__ float4 res_load4(const ConvKParams& p, const ResAddr& ra, int c) {
+  const int64_t o = ra.rpix * p.res_ld + c;
+  if (p.res_mode != FG_RES_DOWN2) return ld4(p.res, p.res_dtype, o);
+  const float4 b0 = ld4(p.res, p.res_dtype, o), b1 = ld4(p.res, p.res_dtype, o + ra.step_w);
+  const float4 b2 = ld4(p.res, p.res_dtype, o + ra.step_h), b3 = ld4(p.res, p.res_dtype, o + ra.step_h + ra.step_w);
+  return make_float4(0.25f * ((b0.x + b1.x) + (b2.x + b3.x)), 0.25f * ((b0.y + b1.y) + (b2.y + b3.y)),
+                     0.25f * ((b0.z + b1.z) + (b2.z + b3.z)), 0.25f * ((b0.w + b1.w) + (b2.w + b3.w)));
+}
+__device__ __forceinline__ float res_load1(const ConvKParams& p, const ResAddr& ra, int c) {
+  const int64_t o = ra.rpix * p.res_ld + c;
+  if (p.res_mode != FG_RES_DOWN2) return ld1(p.res, p.res_dtype, o);
+  return 0.25f * ((ld1(p.res, p.res_dtype, o) + ld1(p.res, p.res_dtype, o + ra.step_w)) +
+                  (ld1(p.res, p.res_dtype, o + ra.step_h) + ld1(p.res, p.res_dtype, o + ra.step_h + ra.step_w)));
+}
+
+// Generic tail for CH accumulator columns of one output pixel, written straight to global memory.
+//   v = acc + bias + rowvec;  v = act(v);  v *= gate;  v += residual;  v *= out_scale
 template <int CH>
 __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint32_t (&v)[CH], int c_base, int img,
                                                int h, int w) {
   const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
-  // residual source pixel(s)
-  int64_t rpix = pix;
-  int64_t rstep_w = 0, rstep_h = 0;
-  if (p.res_mode == FG_RES_UP2) {
-    rpix = (static_cast<int64_t>(img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-  } else if (p.res_mode == FG_RES_DOWN2) {
-    const int64_t W2 = static_cast<int64_t>(p.W) * 2;
-    rpix = (static_cast<int64_t>(img) * (p.H * 2) + 2 * h) * W2 + 2 * w;
-    rstep_w = p.res_ld;
-    rstep_h = W2 * p.res_ld;
-  }
+  const ResAddr ra = res_addr(p, img, h, w);
+  const float* grow = p.gate ? p.gate + (pix / p.gate_rows) * p.gate_ld : nullptr;
 #pragma unroll
   for (int j = 0; j < CH; j += 4) {
     const int c = c_base + j;
@@ -128,17 +189,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint3
           const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowvec + img * p.rowvec_ld + c));
           a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
         }
-        if (p.res_mode == FG_RES_SAME || p.res_mode == FG_RES_UP2) {
-          const float4 b = ld4(p.res, p.res_dtype, rpix * p.res_ld + c);
+        if (p.act) {
+          a.x = apply_act(a.x, p.act), a.y = apply_act(a.y, p.act);
+          a.z = apply_act(a.z, p.act), a.w = apply_act(a.w, p.act);
+        }
+        if (grow) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(grow + c));
+          a.x *= g.x, a.y *= g.y, a.z *= g.z, a.w *= g.w;
+        }
+        if (p.res_mode != FG_RES_NONE) {
+          const float4 b = res_load4(p, ra, c);
           a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-        } else if (p.res_mode == FG_RES_DOWN2) {
-          const int64_t o = rpix * p.res_ld + c;
-          const float4 b0 = ld4(p.res, p.res_dtype, o), b1 = ld4(p.res, p.res_dtype, o + rstep_w);
-          const float4 b2 = ld4(p.res, p.res_dtype, o + rstep_h), b3 = ld4(p.res, p.res_dtype, o + rstep_h + rstep_w);
-          a.x += 0.25f * ((b0.x + b1.x) + (b2.x + b3.x));
-          a.y += 0.25f * ((b0.y + b1.y) + (b2.y + b3.y));
-          a.z += 0.25f * ((b0.z + b1.z) + (b2.z + b3.z));
-          a.w += 0.25f * ((b0.w + b1.w) + (b2.w + b3.w));
         }
         a.x *= p.out_scale, a.y *= p.out_scale, a.z *= p.out_scale, a.w *= p.out_scale;
         if (p.out_dtype == FG_F32) {
@@ -158,13 +219,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint3
           float a = __uint_as_float(v[j + i]);
           if (p.bias) a += __ldg(p.bias + cc);
           if (p.rowvec) a += __ldg(p.rowvec + img * p.rowvec_ld + cc);
-          if (p.res_mode == FG_RES_SAME || p.res_mode == FG_RES_UP2) {
-            a += ld1(p.res, p.res_dtype, rpix * p.res_ld + cc);
-          } else if (p.res_mode == FG_RES_DOWN2) {
-            const int64_t o = rpix * p.res_ld + cc;
-            a += 0.25f * ((ld1(p.res, p.res_dtype, o) + ld1(p.res, p.res_dtype, o + rstep_w)) +
-                          (ld1(p.res, p.res_dtype, o + rstep_h) + ld1(p.res, p.res_dtype, o + rstep_h + rstep_w)));
-          }
+          a = apply_act(a, p.act);
+          if (grow) a *= __ldg(grow + cc);
+          if (p.res_mode != FG_RES_NONE) a += res_load1(p, ra, cc);
           a *= p.out_scale;
           if (p.out_dtype == FG_F32) {
             static_cast<float*>(p.out)[pix * p.out_ld + cc] = a;
@@ -177,55 +234,70 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint3
   }
 }
 
-// Fused tail evaluated into registers (vector path only): a[j] = out_scale * (acc + bias + rowvec + residual).
-template <int CH>
-__device__ __forceinline__ void epilogue_values(const ConvKParams& p, const uint32_t (&v)[CH], int c_base, int img,
-                                                int h, int w, bool valid, float (&a)[CH]) {
-  const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
-  int64_t rpix = pix;
-  int64_t rstep_w = 0, rstep_h = 0;
-  if (p.res_mode == FG_RES_UP2) {
-    rpix = (static_cast<int64_t>(img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-  } else if (p.res_mode == FG_RES_DOWN2) {
-    const int64_t W2 = static_cast<int64_t>(p.W) * 2;
-    rpix = (static_cast<int64_t>(img) * (p.H * 2) + 2 * h) * W2 + 2 * w;
-    rstep_w = p.res_ld;
-    rstep_h = W2 * p.res_ld;
-  }
+// Specialised tail of the TMA-store path for 32 accumulator columns: everything except the residual that arrives
+// through shared memory and the final scale.  Branches are warp-uniform; the rare plain-load residual (FG_RES_DOWN2,
+// or a residual whose type differs from the output's) stays behind one of them.
+template <int RES>
+__device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t (&v)[32], int c_base, int img, int h,
+                                            int w, bool valid, float (&a)[32]) {
 #pragma unroll
-  for (int j = 0; j < CH; j += 4) {
-    const int c = c_base + j;
-    float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                           __uint_as_float(v[j + 3]));
-    if (valid && c < p.Cout) {
-      if (p.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
-      }
-      if (p.rowvec) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowvec + img * p.rowvec_ld + c));
-        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
-      }
-      if (p.res_mode == FG_RES_SAME || p.res_mode == FG_RES_UP2) {
-        const float4 b = ld4(p.res, p.res_dtype, rpix * p.res_ld + c);
-        r.x += b.x, r.y += b.y, r.z += b.z, r.w += b.w;
-      } else if (p.res_mode == FG_RES_DOWN2) {
-        const int64_t o = rpix * p.res_ld + c;
-        const float4 b0 = ld4(p.res, p.res_dtype, o), b1 = ld4(p.res, p.res_dtype, o + rstep_w);
-        const float4 b2 = ld4(p.res, p.res_dtype, o + rstep_h), b3 = ld4(p.res, p.res_dtype, o + rstep_h + rstep_w);
-        r.x += 0.25f * ((b0.x + b1.x) + (b2.x + b3.x));
-        r.y += 0.25f * ((b0.y + b1.y) + (b2.y + b3.y));
-        r.z += 0.25f * ((b0.z + b1.z) + (b2.z + b3.z));
-        r.w += 0.25f * ((b0.w + b1.w) + (b2.w + b3.w));
+  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (c_base + j < p.Cout) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c_base + j));
+        a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
       }
     }
-    a[j] = r.x * p.out_scale, a[j + 1] = r.y * p.out_scale, a[j + 2] = r.z * p.out_scale, a[j + 3] = r.w * p.out_scale;
+  }
+  if (p.rowvec && valid) {
+    const float* rv = p.rowvec + img * p.rowvec_ld + c_base;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (c_base + j < p.Cout) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
+        a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
+      }
+    }
+  }
+  if (p.act) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = apply_act(a[j], p.act);
+  }
+  if (p.gate && valid) {
+    const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
+    const float* g = p.gate + (pix / p.gate_rows) * p.gate_ld + c_base;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (c_base + j < p.Cout) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(g + j));
+        a[j] *= b.x, a[j + 1] *= b.y, a[j + 2] *= b.z, a[j + 3] *= b.w;
+      }
+    }
+  }
+  if constexpr (RES == kResNone) {
+    if (p.res_mode != FG_RES_NONE && valid) {
+      const ResAddr ra = res_addr(p, img, h, w);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {  // (unrolled: a dynamic index would push a[] into local memory)
+        if (c_base + j < p.Cout) {
+          const float4 b = res_load4(p, ra, c_base + j);
+          a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
+        }
+      }
+    }
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
+  constexpr bool kTmaStore = EPI != kEpiGeneric;
+  constexpr bool kOutBf16 = kTmaStore && (EPI & 1);
+  constexpr int kRes = kTmaStore ? (EPI >> 1) : kResNone;
+  static_assert(!kTmaStore || BLOCK_N >= 64, "the TMA-store epilogue needs tiles of at least one bf16 slab");
+
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* out_slabs = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -233,7 +305,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_full = tempty + 2;  // [OUT_SLABS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::OUT_SLABS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,7 +316,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       tma_prefetch_desc(&p.tmA[s]);
       tma_prefetch_desc(&p.tmW[s]);
     }
-    if (p.tma_store) tma_prefetch_desc(&p.tmOut);
+    if (kTmaStore) tma_prefetch_desc(&p.tmOut);
+    if (kRes != kResNone) tma_prefetch_desc(&p.tmRes);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -255,6 +329,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 4);
       }
+      for (int i = 0; i < Cfg::OUT_SLABS; ++i) mbar_init(&res_full[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -271,7 +346,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.total_tiles && !(p.dbg & 4); tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile, BLOCK_N);
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
@@ -307,7 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int it = 0; it < p.k_iters; ++it) {
+        for (int it = 0; it < p.k_iters && !(p.dbg & 4); ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -337,7 +412,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int il = row / (p.BW * p.BH);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // slab ring bookkeeping (slab_idx counts the slabs of this CTA across all its tiles)
+    constexpr uint32_t kResAhead = 2;  // residual slabs in flight ahead of the one being processed
+    constexpr int kSlabCols = kOutBf16 ? 64 : 32;
+    // FG_RES_UP2 prefetch: three output slabs, the fourth buffer holds the four quarter-size residual boxes
+    constexpr uint32_t kOutRing = (kRes == kResUp2) ? Cfg::OUT_SLABS - 1 : Cfg::OUT_SLABS;
+    const bool is_store_thread = (warp == 2 && lane == 0);
+    uint8_t* res_up = out_slabs + (Cfg::OUT_SLABS - 1) * Cfg::OUT_SLAB_BYTES;
     uint32_t slab_idx = 0;
+    uint32_t ld_idx = 0;  // store thread only: next residual slab to request, its tile and channel offset
+    int ld_tile = blockIdx.x, ld_c0 = 0;
+    const uint32_t wkey = row & 7;
+    // residual row inside a quarter-size UP2 box
+    const int rs_up = (il * (p.BH >> 1) + (hl >> 1)) * (p.BW >> 1) + (wl >> 1);
+
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int img = t.img0 + il, h = t.h0 + hl, w = t.w0 + wl;
@@ -345,48 +433,100 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-      if (p.tma_store) {
-        // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem slab -> TMA store (full-line writes,
-        //      out-of-range rows / channels clipped by the tensor map) ----
-        if constexpr (BLOCK_N >= 32) {
-          const bool is_store_thread = (warp == 2 && lane == 0);
-          const int slab_cols = (p.out_dtype == FG_F32) ? 32 : 64;
-          uint8_t* my_row_base = out_slabs + row * 128;
+      if (p.dbg & 8) {
+      } else if constexpr (kTmaStore) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += slab_cols) {
-            if (t.co0 + c0 >= p.Cout) break;  // warp-uniform: nothing left to store in this tile
-            uint8_t* slab = my_row_base + (slab_idx & 1) * Cfg::OUT_SLAB_BYTES;
-            if (is_store_thread) tma_store_wait_read<1>();  // the store that used this slab two slabs ago is done
-            named_bar_sync(1, 128);
-#pragma unroll 1
-            for (int cc = 0; cc < slab_cols; cc += 32) {
-              uint32_t v[32];
-              float a[32];
-              tmem_ld_32x32(taddr + c0 + cc, v);
-              tmem_ld_wait();
-              epilogue_values<32>(p, v, t.co0 + c0 + cc, img, h, w, valid, a);
-              if (p.out_dtype == FG_F32) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  *reinterpret_cast<float4*>(slab + ((j ^ (row & 7)) << 4)) =
-                      make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 u;
-                  u.x = pack_bf16x2(a[8 * j], a[8 * j + 1]), u.y = pack_bf16x2(a[8 * j + 2], a[8 * j + 3]);
-                  u.z = pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), u.w = pack_bf16x2(a[8 * j + 6], a[8 * j + 7]);
-                  *reinterpret_cast<uint4*>(slab + ((((cc >> 3) + j) ^ (row & 7)) << 4)) = u;
+        for (int c0 = 0; c0 < BLOCK_N; c0 += kSlabCols, ++slab_idx) {
+          if (t.co0 + c0 >= p.Cout) break;  // warp-uniform: nothing left to store in this tile
+          const uint32_t ob = slab_idx % kOutRing;        // output slab buffer
+          const uint32_t rb = slab_idx % Cfg::OUT_SLABS;  // residual buffer / barrier
+          uint8_t* slab = out_slabs + ob * Cfg::OUT_SLAB_BYTES;
+          if (is_store_thread) {
+            // every store but the most recent one has finished reading shared memory: the buffer that slab
+            // slab_idx + kResAhead lands in (last stored from two slabs ago) is free again
+            tma_store_wait_read<1>();
+            if constexpr (kRes != kResNone) {
+              while (ld_idx <= slab_idx + kResAhead && ld_tile < p.total_tiles) {
+                const TileCoord lt = decode_tile(p, ld_tile, BLOCK_N);
+                const uint32_t lrb = ld_idx % Cfg::OUT_SLABS;
+                if constexpr (kRes == kResSame) {
+                  mbar_arrive_expect_tx(&res_full[lrb], Cfg::OUT_SLAB_BYTES);
+                  tma_load_4d(out_slabs + lrb * Cfg::OUT_SLAB_BYTES, &p.tmRes, &res_full[lrb], lt.co0 + ld_c0, lt.w0,
+                              lt.h0, lt.img0);
+                } else {
+                  mbar_arrive_expect_tx(&res_full[lrb], Cfg::RES_UP_BYTES);
+                  tma_load_4d(res_up + lrb * Cfg::RES_UP_BYTES, &p.tmRes, &res_full[lrb], lt.co0 + ld_c0, lt.w0 >> 1,
+                              lt.h0 >> 1, lt.img0);
+                }
+                ++ld_idx;
+                ld_c0 += kSlabCols;
+                if (ld_c0 >= BLOCK_N || lt.co0 + ld_c0 >= p.Cout) {
+                  ld_c0 = 0;
+                  ld_tile += gridDim.x;
                 }
               }
             }
-            fence_proxy_async_smem();
-            named_bar_sync(2, 128);
-            if (is_store_thread) {
-              tma_store_4d(&p.tmOut, out_slabs + (slab_idx & 1) * Cfg::OUT_SLAB_BYTES, t.co0 + c0, t.w0, t.h0, t.img0);
-              tma_store_commit();
+          }
+          const uint8_t* rrow = nullptr;
+          uint32_t rkey = 0;
+          if constexpr (kRes == kResSame) {
+            mbar_wait(&res_full[rb], (slab_idx / Cfg::OUT_SLABS) & 1u);
+            rrow = slab + row * 128;
+            rkey = wkey;
+          } else if constexpr (kRes == kResUp2) {
+            mbar_wait(&res_full[rb], (slab_idx / Cfg::OUT_SLABS) & 1u);
+            rrow = res_up + rb * Cfg::RES_UP_BYTES + rs_up * 128;
+            rkey = rs_up & 7;
+          }
+          uint8_t* my_row = slab + row * 128;
+          const float sc = p.out_scale;
+#pragma unroll
+          for (int cc = 0; cc < kSlabCols; cc += 32) {
+            uint32_t v[32];
+            float a[32];
+            if (!(p.dbg & 2)) {
+              tmem_ld_32x32(taddr + c0 + cc, v);
+              tmem_ld_wait();
+              tail_values<kRes>(p, v, t.co0 + c0 + cc, img, h, w, valid, a);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = 1.0f;
             }
-            ++slab_idx;
+            if constexpr (!kOutBf16) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                if constexpr (kRes != kResNone) {
+                  const float4 r = *reinterpret_cast<const float4*>(rrow + ((j ^ rkey) << 4));
+                  o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+                }
+                o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+                *reinterpret_cast<float4*>(my_row + ((j ^ wkey) << 4)) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int chunk = (cc >> 3) + j;
+                if constexpr (kRes != kResNone) {
+                  const uint4 r = *reinterpret_cast<const uint4*>(rrow + ((chunk ^ rkey) << 4));
+                  const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
+                               r3 = unpack_bf16x2(r.w);
+                  a[8 * j] += r0.x, a[8 * j + 1] += r0.y, a[8 * j + 2] += r1.x, a[8 * j + 3] += r1.y;
+                  a[8 * j + 4] += r2.x, a[8 * j + 5] += r2.y, a[8 * j + 6] += r3.x, a[8 * j + 7] += r3.y;
+                }
+                uint4 u;
+                u.x = pack_bf16x2(a[8 * j] * sc, a[8 * j + 1] * sc), u.y = pack_bf16x2(a[8 * j + 2] * sc, a[8 * j + 3] * sc);
+                u.z = pack_bf16x2(a[8 * j + 4] * sc, a[8 * j + 5] * sc);
+                u.w = pack_bf16x2(a[8 * j + 6] * sc, a[8 * j + 7] * sc);
+                *reinterpret_cast<uint4*>(my_row + ((chunk ^ wkey) << 4)) = u;
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (is_store_thread && !(p.dbg & 1)) {
+            tma_store_4d(&p.tmOut, slab, t.co0 + c0, t.w0, t.h0, t.img0);
+            tma_store_commit();
           }
         }
       } else if constexpr (BLOCK_N >= 32) {
@@ -409,7 +549,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait<0>();
+    if (kTmaStore && is_store_thread) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -420,12 +560,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -434,9 +574,25 @@ static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) 
     configured = true;
   }
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-  conv_gemm_kernel<BLOCK_N><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  conv_gemm_kernel<BLOCK_N, EPI><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("conv_gemm");
   return FG_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_t stream) {
+  if constexpr (BLOCK_N >= 64) {
+    switch (epi) {
+      case epi_mode(false, kResNone): return launch_conv<BLOCK_N, epi_mode(false, kResNone)>(kp, num_sms, stream);
+      case epi_mode(true, kResNone): return launch_conv<BLOCK_N, epi_mode(true, kResNone)>(kp, num_sms, stream);
+      case epi_mode(false, kResSame): return launch_conv<BLOCK_N, epi_mode(false, kResSame)>(kp, num_sms, stream);
+      case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame)>(kp, num_sms, stream);
+      case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2)>(kp, num_sms, stream);
+      case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2)>(kp, num_sms, stream);
+      default: break;
+    }
+  }
+  return launch_conv<BLOCK_N, kEpiGeneric>(kp, num_sms, stream);
 }
 
 static int pick_block_n(int cout) {
@@ -471,10 +627,17 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   FG_CHECK_ARG(p->out != nullptr, "conv_gemm: null output");
   FG_CHECK_ARG(p->out_dtype == FG_F32 || p->out_dtype == FG_BF16, "conv_gemm: bad out_dtype %d", p->out_dtype);
   FG_CHECK_ARG(p->out_ld >= p->cout, "conv_gemm: out_ld %lld < cout %d", (long long)p->out_ld, p->cout);
+  FG_CHECK_ARG(p->act >= FG_ACT_NONE && p->act <= FG_ACT_SILU, "conv_gemm: bad act %d", p->act);
+  if (p->gate)
+    FG_CHECK_ARG(p->gate_rows > 0 && p->gate_ld >= p->cout, "conv_gemm: gate needs gate_rows > 0 and gate_ld >= cout");
 
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.N = p->n, kp.H = p->h, kp.W = p->w, kp.Cout = p->cout;
+  {
+    static const int dbg = getenv("FG_CONV_DBG") ? atoi(getenv("FG_CONV_DBG")) : 0;
+    kp.dbg = dbg;
+  }
   if (p->w >= 128) {
     FG_CHECK_ARG(p->w % 128 == 0, "conv_gemm: w=%d must be a power of two or a multiple of 128", p->w);
     kp.BW = 128, kp.BH = 1, kp.BNI = 1;
@@ -531,6 +694,10 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.bias = p->bias;
   kp.rowvec = p->rowvec;
   kp.rowvec_ld = p->rowvec_ld;
+  kp.act = p->act;
+  kp.gate = p->gate;
+  kp.gate_ld = p->gate_ld;
+  kp.gate_rows = p->gate ? p->gate_rows : 1;
   kp.res = p->res;
   kp.res_dtype = p->res_dtype;
   kp.res_mode = p->res ? p->res_mode : FG_RES_NONE;
@@ -548,10 +715,12 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   }
   kp.vec = (p->cout % 4 == 0) && (p->out_ld % 4 == 0) && aligned16(p->out) && (!p->bias || aligned16(p->bias)) &&
            (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
+           (!p->gate || (aligned16(p->gate) && p->gate_ld % 4 == 0)) &&
            (kp.res_mode == FG_RES_NONE || (aligned16(p->res) && p->res_ld % 4 == 0));
 
-  // TMA-store epilogue whenever the output rows are 16-byte addressable and the tile is at least 32 wide
-  kp.tma_store = 0;
+  // TMA-store epilogue whenever the output rows are 16-byte addressable and the tile is at least one slab wide;
+  // the residual rides the same slab ring when it has the output's element type (FG_RES_SAME / FG_RES_UP2)
+  int epi = kEpiGeneric;
   {
     const int esz = p->out_dtype == FG_F32 ? 4 : 2;
     static const bool allow_tma_store = !(getenv("FG_CONV_TMA_STORE") && getenv("FG_CONV_TMA_STORE")[0] == '0');
@@ -562,7 +731,22 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
       const uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
       int r = encode_tmap(&kp.tmOut, p->out, p->out_dtype, 4, dims, strides, box);
       if (r != FG_OK) return r;
-      kp.tma_store = 1;
+      int res_kind = kResNone;
+      static const bool allow_tma_res = !(getenv("FG_CONV_TMA_RES") && getenv("FG_CONV_TMA_RES")[0] == '0');
+      const bool up = kp.res_mode == FG_RES_UP2;
+      if (allow_tma_res && (kp.res_mode == FG_RES_SAME || (up && kp.BW % 2 == 0 && kp.BH % 2 == 0)) &&
+          p->res_dtype == p->out_dtype && (p->res_ld * esz) % 16 == 0) {
+        const int sh = up ? 1 : 0;
+        const uint64_t rdims[4] = {(uint64_t)p->cout, (uint64_t)(p->w >> sh), (uint64_t)(p->h >> sh), (uint64_t)p->n};
+        const uint64_t rldb = (uint64_t)p->res_ld * esz;
+        const uint64_t rstrides[4] = {(uint64_t)esz, rldb, rldb * (p->w >> sh), rldb * (p->w >> sh) * (p->h >> sh)};
+        const uint32_t rbox[4] = {(uint32_t)(128 / esz), (uint32_t)(kp.BW >> sh), (uint32_t)(kp.BH >> sh),
+                                  (uint32_t)kp.BNI};
+        r = encode_tmap(&kp.tmRes, p->res, p->res_dtype, 4, rdims, rstrides, rbox);
+        if (r != FG_OK) return r;
+        res_kind = up ? kResUp2 : kResSame;
+      }
+      epi = epi_mode(p->out_dtype == FG_BF16, res_kind);
     }
   }
 
@@ -573,11 +757,11 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     return FG_ERR_CUDA;
   }
   switch (block_n) {
-    case 16: return launch_conv<16>(kp, num_sms, stream);
-    case 64: return launch_conv<64>(kp, num_sms, stream);
-    case 128: return launch_conv<128>(kp, num_sms, stream);
-    case 192: return launch_conv<192>(kp, num_sms, stream);
-    case 256: return launch_conv<256>(kp, num_sms, stream);
+    case 16: return dispatch_epi<16>(kp, epi, num_sms, stream);
+    case 64: return dispatch_epi<64>(kp, epi, num_sms, stream);
+    case 128: return dispatch_epi<128>(kp, epi, num_sms, stream);
+    case 192: return dispatch_epi<192>(kp, epi, num_sms, stream);
+    case 256: return dispatch_epi<256>(kp, epi, num_sms, stream);
   }
   set_error("conv_gemm: no kernel for block_n=%d", block_n);
   return FG_ERR_UNSUPPORTED;

@@ -49,9 +49,11 @@ def conv_gemm_params(
     rowvec: Optional[torch.Tensor] = None, rowvec_ld: int = 0,
     res: Optional[torch.Tensor] = None, res_ld: int = 0, res_mode: int = L.FG_RES_NONE,
     out_scale: float = 1.0,
+    act: int = L.FG_ACT_NONE,
+    gate: Optional[torch.Tensor] = None, gate_ld: int = 0, gate_rows: int = 0,
 ) -> "L.ConvParams":
     """Fill an ``fg_conv_params`` (the tensors must stay alive and in place while the struct is used)."""
-    _need_cuda(out, bias, rowvec, res, *[s.a for s in segs], *[s.w for s in segs])
+    _need_cuda(out, bias, rowvec, res, gate, *[s.a for s in segs], *[s.w for s in segs])
     p = L.ConvParams()
     p.n, p.h, p.w, p.cout, p.nseg = n, h, w, cout, len(segs)
     if len(segs) > L.FG_MAX_SEG:
@@ -62,6 +64,8 @@ def conv_gemm_params(
         p.seg[i].a, p.seg[i].a_ld, p.seg[i].w, p.seg[i].cin, p.seg[i].taps = s.a.data_ptr(), s.ld, s.w.data_ptr(), s.cin, s.taps
     p.bias = _ptr(bias)
     p.rowvec, p.rowvec_ld = _ptr(rowvec), rowvec_ld
+    p.act = act
+    p.gate, p.gate_ld, p.gate_rows = _ptr(gate), gate_ld, gate_rows
     p.res, p.res_ld, p.res_mode = _ptr(res), res_ld, (res_mode if res is not None else L.FG_RES_NONE)
     p.res_dtype = _DT[res.dtype] if res is not None else 0
     p.out_scale = out_scale

@@ -30,6 +30,7 @@ typedef void* fg_stream_t; /* cudaStream_t */
 typedef enum { FG_OK = 0, FG_ERR_INVALID = -1, FG_ERR_CUDA = -2, FG_ERR_UNSUPPORTED = -3 } fg_status;
 typedef enum { FG_F32 = 0, FG_BF16 = 1, FG_F64 = 2 } fg_dtype;
 typedef enum { FG_RES_NONE = 0, FG_RES_SAME = 1, FG_RES_UP2 = 2, FG_RES_DOWN2 = 3 } fg_resample;
+typedef enum { FG_ACT_NONE = 0, FG_ACT_GELU_TANH = 1, FG_ACT_SILU = 2 } fg_activation;
 
 const char* fg_last_error(void);
 int fg_version(void);
@@ -42,8 +43,8 @@ void fg_launch_count_reset(void);
  * Replaces F.conv2d 3x3/1x1 (fastgen/networks/EDM/network.py:109-123), Linear (:47-51) and the
  * bias / embedding / skip-add / skip_scale elementwise tail of UNetBlock.forward (:276-298).
  *
- *   out[p, co] = out_scale * ( sum_s sum_tap sum_ci  A_s[p + tap, ci] * W_s[co, tap, ci]
- *                              + bias[co] + rowvec[n(p), co] + resample(res)[p, co] )
+ *   v[p, co]   = sum_s sum_tap sum_ci  A_s[p + tap, ci] * W_s[co, tap, ci]  + bias[co] + rowvec[n(p), co]
+ *   out[p, co] = out_scale * ( gate[p / gate_rows, co] * act(v[p, co]) + resample(res)[p, co] )
  *
  * Each K segment s has its own bf16 activation A_s (same N,H,W; zero padding 1 for 3x3) and bf16 weight
  * W_s laid out [cout][taps][cin]; several segments accumulate into one TMEM tile, which is how a block's
@@ -68,6 +69,10 @@ typedef struct {
   const float* bias;    /* [cout] fp32 or NULL */
   const float* rowvec;  /* [n][rowvec_ld] fp32 per-sample additive vector or NULL (UNetBlock `x.add_(params)`) */
   int64_t rowvec_ld;
+  int32_t act;          /* fg_activation applied to v: FFN GELU(tanh) of the Wan/DiT blocks (Wan/network.py:147-149) */
+  const float* gate;    /* [ceil(pixels / gate_rows)][gate_ld] fp32 multiplicative AdaLN gate or NULL: per sample  */
+  int64_t gate_ld;      /* (gate_rows = tokens per sample) or per frame (gate_rows = tokens per frame,            */
+  int32_t gate_rows;    /* Wan/network_causal.py:467-548); pixels are counted row-major over [n][h][w]            */
   const void* res;      /* residual input or NULL; FG_RES_UP2 reads a (h/2,w/2) tensor (nearest), FG_RES_DOWN2 */
   int32_t res_dtype;    /* averages 2x2 of a (2h,2w) tensor: the kernel-0 skip of up/down blocks (:253-262)     */
   int32_t res_mode;

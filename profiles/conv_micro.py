@@ -37,9 +37,11 @@ def run(tag, n, h, w, cin, cout, taps, out_dtype, res=False, bias=True, iters=5)
 
 
 B = 256
-if len(sys.argv) > 1:
-    run("proj 32x32 K384 N384 f32", B, 32, 32, 384, 384, 1, torch.float32, iters=1)
-    run("proj 32x32 K384 N384 f32 +res", B, 32, 32, 384, 384, 1, torch.float32, res=True, iters=1)
+if len(sys.argv) > 1:  # short list for A/B experiments (FG_CONV_* environment switches)
+    run("qkv 32x32 K384 N1152 bf16", B, 32, 32, 384, 1152, 1, torch.bfloat16)
+    run("proj 32x32 K384 N384 f32", B, 32, 32, 384, 384, 1, torch.float32)
+    run("3x3 64x64 K1728 N192 f32", B, 64, 64, 192, 192, 9, torch.float32)
+    run("3x3 32x32 K3456 N384 f32", B, 32, 32, 384, 384, 9, torch.float32)
     sys.exit(0)
 run("qkv 32x32 K384 N1152 bf16", B, 32, 32, 384, 1152, 1, torch.bfloat16)
 run("qkv 32x32 K384 N1152 f32", B, 32, 32, 384, 1152, 1, torch.float32)

@@ -113,6 +113,84 @@ def test_conv_gemm_resampled_residual(mode):
     assert _rel(out.permute(0, 3, 1, 2), ref) < 2e-5
 
 
+RES_RING_CASES = [
+    # n, h, w, cin, cout, taps, dtype, mode  (enough tiles that every CTA wraps the slab ring several times)
+    (64, 32, 32, 64, 384, 1, torch.float32, "same"),
+    (64, 32, 32, 64, 320, 1, torch.float32, "same"),   # ragged last N tile (320 = 192 + 128)
+    (40, 16, 16, 128, 576, 9, torch.float32, "same"),
+    (64, 32, 32, 64, 384, 1, torch.bfloat16, "same"),
+    (48, 32, 32, 64, 384, 1, torch.float32, "up"),
+    (300, 8, 8, 64, 768, 1, torch.float32, "up"),      # two images per tile, ragged image count
+    (9, 64, 64, 64, 192, 9, torch.float32, "up"),
+    (600, 1, 1, 256, 512, 1, torch.float32, "same"),   # linear layer with a residual matrix
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,taps,dtype,mode", RES_RING_CASES)
+def test_conv_gemm_tma_residual_ring(n, h, w, cin, cout, taps, dtype, mode):
+    """residual prefetched by TMA into the epilogue slab ring (FG_RES_SAME in place, FG_RES_UP2 from the half-size box)"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(5)
+    dev = "cuda"
+    k = 3 if taps == 9 else 1
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device=dev) / math.sqrt(cin * k * k)).bfloat16()
+    bias = torch.randn(cout, device=dev)
+    if mode == "up":
+        r = torch.randn(n, cout, h // 2, w // 2, device=dev).to(dtype)
+        rr = F.interpolate(r.float(), scale_factor=2, mode="nearest")
+        rm = 2
+    else:
+        r = torch.randn(n, cout, h, w, device=dev).to(dtype)
+        rr = r.float()
+        rm = 1
+    ref = (F.conv2d(x.float(), wt.float(), bias, padding=k // 2) + rr) * 0.5
+    out = torch.empty(n, h, w, cout, device=dev, dtype=dtype)
+    ops.conv_gemm([ops.Seg(_nhwc(x), cin, wt.permute(0, 2, 3, 1).contiguous(), cin, taps)], n, h, w, cout, out, cout,
+                  bias=bias, res=_nhwc(r), res_ld=cout, res_mode=rm, out_scale=0.5)
+    torch.cuda.synchronize()
+    tol = 2e-5 if dtype == torch.float32 else 4e-3
+    assert _rel(out.permute(0, 3, 1, 2), ref) < tol, _rel(out.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("rows,k,n,out_dtype,act,gate_rows,res", [
+    (4680, 256, 512, torch.bfloat16, 1, 0, False),      # FFN up: GELU(tanh), bf16 out
+    (4680, 512, 256, torch.bfloat16, 0, 1560, True),    # FFN down: per-frame gate * v + residual (bf16 stream)
+    (1000, 128, 384, torch.float32, 2, 250, True),      # SiLU + gate + fp32 residual
+    (300, 64, 40, torch.float32, 1, 100, True),         # generic (non-TMA) epilogue: cout = 40
+])
+def test_linear_activation_gate_residual(rows, k, n, out_dtype, act, gate_rows, res):
+    """transformer tails: out = gate[row // gate_rows] * act(A.W^T + bias) + residual"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(7)
+    dev = "cuda"
+    a = torch.randn(rows, k, device=dev).bfloat16()
+    wt = (torch.randn(n, k, device=dev) / math.sqrt(k)).bfloat16()
+    bias = torch.randn(n, device=dev)
+    v = a.float() @ wt.float().t() + bias
+    if act == 1:
+        v = F.gelu(v, approximate="tanh")
+    elif act == 2:
+        v = F.silu(v)
+    kw = {}
+    if gate_rows:
+        groups = (rows + gate_rows - 1) // gate_rows
+        gate = torch.randn(groups, n + 4, device=dev)
+        v = v * gate[:, :n].repeat_interleave(gate_rows, 0)[:rows]
+        kw.update(gate=gate, gate_ld=n + 4, gate_rows=gate_rows)
+    if res:
+        r = torch.randn(rows, n, device=dev).to(out_dtype)
+        v = v + r.float()
+        kw.update(res=r, res_ld=n, res_mode=1)
+    out = torch.empty(rows, n, device=dev, dtype=out_dtype)
+    ops.conv_gemm([ops.Seg(a, k, wt, k, 1)], rows, 1, 1, n, out, n, bias=bias, act=act, **kw)
+    torch.cuda.synchronize()
+    tol = 5e-3 if out_dtype == torch.bfloat16 else 1e-3  # tanh.approx in the GELU
+    assert _rel(out, v) < tol, _rel(out, v)
+
+
 def test_conv_gemm_split_precision_segments():
     """bf16x3 split products (hi*hi + lo*hi + hi*lo) reach ~fp32 accuracy: the 'fp32 path' of the network"""
     from fastgen_b200 import ops
