@@ -19,7 +19,8 @@ FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU = 0, 1, 2
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
-    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention",
+    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn",
+    "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16",
 )
 
@@ -66,6 +67,41 @@ class EdmStepParams(C.Structure):
     ]
 
 
+class FlashAttnParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_ld", C.c_int64), ("q_bs", C.c_int64),
+        ("k", C.c_void_p * 2), ("v", C.c_void_p * 2),
+        ("kv_ld", C.c_int64 * 2), ("kv_bs", C.c_int64 * 2), ("kv_len", C.c_int32 * 2),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32), ("tq", C.c_int32),
+        ("scale", C.c_float), ("mask_first", C.c_int32), ("mask_chunk", C.c_int32),
+        ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
+    ]
+
+
+class LnModParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ld", C.c_int64), ("rows", C.c_int32), ("d", C.c_int32), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("mod_ld", C.c_int64), ("rows_per_group", C.c_int32),
+        ("y", C.c_void_p), ("y_ld", C.c_int64),
+    ]
+
+
+class QkNormRopeParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("q_ld", C.c_int64), ("k_ld", C.c_int64), ("v_ld", C.c_int64),
+        ("rows", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32), ("eps", C.c_float),
+        ("wq", C.c_void_p), ("wk", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("rope_max_pos", C.c_int32), ("nt", C.c_int32), ("nh", C.c_int32),
+        ("rows_per_batch", C.c_int32), ("ppf", C.c_int32), ("pph", C.c_int32), ("ppw", C.c_int32),
+        ("frame0", C.c_int32),
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("cache_ld", C.c_int64), ("cache_bs", C.c_int64),
+        ("cache_row0", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -93,6 +129,12 @@ def lib() -> C.CDLL:
     l.fg_gn_stats.argtypes = [vp, i32, i64, i32, i32, i32, i32, vp, vp]
     l.fg_gn_apply.argtypes = [C.POINTER(GnApplyParams), vp]
     l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
+    l.fg_flash_attn.argtypes = [C.POINTER(FlashAttnParams), vp]
+    l.fg_ln_modulate.argtypes = [C.POINTER(LnModParams), vp]
+    l.fg_qk_norm_rope.argtypes = [C.POINTER(QkNormRopeParams), vp]
+    l.fg_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
+    l.fg_unpatchify.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+    l.fg_bcast_add.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
     l.fg_axpby.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
@@ -100,7 +142,8 @@ def lib() -> C.CDLL:
     l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",
-                 "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16"):
+                 "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
+                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add"):
         getattr(l, name).restype = C.c_int
     _lib = l
     return l

@@ -1,14 +1,24 @@
-// Fused UNet self-attention for sm_100a: softmax(q.k^T / sqrt(d)) v per (sample, head), flash style.
+// Flash attention for sm_100a: softmax(q.k^T * scale) v per (sample, head), fp32 softmax, bf16 operands.
 //   TMA stages Q once and K/V tiles in a 2-deep ring; S = Q.K^T and O += P.V run on tcgen05 with S (double
 //   buffered) and O accumulators in TMEM; the softmax warps own one query row per thread (tcgen05.ld 32x32b),
 //   keep running max / sum in fp32, write P as the bf16 A operand into 128B-swizzled shared memory, and only
 //   rescale O when the running max grew by more than 2^8 (lazy rescale).
-//   V is consumed straight from the channels-last qkv tensor as an MN-major B operand - no transpose pass.
+//   V is consumed straight from its row-major [token][head][d] storage as an MN-major B operand - no transpose pass.
+//
+// One kernel serves every attention of the hot path:
+//   * the UNet self-attention over a packed channels-last qkv tensor (fg_attention);
+//   * the Wan / DiT self-attention over separate q / k / v views, where the keys are the concatenation of up to two
+//     segments - the KV-cache prefix and the current chunk - so the reference's torch.cat([k_cached, key]) per layer
+//     per call (network_causal.py:372-381) never materialises;
+//   * the block-causal mask of the full-sequence causal forward (network_causal.py:131-196): a query of chunk c sees
+//     the keys up to the end of chunk c;
+//   * cross-attention to the 512 text tokens (Tq != Tkv).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = softmax/epilogue.
 //
-// Replaces: fastgen/networks/EDM/network.py:160-168 (AttentionOp.forward) and :290-296 (the qkv unbind and the
-// two einsums), which materialise the [N*heads, T, T] weight tensor in fp32.
+// Replaces: fastgen/networks/EDM/network.py:160-168, 290-296 (AttentionOp + the two einsums, which materialise the
+// [N*heads, T, T] weights in fp32) and diffusers' dispatch_attention_fn / F.scaled_dot_product_attention as called
+// from fastgen/networks/Wan/network_causal.py:312-320, 350-358, 404-412, 446-454.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -32,12 +42,15 @@ struct AttnCfg {
 };
 
 struct AttnKParams {
-  CUtensorMap tmQ;   // box (64, 1, 128, 1)
-  CUtensorMap tmKV;  // box (64, 1, BKV, 1)
-  int32_t N, T, H, d;
-  float scale_log2;  // log2(e) / sqrt(d)
+  CUtensorMap tmQ;     // dims (d, H, Tq, B), box (64, 1, 128, 1)
+  CUtensorMap tmK[2];  // dims (d, H, len_s, B), box (64, 1, BKV, 1)
+  CUtensorMap tmV[2];
+  int32_t B, Tq, H, d;
+  int32_t kv_len[2];
+  int32_t mask_first, mask_chunk;  // block-causal mask (tokens of the first chunk / of every later chunk); 0 = none
+  float scale_log2;                // log2(e) * scale
   __nv_bfloat16* out;
-  int64_t out_ld;
+  int64_t out_ld, out_bs;
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -52,6 +65,13 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// keys a query token may see under the block-causal mask: up to the end of its own chunk
+__device__ __forceinline__ int causal_limit(const AttnKParams& p, int tok) {
+  if (p.mask_chunk == 0) return 0x7fffffff;
+  if (tok < p.mask_first) return p.mask_first;
+  return p.mask_first + ((tok - p.mask_first) / p.mask_chunk + 1) * p.mask_chunk;
+}
 
 template <int DP, int BKV>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnKParams p) {
@@ -71,16 +91,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tiles = (p.T + kQRows - 1) / kQRows;
+  const int q_tiles = (p.Tq + kQRows - 1) / kQRows;
   const int qt = blockIdx.x % q_tiles;
   const int head = (blockIdx.x / q_tiles) % p.H;
   const int img = blockIdx.x / (q_tiles * p.H);
   const int q0 = qt * kQRows;
-  const int nkv = (p.T + BKV - 1) / BKV;
+  // key tiles: segment 0 then segment 1; under the block-causal mask (single segment) the tile loop stops at the
+  // limit of the last query row of this tile
+  int len0 = p.kv_len[0];
+  if (p.mask_chunk) len0 = min(len0, causal_limit(p, min(q0 + kQRows, p.Tq) - 1));
+  const int n0 = (len0 + BKV - 1) / BKV;
+  const int n1 = (p.kv_len[1] + BKV - 1) / BKV;
+  const int nkv = n0 + n1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmKV);
+    tma_prefetch_desc(&p.tmK[0]);
+    tma_prefetch_desc(&p.tmV[0]);
+    if (n1) {
+      tma_prefetch_desc(&p.tmK[1]);
+      tma_prefetch_desc(&p.tmV[1]);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -109,13 +140,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       for (int dc = 0; dc < Cfg::DC; ++dc) tma_load_4d(sQ + dc * kQRows * 128, &p.tmQ, q_full, dc * 64, head, q0, img);
       for (int j = 0; j < nkv; ++j) {
         const int s = j & 1;
+        const int seg = j >= n0;
+        const int row0 = (seg ? j - n0 : j) * BKV;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1u);
         uint8_t* sk = sKV + s * 2 * Cfg::KV_TILE_BYTES;
         uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
         mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_TILE_BYTES);
         for (int dc = 0; dc < Cfg::DC; ++dc) {
-          tma_load_4d(sk + dc * BKV * 128, &p.tmKV, &kv_full[s], dc * 64, p.H + head, j * BKV, img);
-          tma_load_4d(sv + dc * BKV * 128, &p.tmKV, &kv_full[s], dc * 64, 2 * p.H + head, j * BKV, img);
+          tma_load_4d(sk + dc * BKV * 128, &p.tmK[seg], &kv_full[s], dc * 64, head, row0, img);
+          tma_load_4d(sv + dc * BKV * 128, &p.tmV[seg], &kv_full[s], dc * 64, head, row0, img);
         }
       }
     }
@@ -140,7 +173,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         umma_commit(&s_full[s]);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
+      if (nkv) issue_qk(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
         mbar_wait(p_full, j & 1);
@@ -158,7 +191,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int tok = q0 + row;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int limit = causal_limit(p, tok);
     float m_run = -INFINITY;  // running max in scaled (log2) units
     float l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
@@ -172,7 +207,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(b * BKV + c), chunk);
       }
       tmem_ld_wait();
-      const int kv_valid = p.T - j * BKV;  // columns >= kv_valid are padding
+      // columns >= kv_valid are padding (end of a segment) or masked (beyond this row's causal limit)
+      const int seg = j >= n0;
+      const int col0 = (seg ? j - n0 : j) * BKV;
+      int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
+      if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < BKV; ++c) {
@@ -187,7 +226,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         const bool need = mx > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? mx : m_run;
-          const float alpha = exp2f(m_run - m_new);
+          const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
           m_run = m_new;
           l_run *= alpha;
 #pragma unroll 1
@@ -204,6 +243,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       } else {
         m_run = mx;
       }
+      // a row whose every key so far is masked keeps m_run = -inf: its probabilities are 0, not exp2(-inf + inf)
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
       float lsum = 0.f;
       uint8_t* prow = sP + row * 128;
 #pragma unroll
@@ -211,7 +252,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          pv[i] = exp2f(__uint_as_float(sv[c8 * 8 + i]) - m_run);
+          pv[i] = exp2f(__uint_as_float(sv[c8 * 8 + i]) - m_use);
           lsum += pv[i];
         }
         uint4 u;
@@ -227,17 +268,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16 ----
-    mbar_wait(pv_done, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int tok = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(img) * p.T + tok) * p.out_ld + head * p.d;
+    if (nkv) {
+      mbar_wait(pv_done, (nkv - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + static_cast<int64_t>(img) * p.out_bs + static_cast<int64_t>(tok) * p.out_ld + head * p.d;
 #pragma unroll 1
     for (int c = 0; c < DP; c += 32) {
       uint32_t o[32];
-      tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + c), o);
-      tmem_ld_wait();
-      if (tok < p.T) {
+      if (nkv) {
+        tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + c), o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (tok < p.Tq) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           if (c + i < p.d) {
@@ -262,56 +309,111 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 }
 
 template <int DP, int BKV>
-static int launch_attention(AttnKParams& kp, const void* qkv, int64_t qkv_ld, cudaStream_t stream) {
+static int launch_attention(AttnKParams& kp, const fg_flash_attn_params* p, cudaStream_t stream) {
   using Cfg = AttnCfg<DP, BKV>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("attention: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
     configured = true;
   }
-  const uint64_t ldb = static_cast<uint64_t>(qkv_ld) * 2;
-  const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)(3 * kp.H), (uint64_t)kp.T, (uint64_t)kp.N};
-  const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, ldb, ldb * kp.T};
-  const uint32_t boxq[4] = {64, 1, (uint32_t)kQRows, 1};
-  const uint32_t boxkv[4] = {64, 1, (uint32_t)BKV, 1};
-  int r = encode_tmap_bf16(&kp.tmQ, qkv, 4, dims, strides, boxq);
-  if (r != FG_OK) return r;
-  r = encode_tmap_bf16(&kp.tmKV, qkv, 4, dims, strides, boxkv);
-  if (r != FG_OK) return r;
-  const int q_tiles = (kp.T + kQRows - 1) / kQRows;
-  const int grid = kp.N * kp.H * q_tiles;
+  {
+    const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)kp.H, (uint64_t)kp.Tq, (uint64_t)kp.B};
+    const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, (uint64_t)p->q_ld * 2, (uint64_t)p->q_bs * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)kQRows, 1};
+    int r = encode_tmap_bf16(&kp.tmQ, p->q, 4, dims, strides, box);
+    if (r != FG_OK) return r;
+  }
+  for (int s = 0; s < 2; ++s) {
+    // an empty segment still gets a valid descriptor (of segment 0) so the kernel parameter is well formed
+    const int src = kp.kv_len[s] > 0 ? s : 0;
+    const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)kp.H, (uint64_t)(kp.kv_len[src] > 0 ? kp.kv_len[src] : 1),
+                              (uint64_t)kp.B};
+    const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, (uint64_t)p->kv_ld[src] * 2, (uint64_t)p->kv_bs[src] * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)BKV, 1};
+    int r = encode_tmap_bf16(&kp.tmK[s], p->k[src], 4, dims, strides, box);
+    if (r != FG_OK) return r;
+    r = encode_tmap_bf16(&kp.tmV[s], p->v[src], 4, dims, strides, box);
+    if (r != FG_OK) return r;
+  }
+  const int q_tiles = (kp.Tq + kQRows - 1) / kQRows;
+  const int grid = kp.B * kp.H * q_tiles;
   attention_kernel<DP, BKV><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(kp);
-  FG_CHECK_LAUNCH("attention");
+  FG_CHECK_LAUNCH("flash_attn");
   return FG_OK;
 }
 
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 }  // namespace fg
 
-extern "C" int fg_attention(const void* qkv, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
-                            void* out, int64_t out_ld, fg_stream_t stream_) {
+extern "C" int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream_) {
   using namespace fg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  FG_CHECK_ARG(qkv && out, "attention: null pointer");
-  FG_CHECK_ARG(n > 0 && tokens > 0 && heads > 0 && d > 0, "attention: empty problem");
-  FG_CHECK_ARG(d % 8 == 0 && d <= 256, "attention: head dim %d must be a multiple of 8 and <= 256", d);
-  FG_CHECK_ARG(qkv_ld >= 3 * heads * d && qkv_ld % 8 == 0, "attention: qkv_ld %lld too small / unaligned",
-               (long long)qkv_ld);
-  FG_CHECK_ARG(out_ld >= heads * d && out_ld % 8 == 0, "attention: out_ld %lld too small / unaligned",
-               (long long)out_ld);
-  FG_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
-               "attention: pointers must be 16-byte aligned");
+  FG_CHECK_ARG(p && p->q && p->out && p->k[0] && p->v[0], "flash_attn: null pointer");
+  FG_CHECK_ARG(p->batch > 0 && p->tq > 0 && p->heads > 0 && p->d > 0, "flash_attn: empty problem");
+  FG_CHECK_ARG(p->d % 8 == 0 && p->d <= 256, "flash_attn: head dim %d must be a multiple of 8 and <= 256", p->d);
+  FG_CHECK_ARG(p->kv_len[0] >= 0 && p->kv_len[1] >= 0 && p->kv_len[0] + p->kv_len[1] > 0,
+               "flash_attn: bad key lengths %d + %d", p->kv_len[0], p->kv_len[1]);
+  const int64_t hd = static_cast<int64_t>(p->heads) * p->d;
+  FG_CHECK_ARG(p->q_ld >= hd && p->q_ld % 8 == 0 && p->q_bs % 8 == 0, "flash_attn: q_ld %lld / q_bs %lld too small or unaligned",
+               (long long)p->q_ld, (long long)p->q_bs);
+  FG_CHECK_ARG(p->out_ld >= hd && p->out_ld % 8 == 0 && p->out_bs % 8 == 0, "flash_attn: out_ld %lld too small / unaligned",
+               (long long)p->out_ld);
+  FG_CHECK_ARG(al16(p->q) && al16(p->out), "flash_attn: pointers must be 16-byte aligned");
+  for (int s = 0; s < 2; ++s) {
+    if (p->kv_len[s] == 0) continue;
+    FG_CHECK_ARG(p->k[s] && p->v[s] && al16(p->k[s]) && al16(p->v[s]), "flash_attn: segment %d k/v null or unaligned", s);
+    FG_CHECK_ARG(p->kv_ld[s] >= hd && p->kv_ld[s] % 8 == 0 && p->kv_bs[s] % 8 == 0,
+                 "flash_attn: segment %d kv_ld %lld / kv_bs %lld too small or unaligned", s, (long long)p->kv_ld[s],
+                 (long long)p->kv_bs[s]);
+  }
+  FG_CHECK_ARG(p->mask_chunk >= 0 && p->mask_first >= 0, "flash_attn: negative mask extents");
+  if (p->mask_chunk > 0)
+    FG_CHECK_ARG(p->kv_len[1] == 0 && p->kv_len[0] == p->tq && p->mask_first > 0,
+                 "flash_attn: the block-causal mask needs one key segment of the query length and mask_first > 0");
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.N = n, kp.T = tokens, kp.H = heads, kp.d = d;
-  kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(d));
-  kp.out = static_cast<__nv_bfloat16*>(out);
-  kp.out_ld = out_ld;
-  if (d <= 64) return launch_attention<64, 128>(kp, qkv, qkv_ld, stream);
-  if (d <= 128) return launch_attention<128, 128>(kp, qkv, qkv_ld, stream);
-  return launch_attention<256, 64>(kp, qkv, qkv_ld, stream);
+  kp.B = p->batch, kp.Tq = p->tq, kp.H = p->heads, kp.d = p->d;
+  kp.kv_len[0] = p->kv_len[0], kp.kv_len[1] = p->kv_len[1];
+  if (kp.kv_len[0] == 0) {  // keep segment 0 the non-empty one
+    FG_CHECK_ARG(false, "flash_attn: segment 0 must be non-empty (put a lone segment first)");
+  }
+  kp.mask_first = p->mask_chunk > 0 ? p->mask_first : 0;
+  kp.mask_chunk = p->mask_chunk;
+  const float scale = p->scale > 0.f ? p->scale : 1.0f / sqrtf(static_cast<float>(p->d));
+  kp.scale_log2 = 1.4426950408889634f * scale;
+  kp.out = static_cast<__nv_bfloat16*>(p->out);
+  kp.out_ld = p->out_ld;
+  kp.out_bs = p->out_bs;
+  if (p->d <= 64) return launch_attention<64, 128>(kp, p, stream);
+  if (p->d <= 128) return launch_attention<128, 128>(kp, p, stream);
+  return launch_attention<256, 64>(kp, p, stream);
+}
+
+// packed channels-last qkv of the UNet blocks: [N, T, 3*heads*d] with channel order (q|k|v, head, d)
+extern "C" int fg_attention(const void* qkv, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
+                            void* out, int64_t out_ld, fg_stream_t stream) {
+  fg::set_error("");
+  if (!qkv || !out) {
+    fg::set_error("attention: null pointer");
+    return FG_ERR_INVALID;
+  }
+  if (qkv_ld < 3ll * heads * d) {
+    fg::set_error("attention: qkv_ld %lld too small / unaligned", (long long)qkv_ld);
+    return FG_ERR_INVALID;
+  }
+  fg_flash_attn_params p;
+  memset(&p, 0, sizeof(p));
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  p.q = base, p.q_ld = qkv_ld, p.q_bs = qkv_ld * tokens;
+  p.k[0] = base + static_cast<int64_t>(heads) * d, p.v[0] = base + 2ll * heads * d;
+  p.kv_ld[0] = qkv_ld, p.kv_bs[0] = qkv_ld * tokens, p.kv_len[0] = tokens;
+  p.batch = n, p.heads = heads, p.d = d, p.tq = tokens;
+  p.out = out, p.out_ld = out_ld, p.out_bs = out_ld * tokens;
+  return fg_flash_attn(&p, stream);
 }

@@ -214,3 +214,107 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     L.lib().fg_launch_count_reset()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# transformer (Wan / DiT) kernels
+# ---------------------------------------------------------------------------------------------------------
+def flash_attn_params(q: torch.Tensor, q_ld: int, q_bs: int, segs: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int, int]],
+                      batch: int, heads: int, d: int, tq: int, out: torch.Tensor, out_ld: int, out_bs: int,
+                      scale: float = 0.0, mask_first: int = 0, mask_chunk: int = 0) -> "L.FlashAttnParams":
+    """``segs``: up to two key/value segments ``(k, v, ld, batch_stride, length)`` (cache prefix, current chunk)."""
+    if not 1 <= len(segs) <= 2:
+        raise ValueError("flash_attn: one or two key/value segments")
+    _need_cuda(q, out, *[s[0] for s in segs], *[s[1] for s in segs])
+    p = L.FlashAttnParams()
+    p.q, p.q_ld, p.q_bs = q.data_ptr(), q_ld, q_bs
+    for i, (k, v, ld, bs, ln) in enumerate(segs):
+        if k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+            raise ValueError("flash_attn: operands must be bfloat16")
+        p.k[i], p.v[i], p.kv_ld[i], p.kv_bs[i], p.kv_len[i] = k.data_ptr(), v.data_ptr(), ld, bs, ln
+    p.batch, p.heads, p.d, p.tq = batch, heads, d, tq
+    p.scale, p.mask_first, p.mask_chunk = scale, mask_first, mask_chunk
+    p.out, p.out_ld, p.out_bs = out.data_ptr(), out_ld, out_bs
+    return p
+
+
+def flash_attn(*args, **kwargs) -> None:
+    p = flash_attn_params(*args, **kwargs)
+    L.check(L.lib().fg_flash_attn(C.byref(p), _stream()), "fg_flash_attn")
+
+
+def ln_mod_params(x: torch.Tensor, x_ld: int, rows: int, d: int, eps: float, y: torch.Tensor, y_ld: int,
+                  gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, mod_ld: int = 0,
+                  rows_per_group: int = 0) -> "L.LnModParams":
+    _need_cuda(x, y, gamma, beta, scale, shift)
+    if x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+        raise ValueError("ln_modulate: rows must be bfloat16")
+    p = L.LnModParams()
+    p.x, p.x_ld, p.rows, p.d, p.eps = x.data_ptr(), x_ld, rows, d, eps
+    p.gamma, p.beta, p.scale, p.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
+    p.mod_ld, p.rows_per_group = mod_ld, rows_per_group
+    p.y, p.y_ld = y.data_ptr(), y_ld
+    return p
+
+
+def ln_modulate(*args, **kwargs) -> None:
+    p = ln_mod_params(*args, **kwargs)
+    L.check(L.lib().fg_ln_modulate(C.byref(p), _stream()), "fg_ln_modulate")
+
+
+def qk_norm_rope_params(q: Optional[torch.Tensor], k: Optional[torch.Tensor], q_ld: int, k_ld: int, rows: int,
+                        heads: int, d: int, eps: float, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor],
+                        rows_per_batch: int,
+                        rope: Optional[Tuple[torch.Tensor, torch.Tensor, int, int]] = None,
+                        grid: Tuple[int, int, int] = (1, 1, 1), frame0: int = 0,
+                        v: Optional[torch.Tensor] = None, v_ld: int = 0,
+                        k_cache: Optional[torch.Tensor] = None, v_cache: Optional[torch.Tensor] = None,
+                        cache_ld: int = 0, cache_bs: int = 0, cache_row0: int = 0) -> "L.QkNormRopeParams":
+    """``rope`` = (cos [max_pos, d/2] fp32, sin, nt, nh); ``grid`` = (frames, height, width) of the token grid."""
+    _need_cuda(q, k, v, wq, wk, k_cache, v_cache, *(rope[:2] if rope else ()))
+    p = L.QkNormRopeParams()
+    p.q, p.k, p.v = _ptr(q), _ptr(k), _ptr(v)
+    p.q_ld, p.k_ld, p.v_ld = q_ld, k_ld, v_ld
+    p.rows, p.heads, p.d, p.eps = rows, heads, d, eps
+    p.wq, p.wk = _ptr(wq), _ptr(wk)
+    if rope is not None:
+        cos, sin, nt, nh = rope
+        assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.shape == sin.shape
+        assert cos.shape[1] == d // 2 and cos.is_contiguous() and sin.is_contiguous()
+        p.rope_cos, p.rope_sin, p.rope_max_pos, p.nt, p.nh = cos.data_ptr(), sin.data_ptr(), cos.shape[0], nt, nh
+    p.rows_per_batch = rows_per_batch
+    p.ppf, p.pph, p.ppw, p.frame0 = grid[0], grid[1], grid[2], frame0
+    p.k_cache, p.v_cache, p.cache_ld, p.cache_bs, p.cache_row0 = _ptr(k_cache), _ptr(v_cache), cache_ld, cache_bs, cache_row0
+    return p
+
+
+def qk_norm_rope(*args, **kwargs) -> None:
+    p = qk_norm_rope_params(*args, **kwargs)
+    L.check(L.lib().fg_qk_norm_rope(C.byref(p), _stream()), "fg_qk_norm_rope")
+
+
+def patchify(x: torch.Tensor, ph: int, pw: int, a: torch.Tensor, a_ld: int) -> None:
+    _need_cuda(x, a)
+    assert x.is_contiguous() and x.dim() == 5 and a.dtype == torch.bfloat16
+    b, c, f, h, w = x.shape
+    L.check(L.lib().fg_patchify(x.data_ptr(), _DT[x.dtype], b, c, f, h, w, ph, pw, a.data_ptr(), a_ld, _stream()),
+            "fg_patchify")
+
+
+def unpatchify(y: torch.Tensor, y_ld: int, out: torch.Tensor, ph: int, pw: int) -> None:
+    _need_cuda(y, out)
+    assert out.is_contiguous() and out.dim() == 5 and y.dtype == torch.bfloat16
+    b, c, f, h, w = out.shape
+    L.check(L.lib().fg_unpatchify(y.data_ptr(), y_ld, b, c, f, h, w, ph, pw, out.data_ptr(), _DT[out.dtype], _stream()),
+            "fg_unpatchify")
+
+
+def bcast_add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    """out[i, g, :] = a[i, :] + b[g, :] (fp32)."""
+    _need_cuda(a, b, out)
+    assert a.dtype == b.dtype == out.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    na, d = a.shape
+    nb = b.shape[0]
+    assert b.shape[1] == d and out.numel() == na * nb * d and out.is_contiguous()
+    L.check(L.lib().fg_bcast_add(a.data_ptr(), b.data_ptr(), na, nb, d, out.data_ptr(), _stream()), "fg_bcast_add")

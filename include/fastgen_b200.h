@@ -125,6 +125,88 @@ int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream);
 int fg_attention(const void* qkv /* bf16 */, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
                  void* out /* bf16 [N,T,heads*d] */, int64_t out_ld, fg_stream_t stream);
 
+/* General flash attention (bf16 operands, fp32 softmax): out[b, t, h, :] = softmax(q.k^T * scale) v.
+ * q / k / v are separate strided views [batch][tokens][heads*d] (row stride *_ld, batch stride *_bs, in elements);
+ * the keys are the concatenation of up to two segments -- KV-cache prefix then current chunk -- which replaces the
+ * per-layer torch.cat of fastgen/networks/Wan/network_causal.py:372-381; tq != key length gives cross-attention
+ * (:343-358).  mask_chunk > 0 applies the block-causal mask of :131-196: a query of chunk c (first chunk
+ * mask_first tokens, later chunks mask_chunk tokens) sees the keys up to the end of chunk c. */
+typedef struct {
+  const void* q;        /* bf16 */
+  int64_t q_ld, q_bs;
+  const void* k[2];     /* segment 0 must be non-empty; segment 1 optional (kv_len[1] == 0) */
+  const void* v[2];
+  int64_t kv_ld[2], kv_bs[2];
+  int32_t kv_len[2];
+  int32_t batch, heads, d, tq;
+  float scale;          /* <= 0: 1/sqrt(d) */
+  int32_t mask_first, mask_chunk;
+  void* out;            /* bf16 [batch][tq][heads*d] */
+  int64_t out_ld, out_bs;
+} fg_flash_attn_params;
+
+int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Row kernels of the transformer blocks (Wan / DiT), all HBM-bound, bf16 rows in and out, fp32 statistics.
+ * ---------------------------------------------------------------------------------------------------- */
+/* y = LayerNorm(x) * (1 + scale[g]) + shift[g], g = row / rows_per_group  (AdaLN modulate, per sample or per frame:
+ * fastgen/networks/Wan/network.py:139,150, network_causal.py:503-507,538-542), or LayerNorm(x) * gamma + beta
+ * (norm2, Wan/network.py:144); LayerNorm in fp32 without rounding in between (diffusers FP32LayerNorm). */
+typedef struct {
+  const void* x;        /* bf16 [rows][x_ld] */
+  int64_t x_ld;
+  int32_t rows, d;
+  float eps;
+  const float* gamma;   /* [d] or NULL */
+  const float* beta;
+  const float* scale;   /* [groups][mod_ld] fp32 or NULL */
+  const float* shift;
+  int64_t mod_ld;
+  int32_t rows_per_group;
+  void* y;              /* bf16 [rows][y_ld] */
+  int64_t y_ld;
+} fg_ln_mod_params;
+
+int fg_ln_modulate(const fg_ln_mod_params* p, fg_stream_t stream);
+
+/* In place: q <- RoPE(RMSNorm(q) * wq), k <- RoPE(RMSNorm(k) * wk); the RMS is taken over all heads*d channels of a
+ * row (qk_norm = "rms_norm_across_heads"), the rotary embedding rotates interleaved pairs (x[2i], x[2i+1]) with the
+ * 3-axis tables of WanRotaryPosEmbed: pair i of a head uses the temporal row (frame0 + f) for i < nt, the height row
+ * h for i < nt + nh and the width row w otherwise, token t = (f * pph + h) * ppw + w
+ * (network_causal.py:79-128, 262-291).  rope_cos == NULL: norm only (cross-attention).  With k_cache / v_cache the
+ * roped k and the raw v are also written to row (cache_row0 + t) of the caches (store_kv, :365-368). */
+typedef struct {
+  void* q;              /* bf16 [rows][q_ld] or NULL */
+  void* k;              /* bf16 [rows][k_ld] or NULL */
+  const void* v;        /* bf16 [rows][v_ld], only read for the cache append */
+  int64_t q_ld, k_ld, v_ld;
+  int32_t rows, heads, d;
+  float eps;
+  const void* wq;       /* bf16 [heads*d] */
+  const void* wk;
+  const float* rope_cos; /* fp32 [rope_max_pos][d/2] */
+  const float* rope_sin;
+  int32_t rope_max_pos, nt, nh;
+  int32_t rows_per_batch, ppf, pph, ppw, frame0;
+  void* k_cache;        /* bf16 [batch][cache_bs], row stride cache_ld, or NULL */
+  void* v_cache;
+  int64_t cache_ld, cache_bs;
+  int32_t cache_row0;
+} fg_qk_norm_rope_params;
+
+int fg_qk_norm_rope(const fg_qk_norm_rope_params* p, fg_stream_t stream);
+
+/* latent [B,C,F,H,W] (fp32 | bf16) -> bf16 token rows [B*F*(H/ph)*(W/pw)][a_ld], column (c*ph + i)*pw + j: the
+ * operand of the Conv3d patch embedding written as a GEMM (Wan/network.py:300-301). */
+int fg_patchify(const void* x, int32_t x_dtype, int32_t b, int32_t c, int32_t f, int32_t h, int32_t w, int32_t ph,
+                int32_t pw, void* a, int64_t a_ld, fg_stream_t stream);
+/* token rows [..][y_ld] with column ((i*pw + j)*C + c) -> latent [B,C,F,H,W] (Wan/network.py:262-266). */
+int fg_unpatchify(const void* y, int64_t y_ld, int32_t b, int32_t c, int32_t f, int32_t h, int32_t w, int32_t ph,
+                  int32_t pw, void* out, int32_t out_dtype, fg_stream_t stream);
+/* out[i][g][:] = a[i][:] + b[g][:], fp32: scale_shift_table of every block + timestep projection of every frame. */
+int fg_bcast_add(const float* a, const float* b, int32_t na, int32_t nb, int32_t d, float* out, fg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Sampler-step kernels (fastgen/methods/model.py:346-370, noise_schedule.py:72-88,425-449,544-574,
  * EDM/network.py:755-805).  x tensors are the caller's NCHW latents; `f` is the network's raw output in
