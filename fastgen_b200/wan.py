@@ -1,0 +1,744 @@
+"""Wan 2.1 T2V transformers (bidirectional ``Wan`` and chunk-autoregressive ``CausalWan``) on the B200 kernel library.
+
+Drop-ins for ``fastgen.networks.Wan.network.Wan`` (reference Wan/network.py:540-1163) and
+``fastgen.networks.Wan.network_causal.CausalWan`` (network_causal.py:928-1184): same ``forward`` signature and keyword
+semantics (``cache_tag / cur_start_frame / store_kv / is_ar``, unknown keywords ignored), same ``state_dict`` key names
+as the diffusers ``WanTransformer3DModel`` the reference wraps (``transformer.blocks.0.attn1.to_q.weight`` ...), the
+original-Wan checkpoint key remap of Wan/network.py:990-1075, ``clear_caches()``, ``chunk_size``,
+``total_num_frames``, ``noise_scheduler``.  Inference only, T2V only (no I2V image branch, no ``r`` embedder).
+
+How a forward runs (PyTorch only allocates buffers and computes a [B*F, 256] sinusoid):
+  patchify -> GEMM (Conv3d as a K=64 GEMM) -> per block:
+      ln_modulate -> GEMM(qkv) -> qk_norm_rope (RMSNorm across heads + RoPE, in place, + KV-cache append)
+      -> flash_attn(keys = cache prefix ++ current chunk) -> GEMM(to_out; gate * v + residual)
+      -> ln_modulate(norm2 affine) -> GEMM(q) -> qk_norm -> flash_attn(512 cached text keys) -> GEMM(to_out + residual)
+      -> ln_modulate -> GEMM(ffn up, GELU-tanh) -> GEMM(ffn down; gate * v + residual)
+  -> ln_modulate(head) -> GEMM(proj_out) -> unpatchify -> flow -> x0 conversion (fp64, one rounding).
+The residual stream and every GEMM operand are bf16 (the reference runs these networks in bf16), accumulators,
+LayerNorm / RMSNorm statistics, modulation vectors and softmax are fp32.  The launch list of a (shape, cache position)
+is recorded once as pre-filled C-ABI parameter structs and replayed.
+
+Sequence parallelism (Ulysses): with ``sp_group`` set, every rank holds tokens [rank * n/P, (rank+1) * n/P) of each
+sample, q/k/v are exchanged by an all-to-all (scatter heads, gather tokens) before each self-attention and the
+attention output by the inverse exchange; the KV cache is head-sharded, so cached keys never move again.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Dict, List, Mapping, Optional, Set, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .network import CausalFastGenNetwork, FastGenNetwork
+from .noise_schedule import NET_PRED_TYPES
+
+__all__ = ["Wan", "CausalWan", "WAN_CONFIGS"]
+
+WAN_CONFIGS: Dict[str, Dict[str, Any]] = {
+    "Wan-AI/Wan2.1-T2V-1.3B-Diffusers": dict(dim=1536, heads=12, head_dim=128, ffn_dim=8960, layers=30),
+    "Wan-AI/Wan2.1-T2V-14B-Diffusers": dict(dim=5120, heads=40, head_dim=128, ffn_dim=13824, layers=40),
+}
+_DEFAULTS = dict(in_channels=16, out_channels=16, text_dim=4096, freq_dim=256, patch=(1, 2, 2), eps=1e-6,
+                 rope_max_seq_len=1024)
+TEXT_LEN = 512
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter tree with the diffusers key names
+# ---------------------------------------------------------------------------------------------------------
+class _Attn(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Identity()])
+        self.norm_q = nn.RMSNorm(dim, eps=1e-6)
+        self.norm_k = nn.RMSNorm(dim, eps=1e-6)
+
+
+class _GeluProj(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner)
+
+
+class _FFN(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.net = nn.ModuleList([_GeluProj(dim, inner), nn.Identity(), nn.Linear(inner, dim)])
+
+
+class _Block(nn.Module):
+    def __init__(self, dim: int, ffn_dim: int):
+        super().__init__()
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+        self.attn1, self.attn2 = _Attn(dim), _Attn(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6, elementwise_affine=True)
+        self.ffn = _FFN(dim, ffn_dim)
+
+
+class _TimeEmbedder(nn.Module):
+    def __init__(self, cin: int, dim: int):
+        super().__init__()
+        self.linear_1, self.linear_2 = nn.Linear(cin, dim), nn.Linear(dim, dim)
+
+
+class _CondEmbedder(nn.Module):
+    def __init__(self, dim: int, freq_dim: int, text_dim: int):
+        super().__init__()
+        self.time_embedder = _TimeEmbedder(freq_dim, dim)
+        self.time_proj = nn.Linear(dim, 6 * dim)
+        self.text_embedder = _TimeEmbedder(text_dim, dim)
+
+
+class _WanTransformer(nn.Module):
+    def __init__(self, cfg: Dict[str, Any], logvar: bool):
+        super().__init__()
+        d = cfg["dim"]
+        pt, ph, pw = cfg["patch"]
+        self.patch_embedding = nn.Conv3d(cfg["in_channels"], d, (pt, ph, pw), (pt, ph, pw))
+        self.condition_embedder = _CondEmbedder(d, cfg["freq_dim"], cfg["text_dim"])
+        self.blocks = nn.ModuleList([_Block(d, cfg["ffn_dim"]) for _ in range(cfg["layers"])])
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 2, d) / d ** 0.5)
+        self.proj_out = nn.Linear(d, cfg["out_channels"] * pt * ph * pw)
+        if logvar:
+            self.logvar_linear = nn.Linear(d, 1)
+
+
+def _rope_pair_tables(head_dim: int, max_pos: int, theta: float = 10000.0):
+    """WanRotaryPosEmbed reduced to one entry per rotated pair: cos/sin [max_pos, head_dim/2] fp32 with the temporal,
+    height and width blocks side by side (== freqs_cos[..., 0::2], freqs_sin[..., 1::2])."""
+    h_dim = w_dim = 2 * (head_dim // 6)
+    t_dim = head_dim - h_dim - w_dim
+    pos = torch.arange(max_pos, dtype=torch.float64)
+    cos, sin = [], []
+    for dim in (t_dim, h_dim, w_dim):
+        freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.float64)[: dim // 2] / dim))
+        ang = torch.outer(pos, freqs)
+        cos.append(ang.cos().float())
+        sin.append(ang.sin().float())
+    return torch.cat(cos, 1).contiguous(), torch.cat(sin, 1).contiguous(), t_dim // 2, h_dim // 2
+
+
+def _sinusoid(t: torch.Tensor, dim: int, official: bool) -> torch.Tensor:
+    """[len(t), dim] = [cos | sin]: the official Wan sinusoid in fp64 (reference Wan/network.py:81-103) or diffusers'
+    ``Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0)`` in fp32."""
+    half = dim // 2
+    if official:
+        pos = t.to(torch.float64)
+        s = torch.outer(pos, torch.pow(10000, -torch.arange(half, device=t.device).to(pos).div(half)))
+        return torch.cat([torch.cos(s), torch.sin(s)], dim=1).float()
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
+    emb = t[:, None].float() * torch.exp(exponent)[None, :]
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# recorded launch list
+# ---------------------------------------------------------------------------------------------------------
+class _Plan:
+    def __init__(self):
+        self.steps: List[Tuple[Any, tuple, str, float]] = []
+        self.keep: List[Any] = []
+
+    def add(self, fn, *args, desc: str = "", flops: float = 0.0):
+        self.steps.append((fn, args, desc, flops))
+
+    def run(self, stream: int, profile: Optional[Dict[str, Dict[str, float]]] = None) -> None:
+        if profile is None:
+            for fn, args, _, _ in self.steps:
+                st = fn(*args, stream)
+                if st:
+                    L.check(st, fn.__name__)
+            return
+        evs = []
+        for fn, args, desc, fl in self.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            st = fn(*args, stream)
+            b.record()
+            if st:
+                L.check(st, fn.__name__)
+            evs.append((fn.__name__ + (":" + desc if desc else ""), a, b, fl))
+        torch.cuda.synchronize()
+        for name, a, b, fl in evs:
+            d = profile.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += fl
+
+
+class _WanBase:
+    """Shared implementation (mixed into the two public classes)."""
+
+    def _init_wan(self, model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
+                  r_timestep, norm_temb, encoder_depth):
+        if r_timestep or encoder_depth is not None:
+            raise NotImplementedError("the r-timestep embedder (MeanFlow on Wan) is not built")
+        if norm_temb:
+            raise NotImplementedError("norm_temb (sCM AdaLN normalisation) is not built")
+        cfg = dict(_DEFAULTS)
+        if transformer_config is not None:
+            cfg.update(transformer_config)
+        else:
+            model_id = self.get_model_id(model_id_or_local_path)
+            if model_id not in WAN_CONFIGS:
+                raise ValueError(f"unknown Wan model id '{model_id}' (known: {sorted(WAN_CONFIGS)}); "
+                                 "pass transformer_config=... for a custom architecture")
+            cfg.update(WAN_CONFIGS[model_id])
+        if cfg["dim"] != cfg["heads"] * cfg["head_dim"]:
+            raise ValueError("dim must equal heads * head_dim")
+        if cfg["patch"][0] != 1:
+            raise NotImplementedError("temporal patch size must be 1")
+        self.cfg = cfg
+        self.model_id = model_id_or_local_path
+        self.expand_timesteps = False
+        self._use_wan_official_sinusoidal = use_wan_official_sinusoidal
+        self.transformer = _WanTransformer(cfg, enable_logvar_linear)
+        self.reset_wan_parameters()
+        self._packed: Optional[Dict[str, Any]] = None
+        self._plans: Dict[Any, _Plan] = {}
+        self._ws: Dict[Any, Dict[str, torch.Tensor]] = {}
+        self._kv: Dict[Any, Dict[str, Any]] = {}      # cache_tag -> self-attention KV cache
+        self._cross: Dict[Any, Dict[str, Any]] = {}   # cache_tag -> static cross-attention K/V of the current prompt
+        self.profile: Optional[Dict[str, Dict[str, float]]] = None
+        self.sp_group = None                           # torch.distributed group for Ulysses sequence parallelism
+
+    # ---- reference helpers ------------------------------------------------------------------------------
+    @classmethod
+    def get_model_id(cls, model_path_or_id: str) -> str:
+        """reference Wan/network.py:784-797 (a local directory name carries the model id)"""
+        import os
+
+        if not os.path.isdir(model_path_or_id):
+            return model_path_or_id
+        idx = model_path_or_id.rfind("Wan2.")
+        if idx == -1:
+            raise ValueError("unable to extract model id from path. Expects substring `Wan2.X-`")
+        return "Wan-AI/" + model_path_or_id[idx:].split("/")[0]
+
+    def reset_wan_parameters(self) -> None:
+        """initialisation of reference Wan.reset_parameters (Wan/network.py:709-727)"""
+        for m in self.transformer.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        nn.init.xavier_uniform_(self.transformer.patch_embedding.weight.flatten(1))
+        for m in self.transformer.condition_embedder.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=0.02)
+        nn.init.zeros_(self.transformer.proj_out.weight)
+
+    def _invalidate(self):
+        self._packed = None
+        self._plans = {}
+        self._ws = {}
+        self._kv = {}
+        self._cross = {}
+
+    def _apply(self, fn, *a, **kw):
+        self._invalidate()
+        return super()._apply(fn, *a, **kw)
+
+    _RENAME = [
+        ("time_embedding.0", "condition_embedder.time_embedder.linear_1"),
+        ("time_embedding.2", "condition_embedder.time_embedder.linear_2"),
+        ("text_embedding.0", "condition_embedder.text_embedder.linear_1"),
+        ("text_embedding.2", "condition_embedder.text_embedder.linear_2"),
+        ("time_projection.1", "condition_embedder.time_proj"),
+        ("head.modulation", "scale_shift_table"), ("head.head", "proj_out"), ("modulation", "scale_shift_table"),
+        ("ffn.0", "ffn.net.0.proj"), ("ffn.2", "ffn.net.2"),
+        ("norm2", "norm__placeholder"), ("norm3", "norm2"), ("norm__placeholder", "norm3"),
+        ("self_attn.q", "attn1.to_q"), ("self_attn.k", "attn1.to_k"), ("self_attn.v", "attn1.to_v"),
+        ("self_attn.o", "attn1.to_out.0"), ("self_attn.norm_q", "attn1.norm_q"), ("self_attn.norm_k", "attn1.norm_k"),
+        ("cross_attn.q", "attn2.to_q"), ("cross_attn.k", "attn2.to_k"), ("cross_attn.v", "attn2.to_v"),
+        ("cross_attn.o", "attn2.to_out.0"), ("cross_attn.norm_q", "attn2.norm_q"), ("cross_attn.norm_k", "attn2.norm_k"),
+    ]
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], **kwargs):
+        """Also accepts original-Wan checkpoints, optionally nested under 'generator' / 'state_dict' / ... (reference
+        Wan/network.py:990-1075)."""
+        if self._use_wan_official_sinusoidal and not any(k.startswith("transformer.") for k in state_dict.keys()):
+            state = None
+            for k in ["generator", "state_dict", "model", "module", "net", None]:
+                if k is None:
+                    if all(isinstance(v, torch.Tensor) for v in state_dict.values()):
+                        state = state_dict
+                    break
+                if k in state_dict and isinstance(state_dict[k], dict):
+                    state = state_dict[k]
+                    break
+            assert state is not None, "Could not find a state_dict in checkpoint."
+
+            def rename(key: str) -> str:
+                for prefix in ["model.", "module.", "transformer."]:
+                    if key.startswith(prefix):
+                        key = key[len(prefix):]
+                for old, new in self._RENAME:
+                    if old in key:
+                        key = key.replace(old, new)
+                return "transformer." + key
+
+            state_dict = {rename(k): v for k, v in state.items()}
+        self._invalidate()
+        return super().load_state_dict(state_dict, **kwargs)
+
+    # ---- weight packing ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def repack(self) -> None:
+        tr = self.transformer
+        dev = tr.proj_out.weight.device
+        if dev.type != "cuda":
+            raise L.FastGenB200Error("Wan (B200) must live on a CUDA device: there is no CPU path")
+        L.lib()
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def w(lin):
+            return lin.weight.detach().to(bf).contiguous()
+
+        def b(lin):
+            return lin.bias.detach().to(bf).to(f32).contiguous()  # the reference adds the bf16 bias
+
+        pk: Dict[str, Any] = {}
+        pe = tr.patch_embedding
+        pk["patch.w"] = pe.weight.detach().reshape(pe.weight.shape[0], -1).to(bf).contiguous()
+        pk["patch.b"] = pe.bias.detach().to(bf).to(f32).contiguous()
+        ce = tr.condition_embedder
+        for nm, lin in (("t1", ce.time_embedder.linear_1), ("t2", ce.time_embedder.linear_2), ("tp", ce.time_proj),
+                        ("x1", ce.text_embedder.linear_1), ("x2", ce.text_embedder.linear_2), ("out", tr.proj_out)):
+            pk[nm + ".w"], pk[nm + ".b"] = w(lin), b(lin)
+        tables = []
+        for i, blk in enumerate(tr.blocks):
+            a1, a2 = blk.attn1, blk.attn2
+            pk[f"{i}.qkv.w"] = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0).detach().to(bf).contiguous()
+            pk[f"{i}.qkv.b"] = torch.cat([a1.to_q.bias, a1.to_k.bias, a1.to_v.bias], 0).detach().to(bf).to(f32).contiguous()
+            pk[f"{i}.o1.w"], pk[f"{i}.o1.b"] = w(a1.to_out[0]), b(a1.to_out[0])
+            pk[f"{i}.nq1"], pk[f"{i}.nk1"] = a1.norm_q.weight.detach().to(bf).contiguous(), a1.norm_k.weight.detach().to(bf).contiguous()
+            pk[f"{i}.q2.w"], pk[f"{i}.q2.b"] = w(a2.to_q), b(a2.to_q)
+            pk[f"{i}.kv2.w"] = torch.cat([a2.to_k.weight, a2.to_v.weight], 0).detach().to(bf).contiguous()
+            pk[f"{i}.kv2.b"] = torch.cat([a2.to_k.bias, a2.to_v.bias], 0).detach().to(bf).to(f32).contiguous()
+            pk[f"{i}.o2.w"], pk[f"{i}.o2.b"] = w(a2.to_out[0]), b(a2.to_out[0])
+            pk[f"{i}.nq2"], pk[f"{i}.nk2"] = a2.norm_q.weight.detach().to(bf).contiguous(), a2.norm_k.weight.detach().to(bf).contiguous()
+            pk[f"{i}.n2.g"] = blk.norm2.weight.detach().to(bf).to(f32).contiguous()
+            pk[f"{i}.n2.b"] = blk.norm2.bias.detach().to(bf).to(f32).contiguous()
+            pk[f"{i}.f1.w"], pk[f"{i}.f1.b"] = w(blk.ffn.net[0].proj), b(blk.ffn.net[0].proj)
+            pk[f"{i}.f2.w"], pk[f"{i}.f2.b"] = w(blk.ffn.net[2]), b(blk.ffn.net[2])
+            tables.append(blk.scale_shift_table.detach().to(bf).to(f32).reshape(-1))
+        pk["tables"] = torch.stack(tables, 0).contiguous()                       # [L, 6D] fp32
+        pk["head_table"] = tr.scale_shift_table.detach().to(bf).reshape(2, -1)   # bf16: the head adds in bf16
+        cos, sin, nt, nh = _rope_pair_tables(self.cfg["head_dim"], self.cfg["rope_max_seq_len"])
+        pk["rope"] = (cos.to(dev), sin.to(dev), nt, nh)
+        self._packed = pk
+        self._plans, self._ws = {}, {}
+
+    # ---- workspace --------------------------------------------------------------------------------------
+    def _workspace(self, B: int, F: int, Hh: int, Ww: int, x_dtype: torch.dtype) -> Dict[str, torch.Tensor]:
+        key = (B, F, Hh, Ww, x_dtype)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        cfg = self.cfg
+        dev = self.transformer.proj_out.weight.device
+        D, Fd = cfg["dim"], cfg["ffn_dim"]
+        _, ph, pw = cfg["patch"]
+        n = F * (Hh // ph) * (Ww // pw)
+        rows = B * n
+        P = self._sp_size()
+        if n % P:
+            raise ValueError(f"tokens per sample ({n}) must divide by the sequence-parallel size ({P})")
+        lrows = rows // P                      # rows this rank owns
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dt=bf: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        kin = cfg["in_channels"] * ph * pw
+        kout = cfg["out_channels"] * ph * pw
+        groups = B * F
+        ws = dict(
+            x_in=z(B, cfg["in_channels"], F, Hh, Ww, dt=x_dtype), tok=z(rows, kin), hs=z(lrows, D), nrm=z(lrows, D),
+            qkv=z(lrows, 3 * D), att=z(lrows, D), q2=z(lrows, D), f1=z(lrows, Fd), tok_out=z(rows, kout),
+            flow=z(B, cfg["out_channels"], F, Hh, Ww, dt=x_dtype),
+            emb=z(groups, cfg["freq_dim"]), te1=z(groups, D), temb=z(groups, D), temb_act=z(groups, D),
+            tproj=z(groups, 6 * D, dt=f32), mod=z(cfg["layers"], groups, 6 * D, dt=f32), head_mod=z(groups, 2 * D, dt=f32),
+        )
+        if P > 1:
+            # Ulysses exchange buffers: [P, B, n/P, 3, H/P, d] send/recv for q,k,v and [P, B, n/P, H/P, d] for the output
+            Hl = cfg["heads"] // P
+            ws.update(a2a_s=z(P * B * (n // P) * 3 * Hl * cfg["head_dim"]), a2a_r=z(P * B * (n // P) * 3 * Hl * cfg["head_dim"]),
+                      qkv_full=z(B * n, 3 * Hl * cfg["head_dim"]), att_full=z(B * n, Hl * cfg["head_dim"]))
+        self._ws[key] = ws
+        return ws
+
+    def _sp_size(self) -> int:
+        if self.sp_group is None:
+            return 1
+        import torch.distributed as dist
+
+        return dist.get_world_size(self.sp_group)
+
+    def _sp_rank(self) -> int:
+        if self.sp_group is None:
+            return 0
+        import torch.distributed as dist
+
+        return dist.get_rank(self.sp_group)
+
+    # ---- launch helpers ---------------------------------------------------------------------------------
+    def _gemm(self, plan: _Plan, a: torch.Tensor, k: int, wt: torch.Tensor, rows: int, cout: int, out: torch.Tensor,
+              out_ld: int, desc: str, **kw):
+        p = ops.conv_gemm_params([ops.Seg(a, a.stride(0), wt, k, 1)], rows, 1, 1, cout, out, out_ld, **kw)
+        plan.keep.append((p, a, wt, out, kw))
+        plan.add(L.lib().fg_conv_gemm, C.byref(p), desc=desc, flops=2.0 * rows * k * cout)
+
+    def _ln(self, plan: _Plan, x, rows, y, desc, **kw):
+        D = self.cfg["dim"]
+        p = ops.ln_mod_params(x, D, rows, D, self.cfg["eps"], y, D, **kw)
+        plan.keep.append((p, x, y, kw))
+        plan.add(L.lib().fg_ln_modulate, C.byref(p), desc=desc)
+
+    # ---- cross-attention K/V of a prompt (static: computed once per condition tensor) --------------------
+    def _cross_kv(self, condition: torch.Tensor, cache_tag: str) -> Dict[str, Any]:
+        """text embedder + per-layer k/v projections + RMSNorm(k): [L, B*Ln, 2D] bf16.  The buffers of a cache tag are
+        persistent (forward plans point into them); their contents are recomputed when the condition tensor changes
+        or after clear_caches() -- the reference recomputes them per call until the first store_kv pass
+        (network_causal.py:326-345), with identical values."""
+        key = (condition.data_ptr(), condition._version, tuple(condition.shape), condition.dtype)
+        cfg, pk = self.cfg, self._packed
+        D, Ln, Td = cfg["dim"], condition.shape[1], cfg["text_dim"]
+        B = condition.shape[0]
+        ent = self._cross.get(cache_tag)
+        if ent is None or ent["batch"] != B or ent["len"] != Ln:
+            dev = condition.device
+            bf = torch.bfloat16
+            ent = {"key": None, "len": Ln, "batch": B,
+                   "text": torch.empty(B * Ln, Td, device=dev, dtype=bf), "x1": torch.empty(B * Ln, D, device=dev, dtype=bf),
+                   "enc": torch.empty(B * Ln, D, device=dev, dtype=bf),
+                   "kv": torch.empty(cfg["layers"], B * Ln, 2 * D, device=dev, dtype=bf)}
+            plan = _Plan()
+            self._gemm(plan, ent["text"], Td, pk["x1.w"], B * Ln, D, ent["x1"], D, "text1", bias=pk["x1.b"],
+                       act=L.FG_ACT_GELU_TANH)
+            self._gemm(plan, ent["x1"], D, pk["x2.w"], B * Ln, D, ent["enc"], D, "text2", bias=pk["x2.b"])
+            for i in range(cfg["layers"]):
+                self._gemm(plan, ent["enc"], D, pk[f"{i}.kv2.w"], B * Ln, 2 * D, ent["kv"][i], 2 * D, "kv2",
+                           bias=pk[f"{i}.kv2.b"])
+                p = ops.qk_norm_rope_params(None, ent["kv"][i], 0, 2 * D, B * Ln, cfg["heads"], cfg["head_dim"],
+                                            cfg["eps"], None, pk[f"{i}.nk2"], Ln)
+                plan.keep.append(p)
+                plan.add(L.lib().fg_qk_norm_rope, C.byref(p), desc="k2norm")
+            ent["plan"] = plan
+            self._cross[cache_tag] = ent
+            self._plans = {}   # forward plans hold pointers into the previous buffers
+        if ent["key"] != key:
+            ent["text"].copy_(condition.reshape(B * Ln, Td))
+            ent["plan"].run(torch.cuda.current_stream().cuda_stream, self.profile)
+            ent["key"] = key
+            ent["keep"] = condition
+        return ent
+
+    # ---- self-attention KV cache -------------------------------------------------------------------------
+    def _self_kv(self, cache_tag: str, B: int, capacity: int) -> Dict[str, Any]:
+        ent = self._kv.get(cache_tag)
+        cfg = self.cfg
+        Dl = cfg["dim"] // self._sp_size()   # head-sharded under sequence parallelism
+        if ent is None or ent["k"].shape[1] != B or ent["k"].shape[2] != capacity:
+            dev = self.transformer.proj_out.weight.device
+            ent = {"k": torch.zeros(cfg["layers"], B, capacity, Dl, device=dev, dtype=torch.bfloat16),
+                   "v": torch.zeros(cfg["layers"], B, capacity, Dl, device=dev, dtype=torch.bfloat16), "len": 0}
+            self._kv[cache_tag] = ent
+            self._plans = {}   # forward plans hold pointers into the previous buffers
+        return ent
+
+    def clear_caches(self) -> None:
+        """reference network_causal.py:1030-1056: lengths to 0, buffers zeroed (here: in place, no re-allocation)"""
+        for ent in self._kv.values():
+            ent["k"].zero_()
+            ent["v"].zero_()
+            ent["len"] = 0
+        for ent in self._cross.values():
+            ent["key"] = None
+
+    # ---- the forward plan --------------------------------------------------------------------------------
+    def _build_plan(self, B, F, Hh, Ww, x_dtype, per_frame: bool, kv: Optional[Dict[str, Any]], cache_start: int,
+                    store_kv: bool, frame0: int, mask: Optional[Tuple[int, int]], cross: Dict[str, Any]) -> _Plan:
+        cfg, pk = self.cfg, self._packed
+        lib = L.lib()
+        D, Fd, H, d = cfg["dim"], cfg["ffn_dim"], cfg["heads"], cfg["head_dim"]
+        _, ph, pw = cfg["patch"]
+        pph, ppw = Hh // ph, Ww // pw
+        n = F * pph * ppw
+        rows = B * n
+        ws = self._workspace(B, F, Hh, Ww, x_dtype)
+        plan = _Plan()
+        plan.keep.append((ws, cross["kv"], kv))
+        groups = B * F
+        kin = cfg["in_channels"] * ph * pw
+        kout = cfg["out_channels"] * ph * pw
+        P, rank = self._sp_size(), self._sp_rank()
+        if P > 1:
+            raise NotImplementedError("sequence-parallel plans are built by fastgen_b200.parallel_wan")
+        # ---- embeddings ----
+        plan.add(lib.fg_patchify, ws["x_in"].data_ptr(), ops._DT[x_dtype], B, cfg["in_channels"], F, Hh, Ww, ph, pw,
+                 ws["tok"].data_ptr(), kin, desc="patchify")
+        self._gemm(plan, ws["tok"], kin, pk["patch.w"], rows, D, ws["hs"], D, "patch", bias=pk["patch.b"])
+        self._gemm(plan, ws["emb"], cfg["freq_dim"], pk["t1.w"], groups, D, ws["te1"], D, "time1", bias=pk["t1.b"],
+                   act=L.FG_ACT_SILU)
+        self._gemm(plan, ws["te1"], D, pk["t2.w"], groups, D, ws["temb"], D, "time2", bias=pk["t2.b"])
+        self._gemm(plan, ws["te1"], D, pk["t2.w"], groups, D, ws["temb_act"], D, "time2s", bias=pk["t2.b"],
+                   act=L.FG_ACT_SILU)
+        self._gemm(plan, ws["temb_act"], D, pk["tp.w"], groups, 6 * D, ws["tproj"], 6 * D, "tproj", bias=pk["tp.b"])
+        plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["tproj"].data_ptr(), cfg["layers"], groups, 6 * D,
+                 ws["mod"].data_ptr(), desc="mod")
+        rpg = pph * ppw if per_frame else n   # rows sharing one modulation vector
+        mod_groups = groups if per_frame else B
+        if not per_frame and F != 1:
+            # global AdaLN: the [B] timesteps were staged once per sample; groups == B
+            pass
+        hs, nrm, qkv, att, q2, f1 = ws["hs"], ws["nrm"], ws["qkv"], ws["att"], ws["q2"], ws["f1"]
+        ckv, clen = cross["kv"], cross["len"]
+        for i in range(cfg["layers"]):
+            mod = ws["mod"][i]                                      # [groups, 6D]
+            m = lambda j: mod[:, j * D:(j + 1) * D]                 # noqa: E731
+            # 1. self-attention
+            self._ln(plan, hs, rows, nrm, "ln1", scale=m(1), shift=m(0), mod_ld=6 * D, rows_per_group=rpg)
+            self._gemm(plan, nrm, D, pk[f"{i}.qkv.w"], rows, 3 * D, qkv, 3 * D, "qkv", bias=pk[f"{i}.qkv.b"])
+            kw = {}
+            if kv is not None and store_kv:
+                kw = dict(v=qkv[:, 2 * D:], v_ld=3 * D, k_cache=kv["k"][i], v_cache=kv["v"][i], cache_ld=D,
+                          cache_bs=kv["k"].shape[2] * D, cache_row0=cache_start)
+            p = ops.qk_norm_rope_params(qkv, qkv[:, D:], 3 * D, 3 * D, rows, H, d, cfg["eps"], pk[f"{i}.nq1"],
+                                        pk[f"{i}.nk1"], n, rope=pk["rope"], grid=(F, pph, ppw), frame0=frame0, **kw)
+            plan.keep.append(p)
+            plan.add(lib.fg_qk_norm_rope, C.byref(p), desc="qknorm_rope")
+            cur = (qkv[:, D:], qkv[:, 2 * D:], 3 * D, n * 3 * D, n)
+            if kv is not None and cache_start > 0:
+                segs = [(kv["k"][i], kv["v"][i], D, kv["k"].shape[2] * D, cache_start), cur]
+            else:
+                segs = [cur]
+            mk = dict(mask_first=mask[0], mask_chunk=mask[1]) if mask else {}
+            p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, **mk)
+            plan.keep.append(p)
+            kv_tot = n + (cache_start if kv is not None else 0)
+            plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * D)
+            self._gemm(plan, att, D, pk[f"{i}.o1.w"], rows, D, hs, D, "o1", bias=pk[f"{i}.o1.b"], gate=m(2), gate_ld=6 * D,
+                       gate_rows=rpg, res=hs, res_ld=D, res_mode=L.FG_RES_SAME)
+            # 2. cross-attention
+            self._ln(plan, hs, rows, nrm, "ln2", gamma=pk[f"{i}.n2.g"], beta=pk[f"{i}.n2.b"])
+            self._gemm(plan, nrm, D, pk[f"{i}.q2.w"], rows, D, q2, D, "q2", bias=pk[f"{i}.q2.b"])
+            p = ops.qk_norm_rope_params(q2, None, D, 0, rows, H, d, cfg["eps"], pk[f"{i}.nq2"], None, n)
+            plan.keep.append(p)
+            plan.add(lib.fg_qk_norm_rope, C.byref(p), desc="q2norm")
+            p = ops.flash_attn_params(q2, D, n * D, [(ckv[i], ckv[i][:, D:], 2 * D, clen * 2 * D, clen)], B, H, d, n, att,
+                                      D, n * D)
+            plan.keep.append(p)
+            plan.add(lib.fg_flash_attn, C.byref(p), desc="cross_attn", flops=4.0 * B * n * clen * D)
+            self._gemm(plan, att, D, pk[f"{i}.o2.w"], rows, D, hs, D, "o2", bias=pk[f"{i}.o2.b"], res=hs, res_ld=D,
+                       res_mode=L.FG_RES_SAME)
+            # 3. feed-forward
+            self._ln(plan, hs, rows, nrm, "ln3", scale=m(4), shift=m(3), mod_ld=6 * D, rows_per_group=rpg)
+            self._gemm(plan, nrm, D, pk[f"{i}.f1.w"], rows, Fd, f1, Fd, "ffn1", bias=pk[f"{i}.f1.b"],
+                       act=L.FG_ACT_GELU_TANH)
+            self._gemm(plan, f1, Fd, pk[f"{i}.f2.w"], rows, D, hs, D, "ffn2", bias=pk[f"{i}.f2.b"], gate=m(5),
+                       gate_ld=6 * D, gate_rows=rpg, res=hs, res_ld=D, res_mode=L.FG_RES_SAME)
+        # ---- head ----
+        hm = ws["head_mod"]
+        self._ln(plan, hs, rows, nrm, "ln_out", scale=hm[:, D:], shift=hm[:, :D], mod_ld=2 * D, rows_per_group=rpg)
+        self._gemm(plan, nrm, D, pk["out.w"], rows, kout, ws["tok_out"], kout, "proj_out", bias=pk["out.b"])
+        plan.add(lib.fg_unpatchify, ws["tok_out"].data_ptr(), kout, B, cfg["out_channels"], F, Hh, Ww, ph, pw,
+                 ws["flow"].data_ptr(), ops._DT[x_dtype], desc="unpatchify")
+        assert mod_groups <= groups
+        return plan
+
+    def _run_transformer(self, x_t: torch.Tensor, timestep: torch.Tensor, condition: torch.Tensor, per_frame: bool,
+                         cache_tag: str = "pos", use_cache: bool = False, cur_start_frame: int = 0,
+                         store_kv: bool = False, total_num_frames: int = 21,
+                         mask: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """timestep: rescaled (1000 t), [B] (global AdaLN) or [B, F] (per frame).  Returns the raw output [B,C,F,H,W]."""
+        if not x_t.is_cuda:
+            raise L.FastGenB200Error("Wan (B200) needs CUDA tensors: there is no CPU path")
+        if x_t.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"x_t must be float32 or bfloat16, got {x_t.dtype}")
+        if self._packed is None:
+            self.repack()
+        cfg = self.cfg
+        B, Cc, F, Hh, Ww = x_t.shape
+        _, ph, pw = cfg["patch"]
+        if Cc != cfg["in_channels"] or Hh % ph or Ww % pw:
+            raise ValueError(f"x_t shape {tuple(x_t.shape)} does not match the network")
+        if condition is None:
+            raise ValueError("Wan needs text embeddings as the condition")
+        if condition.shape[0] == 1 and B > 1:
+            condition = condition.expand(B, -1, -1)
+        if condition.shape[0] != B or condition.shape[-1] != cfg["text_dim"]:
+            raise ValueError(f"condition shape {tuple(condition.shape)} does not match batch {B} / text_dim {cfg['text_dim']}")
+        fs = (Hh // ph) * (Ww // pw)
+        cross = self._cross_kv(condition, cache_tag)
+        kv, cache_start, frame0 = None, 0, cur_start_frame
+        if use_cache:
+            kv = self._self_kv(cache_tag, B, fs * total_num_frames)
+            cache_start = cur_start_frame * fs
+            if cache_start + F * fs > kv["k"].shape[2]:
+                raise ValueError("chunk does not fit the KV cache (cur_start_frame + frames > total_num_frames)")
+            if cur_start_frame == 0:
+                # reference network_causal.py:605-617: without an explicit start frame the rotary offset continues
+                # from the cached length (0 right after clear_caches())
+                frame0 = kv["len"] // fs
+            if store_kv:
+                kv["len"] = cache_start + F * fs
+        key = (B, F, Hh, Ww, x_t.dtype, per_frame, use_cache, cache_start, store_kv, frame0, mask, cache_tag)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._build_plan(B, F, Hh, Ww, x_t.dtype, per_frame, kv, cache_start, store_kv, frame0, mask, cross)
+            if len(self._plans) > 64:
+                self._plans.clear()
+            self._plans[key] = plan
+        ws = self._workspace(B, F, Hh, Ww, x_t.dtype)
+        # ---- stage the dynamic inputs ----
+        ws["x_in"].copy_(x_t)
+        ts = timestep.reshape(B, -1)
+        groups = B * F
+        tsf = (ts.expand(B, F) if ts.shape[1] != F else ts).reshape(-1) if per_frame else ts[:, 0]
+        emb = _sinusoid(tsf, cfg["freq_dim"], self._use_wan_official_sinusoidal).to(torch.bfloat16)
+        if per_frame:
+            ws["emb"].copy_(emb)
+        else:
+            ws["emb"].zero_()
+            ws["emb"][:B].copy_(emb)   # rows [0, B): one modulation group per sample (rows_per_group = n)
+        stream = torch.cuda.current_stream().cuda_stream
+        # the head adds table + temb in bf16 (reference Wan/network.py:229,250): needs temb, so run the embedding
+        # launches first, then that one tiny add, then the rest of the plan
+        self._run_split(plan, ws, stream)
+        return ws["flow"]
+
+    def _run_split(self, plan: _Plan, ws, stream: int) -> None:
+        D = self.cfg["dim"]
+        pk = self._packed
+        # steps 0..6 are patchify, patch, time1, time2, time2s, tproj, mod
+        head = _Plan()
+        head.steps, rest = plan.steps[:7], plan.steps[7:]
+        head.run(stream, self.profile)
+        hm = (pk["head_table"][None] + ws["temb"][:, None, :]).reshape(ws["temb"].shape[0], 2 * D)
+        ws["head_mod"].copy_(hm)
+        tail = _Plan()
+        tail.steps = rest
+        tail.run(stream, self.profile)
+
+    def _check_fwd_args(self, feature_indices, return_features_early, return_logvar, fwd_pred_type, r):
+        if feature_indices is None:
+            feature_indices = {}
+        if return_features_early and len(feature_indices) == 0:
+            return None, True
+        if fwd_pred_type is None:
+            fwd_pred_type = self.net_pred_type
+        else:
+            assert fwd_pred_type in NET_PRED_TYPES, f"{fwd_pred_type} is not supported as fwd_pred_type"
+        if return_features_early or len(feature_indices) or return_logvar:
+            raise NotImplementedError("feature / logvar outputs are training-time paths of the reference")
+        if r is not None:
+            raise ValueError("r_timestep provided but no r_embedder is present")
+        return fwd_pred_type, False
+
+
+class Wan(_WanBase, FastGenNetwork):
+    """B200 drop-in for ``fastgen.networks.Wan.network.Wan`` (bidirectional, global AdaLN)."""
+
+    MODEL_ID_14B = "Wan-AI/Wan2.1-T2V-14B-Diffusers"
+    MODEL_ID_1_3B = "Wan-AI/Wan2.1-T2V-1.3B-Diffusers"
+
+    def __init__(self, model_id_or_local_path: str = MODEL_ID_1_3B, r_timestep: bool = False,
+                 disable_efficient_attn: bool = False, disable_grad_ckpt: bool = False,
+                 enable_logvar_linear: bool = True, r_embedder_init: str = "pretrained", time_cond_type: str = "diff",
+                 norm_temb: bool = False, net_pred_type: str = "flow", schedule_type: str = "rf",
+                 encoder_depth: Optional[int] = None, load_pretrained: bool = False, use_fsdp_checkpoint: bool = True,
+                 use_wan_official_sinusoidal: bool = False, transformer_config: Optional[Dict[str, Any]] = None,
+                 **model_kwargs):
+        FastGenNetwork.__init__(self, net_pred_type=net_pred_type, schedule_type=schedule_type, **model_kwargs)
+        if load_pretrained:
+            raise NotImplementedError("no hub access: build with load_pretrained=False and call load_state_dict")
+        self._init_wan(model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
+                       r_timestep, norm_temb, encoder_depth)
+
+    def forward(self, x_t: torch.Tensor, t: torch.Tensor, condition: Any = None, r: Optional[torch.Tensor] = None,
+                return_features_early: bool = False, feature_indices: Optional[Set[int]] = None,
+                return_logvar: bool = False, fwd_pred_type: Optional[str] = None, skip_layers=None,
+                unpatchify_features: bool = True, **fwd_kwargs):
+        fwd_pred_type, early = self._check_fwd_args(feature_indices, return_features_early, return_logvar, fwd_pred_type, r)
+        if early:
+            return []
+        if skip_layers:
+            raise NotImplementedError("skip-layer guidance is a teacher-sampling feature")
+        with torch.no_grad():
+            condition = torch.stack(condition, dim=0) if isinstance(condition, list) else condition
+            t = torch.atleast_1d(t).to(x_t.device)
+            if t.numel() == 1 and x_t.shape[0] > 1:
+                t = t.expand(x_t.shape[0])
+            timestep = self.noise_scheduler.rescale_t(t)
+            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False, cache_tag="__bidir__")
+            return self.noise_scheduler.convert_model_output(x_t, out, t, src_pred_type=self.net_pred_type,
+                                                             target_pred_type=fwd_pred_type)
+
+
+class CausalWan(_WanBase, CausalFastGenNetwork):
+    """B200 drop-in for ``fastgen.networks.Wan.network_causal.CausalWan`` (per-frame AdaLN, KV-cached chunks)."""
+
+    MODEL_ID_14B = Wan.MODEL_ID_14B
+    MODEL_ID_1_3B = Wan.MODEL_ID_1_3B
+
+    def __init__(self, model_id_or_local_path: str = Wan.MODEL_ID_1_3B, r_timestep: bool = False,
+                 disable_efficient_attn: bool = False, disable_grad_ckpt: bool = False,
+                 enable_logvar_linear: bool = True, r_embedder_init: str = "pretrained", time_cond_type: str = "diff",
+                 norm_temb: bool = False, net_pred_type: str = "flow", schedule_type: str = "rf",
+                 encoder_depth: Optional[int] = None, load_pretrained: bool = False, use_fsdp_checkpoint: bool = True,
+                 chunk_size: int = 3, total_num_frames: int = 21, delete_cache_on_clear: bool = False,
+                 use_wan_official_sinusoidal: bool = False, transformer_config: Optional[Dict[str, Any]] = None,
+                 **model_kwargs):
+        CausalFastGenNetwork.__init__(self, net_pred_type=net_pred_type, schedule_type=schedule_type,
+                                      chunk_size=chunk_size, total_num_frames=total_num_frames, **model_kwargs)
+        if load_pretrained:
+            raise NotImplementedError("no hub access: build with load_pretrained=False and call load_state_dict")
+        self._delete_cache_on_clear = delete_cache_on_clear
+        self._init_wan(model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
+                       r_timestep, norm_temb, encoder_depth)
+
+    def clear_caches(self) -> None:
+        if self._delete_cache_on_clear:
+            self._kv, self._cross, self._plans = {}, {}, {}
+            torch.cuda.empty_cache()
+            return
+        _WanBase.clear_caches(self)
+
+    def forward(self, x_t: torch.Tensor, t: torch.Tensor, condition: Any = None, r: Optional[torch.Tensor] = None,
+                return_features_early: bool = False, feature_indices: Optional[Set[int]] = None,
+                return_logvar: bool = False, unpatchify_features: bool = True, fwd_pred_type: Optional[str] = None,
+                skip_layers=None, cache_tag: str = "pos", cur_start_frame: int = 0, store_kv: bool = False,
+                is_ar: bool = False, **fwd_kwargs):
+        fwd_pred_type, early = self._check_fwd_args(feature_indices, return_features_early, return_logvar, fwd_pred_type, r)
+        if early:
+            return []
+        if skip_layers:
+            raise NotImplementedError("skip-layer guidance is a teacher-sampling feature")
+        with torch.no_grad():
+            condition = torch.stack(condition, dim=0) if isinstance(condition, list) else condition
+            B, _, F, Hh, Ww = x_t.shape
+            t = torch.atleast_1d(t).to(x_t.device)
+            if t.ndim == 1 and t.numel() == 1 and B > 1:
+                t = t.expand(B)
+            timestep = self.noise_scheduler.rescale_t(t)
+            if timestep.ndim == 1:
+                timestep = timestep.view(-1, 1)
+            timestep = timestep.expand(B, F) if timestep.shape[1] != F else timestep   # mask of ones * timestep
+            use_cache = F < self.total_num_frames
+            mask = None
+            _, ph, pw = self.cfg["patch"]
+            fs = (Hh // ph) * (Ww // pw)
+            if not use_cache and not is_ar:
+                nc, rem = F // self.chunk_size, F % self.chunk_size
+                first = (self.chunk_size + rem) * fs if nc else rem * fs
+                mask = (first, self.chunk_size * fs)
+            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=True, cache_tag=cache_tag,
+                                        use_cache=use_cache, cur_start_frame=cur_start_frame, store_kv=store_kv,
+                                        total_num_frames=self.total_num_frames, mask=mask)
+            t_conv = t[:, None, :, None, None] if t.ndim == 2 else t
+            return self.noise_scheduler.convert_model_output(x_t, out, t_conv, src_pred_type=self.net_pred_type,
+                                                             target_pred_type=fwd_pred_type)

@@ -154,3 +154,38 @@ def causal_chunks(num_frames: int, chunk_size: int) -> List[Tuple[int, int]]:
     if nchunks == 0:
         return [(0, rem)]
     return [(0 if i == 0 else chunk_size * i + rem, chunk_size * (i + 1) + rem) for i in range(nchunks)]
+
+
+def causvid_sample_loop(net: Callable[..., torch.Tensor], sched: Schedule, x: torch.Tensor, t_list: torch.Tensor,
+                        chunk_size: int, eps_list: Sequence[torch.Tensor], sample_type: str = "sde",
+                        context_noise: float = 0.0, clear_caches: Optional[Callable[[], None]] = None) -> torch.Tensor:
+    """causvid.py:87-185 with the `randn_like` draws supplied in call order.
+    ``net(x_chunk, t_batch, cur_start_frame=..., store_kv=...) -> x0`` (cache_tag 'pos', is_ar True implied)."""
+    if clear_caches:
+        clear_caches()
+    b, frames = x.shape[0], x.shape[2]
+    draws = iter(eps_list)
+    x = x.clone()
+    for start, end in causal_chunks(frames, chunk_size):
+        x_next = x[:, :, start:end]
+        for t_cur, t_next in zip(t_list[:-1], t_list[1:]):
+            tb = t_cur.expand(b)
+            x_cur = x_next
+            x_next = net(x_cur, tb, cur_start_frame=start, store_kv=False)
+            if t_next > 0:
+                if sample_type == "sde":
+                    eps = next(draws)
+                elif sample_type == "ode":
+                    eps = sched.x0_to_eps(x_cur, x_next, tb)
+                else:
+                    raise NotImplementedError(f"student_sample_type must be one of 'sde', 'ode' but got {sample_type}")
+                x_next = sched.forward_process(x_next, eps, t_next.expand(b))
+        x[:, :, start:end] = x_next
+        x_cache, t_cache = x_next, t_list[-1].expand(b)
+        if context_noise > 0:
+            t_cache = torch.full((b,), context_noise, dtype=x.dtype)
+            x_cache = sched.forward_process(x_next, next(draws), t_cache)
+        net(x_cache, t_cache, cur_start_frame=start, store_kv=True)
+    if clear_caches:
+        clear_caches()
+    return x
