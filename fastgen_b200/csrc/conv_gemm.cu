@@ -20,6 +20,8 @@
 // Replaces: fastgen/networks/EDM/network.py:93-126 (Conv2d.forward), :47-51 (Linear.forward), the elementwise tail
 // of UNetBlock.forward (:283, :286-287, :297-298); and, for the transformer networks, the Linear + bias + GELU /
 // gate * x + residual tails of the Wan / DiT blocks (fastgen/networks/Wan/network.py:116-151, DiT/network.py:184-201).
+#include <limits.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -261,9 +263,17 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
       }
     }
   }
-  if (p.act) {
+  if (p.act == FG_ACT_GELU_TANH) {  // (the switch is hoisted: one warp-uniform branch per 32 columns)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = apply_act(a[j], p.act);
+    for (int j = 0; j < 32; ++j) {
+      const float x = a[j];
+      const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+      const float hx = 0.5f * x;
+      a[j] = fmaf(hx, tanh_fast(u), hx);
+    }
+  } else if (p.act == FG_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = silu_f(a[j]);
   }
   if (p.gate && valid) {
     const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
@@ -595,16 +605,21 @@ static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_
   return launch_conv<BLOCK_N, kEpiGeneric>(kp, num_sms, stream);
 }
 
-static int pick_block_n(int cout) {
+// Tile width: the candidate that minimises (waves of tiles over the SMs) x (tile cost ~ width), i.e. padding waste in
+// N and wave quantisation are weighed together; ties go to the wider tile (fewer A re-reads from L2).
+static int pick_block_n(int cout, int m_tiles, int num_sms) {
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
   if (cout <= 128) return 128;
-  int best = 128, best_cost = 1 << 30;
+  int best = 128;
+  int64_t best_cost = INT64_MAX;
   const int cands[3] = {128, 192, 256};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
-    const int cost = ((cout + bn - 1) / bn) * bn;
-    if (cost <= best_cost) {  // ties go to the larger tile (fewer A re-reads)
+    const int64_t tiles = static_cast<int64_t>(m_tiles) * ((cout + bn - 1) / bn);
+    const int64_t waves = (tiles + num_sms - 1) / num_sms;
+    const int64_t cost = waves * (bn + 16);  // + fixed per-tile cost (pipeline fill, barriers)
+    if (cost <= best_cost) {
       best_cost = cost;
       best = bn;
     }
@@ -656,7 +671,14 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.tiles_w = p->w / kp.BW;
   kp.tiles_h = p->h / kp.BH;
   kp.tiles_img = (p->n + kp.BNI - 1) / kp.BNI;
-  const int block_n = pick_block_n(p->cout);
+  int dev = 0, num_sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    // no device (argument checking on a CPU-only host): the tile choice does not matter
+    cudaGetLastError();
+    num_sms = 148;
+  }
+  const int block_n = pick_block_n(p->cout, kp.tiles_w * kp.tiles_h * kp.tiles_img, num_sms);
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_img * kp.tiles_n;
 
@@ -750,12 +772,6 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     }
   }
 
-  int dev = 0, num_sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    set_error("conv_gemm: cannot query device");
-    return FG_ERR_CUDA;
-  }
   switch (block_n) {
     case 16: return dispatch_epi<16>(kp, epi, num_sms, stream);
     case 64: return dispatch_epi<64>(kp, epi, num_sms, stream);
