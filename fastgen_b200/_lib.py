@@ -19,7 +19,7 @@ FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU = 0, 1, 2
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
-    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn",
+    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn", "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16",
 )
@@ -75,6 +75,7 @@ class FlashAttnParams(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32), ("tq", C.c_int32),
         ("scale", C.c_float), ("mask_first", C.c_int32), ("mask_chunk", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -130,6 +131,8 @@ def lib() -> C.CDLL:
     l.fg_gn_apply.argtypes = [C.POINTER(GnApplyParams), vp]
     l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
     l.fg_flash_attn.argtypes = [C.POINTER(FlashAttnParams), vp]
+    l.fg_flash_attn_workspace_size.argtypes = [C.POINTER(FlashAttnParams)]
+    l.fg_flash_attn_workspace_size.restype = C.c_int64
     l.fg_ln_modulate.argtypes = [C.POINTER(LnModParams), vp]
     l.fg_qk_norm_rope.argtypes = [C.POINTER(QkNormRopeParams), vp]
     l.fg_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]

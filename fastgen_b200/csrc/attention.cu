@@ -19,6 +19,8 @@
 // Replaces: fastgen/networks/EDM/network.py:160-168, 290-296 (AttentionOp + the two einsums, which materialise the
 // [N*heads, T, T] weights in fp32) and diffusers' dispatch_attention_fn / F.scaled_dot_product_attention as called
 // from fastgen/networks/Wan/network_causal.py:312-320, 350-358, 404-412, 446-454.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -52,19 +54,6 @@ struct AttnKParams {
   __nv_bfloat16* out;
   int64_t out_ld, out_bs;
 };
-
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // keys a query token may see under the block-causal mask: up to the end of its own chunk
 __device__ __forceinline__ int causal_limit(const AttnKParams& p, int tok) {
@@ -349,6 +338,9 @@ static int launch_attention(AttnKParams& kp, const fg_flash_attn_params* p, cuda
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t stream);  // attention2.cu
+size_t flash_attn_v2_workspace(const fg_flash_attn_params* p);
+
 }  // namespace fg
 
 extern "C" int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream_) {
@@ -386,6 +378,11 @@ extern "C" int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream_)
   kp.mask_first = p->mask_chunk > 0 ? p->mask_first : 0;
   kp.mask_chunk = p->mask_chunk;
   const float scale = p->scale > 0.f ? p->scale : 1.0f / sqrtf(static_cast<float>(p->d));
+  {
+    // long sequences: two query tiles per CTA, P in tensor memory (attention2.cu)
+    static const bool allow_v2 = !(getenv("FG_ATTN_V2") && getenv("FG_ATTN_V2")[0] == '0');
+    if (allow_v2 && p->d <= 128 && p->tq > 128) return flash_attn_v2(p, scale, stream);
+  }
   kp.scale_log2 = 1.4426950408889634f * scale;
   kp.out = static_cast<__nv_bfloat16*>(p->out);
   kp.out_ld = p->out_ld;
@@ -393,6 +390,11 @@ extern "C" int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream_)
   if (p->d <= 64) return launch_attention<64, 128>(kp, p, stream);
   if (p->d <= 128) return launch_attention<128, 128>(kp, p, stream);
   return launch_attention<256, 64>(kp, p, stream);
+}
+
+extern "C" int64_t fg_flash_attn_workspace_size(const fg_flash_attn_params* p) {
+  if (!p || p->d > 128 || p->tq <= 128 || p->mask_chunk > 0) return 0;
+  return static_cast<int64_t>(fg::flash_attn_v2_workspace(p));
 }
 
 // packed channels-last qkv of the UNet blocks: [N, T, 3*heads*d] with channel order (q|k|v, head, d)

@@ -1,0 +1,576 @@
+// Flash attention, second generation, for long sequences (head dim <= 128, more than 128 queries):
+//   * one CTA owns TWO 128-row query tiles; two softmax warpgroups (one per tile) alternate with the single MMA
+//     issuer so that the tensor pipe computes S = Q.K^T / O += P.V of one tile while the other tile's softmax runs;
+//   * S (fp32) and O (fp32) accumulators live in TMEM; P is written back as bf16 OVER the S columns by the softmax
+//     threads (tcgen05.st) and consumed by the P.V product straight from tensor memory (A operand in TMEM) -- no
+//     shared-memory round trip for P;
+//   * exp2: the log2(e)/sqrt(d) scale is folded into one FFMA per element, half of the exponentials run on the MUFU
+//     unit and half as a degree-3 polynomial on the FMA pipe (Cody-Waite range reduction), since at 16 MUFU/clk/SM
+//     the exponential, not the tensor pipe, would otherwise bound the kernel;
+//   * O is rescaled lazily (only when the running max grows by more than 2^8);
+//   * O leaves through 128B-swizzled shared memory (the Q buffers, free by then) and TMA stores.
+// Same arguments and semantics as the first-generation kernel in attention.cu (two key segments, block-causal mask,
+// ragged lengths); fg_flash_attn picks between them.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = softmax of query
+// tile 0, warps 6..9 = softmax of query tile 1 (TMEM lane quarter = warp_idx % 4).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fg {
+
+constexpr int kA2Threads = 320;
+constexpr int kA2BKV = 128;
+
+template <int DP>
+struct Attn2Cfg {
+  static constexpr int DC = DP / 64;
+  static constexpr int Q_TILE_BYTES = DC * 128 * 128;
+  static constexpr int KV_TILE_BYTES = DC * kA2BKV * 128;
+  static constexpr int STAGES = DP == 128 ? 2 : 4;
+  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + STAGES * 2 * KV_TILE_BYTES + 1024 + 256;
+  static constexpr int TMEM_S = 0;        // S0 at 0, S1 at 128 (P aliases the first 64 columns of each)
+  static constexpr int TMEM_O = 256;      // O0 at 256, O1 at 256 + DP
+  static constexpr int TMEM_COLS = 512;
+  static_assert(256 + 2 * DP <= 512, "TMEM budget");
+};
+
+struct Attn2KParams {
+  CUtensorMap tmQ;     // dims (d, H, Tq, B), box (64, 1, 128, 1)
+  CUtensorMap tmK[2];  // dims (d, H, len_s, B), box (64, 1, 128, 1)
+  CUtensorMap tmV[2];
+  CUtensorMap tmO;     // dims (d, H, Tq, B) of the output, box (64, 1, 128, 1)
+  int32_t B, Tq, H, d;
+  int32_t kv_len[2];
+  int32_t mask_first, mask_chunk;
+  float scale_log2;
+  // split-KV: CTA (.., split) handles an equal share of the key tiles and writes a partial result -- its own
+  // normalised O (bf16, through tmO, which then maps the workspace [B*H][Tq][nsplit][DP]) and (max, sum) per row --
+  // that attn2_merge_kernel combines.  nsplit == 1: the final output is written directly.
+  int32_t nsplit;
+  float2* part_ml;  // [B*H][Tq][nsplit]
+};
+
+__device__ __forceinline__ int causal_limit2(const Attn2KParams& p, int tok) {
+  if (p.mask_chunk == 0) return 0x7fffffff;
+  if (tok < p.mask_first) return p.mask_first;
+  return p.mask_first + ((tok - p.mask_first) / p.mask_chunk + 1) * p.mask_chunk;
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2) and the 3-input max of sm_100: the softmax inner loop is bound by
+//      instruction issue and by the 16/clk MUFU unit, so every pair of elements shares its FMA-pipe instructions ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float exp2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for a pair, on the FMA pipe: x = n + f with f in [-0.5, 0.5] (adding 1.5 * 2^23 rounds to the nearest integer
+// and leaves n in the low mantissa bits), 2^f by a degree-3 polynomial (max relative error 1.8e-4; the result is
+// rounded to bf16 anyway), 2^n by adding n << 23 to the exponent field -- (bits(x + magic) << 23) is exactly n << 23.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);
+  const uint64_t xr = fadd2(x2, magic);
+  const uint64_t tr = fadd2(xr, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = ffma2(tr, pack2(-1.0f, -1.0f), x2);
+  uint64_t pl = ffma2(f, pack2(0.05460262f, 0.05460262f), pack2(0.24192413f, 0.24192413f));
+  pl = ffma2(pl, f, pack2(0.69331648f, 0.69331648f));
+  pl = ffma2(pl, f, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(pl, p0, p1);
+  unpack2(xr, r0, r1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
+template <int DP, int POLY>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+__global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+  using Cfg = Attn2Cfg<DP>;
+  constexpr int BKV = kA2BKV;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // tile t at t * Q_TILE_BYTES
+  uint8_t* sKV = sQ + 2 * Cfg::Q_TILE_BYTES;        // stage s: K at s*2*KV_TILE_BYTES, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + S * 2 * Cfg::KV_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;        // [S]
+  uint64_t* kv_empty = kv_full + S;    // [S]
+  uint64_t* s_full = kv_empty + S;     // [2]
+  uint64_t* p_full = s_full + 2;       // [2]
+  uint64_t* pv_done = p_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_blocks = (p.Tq + 255) / 256;
+  const int split = blockIdx.x % p.nsplit;
+  const int qb = (blockIdx.x / p.nsplit) % q_blocks;
+  const int head = (blockIdx.x / (p.nsplit * q_blocks)) % p.H;
+  const int img = blockIdx.x / (p.nsplit * q_blocks * p.H);
+  const int q0 = qb * 256;
+  int len0 = p.kv_len[0];
+  if (p.mask_chunk) len0 = min(len0, causal_limit2(p, min(q0 + 256, p.Tq) - 1));
+  const int n0 = (len0 + BKV - 1) / BKV;
+  const int n1 = (p.kv_len[1] + BKV - 1) / BKV;
+  // this CTA's share [jb, jb + nkv) of the n0 + n1 key tiles
+  const int jb = static_cast<int>(static_cast<int64_t>(n0 + n1) * split / p.nsplit);
+  const int nkv = static_cast<int>(static_cast<int64_t>(n0 + n1) * (split + 1) / p.nsplit) - jb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK[0]);
+    tma_prefetch_desc(&p.tmV[0]);
+    tma_prefetch_desc(&p.tmO);
+    if (n1) {
+      tma_prefetch_desc(&p.tmK[1]);
+      tma_prefetch_desc(&p.tmV[1]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < S; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 4);
+        mbar_init(&pv_done[i], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int dc = 0; dc < Cfg::DC; ++dc)
+          tma_load_4d(sQ + t * Cfg::Q_TILE_BYTES + dc * 128 * 128, &p.tmQ, q_full, dc * 64, head, q0 + t * 128, img);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        const int seg = (jb + j) >= n0;
+        const int row0 = (seg ? jb + j - n0 : jb + j) * BKV;
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        uint8_t* sk = sKV + stage * 2 * Cfg::KV_TILE_BYTES;
+        uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * Cfg::KV_TILE_BYTES);
+        for (int dc = 0; dc < Cfg::DC; ++dc) {
+          tma_load_4d(sk + dc * BKV * 128, &p.tmK[seg], &kv_full[stage], dc * 64, head, row0, img);
+          tma_load_4d(sv + dc * BKV * 128, &p.tmV[seg], &kv_full[stage], dc * 64, head, row0, img);
+        }
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0 && nkv > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DP, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_qk = [&](int t, int stage) {
+        const uint32_t k_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES);
+        const uint32_t qa = q_addr + t * Cfg::Q_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
+#pragma unroll
+        for (int dc = 0; dc < Cfg::DC; ++dc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
+                         umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk, (dc | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int stage, int j) {
+        const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
+        const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP);
+        const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_bf16_ts(o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv,
+                       (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&pv_done[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == S) {
+          nstage = 0;
+          nphase ^= 1u;
+        }
+        const bool more = j + 1 < nkv;
+        // query tile 0: O0 += P0.V_j, then S0 <- Q0.K_{j+1}^T (overwrites P0: issued after the product that reads it)
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, stage, j);
+        if (more) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_qk(0, nstage);
+        }
+        // query tile 1
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, stage, j);
+        umma_commit(&kv_empty[stage]);  // every reader of K_j / V_j has been issued before this commit
+        if (more) issue_qk(1, nstage);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int q = warp & 3;         // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const int tok = q0 + t * 128 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
+    const uint32_t o_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP);
+    const int limit = causal_limit2(p, tok);
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY;  // running max in scaled (log2) units
+    float l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t sv[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c]);
+        tmem_ld_32x32(s_addr + c, chunk);
+      }
+      tmem_ld_wait();
+      const int seg = (jb + j) >= n0;
+      const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
+      int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
+      if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
+      if (kv_valid < BKV) {  // ragged end of a segment / causal limit inside this tile (rare)
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (c >= kv_valid) sv[c] = 0xff800000u;  // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 2) mx = fmax3(mx, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+      mx *= sc;  // scale > 0: max commutes with the scaling
+      if (j > 0) {
+        const bool need = mx > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);  // O stable until this tile's P is published
+          tc_fence_after();
+          const float m_new = need ? mx : m_run;
+          const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < DP; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+      } else {
+        m_run = mx;
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
+      uint64_t lsum2 = pack2(0.f, 0.f);
+      // P = exp2(s * scale - m) as bf16, written over the S columns: 32 keys -> 16 packed columns per store.
+      // kPolyOf8 of every 8 pairs take the polynomial, the rest the MUFU unit (balances MUFU time against issue slots)
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c + i]), __uint_as_float(sv[c + i + 1])), sc2, negm2);
+          float e0, e1;
+          if (((i >> 1) & 7) < POLY) {
+            exp2_poly2(x2, e0, e1);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
+          }
+          lsum2 = fadd2(lsum2, pack2(e0, e1));
+          pk[i >> 1] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x16(s_addr + (c >> 1), pk);
+      }
+      float lsum0, lsum1;
+      unpack2(lsum2, lsum0, lsum1);
+      l_run += lsum0 + lsum1;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ----
+    if (nkv) {
+      mbar_wait(&pv_done[t], (nkv - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    uint8_t* so = sQ + t * Cfg::Q_TILE_BYTES;
+#pragma unroll 1
+    for (int c = 0; c < DP; c += 32) {
+      uint32_t o[32];
+      if (nkv) {
+        tmem_ld_32x32(o_addr + c, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      uint8_t* rowp = so + (c >> 6) * (128 * 128) + row * 128;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        const int chunk = ((c & 63) + i) >> 3;
+        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + t, 128);
+    if (p.nsplit > 1 && tok < p.Tq)
+      p.part_ml[(static_cast<int64_t>(img * p.H + head) * p.Tq + tok) * p.nsplit + split] = make_float2(m_run, l_run);
+    if (q == 0 && lane == 0 && q0 + t * 128 < p.Tq) {
+      for (int dc = 0; dc < Cfg::DC; ++dc) {
+        if (p.nsplit > 1)
+          tma_store_4d(&p.tmO, so + dc * 128 * 128, dc * 64, split, q0 + t * 128, img * p.H + head);
+        else if (dc * 64 < p.d)
+          tma_store_4d(&p.tmO, so + dc * 128 * 128, dc * 64, head, q0 + t * 128, img);
+      }
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// out[b, tok, h, :] = sum_s w_s O_s / sum_s w_s,  w_s = l_s 2^(m_s - max m): one warp per (b, h, tok)
+template <int DP>
+__global__ void __launch_bounds__(256) attn2_merge_kernel(const __nv_bfloat16* __restrict__ part_o,
+                                                          const float2* __restrict__ part_ml, int B, int H, int Tq,
+                                                          int d, int nsplit, __nv_bfloat16* __restrict__ out,
+                                                          int64_t out_ld, int64_t out_bs) {
+  constexpr int EPL = DP / 32;  // elements per lane
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = static_cast<int64_t>(B) * H * Tq;
+  for (int64_t r = blockIdx.x * 8ll + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8ll) {
+    const int tok = static_cast<int>(r % Tq);
+    const int bh = static_cast<int>(r / Tq);
+    const float2* ml = part_ml + r * nsplit;
+    float m = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, ml[s].x);
+    float acc[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+    float wsum = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float2 v = ml[s];
+      if (v.y <= 0.f) continue;
+      const float w = v.y * exp2f(v.x - m);
+      wsum += w;
+      const __nv_bfloat16* po = part_o + (r * nsplit + s) * DP + lane * EPL;
+      if constexpr (EPL == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(po);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        acc[0] = fmaf(w, a.x, acc[0]), acc[1] = fmaf(w, a.y, acc[1]), acc[2] = fmaf(w, b.x, acc[2]), acc[3] = fmaf(w, b.y, acc[3]);
+      } else {
+        const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(po));
+        acc[0] = fmaf(w, a.x, acc[0]), acc[1] = fmaf(w, a.y, acc[1]);
+      }
+    }
+    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+    const int c = lane * EPL;
+    if (c < d) {
+      __nv_bfloat16* o = out + static_cast<int64_t>(bh / H) * out_bs + static_cast<int64_t>(tok) * out_ld + (bh % H) * d + c;
+      if constexpr (EPL == 4) {
+        uint2 u;
+        u.x = pack_bf16x2(acc[0] * inv, acc[1] * inv), u.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+        *reinterpret_cast<uint2*>(o) = u;
+      } else {
+        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+      }
+    }
+  }
+}
+
+// number of KV splits: minimise (waves of CTAs over the SMs) x (key tiles per CTA + fixed per-CTA cost, in key-tile
+// units: Q load, pipeline fill, partial-result epilogue); one more tile-time for the merge pass when splitting
+static int pick_nsplit(int ctas, int kv_tiles, int num_sms) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ns = 1; ns <= 8 && ns <= kv_tiles; ++ns) {
+    const int64_t waves = (static_cast<int64_t>(ctas) * ns + num_sms - 1) / num_sms;
+    const double cost = static_cast<double>(waves) * (static_cast<double>(kv_tiles) / ns + 5.0) + (ns > 1 ? 2.0 : 0.0);
+    if (cost < best_cost * 0.97) {  // split only for a clear win
+      best_cost = cost;
+      best = ns;
+    }
+  }
+  return best;
+}
+
+size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
+  const int dp = p->d <= 64 ? 64 : 128;
+  const size_t rows = static_cast<size_t>(p->batch) * p->heads * p->tq;
+  return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256;  // up to 8 splits: bf16 O + (m, l)
+}
+
+template <int DP, int POLY>
+static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
+  using Cfg = Attn2Cfg<DP>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return FG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  Attn2KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = p->batch, kp.Tq = p->tq, kp.H = p->heads, kp.d = p->d;
+  kp.kv_len[0] = p->kv_len[0], kp.kv_len[1] = p->kv_len[1];
+  kp.mask_first = p->mask_chunk > 0 ? p->mask_first : 0;
+  kp.mask_chunk = p->mask_chunk;
+  kp.scale_log2 = 1.4426950408889634f * scale;
+  const uint32_t box[4] = {64, 1, 128, 1};
+  const int q_blocks = (kp.Tq + 255) / 256;
+  // split the key range over several CTAs when the (sample, head, query block) grid alone leaves SMs idle or ends in
+  // a mostly empty wave; needs the caller's workspace, and is not combined with the causal mask (uneven key counts)
+  int nsplit = 1;
+  __nv_bfloat16* part_o = nullptr;
+  if (p->workspace && static_cast<size_t>(p->workspace_bytes) >= flash_attn_v2_workspace(p) && p->mask_chunk == 0) {
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int force = getenv("FG_ATTN_SPLIT") ? atoi(getenv("FG_ATTN_SPLIT")) : 0;
+    const int tiles = (kp.kv_len[0] + kA2BKV - 1) / kA2BKV + (kp.kv_len[1] + kA2BKV - 1) / kA2BKV;
+    nsplit = force > 0 ? (force < tiles ? force : tiles) : pick_nsplit(kp.B * kp.H * q_blocks, tiles, num_sms);
+    if (nsplit > 8) nsplit = 8;
+    if (nsplit > 1) {
+      const size_t rows = static_cast<size_t>(kp.B) * kp.H * kp.Tq;
+      kp.part_ml = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(p->workspace) + 255) & ~uintptr_t(255));
+      part_o = reinterpret_cast<__nv_bfloat16*>(kp.part_ml + rows * nsplit);
+      part_o = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(part_o) + 127) & ~uintptr_t(127));
+    }
+  }
+  kp.nsplit = nsplit;
+  {
+    const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)kp.H, (uint64_t)kp.Tq, (uint64_t)kp.B};
+    const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, (uint64_t)p->q_ld * 2, (uint64_t)p->q_bs * 2};
+    int r = encode_tmap_bf16(&kp.tmQ, p->q, 4, dims, strides, box);
+    if (r != FG_OK) return r;
+    if (nsplit > 1) {
+      const uint64_t pdims[4] = {(uint64_t)DP, (uint64_t)nsplit, (uint64_t)kp.Tq, (uint64_t)kp.B * kp.H};
+      const uint64_t pstrides[4] = {2, (uint64_t)DP * 2, (uint64_t)DP * nsplit * 2, (uint64_t)DP * nsplit * kp.Tq * 2};
+      r = encode_tmap_bf16(&kp.tmO, part_o, 4, pdims, pstrides, box);
+    } else {
+      const uint64_t ostrides[4] = {2, (uint64_t)kp.d * 2, (uint64_t)p->out_ld * 2, (uint64_t)p->out_bs * 2};
+      r = encode_tmap_bf16(&kp.tmO, p->out, 4, dims, ostrides, box);
+    }
+    if (r != FG_OK) return r;
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int src = kp.kv_len[s] > 0 ? s : 0;
+    const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)kp.H, (uint64_t)kp.kv_len[src], (uint64_t)kp.B};
+    const uint64_t strides[4] = {2, (uint64_t)kp.d * 2, (uint64_t)p->kv_ld[src] * 2, (uint64_t)p->kv_bs[src] * 2};
+    int r = encode_tmap_bf16(&kp.tmK[s], p->k[src], 4, dims, strides, box);
+    if (r != FG_OK) return r;
+    r = encode_tmap_bf16(&kp.tmV[s], p->v[src], 4, dims, strides, box);
+    if (r != FG_OK) return r;
+  }
+  const int grid = kp.B * kp.H * q_blocks * nsplit;
+  attention2_kernel<DP, POLY><<<grid, kA2Threads, Cfg::SMEM_BYTES, stream>>>(kp);
+  FG_CHECK_LAUNCH("flash_attn");
+  if (nsplit > 1) {
+    const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
+    const int mgrid = static_cast<int>(rows / 8 + 1 < 148 * 8 ? rows / 8 + 1 : 148 * 8);
+    attn2_merge_kernel<DP><<<mgrid, 256, 0, stream>>>(part_o, kp.part_ml, kp.B, kp.H, kp.Tq, kp.d, nsplit,
+                                                      static_cast<__nv_bfloat16*>(p->out), p->out_ld, p->out_bs);
+    FG_CHECK_LAUNCH("flash_attn_merge");
+  }
+  return FG_OK;
+}
+
+// called by fg_flash_attn after argument validation
+int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
+  static const int poly = getenv("FG_ATTN_POLY") ? atoi(getenv("FG_ATTN_POLY")) : 2;  // (0|2|3|4: tuning experiments)
+  if (p->d <= 64) {
+    if (poly == 0) return launch_attention2<64, 0>(p, scale, stream);
+    if (poly == 3) return launch_attention2<64, 3>(p, scale, stream);
+    if (poly == 4) return launch_attention2<64, 4>(p, scale, stream);
+    return launch_attention2<64, 2>(p, scale, stream);
+  }
+  if (poly == 0) return launch_attention2<128, 0>(p, scale, stream);
+  if (poly == 3) return launch_attention2<128, 3>(p, scale, stream);
+  if (poly == 4) return launch_attention2<128, 4>(p, scale, stream);
+  return launch_attention2<128, 2>(p, scale, stream);
+}
+
+}  // namespace fg

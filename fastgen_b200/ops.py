@@ -221,7 +221,8 @@ def launch_count_reset() -> None:
 # ---------------------------------------------------------------------------------------------------------
 def flash_attn_params(q: torch.Tensor, q_ld: int, q_bs: int, segs: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int, int]],
                       batch: int, heads: int, d: int, tq: int, out: torch.Tensor, out_ld: int, out_bs: int,
-                      scale: float = 0.0, mask_first: int = 0, mask_chunk: int = 0) -> "L.FlashAttnParams":
+                      scale: float = 0.0, mask_first: int = 0, mask_chunk: int = 0,
+                      workspace: Optional[torch.Tensor] = None) -> "L.FlashAttnParams":
     """``segs``: up to two key/value segments ``(k, v, ld, batch_stride, length)`` (cache prefix, current chunk)."""
     if not 1 <= len(segs) <= 2:
         raise ValueError("flash_attn: one or two key/value segments")
@@ -235,7 +236,14 @@ def flash_attn_params(q: torch.Tensor, q_ld: int, q_bs: int, segs: Sequence[Tupl
     p.batch, p.heads, p.d, p.tq = batch, heads, d, tq
     p.scale, p.mask_first, p.mask_chunk = scale, mask_first, mask_chunk
     p.out, p.out_ld, p.out_bs = out.data_ptr(), out_ld, out_bs
+    if workspace is not None:
+        _need_cuda(workspace)
+        p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     return p
+
+
+def flash_attn_workspace_size(p: "L.FlashAttnParams") -> int:
+    return int(L.lib().fg_flash_attn_workspace_size(C.byref(p)))
 
 
 def flash_attn(*args, **kwargs) -> None:

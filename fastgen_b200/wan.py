@@ -363,6 +363,10 @@ class _WanBase:
             emb=z(groups, cfg["freq_dim"]), te1=z(groups, D), temb=z(groups, D), temb_act=z(groups, D),
             tproj=z(groups, 6 * D, dt=f32), mod=z(cfg["layers"], groups, 6 * D, dt=f32), head_mod=z(groups, 2 * D, dt=f32),
         )
+        # scratch for the split-KV attention path (partial results of up to 8 key splits)
+        probe = L.FlashAttnParams()
+        probe.batch, probe.heads, probe.d, probe.tq = B, cfg["heads"] // P, cfg["head_dim"], n
+        ws["attn_ws"] = torch.empty(max(ops.flash_attn_workspace_size(probe), 16), device=dev, dtype=torch.uint8)
         if P > 1:
             # Ulysses exchange buffers: [P, B, n/P, 3, H/P, d] send/recv for q,k,v and [P, B, n/P, H/P, d] for the output
             Hl = cfg["heads"] // P
@@ -517,7 +521,7 @@ class _WanBase:
             else:
                 segs = [cur]
             mk = dict(mask_first=mask[0], mask_chunk=mask[1]) if mask else {}
-            p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, **mk)
+            p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, workspace=ws["attn_ws"], **mk)
             plan.keep.append(p)
             kv_tot = n + (cache_start if kv is not None else 0)
             plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * D)
@@ -530,7 +534,7 @@ class _WanBase:
             plan.keep.append(p)
             plan.add(lib.fg_qk_norm_rope, C.byref(p), desc="q2norm")
             p = ops.flash_attn_params(q2, D, n * D, [(ckv[i], ckv[i][:, D:], 2 * D, clen * 2 * D, clen)], B, H, d, n, att,
-                                      D, n * D)
+                                      D, n * D, workspace=ws["attn_ws"])
             plan.keep.append(p)
             plan.add(lib.fg_flash_attn, C.byref(p), desc="cross_attn", flops=4.0 * B * n * clen * D)
             self._gemm(plan, att, D, pk[f"{i}.o2.w"], rows, D, hs, D, "o2", bias=pk[f"{i}.o2.b"], res=hs, res_ld=D,

@@ -143,9 +143,13 @@ typedef struct {
   int32_t mask_first, mask_chunk;
   void* out;            /* bf16 [batch][tq][heads*d] */
   int64_t out_ld, out_bs;
+  void* workspace;      /* optional scratch of fg_flash_attn_workspace_size() bytes: lets the library split the key  */
+  int64_t workspace_bytes; /* range over several CTAs (partial results + merge) when the grid would leave SMs idle */
 } fg_flash_attn_params;
 
 int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream);
+/* bytes of scratch the split-KV path may use for this problem (0 if it never splits it) */
+int64_t fg_flash_attn_workspace_size(const fg_flash_attn_params* p);
 
 /* ------------------------------------------------------------------------------------------------------
  * Row kernels of the transformer blocks (Wan / DiT), all HBM-bound, bf16 rows in and out, fp32 statistics.

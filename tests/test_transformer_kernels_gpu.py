@@ -158,6 +158,16 @@ def test_flash_attn_segments(b, tq, heads, d, l0, l1):
     torch.cuda.synchronize()
     ref = _sdpa(q.view(b, tq, heads, d), k_all.reshape(b, -1, heads, d), v_all.reshape(b, -1, heads, d))
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    # with caller-provided scratch the library may split the key range over several CTAs and merge the partials
+    p = ops.flash_attn_params(q, dm, tq * dm, segs, b, heads, d, tq, out, dm, tq * dm)
+    wsz = ops.flash_attn_workspace_size(p)
+    if tq > 128 and d <= 128:
+        assert wsz > 0
+        ws = torch.empty(wsz, device=DEV, dtype=torch.uint8)
+        out2 = torch.zeros_like(out)
+        ops.flash_attn(q, dm, tq * dm, segs, b, heads, d, tq, out2, dm, tq * dm, workspace=ws)
+        torch.cuda.synchronize()
+        assert _rel(out2, ref) < 1e-2, _rel(out2, ref)
 
 
 @pytest.mark.parametrize("frames,chunk,fs", [(7, 3, 40), (6, 3, 130), (5, 2, 97)])
