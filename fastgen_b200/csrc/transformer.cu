@@ -140,6 +140,7 @@ struct QkK {
   const float* rope_sin;
   int rope_max_pos, nt, nh;
   int rows_per_batch, ppf, pph, ppw, frame0;
+  int frame_rows, tok0;    // rows of one frame held here and the in-frame index of the first (sequence-parallel shard)
   __nv_bfloat16* k_cache;  // [batch][cache_bs]: row (cache_row0 + t) * cache_ld
   __nv_bfloat16* v_cache;
   int64_t cache_ld, cache_bs;
@@ -200,9 +201,10 @@ __global__ void __launch_bounds__(kRowThreads) qk_norm_rope_kernel(const QkK p) 
     const int b = row / p.rows_per_batch, t = row % p.rows_per_batch;
     int pf = 0, ph = 0, pw = 0;
     if (p.rope_cos) {
-      pf = min(p.frame0 + t / (p.pph * p.ppw), p.rope_max_pos - 1);  // clamp like the reference pads with the last row
-      ph = (t / p.ppw) % p.pph;
-      pw = t % p.ppw;
+      pf = min(p.frame0 + t / p.frame_rows, p.rope_max_pos - 1);  // clamp like the reference pads with the last row
+      const int tf = p.tok0 + t % p.frame_rows;                     // token index inside its frame
+      ph = tf / p.ppw;
+      pw = tf % p.ppw;
     }
     __nv_bfloat16* kc = nullptr;
     if (p.k_cache) kc = p.k_cache + static_cast<int64_t>(b) * p.cache_bs + static_cast<int64_t>(p.cache_row0 + t) * p.cache_ld;
@@ -290,6 +292,32 @@ __global__ void unpatchify_kernel<__nv_bfloat16>(const __nv_bfloat16* __restrict
   }
 }
 
+// out[(i0, i1, i2, i3)] <- in[(i0, i1, i2, i3)] for a 4-D index space, 16-byte vectors, arbitrary strides on both sides
+struct CopyK {
+  const uint4* src;
+  uint4* dst;
+  int n[4];
+  int64_t ss[4], ds[4];  // strides in 16-byte units
+  int vec;               // 16-byte vectors per innermost item
+};
+__global__ void strided_copy_kernel(const CopyK p) {
+  const int64_t items = static_cast<int64_t>(p.n[0]) * p.n[1] * p.n[2] * p.n[3];
+  const int64_t total = items * p.vec;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % p.vec);
+    int64_t r = idx / p.vec;
+    const int i3 = static_cast<int>(r % p.n[3]);
+    r /= p.n[3];
+    const int i2 = static_cast<int>(r % p.n[2]);
+    r /= p.n[2];
+    const int i1 = static_cast<int>(r % p.n[1]);
+    const int i0 = static_cast<int>(r / p.n[1]);
+    p.dst[i0 * p.ds[0] + i1 * p.ds[1] + i2 * p.ds[2] + i3 * p.ds[3] + v] =
+        p.src[i0 * p.ss[0] + i1 * p.ss[1] + i2 * p.ss[2] + i3 * p.ss[3] + v];
+  }
+}
+
 __global__ void bcast_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int na, int nb, int d,
                                  float* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(na) * nb * d;
@@ -363,6 +391,9 @@ extern "C" int fg_qk_norm_rope(const fg_qk_norm_rope_params* p, fg_stream_t stre
                      p->nt + p->nh <= p->d / 2 && p->frame0 >= 0,
                  "qk_norm_rope: bad rotary table description");
     FG_CHECK_ARG(p->pph <= p->rope_max_pos && p->ppw <= p->rope_max_pos, "qk_norm_rope: grid exceeds the rotary table");
+    FG_CHECK_ARG(p->frame_rows >= 0 && p->tok0 >= 0 &&
+                     p->tok0 + (p->frame_rows > 0 ? p->frame_rows : p->pph * p->ppw) <= p->pph * p->ppw,
+                 "qk_norm_rope: frame shard [tok0, tok0 + frame_rows) exceeds the frame");
   }
   if (p->k_cache || p->v_cache) {
     FG_CHECK_ARG(p->k && p->k_cache && p->v_cache && p->v && p->v_ld >= dm && p->v_ld % 8 == 0 && al16(p->v) &&
@@ -378,6 +409,8 @@ extern "C" int fg_qk_norm_rope(const fg_qk_norm_rope_params* p, fg_stream_t stre
   k.wq = static_cast<const __nv_bfloat16*>(p->wq), k.wk = static_cast<const __nv_bfloat16*>(p->wk);
   k.rope_cos = p->rope_cos, k.rope_sin = p->rope_sin, k.rope_max_pos = p->rope_max_pos, k.nt = p->nt, k.nh = p->nh;
   k.rows_per_batch = p->rows_per_batch, k.ppf = p->ppf, k.pph = p->pph, k.ppw = p->ppw, k.frame0 = p->frame0;
+  k.frame_rows = p->frame_rows > 0 ? p->frame_rows : p->pph * p->ppw;
+  k.tok0 = p->tok0;
   k.k_cache = static_cast<__nv_bfloat16*>(p->k_cache), k.v_cache = static_cast<__nv_bfloat16*>(p->v_cache);
   k.cache_ld = p->cache_ld, k.cache_bs = p->cache_bs, k.cache_row0 = p->cache_row0;
   const int grid = row_grid(p->rows);
@@ -445,5 +478,23 @@ extern "C" int fg_bcast_add(const float* a, const float* b, int32_t na, int32_t 
   const int grid = ew_grid2(static_cast<int64_t>(na) * nb * d);
   bcast_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(a, b, na, nb, d, out);
   FG_CHECK_LAUNCH("bcast_add");
+  return FG_OK;
+}
+
+extern "C" int fg_strided_copy(const void* src, void* dst, const int32_t* n, const int64_t* src_strides,
+                               const int64_t* dst_strides, int32_t item_bytes, fg_stream_t stream_) {
+  using namespace fg;
+  FG_CHECK_ARG(src && dst && n && src_strides && dst_strides, "strided_copy: null pointer");
+  FG_CHECK_ARG(item_bytes > 0 && item_bytes % 16 == 0 && al16(src) && al16(dst), "strided_copy: items must be 16-byte multiples, 16-byte aligned");
+  CopyK k;
+  k.src = static_cast<const uint4*>(src), k.dst = static_cast<uint4*>(dst), k.vec = item_bytes / 16;
+  int64_t items = 1;
+  for (int i = 0; i < 4; ++i) {
+    FG_CHECK_ARG(n[i] > 0 && src_strides[i] % 16 == 0 && dst_strides[i] % 16 == 0, "strided_copy: extents must be positive, strides (bytes) multiples of 16");
+    k.n[i] = n[i], k.ss[i] = src_strides[i] / 16, k.ds[i] = dst_strides[i] / 16;
+    items *= n[i];
+  }
+  strided_copy_kernel<<<ew_grid2(items * k.vec), 256, 0, static_cast<cudaStream_t>(stream_)>>>(k);
+  FG_CHECK_LAUNCH("strided_copy");
   return FG_OK;
 }

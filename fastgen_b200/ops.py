@@ -275,7 +275,7 @@ def qk_norm_rope_params(q: Optional[torch.Tensor], k: Optional[torch.Tensor], q_
                         heads: int, d: int, eps: float, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor],
                         rows_per_batch: int,
                         rope: Optional[Tuple[torch.Tensor, torch.Tensor, int, int]] = None,
-                        grid: Tuple[int, int, int] = (1, 1, 1), frame0: int = 0,
+                        grid: Tuple[int, int, int] = (1, 1, 1), frame0: int = 0, frame_rows: int = 0, tok0: int = 0,
                         v: Optional[torch.Tensor] = None, v_ld: int = 0,
                         k_cache: Optional[torch.Tensor] = None, v_cache: Optional[torch.Tensor] = None,
                         cache_ld: int = 0, cache_bs: int = 0, cache_row0: int = 0) -> "L.QkNormRopeParams":
@@ -293,6 +293,7 @@ def qk_norm_rope_params(q: Optional[torch.Tensor], k: Optional[torch.Tensor], q_
         p.rope_cos, p.rope_sin, p.rope_max_pos, p.nt, p.nh = cos.data_ptr(), sin.data_ptr(), cos.shape[0], nt, nh
     p.rows_per_batch = rows_per_batch
     p.ppf, p.pph, p.ppw, p.frame0 = grid[0], grid[1], grid[2], frame0
+    p.frame_rows, p.tok0 = frame_rows, tok0
     p.k_cache, p.v_cache, p.cache_ld, p.cache_bs, p.cache_row0 = _ptr(k_cache), _ptr(v_cache), cache_ld, cache_bs, cache_row0
     return p
 
@@ -326,3 +327,21 @@ def bcast_add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
     nb = b.shape[0]
     assert b.shape[1] == d and out.numel() == na * nb * d and out.is_contiguous()
     L.check(L.lib().fg_bcast_add(a.data_ptr(), b.data_ptr(), na, nb, d, out.data_ptr(), _stream()), "fg_bcast_add")
+
+
+def strided_copy_args(src: torch.Tensor, dst: torch.Tensor, n: Sequence[int], src_strides: Sequence[int],
+                      dst_strides: Sequence[int], item_elems: int):
+    """ctypes arguments of ``fg_strided_copy`` for a 4-D index space; strides / item size in ELEMENTS of the tensors'
+    (common) dtype.  Returns (args tuple, keep-alive objects)."""
+    _need_cuda(src, dst)
+    assert src.dtype == dst.dtype and len(n) == 4
+    es = src.element_size()
+    na = (C.c_int32 * 4)(*n)
+    sa = (C.c_int64 * 4)(*[s * es for s in src_strides])
+    da = (C.c_int64 * 4)(*[s * es for s in dst_strides])
+    return (src.data_ptr(), dst.data_ptr(), na, sa, da, item_elems * es), (na, sa, da, src, dst)
+
+
+def strided_copy(src, dst, n, src_strides, dst_strides, item_elems) -> None:
+    args, _keep = strided_copy_args(src, dst, n, src_strides, dst_strides, item_elems)
+    L.check(L.lib().fg_strided_copy(*args, _stream()), "fg_strided_copy")

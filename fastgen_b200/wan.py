@@ -33,6 +33,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
+from . import parallel as PL
 from .network import CausalFastGenNetwork, FastGenNetwork
 from .noise_schedule import NET_PRED_TYPES
 
@@ -147,9 +148,16 @@ class _Plan:
     def add(self, fn, *args, desc: str = "", flops: float = 0.0):
         self.steps.append((fn, args, desc, flops))
 
+    def add_py(self, fn, desc: str):
+        """a host-side step (a torch.distributed collective on the current stream)"""
+        self.steps.append((fn, None, desc, 0.0))
+
     def run(self, stream: int, profile: Optional[Dict[str, Dict[str, float]]] = None) -> None:
         if profile is None:
             for fn, args, _, _ in self.steps:
+                if args is None:
+                    fn()
+                    continue
                 st = fn(*args, stream)
                 if st:
                     L.check(st, fn.__name__)
@@ -158,11 +166,15 @@ class _Plan:
         for fn, args, desc, fl in self.steps:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            st = fn(*args, stream)
+            if args is None:
+                fn()
+                st = 0
+            else:
+                st = fn(*args, stream)
             b.record()
             if st:
                 L.check(st, fn.__name__)
-            evs.append((fn.__name__ + (":" + desc if desc else ""), a, b, fl))
+            evs.append(((fn.__name__ if args is not None else "collective") + (":" + desc if desc else ""), a, b, fl))
         torch.cuda.synchronize()
         for name, a, b, fl in evs:
             d = profile.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
@@ -348,14 +360,18 @@ class _WanBase:
         n = F * (Hh // ph) * (Ww // pw)
         rows = B * n
         P = self._sp_size()
-        if n % P:
-            raise ValueError(f"tokens per sample ({n}) must divide by the sequence-parallel size ({P})")
+        fs_tok = (Hh // ph) * (Ww // pw)
+        if fs_tok % P or cfg["heads"] % P:
+            raise ValueError(f"sequence parallelism over {P} ranks needs tokens per frame ({fs_tok}) and heads "
+                             f"({cfg['heads']}) divisible by {P}")
         lrows = rows // P                      # rows this rank owns
         bf, f32 = torch.bfloat16, torch.float32
         z = lambda *s, dt=bf: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
         kin = cfg["in_channels"] * ph * pw
         kout = cfg["out_channels"] * ph * pw
         groups = B * F
+        Hl = cfg["heads"] // P
+        Dl = Hl * cfg["head_dim"]
         ws = dict(
             x_in=z(B, cfg["in_channels"], F, Hh, Ww, dt=x_dtype), tok=z(rows, kin), hs=z(lrows, D), nrm=z(lrows, D),
             qkv=z(lrows, 3 * D), att=z(lrows, D), q2=z(lrows, D), f1=z(lrows, Fd), tok_out=z(rows, kout),
@@ -363,15 +379,14 @@ class _WanBase:
             emb=z(groups, cfg["freq_dim"]), te1=z(groups, D), temb=z(groups, D), temb_act=z(groups, D),
             tproj=z(groups, 6 * D, dt=f32), mod=z(cfg["layers"], groups, 6 * D, dt=f32), head_mod=z(groups, 2 * D, dt=f32),
         )
+        if P > 1:
+            # Ulysses exchange buffers (per sample b: [P][n/P][3][H/P*d] for q,k,v and [P][n/P][H/P*d] for the output)
+            ws.update(hs_full=z(rows, D), a2a_s=z(B, P, n // P, 3 * Dl), qkv_full=z(B, n, 3 * Dl), att_full=z(B, n, Dl),
+                      a2a_r=z(B, P, n // P, Dl), tok_out_l=z(lrows, kout), tok_out_g=z(P, lrows, kout))
         # scratch for the split-KV attention path (partial results of up to 8 key splits)
         probe = L.FlashAttnParams()
         probe.batch, probe.heads, probe.d, probe.tq = B, cfg["heads"] // P, cfg["head_dim"], n
         ws["attn_ws"] = torch.empty(max(ops.flash_attn_workspace_size(probe), 16), device=dev, dtype=torch.uint8)
-        if P > 1:
-            # Ulysses exchange buffers: [P, B, n/P, 3, H/P, d] send/recv for q,k,v and [P, B, n/P, H/P, d] for the output
-            Hl = cfg["heads"] // P
-            ws.update(a2a_s=z(P * B * (n // P) * 3 * Hl * cfg["head_dim"]), a2a_r=z(P * B * (n // P) * 3 * Hl * cfg["head_dim"]),
-                      qkv_full=z(B * n, 3 * Hl * cfg["head_dim"]), att_full=z(B * n, Hl * cfg["head_dim"]))
         self._ws[key] = ws
         return ws
 
@@ -464,14 +479,28 @@ class _WanBase:
             ent["key"] = None
 
     # ---- the forward plan --------------------------------------------------------------------------------
+    def _copy(self, plan: _Plan, src, dst, n, ss, ds, item, desc):
+        args, keep = ops.strided_copy_args(src, dst, n, ss, ds, item)
+        plan.keep.append(keep)
+        plan.add(L.lib().fg_strided_copy, *args, desc=desc)
+
+    def _copy_desc(self, plan: _Plan, src, dst, dsc, desc):
+        self._copy(plan, src.reshape(-1)[dsc["src_off"]:], dst.reshape(-1)[dsc["dst_off"]:], dsc["n"], dsc["ss"],
+                   dsc["ds"], dsc["item"], desc)
+
     def _build_plan(self, B, F, Hh, Ww, x_dtype, per_frame: bool, kv: Optional[Dict[str, Any]], cache_start: int,
                     store_kv: bool, frame0: int, mask: Optional[Tuple[int, int]], cross: Dict[str, Any]) -> _Plan:
+        """Launch list of one forward.  With sequence parallelism (P ranks) a rank owns tokens
+        [rank * fs/P, (rank+1) * fs/P) of EVERY frame (so modulation groups stay contiguous), all heads; around each
+        self-attention q/k/v are exchanged to (all tokens, H/P heads) and the output back (Ulysses); the KV cache holds
+        this rank's heads only."""
         cfg, pk = self.cfg, self._packed
         lib = L.lib()
         D, Fd, H, d = cfg["dim"], cfg["ffn_dim"], cfg["heads"], cfg["head_dim"]
         _, ph, pw = cfg["patch"]
         pph, ppw = Hh // ph, Ww // pw
-        n = F * pph * ppw
+        fs = pph * ppw
+        n = F * fs
         rows = B * n
         ws = self._workspace(B, F, Hh, Ww, x_dtype)
         plan = _Plan()
@@ -480,12 +509,19 @@ class _WanBase:
         kin = cfg["in_channels"] * ph * pw
         kout = cfg["out_channels"] * ph * pw
         P, rank = self._sp_size(), self._sp_rank()
-        if P > 1:
-            raise NotImplementedError("sequence-parallel plans are built by fastgen_b200.parallel_wan")
-        # ---- embeddings ----
+        fs_l, n_l = fs // P, n // P
+        lrows = B * n_l                 # token rows this rank owns
+        Hl, Dl = H // P, (H // P) * d   # heads this rank attends with
+        if P > 1 and mask:
+            raise NotImplementedError("the block-causal mask (full-sequence causal forward) is not sequence-parallel")
+        if P > 1 and not per_frame:
+            # global AdaLN: one group per sample; local rows of a sample are contiguous, so nothing else changes
+            pass
+        # ---- embeddings (steps 0..6: see _run_split) ----
         plan.add(lib.fg_patchify, ws["x_in"].data_ptr(), ops._DT[x_dtype], B, cfg["in_channels"], F, Hh, Ww, ph, pw,
                  ws["tok"].data_ptr(), kin, desc="patchify")
-        self._gemm(plan, ws["tok"], kin, pk["patch.w"], rows, D, ws["hs"], D, "patch", bias=pk["patch.b"])
+        self._gemm(plan, ws["tok"], kin, pk["patch.w"], rows, D, ws["hs_full"] if P > 1 else ws["hs"], D, "patch",
+                   bias=pk["patch.b"])
         self._gemm(plan, ws["emb"], cfg["freq_dim"], pk["t1.w"], groups, D, ws["te1"], D, "time1", bias=pk["t1.b"],
                    act=L.FG_ACT_SILU)
         self._gemm(plan, ws["te1"], D, pk["t2.w"], groups, D, ws["temb"], D, "time2", bias=pk["t2.b"])
@@ -494,64 +530,93 @@ class _WanBase:
         self._gemm(plan, ws["temb_act"], D, pk["tp.w"], groups, 6 * D, ws["tproj"], 6 * D, "tproj", bias=pk["tp.b"])
         plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["tproj"].data_ptr(), cfg["layers"], groups, 6 * D,
                  ws["mod"].data_ptr(), desc="mod")
-        rpg = pph * ppw if per_frame else n   # rows sharing one modulation vector
-        mod_groups = groups if per_frame else B
-        if not per_frame and F != 1:
-            # global AdaLN: the [B] timesteps were staged once per sample; groups == B
-            pass
         hs, nrm, qkv, att, q2, f1 = ws["hs"], ws["nrm"], ws["qkv"], ws["att"], ws["q2"], ws["f1"]
+        if P > 1:
+            # this rank's token rows (b, f, i) <- global rows (b, f, rank*fs_l + i)
+            self._copy_desc(plan, ws["hs_full"], hs, PL.shard_rows_desc(B, F, fs, P, rank, D), "shard")
+            import torch.distributed as dist
+
+            group = self.sp_group
+        rpg = fs_l if per_frame else n_l   # local rows sharing one modulation vector
         ckv, clen = cross["kv"], cross["len"]
+        cap = kv["k"].shape[2] if kv is not None else 0
         for i in range(cfg["layers"]):
             mod = ws["mod"][i]                                      # [groups, 6D]
             m = lambda j: mod[:, j * D:(j + 1) * D]                 # noqa: E731
             # 1. self-attention
-            self._ln(plan, hs, rows, nrm, "ln1", scale=m(1), shift=m(0), mod_ld=6 * D, rows_per_group=rpg)
-            self._gemm(plan, nrm, D, pk[f"{i}.qkv.w"], rows, 3 * D, qkv, 3 * D, "qkv", bias=pk[f"{i}.qkv.b"])
+            self._ln(plan, hs, lrows, nrm, "ln1", scale=m(1), shift=m(0), mod_ld=6 * D, rows_per_group=rpg)
+            self._gemm(plan, nrm, D, pk[f"{i}.qkv.w"], lrows, 3 * D, qkv, 3 * D, "qkv", bias=pk[f"{i}.qkv.b"])
             kw = {}
-            if kv is not None and store_kv:
+            if P == 1 and kv is not None and store_kv:
                 kw = dict(v=qkv[:, 2 * D:], v_ld=3 * D, k_cache=kv["k"][i], v_cache=kv["v"][i], cache_ld=D,
-                          cache_bs=kv["k"].shape[2] * D, cache_row0=cache_start)
-            p = ops.qk_norm_rope_params(qkv, qkv[:, D:], 3 * D, 3 * D, rows, H, d, cfg["eps"], pk[f"{i}.nq1"],
-                                        pk[f"{i}.nk1"], n, rope=pk["rope"], grid=(F, pph, ppw), frame0=frame0, **kw)
+                          cache_bs=cap * D, cache_row0=cache_start)
+            p = ops.qk_norm_rope_params(qkv, qkv[:, D:], 3 * D, 3 * D, lrows, H, d, cfg["eps"], pk[f"{i}.nq1"],
+                                        pk[f"{i}.nk1"], n_l, rope=pk["rope"], grid=(F, pph, ppw), frame0=frame0,
+                                        frame_rows=fs_l, tok0=rank * fs_l, **kw)
             plan.keep.append(p)
             plan.add(lib.fg_qk_norm_rope, C.byref(p), desc="qknorm_rope")
-            cur = (qkv[:, D:], qkv[:, 2 * D:], 3 * D, n * 3 * D, n)
-            if kv is not None and cache_start > 0:
-                segs = [(kv["k"][i], kv["v"][i], D, kv["k"].shape[2] * D, cache_start), cur]
-            else:
-                segs = [cur]
             mk = dict(mask_first=mask[0], mask_chunk=mask[1]) if mask else {}
-            p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, workspace=ws["attn_ws"], **mk)
-            plan.keep.append(p)
             kv_tot = n + (cache_start if kv is not None else 0)
-            plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * D)
-            self._gemm(plan, att, D, pk[f"{i}.o1.w"], rows, D, hs, D, "o1", bias=pk[f"{i}.o1.b"], gate=m(2), gate_ld=6 * D,
+            if P == 1:
+                cur = (qkv[:, D:], qkv[:, 2 * D:], 3 * D, n * 3 * D, n)
+                segs = [(kv["k"][i], kv["v"][i], D, cap * D, cache_start), cur] if kv is not None and cache_start > 0 else [cur]
+                p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, workspace=ws["attn_ws"], **mk)
+                plan.keep.append(p)
+                plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * D)
+            else:
+                send, full, attf, recv = ws["a2a_s"], ws["qkv_full"], ws["att_full"], ws["a2a_r"]
+                # pack: qkv[b][r][j][dst][Dl] -> send[b][dst][r][j][Dl]   (one launch per sample keeps it 4-D)
+                for b in range(B):
+                    self._copy_desc(plan, qkv[b * n_l:(b + 1) * n_l], send[b], PL.a2a_pack_desc(n_l, P, D, Dl), "a2a_pack")
+                    plan.add_py(lambda o=full[b], s_=send[b]: dist.all_to_all_single(o, s_, group=group), "a2a_qkv")
+                # full[b] = [src][r][3][Dl] = all n tokens of the chunk (gathered order) x this rank's heads
+                if kv is not None and store_kv:
+                    self._copy(plan, full[:, :, Dl:], kv["k"][i][:, cache_start:], [B, n, 1, 1], [n * 3 * Dl, 3 * Dl, 0, 0],
+                               [cap * Dl, Dl, 0, 0], Dl, "k_append")
+                    self._copy(plan, full[:, :, 2 * Dl:], kv["v"][i][:, cache_start:], [B, n, 1, 1],
+                               [n * 3 * Dl, 3 * Dl, 0, 0], [cap * Dl, Dl, 0, 0], Dl, "v_append")
+                cur = (full[:, :, Dl:], full[:, :, 2 * Dl:], 3 * Dl, n * 3 * Dl, n)
+                segs = [(kv["k"][i], kv["v"][i], Dl, cap * Dl, cache_start), cur] if kv is not None and cache_start > 0 else [cur]
+                p = ops.flash_attn_params(full, 3 * Dl, n * 3 * Dl, segs, B, Hl, d, n, attf, Dl, n * Dl,
+                                          workspace=ws["attn_ws"])
+                plan.keep.append(p)
+                plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * Dl)
+                for b in range(B):
+                    plan.add_py(lambda o=recv[b], s_=attf[b]: dist.all_to_all_single(o, s_, group=group), "a2a_out")
+                # unpack: recv[b][src][r][Dl] -> att[b][r][src][Dl]
+                self._copy_desc(plan, recv, att, PL.a2a_unpack_desc(B, P, n_l, D, Dl), "a2a_unpack")
+            self._gemm(plan, att, D, pk[f"{i}.o1.w"], lrows, D, hs, D, "o1", bias=pk[f"{i}.o1.b"], gate=m(2), gate_ld=6 * D,
                        gate_rows=rpg, res=hs, res_ld=D, res_mode=L.FG_RES_SAME)
-            # 2. cross-attention
-            self._ln(plan, hs, rows, nrm, "ln2", gamma=pk[f"{i}.n2.g"], beta=pk[f"{i}.n2.b"])
-            self._gemm(plan, nrm, D, pk[f"{i}.q2.w"], rows, D, q2, D, "q2", bias=pk[f"{i}.q2.b"])
-            p = ops.qk_norm_rope_params(q2, None, D, 0, rows, H, d, cfg["eps"], pk[f"{i}.nq2"], None, n)
+            # 2. cross-attention (text keys replicated on every rank: no exchange)
+            self._ln(plan, hs, lrows, nrm, "ln2", gamma=pk[f"{i}.n2.g"], beta=pk[f"{i}.n2.b"])
+            self._gemm(plan, nrm, D, pk[f"{i}.q2.w"], lrows, D, q2, D, "q2", bias=pk[f"{i}.q2.b"])
+            p = ops.qk_norm_rope_params(q2, None, D, 0, lrows, H, d, cfg["eps"], pk[f"{i}.nq2"], None, n_l)
             plan.keep.append(p)
             plan.add(lib.fg_qk_norm_rope, C.byref(p), desc="q2norm")
-            p = ops.flash_attn_params(q2, D, n * D, [(ckv[i], ckv[i][:, D:], 2 * D, clen * 2 * D, clen)], B, H, d, n, att,
-                                      D, n * D, workspace=ws["attn_ws"])
+            p = ops.flash_attn_params(q2, D, n_l * D, [(ckv[i], ckv[i][:, D:], 2 * D, clen * 2 * D, clen)], B, H, d, n_l,
+                                      att, D, n_l * D, workspace=ws["attn_ws"] if P == 1 else None)
             plan.keep.append(p)
-            plan.add(lib.fg_flash_attn, C.byref(p), desc="cross_attn", flops=4.0 * B * n * clen * D)
-            self._gemm(plan, att, D, pk[f"{i}.o2.w"], rows, D, hs, D, "o2", bias=pk[f"{i}.o2.b"], res=hs, res_ld=D,
+            plan.add(lib.fg_flash_attn, C.byref(p), desc="cross_attn", flops=4.0 * B * n_l * clen * D)
+            self._gemm(plan, att, D, pk[f"{i}.o2.w"], lrows, D, hs, D, "o2", bias=pk[f"{i}.o2.b"], res=hs, res_ld=D,
                        res_mode=L.FG_RES_SAME)
             # 3. feed-forward
-            self._ln(plan, hs, rows, nrm, "ln3", scale=m(4), shift=m(3), mod_ld=6 * D, rows_per_group=rpg)
-            self._gemm(plan, nrm, D, pk[f"{i}.f1.w"], rows, Fd, f1, Fd, "ffn1", bias=pk[f"{i}.f1.b"],
+            self._ln(plan, hs, lrows, nrm, "ln3", scale=m(4), shift=m(3), mod_ld=6 * D, rows_per_group=rpg)
+            self._gemm(plan, nrm, D, pk[f"{i}.f1.w"], lrows, Fd, f1, Fd, "ffn1", bias=pk[f"{i}.f1.b"],
                        act=L.FG_ACT_GELU_TANH)
-            self._gemm(plan, f1, Fd, pk[f"{i}.f2.w"], rows, D, hs, D, "ffn2", bias=pk[f"{i}.f2.b"], gate=m(5),
+            self._gemm(plan, f1, Fd, pk[f"{i}.f2.w"], lrows, D, hs, D, "ffn2", bias=pk[f"{i}.f2.b"], gate=m(5),
                        gate_ld=6 * D, gate_rows=rpg, res=hs, res_ld=D, res_mode=L.FG_RES_SAME)
         # ---- head ----
         hm = ws["head_mod"]
-        self._ln(plan, hs, rows, nrm, "ln_out", scale=hm[:, D:], shift=hm[:, :D], mod_ld=2 * D, rows_per_group=rpg)
-        self._gemm(plan, nrm, D, pk["out.w"], rows, kout, ws["tok_out"], kout, "proj_out", bias=pk["out.b"])
+        self._ln(plan, hs, lrows, nrm, "ln_out", scale=hm[:, D:], shift=hm[:, :D], mod_ld=2 * D, rows_per_group=rpg)
+        if P == 1:
+            self._gemm(plan, nrm, D, pk["out.w"], rows, kout, ws["tok_out"], kout, "proj_out", bias=pk["out.b"])
+        else:
+            self._gemm(plan, nrm, D, pk["out.w"], lrows, kout, ws["tok_out_l"], kout, "proj_out", bias=pk["out.b"])
+            plan.add_py(lambda: dist.all_gather_into_tensor(ws["tok_out_g"], ws["tok_out_l"], group=group), "gather_out")
+            # gathered[src][(b, f)][i] -> natural token order [(b, f)][src * fs_l + i]
+            self._copy_desc(plan, ws["tok_out_g"], ws["tok_out"], PL.unshard_desc(P, B, F, fs, kout), "unshard")
         plan.add(lib.fg_unpatchify, ws["tok_out"].data_ptr(), kout, B, cfg["out_channels"], F, Hh, Ww, ph, pw,
                  ws["flow"].data_ptr(), ops._DT[x_dtype], desc="unpatchify")
-        assert mod_groups <= groups
         return plan
 
     def _run_transformer(self, x_t: torch.Tensor, timestep: torch.Tensor, condition: torch.Tensor, per_frame: bool,

@@ -193,6 +193,8 @@ typedef struct {
   const float* rope_sin;
   int32_t rope_max_pos, nt, nh;
   int32_t rows_per_batch, ppf, pph, ppw, frame0;
+  int32_t frame_rows;   /* rows per frame in this buffer (0: pph*ppw) and in-frame index of the first one: a        */
+  int32_t tok0;         /* sequence-parallel rank holds tokens [tok0, tok0 + frame_rows) of every frame             */
   void* k_cache;        /* bf16 [batch][cache_bs], row stride cache_ld, or NULL */
   void* v_cache;
   int64_t cache_ld, cache_bs;
@@ -208,6 +210,10 @@ int fg_patchify(const void* x, int32_t x_dtype, int32_t b, int32_t c, int32_t f,
 /* token rows [..][y_ld] with column ((i*pw + j)*C + c) -> latent [B,C,F,H,W] (Wan/network.py:262-266). */
 int fg_unpatchify(const void* y, int64_t y_ld, int32_t b, int32_t c, int32_t f, int32_t h, int32_t w, int32_t ph,
                   int32_t pw, void* out, int32_t out_dtype, fg_stream_t stream);
+/* 4-D strided copy of items of item_bytes (a multiple of 16) bytes; strides in BYTES (multiples of 16): the pack /
+ * unpack permutations around the Ulysses all-to-all (tokens <-> heads) and the head-sharded KV-cache append. */
+int fg_strided_copy(const void* src, void* dst, const int32_t* n, const int64_t* src_strides,
+                    const int64_t* dst_strides, int32_t item_bytes, fg_stream_t stream);
 /* out[i][g][:] = a[i][:] + b[g][:], fp32: scale_shift_table of every block + timestep projection of every frame. */
 int fg_bcast_add(const float* a, const float* b, int32_t na, int32_t nb, int32_t d, float* out, fg_stream_t stream);
 

@@ -1,0 +1,89 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): batch sharding of the image samplers and the Ulysses exchange layout
+of the Wan path (pack -> all_to_all -> attention over (all tokens, local heads) -> all_to_all -> unpack)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from fastgen_b200 import parallel as PL
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_rank_batches_partition_like_the_reference():
+    batches = list(range(11))
+    parts = [PL.rank_batches(batches, r, 4) for r in range(4)]
+    assert parts[0] == [0, 4, 8] and parts[3] == [3, 7]
+    assert sorted(sum(parts, [])) == batches
+    assert PL.rank_seed(7, 3) == 10
+
+
+def _ulysses_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)  # identical "global" tensors on every rank
+        B, Fr, fs, H, d = 2, 3, 8, 4, 16
+        D, P = H * d, world
+        n, fs_l = Fr * fs, fs // P
+        n_l, Hl = n // P, H // P
+        Dl = Hl * d
+        hs_full = torch.randn(B * n, D)
+        qkv_full = torch.randn(B * n, 3 * D)          # what every rank WOULD compute for all tokens
+        # 1. token shard of this rank
+        hs = torch.zeros(B * n_l, D)
+        PL.apply_desc_cpu(PL.shard_rows_desc(B, Fr, fs, P, rank, D), hs_full, hs)
+        idx = torch.arange(B * n).view(B, Fr, fs)[:, :, rank * fs_l:(rank + 1) * fs_l].reshape(-1)
+        assert torch.equal(hs, hs_full[idx])
+        qkv = qkv_full[idx].contiguous()              # local rows, all heads
+        # 2. pack + all-to-all: (local tokens, all heads) -> (all tokens, local heads)
+        send = torch.zeros(B, P, n_l, 3 * Dl)
+        full = torch.zeros(B, n, 3 * Dl)
+        for b in range(B):
+            PL.apply_desc_cpu(PL.a2a_pack_desc(n_l, P, D, Dl), qkv[b * n_l:(b + 1) * n_l], send[b])
+            dist.all_to_all_single(full[b], send[b])
+        # gathered token order of sample b: (src, f, i); heads [rank*Hl, (rank+1)*Hl)
+        order = torch.arange(n).view(Fr, P, fs_l).permute(1, 0, 2).reshape(-1)
+        for b in range(B):
+            want = qkv_full[b * n:(b + 1) * n][order].view(n, 3, H, d)[:, :, rank * Hl:(rank + 1) * Hl].reshape(n, 3 * Dl)
+            assert torch.equal(full[b], want)
+        # 3. attention on local heads (keys in the gathered order: softmax is permutation invariant)
+        q, k, v = (full.view(B, n, 3, Hl, d)[:, :, j].transpose(1, 2) for j in range(3))
+        attf = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, n, Dl).contiguous()
+        # 4. all-to-all back + unpack: (all tokens, local heads) -> (local tokens, all heads)
+        recv = torch.zeros(B, P, n_l, Dl)
+        for b in range(B):
+            dist.all_to_all_single(recv[b], attf[b])
+        att = torch.zeros(B * n_l, D)
+        PL.apply_desc_cpu(PL.a2a_unpack_desc(B, P, n_l, D, Dl), recv, att)
+        qa, ka, va = (qkv_full.view(B, n, 3, H, d)[:, :, j].transpose(1, 2) for j in range(3))
+        ref = F.scaled_dot_product_attention(qa, ka, va).transpose(1, 2).reshape(B * n, D)
+        assert torch.allclose(att, ref[idx], atol=1e-5)
+        # 5. gather the per-rank outputs back into natural token order
+        kout = 8
+        out_full = torch.randn(B * n, kout)
+        parts = [torch.zeros(B * n_l, kout) for _ in range(P)]
+        dist.all_gather(parts, out_full[idx].contiguous())   # (gloo has no all_gather_into_tensor)
+        gathered = torch.stack(parts, 0)
+        nat = torch.zeros(B * n, kout)
+        PL.apply_desc_cpu(PL.unshard_desc(P, B, Fr, fs, kout), gathered, nat)
+        assert torch.equal(nat, out_full)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ulysses_layout_world_size_2():
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ulysses_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        assert all(ret.get(r) for r in range(world))

@@ -1,0 +1,79 @@
+"""Ulysses sequence-parallel Wan on 2 GPUs (NCCL all-to-all) against the single-GPU path: same weights, same inputs,
+KV-cached chunks.  Needs two CUDA devices (run with `gpurun --gpus 2`); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import wan_oracle as WO
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _run_chunks(net, x, text, total, dev):
+    outs = []
+    net.clear_caches()
+    for (s, e) in [(0, 4), (4, 7)]:
+        xc = x[:, :, s:e].contiguous().to(dev)
+        for tval, store in [(0.937, False), (0.0, True)]:
+            t = torch.full((x.shape[0],), tval, dtype=torch.float64, device=dev)
+            outs.append(net(xc, t, condition=text.to(dev), fwd_pred_type="x0", cur_start_frame=s, store_kv=store,
+                            is_ar=True).float().cpu())
+    return outs
+
+
+def _worker(rank, world, port, ret):
+    import fastgen_b200.wan as W
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        cfg = WO.tiny_config(layers=2)
+        total = 7
+        sd = {k: v.bfloat16() for k, v in WO.make_state_dict(cfg, 1).items()}
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(2, 16, total, 8, 8, generator=g).bfloat16()
+        text = torch.randn(2, 24, cfg["text_dim"], generator=g).bfloat16()
+
+        def build():
+            net = W.CausalWan(transformer_config=cfg, enable_logvar_linear=False, total_num_frames=total, chunk_size=3)
+            net.load_state_dict(sd, strict=True)
+            return net.to(torch.bfloat16).to(dev).eval()
+
+        single = _run_chunks(build(), x, text, total, dev)
+        net = build()
+        net.sp_group = dist.group.WORLD
+        sp = _run_chunks(net, x, text, total, dev)
+        errs = [_rel(a, b) for a, b in zip(sp, single)]
+        # head-sharded cache: this rank holds heads [rank*H/P, (rank+1)*H/P)
+        assert net._kv["pos"]["k"].shape[-1] == cfg["dim"] // world
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sequence_parallel_matches_single_gpu():
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        for r in range(world):
+            errs = ret[r]
+            assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
