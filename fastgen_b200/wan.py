@@ -144,6 +144,8 @@ class _Plan:
     def __init__(self):
         self.steps: List[Tuple[Any, tuple, str, float]] = []
         self.keep: List[Any] = []
+        self.runs = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
 
     def add(self, fn, *args, desc: str = "", flops: float = 0.0):
         self.steps.append((fn, args, desc, flops))
@@ -217,6 +219,10 @@ class _WanBase:
         self._kv: Dict[Any, Dict[str, Any]] = {}      # cache_tag -> self-attention KV cache
         self._cross: Dict[Any, Dict[str, Any]] = {}   # cache_tag -> static cross-attention K/V of the current prompt
         self.profile: Optional[Dict[str, Dict[str, float]]] = None
+        # replay each recorded launch list as a CUDA graph from its second use on (the kernels are short enough for
+        # the ~10 us per launch of the host to show, above all under sequence parallelism)
+        self.use_cuda_graphs = True
+        self.graph_launches = 0                        # kernel launches replayed through graphs (bench bookkeeping)
         self.sp_group = None                           # torch.distributed group for Ulysses sequence parallelism
 
     # ---- reference helpers ------------------------------------------------------------------------------
@@ -674,10 +680,22 @@ class _WanBase:
         else:
             ws["emb"].zero_()
             ws["emb"][:B].copy_(emb)   # rows [0, B): one modulation group per sample (rows_per_group = n)
-        stream = torch.cuda.current_stream().cuda_stream
         # the head adds table + temb in bf16 (reference Wan/network.py:229,250): needs temb, so run the embedding
         # launches first, then that one tiny add, then the rest of the plan
-        self._run_split(plan, ws, stream)
+        # (not under sequence parallelism: capturing the NCCL all-to-all into a graph deadlocked the NCCL watchdog)
+        if self.use_cuda_graphs and self.profile is None and self.sp_group is None:
+            if plan.graph is None and plan.runs >= 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_split(plan, ws, torch.cuda.current_stream().cuda_stream)
+                plan.graph = g
+            if plan.graph is not None:
+                plan.graph.replay()
+                self.graph_launches += sum(1 for st in plan.steps if st[1] is not None)
+                plan.runs += 1
+                return ws["flow"]
+        self._run_split(plan, ws, torch.cuda.current_stream().cuda_stream)
+        plan.runs += 1
         return ws["flow"]
 
     def _run_split(self, plan: _Plan, ws, stream: int) -> None:
