@@ -1,0 +1,87 @@
+"""CPU tests of host-side logic that needs no kernel: checkpoint key conversions, schedules on the host, argument
+validation of the network wrappers (the compute path itself raises without CUDA)."""
+import pytest
+import torch
+
+from oracle import dit_oracle as DO
+from oracle import wan_oracle as WO
+
+
+def test_dit_facebook_checkpoint_key_conversion():
+    """reference DiT/network.py:346-401: Facebook-DiT names map onto ours; pos_embed goes straight into the buffer"""
+    from fastgen_b200.dit import DiT
+
+    cfg = DO.tiny_config()
+    sd = DO.make_state_dict(cfg, 2)
+    fb = {}
+    for k, v in sd.items():
+        k = k.replace("t_embedder.proj_net", "t_embedder.mlp").replace(".attention.", ".attn.")
+        k = k.replace(".feed_forward.", ".mlp.").replace("y_embedder.class_embeddings", "y_embedder.embedding_table")
+        k = k.replace("final_layer.projection", "final_layer.linear")
+        k = k.replace("final_layer.adaptive_params", "final_layer.adaLN_modulation")
+        k = k.replace(".conditioning_net.", ".adaLN_modulation.")
+        fb[k] = v
+    fb["pos_embed"] = sd["pos_embed"] + 1.0
+    net = DiT(**cfg)
+    missing, unexpected = net.load_state_dict(fb, strict=False)
+    assert missing == ["pos_embed"] and not unexpected
+    for k, v in sd.items():
+        want = v + 1.0 if k == "pos_embed" else v
+        assert torch.equal(net.state_dict()[k], want), k
+    assert set(net.state_dict().keys()) == set(sd.keys())
+
+
+def test_dit_positional_embedding_matches_oracle_restatement():
+    from fastgen_b200.dit import DiT
+
+    net = DiT(**DO.tiny_config())
+    assert torch.equal(net.pos_embed, DO.pos_embed_2d(128, 4))
+
+
+def test_networks_refuse_cpu_tensors_and_training_outputs():
+    from fastgen_b200 import _lib
+    from fastgen_b200.dit import DiT
+    from fastgen_b200.wan import CausalWan, Wan
+
+    dit = DiT(**DO.tiny_config())
+    with pytest.raises(_lib.FastGenB200Error):
+        dit(torch.zeros(1, 4, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 10))
+    with pytest.raises(NotImplementedError):
+        dit(torch.zeros(1, 4, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 10), return_logvar=True)
+    cfg = WO.tiny_config(layers=1)
+    wan = Wan(transformer_config=cfg)
+    with pytest.raises(_lib.FastGenB200Error):
+        wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64))
+    assert wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), return_features_early=True) == []
+    with pytest.raises(NotImplementedError):
+        wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64), feature_indices={0})
+    with pytest.raises(AssertionError):
+        wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64), fwd_pred_type="nope")
+    with pytest.raises(ValueError):
+        wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64), r=torch.ones(1))
+    with pytest.raises(NotImplementedError):
+        Wan(transformer_config=cfg, r_timestep=True)
+    cw = CausalWan(transformer_config=cfg, chunk_size=2, total_num_frames=5)
+    assert cw.chunk_size == 2 and cw.total_num_frames == 5 and cw.net_pred_type == "flow" and cw.schedule_type == "rf"
+    cw.clear_caches()  # no caches yet: a no-op
+    with pytest.raises(ValueError):
+        Wan(model_id_or_local_path="Wan-AI/unknown")
+    assert Wan.get_model_id("Wan-AI/Wan2.1-T2V-14B-Diffusers") == Wan.MODEL_ID_14B
+
+
+def test_wan_rope_pair_tables_match_oracle_tables():
+    from fastgen_b200.wan import _rope_pair_tables
+
+    cfg = WO.tiny_config()
+    cos, sin, nt, nh = _rope_pair_tables(cfg["head_dim"], cfg["rope_max_seq_len"])
+    fc, fs = WO.rope_tables(cfg)
+    assert torch.equal(cos, fc[:, 0::2]) and torch.equal(sin, fs[:, 1::2])
+    assert (nt, nh) == (22, 21)
+
+
+def test_sinusoid_variants_match_oracle():
+    from fastgen_b200.wan import _sinusoid
+
+    t = torch.tensor([999.0, 937.0, 0.0], dtype=torch.float64)
+    assert torch.equal(_sinusoid(t, 256, True), WO.sinusoidal_embedding_1d_wan(256, t))
+    assert torch.equal(_sinusoid(t, 256, False), WO.timesteps_diffusers(t, 256))
