@@ -21,7 +21,7 @@ SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
     "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn", "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_bcast_add",
-    "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16",
+    "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
 )
 
 
@@ -38,6 +38,7 @@ class ConvParams(C.Structure):
         ("res", C.c_void_p), ("res_dtype", C.c_int32), ("res_mode", C.c_int32), ("res_ld", C.c_int64),
         ("out_scale", C.c_float),
         ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_ld", C.c_int64),
+        ("stats", C.c_void_p), ("stats_groups", C.c_int32), ("stats_cg", C.c_int32), ("stats_ch0", C.c_int32),
     ]
 
 
@@ -143,11 +144,12 @@ def lib() -> C.CDLL:
     l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
     l.fg_axpby.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
     l.fg_sub_div.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
+    l.fg_zero.argtypes = [vp, i64, vp]
     l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",
                  "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
-                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy"):
+                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero"):
         getattr(l, name).restype = C.c_int
     _lib = l
     return l

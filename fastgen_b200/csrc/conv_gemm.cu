@@ -89,6 +89,9 @@ struct ConvKParams {
   void* out;
   int32_t out_dtype;
   int64_t out_ld;
+  // fused GroupNorm statistics of the output (fp32 TMA-store path): per (image, group) sum / sum of squares
+  double* stats;
+  int32_t stats_groups, stats_cg, stats_ch0;
 };
 
 struct TileCoord {
@@ -538,6 +541,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             tma_store_4d(&p.tmOut, slab, t.co0 + c0, t.w0, t.h0, t.img0);
             tma_store_commit();
           }
+          if constexpr (!kOutBf16) {
+            if (p.stats) {
+              // GroupNorm statistics of the finished slab (the next consumer's fg_gn_stats pass disappears): thread
+              // (row block rb, column) sums 32 rows of one column out of shared memory, runs of lanes that fall into
+              // the same group are combined with a segmented shuffle reduction, one fp64 atomic pair per run.
+              const int col = row & 31, rb = row >> 5;
+              const int ch = t.co0 + c0 + col;
+              const int simg = t.img0 + (rb * 32) / (p.BW * p.BH);
+              float s1 = 0.f, s2 = 0.f;
+              if (ch < p.Cout && simg < p.N) {
+                const uint8_t* base = slab + (rb * 32) * 128 + (col & 3) * 4;
+                const uint32_t cchunk = static_cast<uint32_t>(col >> 2);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const float v = *reinterpret_cast<const float*>(base + r * 128 + ((cchunk ^ (r & 7)) << 4));
+                  s1 += v;
+                  s2 = fmaf(v, v, s2);
+                }
+              }
+              const int g = (ch < p.Cout) ? (p.stats_ch0 + ch) / p.stats_cg : -1 - col;  // invalid lanes: singleton runs
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const float o1 = __shfl_down_sync(0xffffffffu, s1, off);
+                const float o2 = __shfl_down_sync(0xffffffffu, s2, off);
+                const int og = __shfl_down_sync(0xffffffffu, g, off);
+                if (lane + off < 32 && og == g) s1 += o1, s2 += o2;
+              }
+              const int pg = __shfl_up_sync(0xffffffffu, g, 1);
+              if ((lane == 0 || pg != g) && g >= 0 && simg < p.N) {
+                double* dst = p.stats + (static_cast<int64_t>(simg) * p.stats_groups + g) * 2;
+                atomicAdd(dst, static_cast<double>(s1));
+                atomicAdd(dst + 1, static_cast<double>(s2));
+              }
+            }
+          }
         }
       } else if constexpr (BLOCK_N >= 32) {
 #pragma unroll 1
@@ -728,6 +766,12 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.out = p->out;
   kp.out_dtype = p->out_dtype;
   kp.out_ld = p->out_ld;
+  if (p->stats) {
+    FG_CHECK_ARG(p->out_dtype == FG_F32 && p->stats_groups > 0 && p->stats_cg > 0 && p->stats_ch0 >= 0,
+                 "conv_gemm: fused GroupNorm statistics need an fp32 output, stats_groups > 0, stats_cg > 0");
+    FG_CHECK_ARG(kp.BW * kp.BH >= 32, "conv_gemm: fused GroupNorm statistics need images of at least 32 pixels");
+    kp.stats = p->stats, kp.stats_groups = p->stats_groups, kp.stats_cg = p->stats_cg, kp.stats_ch0 = p->stats_ch0;
+  }
   FG_CHECK_ARG(kp.res_mode >= FG_RES_NONE && kp.res_mode <= FG_RES_DOWN2, "conv_gemm: bad res_mode %d", kp.res_mode);
   if (kp.res_mode != FG_RES_NONE) {
     FG_CHECK_ARG(p->res_dtype == FG_F32 || p->res_dtype == FG_BF16, "conv_gemm: bad res_dtype %d", p->res_dtype);
@@ -771,6 +815,7 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
       epi = epi_mode(p->out_dtype == FG_BF16, res_kind);
     }
   }
+  if (kp.stats) FG_CHECK_ARG(epi != kEpiGeneric, "conv_gemm: fused GroupNorm statistics need the TMA-store epilogue (cout %% 4 == 0, cout > 16, 16-byte aligned rows)");
 
   switch (block_n) {
     case 16: return dispatch_epi<16>(kp, epi, num_sms, stream);

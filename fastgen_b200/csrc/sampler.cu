@@ -345,3 +345,14 @@ extern "C" int fg_split_bf16(const float* x, int64_t x_ld, const float* add, int
   FG_CHECK_LAUNCH("split_bf16");
   return FG_OK;
 }
+
+extern "C" int fg_zero(void* ptr, int64_t bytes, fg_stream_t stream_) {
+  using namespace fg;
+  FG_CHECK_ARG(ptr && bytes >= 0, "zero: bad arguments");
+  if (cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream_)) != cudaSuccess) {
+    set_error("zero: cudaMemsetAsync failed");
+    return FG_ERR_CUDA;
+  }
+  count_launch();
+  return FG_OK;
+}

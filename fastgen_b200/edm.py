@@ -334,17 +334,34 @@ class _Plan:
         self._launch(L.lib().fg_conv_gemm, C.byref(p), flops=flops, nbytes=nbytes,
                      desc=f"conv {h}x{w} K={ktot} N={cout} out={str(out.dtype)[6:]} res={kw.get('res_mode', 0)}")
 
+    def new_stats(self) -> torch.Tensor:
+        """one [n, 32, 2] fp64 slot of the statistics arena (zeroed by the first step of the plan)"""
+        i = self._stats_used
+        self._stats_used += 1
+        assert i < self.stats_arena.shape[0], "planner bug: statistics arena too small"
+        return self.stats_arena[i]
+
+    def fused_stats(self, h: int, w: int, cout: int, out_ld: int, norm: "_GroupNorm", c_norm: int):
+        """kwargs that make a conv accumulate the GroupNorm statistics `norm` needs of its output, or None when the
+        producer cannot (tiny images, narrow or unaligned outputs): the consumer then runs fg_gn_stats itself."""
+        if not self.net.fuse_gn_stats or h * w < 32 or cout % 4 or cout <= 16 or out_ld % 4 or cout != c_norm:
+            return None
+        slot = self.new_stats()
+        return dict(stats=slot, stats_groups=norm.num_groups, stats_cg=c_norm // norm.num_groups, stats_ch0=0)
+
     def gn(self, x: _Act, norm: _GroupNorm, pk: Dict[str, torch.Tensor], y: torch.Tensor, silu: bool, resample: int = 0,
-           scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None):
+           scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None, stats: Optional[torch.Tensor] = None):
         n, h, w, c = x.n, x.h, x.w, x.c
         groups = norm.num_groups
         xv = x.t
-        self._launch(L.lib().fg_gn_stats, xv.data_ptr(), ops._DT[xv.dtype], x.ld, n, h * w, c, groups,
-                     self.stats.data_ptr(), desc=f"gn_stats {h}x{w} c={c}", nbytes=n * h * w * c * xv.element_size())
-        p = ops.gn_apply_params(xv, x.ld, n, h, w, c, groups, self.stats, norm.eps, pk["gamma"], pk["beta"], y, c,
+        if stats is None:   # not produced by the conv that wrote x: one streaming pass over x
+            stats = self.new_stats()
+            self._launch(L.lib().fg_gn_stats, xv.data_ptr(), ops._DT[xv.dtype], x.ld, n, h * w, c, groups,
+                         stats.data_ptr(), desc=f"gn_stats {h}x{w} c={c}", nbytes=n * h * w * c * xv.element_size())
+        p = ops.gn_apply_params(xv, x.ld, n, h, w, c, groups, stats, norm.eps, pk["gamma"], pk["beta"], y, c,
                                 scale=scale, shift=shift, mod_ld=mod_ld, silu=silu, resample=resample, y_lo=y_lo,
                                 raw=raw, raw_ld=c, raw_lo=raw_lo)
-        self.keep.append((p, xv, y, y_lo, raw, raw_lo, scale, shift))
+        self.keep.append((p, xv, y, y_lo, raw, raw_lo, scale, shift, stats))
         outs = 1 + (y_lo is not None) + (raw is not None) + (raw_lo is not None)
         opix = h * w * (4 if resample == L.FG_RES_UP2 else 1) // (4 if resample == L.FG_RES_DOWN2 else 1)
         self._launch(L.lib().fg_gn_apply, C.byref(p), desc=f"gn_apply {h}x{w} c={c} outs={outs} rs={resample}",
@@ -376,7 +393,10 @@ class _Plan:
         song = m.model_type == "SongUNet"
         R = m.img_resolution
         f32, bf16 = torch.float32, torch.bfloat16
-        self.stats = self._new([n, 32, 2], torch.float64)
+        n_blocks = sum(isinstance(b, _Block) for md in (m.enc, m.dec) for b in md.values())
+        self.stats_arena = self._new([3 * n_blocks + 4, n, 32, 2], torch.float64)
+        self._stats_used = 0
+        self._launch(L.lib().fg_zero, self.stats_arena.data_ptr(), self.stats_arena.numel() * 8, desc="zero_stats")
         self._size_scratch()
 
         # ---------------- inputs staged by forward() ----------------
@@ -471,46 +491,62 @@ class _Plan:
                 return _Act(home[0], home[1], c)
             return _Act(self._new([n, res, res, c], f32), 0, c)
 
-        # ---------------- encoder ----------------
+        # ---------------- encoder / decoder ----------------
+        # entry list with look-ahead: the conv that writes a block's output also accumulates the GroupNorm statistics
+        # of the NEXT entry's norm0 when that norm sees exactly this tensor (not a skip concatenation)
+        entries = [("enc", nm) for nm in enc_names] + [("dec", nm) for nm in dec_names]
+        final_norm, final_conv = m.final_layers()
+
+        def next_norm(i: int):
+            if i + 1 < len(entries):
+                side, nm = entries[i + 1]
+                if side == "dec" and nm in x_home:
+                    return None          # the next block normalises a concatenation
+                return m.enc[nm].norm0 if side == "enc" else m.dec[nm].norm0
+            return final_norm
+
         x: Optional[_Act] = None
-        for name in enc_names:
-            mod = m.enc[name]
+        x_stats: Optional[torch.Tensor] = None
+        for i, (side, name) in enumerate(entries):
+            mod = m.enc[name] if side == "enc" else m.dec[name]
             res = res_of(name)
-            dst = out_act(mod.out_channels, res, skip_home.get(name))
+            if side == "enc":
+                dst = out_act(mod.out_channels, res, skip_home.get(name))
+            else:
+                if name in x_home:
+                    buf, _ = x_home[name]
+                    assert x.buf is buf, "planner bug: decoder input was not written into its concat buffer"
+                    x = _Act(buf, 0, mod.in_channels)
+                    x_stats = None
+                di = dec_names.index(name)
+                nxt = dec_names[di + 1] if di + 1 < len(dec_names) else None
+                dst = out_act(mod.out_channels, res, x_home.get(nxt) if nxt is not None else None)
+            nn_ = next_norm(i)
+            out_stats = self.fused_stats(res, res, mod.out_channels, dst.ld, nn_, mod.out_channels) if nn_ is not None else None
             if isinstance(mod, _Conv):
                 w = pk[f"enc.{name}"]
                 self.conv(self.segs3(self.xin, self.xin_lo, cin_pad, w["hi"], w.get("lo"), cin_pad, 9), n, R, R,
-                          mod.out_channels, dst.t, dst.ld, bias=w["bias"])
+                          mod.out_channels, dst.t, dst.ld, bias=w["bias"], **(out_stats or {}))
             else:
-                self._block(f"enc.{name}", mod, x, dst)
+                self._block(f"{side}.{name}", mod, x, dst, x_stats, out_stats)
             x = dst
-        # ---------------- decoder ----------------
-        for i, name in enumerate(dec_names):
-            mod = m.dec[name]
-            res = res_of(name)
-            if name in x_home:
-                buf, _ = x_home[name]
-                assert x.buf is buf, "planner bug: decoder input was not written into its concat buffer"
-                x = _Act(buf, 0, mod.in_channels)
-            nxt = dec_names[i + 1] if i + 1 < len(dec_names) else None
-            home = x_home.get(nxt) if nxt is not None else None
-            dst = out_act(mod.out_channels, res, home)
-            self._block(f"dec.{name}", mod, x, dst)
-            x = dst
+            x_stats = out_stats["stats"] if out_stats else None
         # ---------------- output head ----------------
-        norm, conv = m.final_layers()
+        norm, conv = final_norm, final_conv
         key = "final"
         hb = self._scratch("h0", [n, R, R, x.c])
         hb_lo = self._scratch("h0_lo", [n, R, R, x.c]) if self.x3 else None
-        self.gn(x, norm, pk[key + ".norm"], hb, silu=True, y_lo=hb_lo)
+        self.gn(x, norm, pk[key + ".norm"], hb, silu=True, y_lo=hb_lo, stats=x_stats)
         self.f_ld = 4 if m.out_channels <= 4 else _pad8(m.out_channels)
         self.f_out = self._new([n, R, R, self.f_ld], f32)
         w = pk[key + ".conv"]
         self.conv(self.segs3(hb, hb_lo, x.c, w["hi"], w.get("lo"), x.c, 9), n, R, R, m.out_channels, self.f_out, self.f_ld,
                   bias=w["bias"])
 
-    def _block(self, key: str, b: _Block, x: _Act, dst: _Act):
-        """Launch list of one UNetBlock (reference EDM/network.py:274-299)."""
+    def _block(self, key: str, b: _Block, x: _Act, dst: _Act, x_stats: Optional[torch.Tensor] = None,
+               out_stats: Optional[Dict[str, Any]] = None):
+        """Launch list of one UNetBlock (reference EDM/network.py:274-299).  `x_stats`: norm0 statistics already
+        accumulated by the producer of x; `out_stats`: conv kwargs that accumulate the next norm0's statistics."""
         n = self.n
         pk = self.net._packed
         f32, bf16 = torch.float32, torch.bfloat16
@@ -524,7 +560,8 @@ class _Plan:
         h0_lo = self._scratch("h0_lo", [n, ho, wo, cin]) if self.x3 else None
         raw = self._scratch("raw", [n, ho, wo, cin]) if skip_conv else None
         raw_lo = self._scratch("raw_lo", [n, ho, wo, cin]) if (skip_conv and self.x3) else None
-        self.gn(x, b.norm0, pk[key + ".norm0"], h0, silu=True, resample=resample, y_lo=h0_lo, raw=raw, raw_lo=raw_lo)
+        self.gn(x, b.norm0, pk[key + ".norm0"], h0, silu=True, resample=resample, y_lo=h0_lo, raw=raw, raw_lo=raw_lo,
+                stats=x_stats)
         # conv0 (+ bias, + additive embedding)
         aff_off = pk[key + ".affine_off"]
         aff = self.affine[:, aff_off:]
@@ -533,17 +570,19 @@ class _Plan:
         kw = {}
         if not b.adaptive_scale:
             kw = dict(rowvec=aff, rowvec_ld=self.affine.shape[1])
+        st1 = self.fused_stats(ho, wo, cout, cout, b.norm1, cout)
         self.conv(self.segs3(h0, h0_lo, cin, w0["hi"], w0.get("lo"), cin, 9), n, ho, wo, cout, h1, cout, bias=w0["bias"],
-                  **kw)
+                  **kw, **(st1 or {}))
+        s1 = st1["stats"] if st1 else None
         # norm1 (+ adaptive scale/shift) + SiLU -> conv1 operand
         h2 = self._scratch("h2", [n, ho, wo, cout])
         h2_lo = self._scratch("h2_lo", [n, ho, wo, cout]) if self.x3 else None
         h1a = _Act(h1, 0, cout)
         if b.adaptive_scale:
             self.gn(h1a, b.norm1, pk[key + ".norm1"], h2, silu=True, scale=aff, shift=self.affine[:, aff_off + cout:],
-                    mod_ld=self.affine.shape[1], y_lo=h2_lo)
+                    mod_ld=self.affine.shape[1], y_lo=h2_lo, stats=s1)
         else:
-            self.gn(h1a, b.norm1, pk[key + ".norm1"], h2, silu=True, y_lo=h2_lo)
+            self.gn(h1a, b.norm1, pk[key + ".norm1"], h2, silu=True, y_lo=h2_lo, stats=s1)
         # conv1 (+ 1x1 skip projection as extra K segments | + resampled identity skip), * skip_scale
         w1 = pk[key + ".conv1"]
         segs = self.segs3(h2, h2_lo, cout, w1["hi"], w1.get("lo"), cout, 9)
@@ -557,13 +596,14 @@ class _Plan:
             mode = L.FG_RES_SAME if b.skip is None else resample
             rkw = dict(res=x.t, res_ld=x.ld, res_mode=mode)
         mid = dst if not b.num_heads else _Act(self._scratch("mid", [n, ho, wo, cout]), 0, cout)
-        self.conv(segs, n, ho, wo, cout, mid.t, mid.ld, bias=bias, out_scale=float(b.skip_scale), **rkw)
+        st2 = self.fused_stats(ho, wo, cout, mid.ld, b.norm2, cout) if b.num_heads else out_stats
+        self.conv(segs, n, ho, wo, cout, mid.t, mid.ld, bias=bias, out_scale=float(b.skip_scale), **rkw, **(st2 or {}))
         if not b.num_heads:
             return
         # attention: norm2 -> qkv (rows permuted to q|k|v, head, d) -> flash attention -> proj + residual
         h3 = self._scratch("h3", [n, ho, wo, cout])
         h3_lo = self._scratch("h3_lo", [n, ho, wo, cout]) if self.x3 else None
-        self.gn(mid, b.norm2, pk[key + ".norm2"], h3, silu=False, y_lo=h3_lo)
+        self.gn(mid, b.norm2, pk[key + ".norm2"], h3, silu=False, y_lo=h3_lo, stats=st2["stats"] if st2 else None)
         qkv = self._scratch("qkv", [n, ho, wo, 3 * cout])
         wq = pk[key + ".qkv"]
         self.conv(self.segs3(h3, h3_lo, cout, wq["hi"], wq.get("lo"), cout, 1), n, ho, wo, 3 * cout, qkv, 3 * cout,
@@ -576,7 +616,7 @@ class _Plan:
         if self.x3:
             segs.append(ops.Seg(att, cout, wp["lo"], cout, 1, alg=False))
         self.conv(segs, n, ho, wo, cout, dst.t, dst.ld, bias=wp["bias"], res=mid.t, res_ld=mid.ld,
-                  res_mode=L.FG_RES_SAME, out_scale=float(b.skip_scale))
+                  res_mode=L.FG_RES_SAME, out_scale=float(b.skip_scale), **(out_stats or {}))
 
     def run(self, stream: int) -> None:
         check = L.check
@@ -628,6 +668,7 @@ class EDMPrecond(FastGenNetwork):
         self.img_resolution, self.img_channels, self.label_dim = img_resolution, img_channels, label_dim
         self.sigma_data, self.sigma_shift, self.drop_precond = sigma_data, sigma_shift, drop_precond
         self.compute = compute
+        self.fuse_gn_stats = True   # GroupNorm statistics accumulated by the conv that writes the tensor
         self.model = _UNet(model_type, img_resolution=img_resolution, in_channels=img_channels,
                            out_channels=img_channels, label_dim=label_dim, **model_kwargs)
         self._packed: Optional[Dict[str, Any]] = None

@@ -51,6 +51,7 @@ def conv_gemm_params(
     out_scale: float = 1.0,
     act: int = L.FG_ACT_NONE,
     gate: Optional[torch.Tensor] = None, gate_ld: int = 0, gate_rows: int = 0,
+    stats: Optional[torch.Tensor] = None, stats_groups: int = 0, stats_cg: int = 0, stats_ch0: int = 0,
 ) -> "L.ConvParams":
     """Fill an ``fg_conv_params`` (the tensors must stay alive and in place while the struct is used)."""
     _need_cuda(out, bias, rowvec, res, gate, *[s.a for s in segs], *[s.w for s in segs])
@@ -70,6 +71,10 @@ def conv_gemm_params(
     p.res_dtype = _DT[res.dtype] if res is not None else 0
     p.out_scale = out_scale
     p.out, p.out_dtype, p.out_ld = out.data_ptr(), _DT[out.dtype], out_ld
+    if stats is not None:
+        _need_cuda(stats)
+        assert stats.dtype == torch.float64
+        p.stats, p.stats_groups, p.stats_cg, p.stats_ch0 = stats.data_ptr(), stats_groups, stats_cg, stats_ch0
     return p
 
 

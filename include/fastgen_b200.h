@@ -81,6 +81,10 @@ typedef struct {
   void* out;            /* [N,H,W,cout] fp32 or bf16, pixel stride out_ld */
   int32_t out_dtype;
   int64_t out_ld;
+  double* stats;        /* optional: accumulate GroupNorm statistics of `out` (fp32 only) into stats[n][g][{sum,sumsq}], */
+  int32_t stats_groups; /* g = (stats_ch0 + co) / stats_cg -- the fg_gn_stats pass of the consumer fused into the      */
+  int32_t stats_cg;     /* producer (the caller zeroes the buffer, e.g. fg_zero, before the launch)                     */
+  int32_t stats_ch0;
 } fg_conv_params;
 
 int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream);
@@ -261,6 +265,9 @@ int fg_axpby(const void* a, const void* b, int32_t dtype, int64_t total, int64_t
 /* (a - b*cb[k]) / cd[k] in fp64, one rounding: x0_to_eps / eps_to_x0 (noise_schedule.py:544-608). */
 int fg_sub_div(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid, int64_t inner,
                const double* cb, const double* cd, void* out, fg_stream_t stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes) as a plan step (statistics arenas) */
+int fg_zero(void* ptr, int64_t bytes, fg_stream_t stream);
 
 /* small helpers used by the embedding path */
 /* PositionalEmbedding (:306-319): out[n, :] = [cos(t*f) | sin(t*f)] (optionally swapped), fp32 */

@@ -191,6 +191,40 @@ def test_linear_activation_gate_residual(rows, k, n, out_dtype, act, gate_rows, 
     assert _rel(out, v) < tol, _rel(out, v)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,taps,groups,ch0,ctot,res", [
+    (20, 32, 32, 64, 192, 9, 32, 0, 192, True),      # cg = 6: groups straddle the 32-column slabs
+    (300, 8, 8, 64, 768, 1, 32, 0, 768, False),      # two images per tile, ragged image count
+    (6, 64, 64, 32, 384, 9, 32, 0, 384, True),
+    (16, 16, 16, 64, 320, 1, 32, 64, 576, False),    # channels [64, 384) of a wider normalised tensor, ragged N tile
+])
+def test_conv_gemm_fused_groupnorm_statistics(n, h, w, cin, cout, taps, groups, ch0, ctot, res):
+    """the conv epilogue accumulates per (image, group) sum / sum of squares of its fp32 output"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(9)
+    dev = "cuda"
+    k = 3 if taps == 9 else 1
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device=dev) / math.sqrt(cin * k * k)).bfloat16()
+    bias = torch.randn(cout, device=dev)
+    kw = {}
+    if res:
+        r = torch.randn(n, h, w, cout, device=dev)
+        kw = dict(res=r, res_ld=cout, res_mode=1)
+    out = torch.empty(n, h, w, cout, device=dev)
+    stats = torch.zeros(n, groups, 2, device=dev, dtype=torch.float64)
+    cg = ctot // groups
+    ops.conv_gemm([ops.Seg(_nhwc(x), cin, wt.permute(0, 2, 3, 1).contiguous(), cin, taps)], n, h, w, cout, out, cout,
+                  bias=bias, out_scale=0.7, stats=stats, stats_groups=groups, stats_cg=cg, stats_ch0=ch0, **kw)
+    torch.cuda.synchronize()
+    ref = torch.zeros(n, groups, 2, device=dev, dtype=torch.float64)
+    o = out.double()
+    gidx = (ch0 + torch.arange(cout, device=dev)) // cg
+    ref[:, :, 0].index_add_(1, gidx, o.sum(dim=(1, 2)))
+    ref[:, :, 1].index_add_(1, gidx, (o * o).sum(dim=(1, 2)))
+    assert torch.allclose(stats, ref, rtol=2e-5, atol=1e-3), (stats - ref).abs().max().item()
+
+
 def test_conv_gemm_split_precision_segments():
     """bf16x3 split products (hi*hi + lo*hi + hi*lo) reach ~fp32 accuracy: the 'fp32 path' of the network"""
     from fastgen_b200 import ops
