@@ -288,6 +288,20 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK 
   }
 }
 
+// fg_gn_apply has no accumulation, so its slab may depend on the batch: large enough that the per-CTA prologue
+// (coefficients from the fp64 statistics) amortises, small enough that ~8 CTAs per SM exist.
+static int pick_slab_apply(int n, int pixels, int c, int* pix_per_slab) {
+  const int64_t total = static_cast<int64_t>(n) * pixels * c;
+  int64_t per_cta = total / (148 * 8);
+  if (per_cta < 32768) per_cta = 32768;
+  if (per_cta > 262144) per_cta = 262144;
+  int64_t slabs = (static_cast<int64_t>(pixels) * c + per_cta - 1) / per_cta;
+  if (slabs > pixels) slabs = pixels;
+  if (slabs < 1) slabs = 1;
+  *pix_per_slab = static_cast<int>((pixels + slabs - 1) / slabs);
+  return static_cast<int>((pixels + *pix_per_slab - 1) / *pix_per_slab);
+}
+
 static int pick_slab(int n, int pixels, int c, int* pix_per_slab) {
   // ~32K elements per CTA.  Deliberately independent of the batch size: a sample's partial sums are then
   // accumulated in the same order whatever batch it is part of.
@@ -354,7 +368,7 @@ extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
   k.y = static_cast<__nv_bfloat16*>(p->y), k.y_ld = p->y_ld, k.y_lo = static_cast<__nv_bfloat16*>(p->y_lo);
   k.raw = static_cast<__nv_bfloat16*>(p->raw), k.raw_ld = p->raw_ld, k.raw_lo = static_cast<__nv_bfloat16*>(p->raw_lo);
   const int pixels = p->resample == FG_RES_DOWN2 ? (p->h / 2) * (p->w / 2) : p->h * p->w;
-  const int slabs = pick_slab(p->n, pixels, p->c, &k.pix_per_slab);
+  const int slabs = pick_slab_apply(p->n, pixels, p->c, &k.pix_per_slab);
   const dim3 grid(slabs, p->n);
   const size_t smem = sizeof(float) * 2 * p->c;
   const int nvec = p->c / 8;
