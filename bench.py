@@ -406,9 +406,119 @@ def run_wan(args):
         dist.destroy_process_group()
 
 
+SDXL_TFLOP_PER_SAMPLE_FORWARD = 6.75  # counted from our own layer table (sum of 2*M*N*K of every GEMM/conv + 4*N*Nk*d
+                                      # of every attention at a 128x128 latent, 77 text tokens), see DESIGN.md
+
+
+def run_sdxl(args):
+    """BASELINE configs[2]: SDXL 1024x1024 (128x128 latent) DMD2 4-step UNet generation, batch 16 per GPU, bf16."""
+    import torch.distributed as dist
+
+    from fastgen_b200 import ops
+    from fastgen_b200.sampler import FastGenModel
+    from fastgen_b200.sdxl import StableDiffusionXL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 0)
+    B = args.batch if args.batch != BATCH else 16
+    torch.manual_seed(0)
+    with torch.device(dev):
+        net = StableDiffusionXL()
+    net = net.to(torch.bfloat16).eval()
+    torch.manual_seed(1 + rank)
+    noise_h = torch.randn(B, 4, 128, 128).bfloat16().pin_memory()
+    text_h = torch.randn(B, 77, 2048).bfloat16().pin_memory()
+    pooled_h = torch.randn(B, 1280).bfloat16().pin_memory()
+    out_h = torch.empty(B, 4, 128, 128, dtype=torch.bfloat16).pin_memory()
+    noise, text, pooled = noise_h.to(dev), text_h.to(dev), pooled_h.to(dev)
+
+    def gen(n_, c_):
+        return FastGenModel.generator_fn(net, n_, student_sample_steps=4, condition=c_, student_sample_type="sde")
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        out = gen(noise, [text, pooled])
+    assert torch.isfinite(out.float()).all(), "non-finite samples"
+    ops.launch_count_reset()
+    with ClockSampler(local) as clk:
+        ms = timed(lambda: gen(noise, [text, pooled]), K)
+    launches = ops.launch_count()
+    value = world * B * K / (ms / 1000.0)
+
+    def e2e_step():
+        c = [text_h.to(dev, non_blocking=True), pooled_h.to(dev, non_blocking=True)]
+        out_h.copy_(gen(noise_h.to(dev, non_blocking=True), c), non_blocking=True)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    hbm, tf_sus, tf_burst, peak_src = _peaks()
+    net.profile = {}
+    barrier()
+    gen(noise, [text, pooled])
+    barrier()
+    prof, net.profile = net.profile, None
+    tot_ms = sum(d["ms"] for d in prof.values())
+    gemm_ms = sum(d["ms"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
+    gemm_fl = sum(d["flops"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
+    gemm_n = sum(d["launches"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
+    gemm_tf = gemm_fl / (gemm_ms / 1000.0) / 1e12 if gemm_ms else 0.0
+    if rank == 0:
+        line = {
+            "metric": "samples/sec, 4-step DMD2 SDXL 1024x1024 UNet generation", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SDXL 1024x1024 DMD2 4-step UNet generation, batch {B} per GPU bf16 (BASELINE configs[2])",
+                       "latent": [B, 4, 128, 128], "t_list": "linspace(0.999, 0, 5)", "sample_type": "sde",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": "inputs exceed L2: 5.1 GB of bf16 weights and >10 GB of activations streamed per forward"},
+            "e2e": {"value": world * B * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": 2 * (noise_h.numel() + text_h.numel() + pooled_h.numel()),
+                    "d2h_bytes_per_step": 2 * out_h.numel()},
+            "gpu_launches": launches, "clocks": clk.summary(),
+            "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
+                         "achieved": gemm_tf, "peak": tf_sus, "unit": "TFLOP/s", "frac": gemm_tf / tf_sus if tf_sus else None,
+                         "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                         "how": "sum of algorithmic FLOPs of all fg_conv_gemm launches / sum of their CUDA-event durations, "
+                                "separate profiled pass of one 4-step generation",
+                         "launches_per_step": gemm_n, "share_of_step": gemm_ms / tot_ms if tot_ms else None,
+                         "per_kernel_ms": {k: round(d["ms"], 2) for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:24]},
+                         "per_kernel_tflops": {k: round(d["flops"] / d["ms"] / 1e9, 1) for k, d in prof.items() if d["flops"] and d["ms"]},
+                         "model_flops_utilisation": (value * 4 * SDXL_TFLOP_PER_SAMPLE_FORWARD) / (world * tf_sus)},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="in64", choices=["in64", "wan"],
+    ap.add_argument("--workload", default="in64", choices=["in64", "wan", "sdxl"],
                     help="in64 = the headline line the driver records; wan = secondary workload for profiles/")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -421,6 +531,8 @@ def main():
         run_reference(args)
     elif args.workload == "wan":
         run_wan(args)
+    elif args.workload == "sdxl":
+        run_sdxl(args)
     else:
         run_ours(args)
 

@@ -20,7 +20,7 @@ FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU = 0, 1, 2
 SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
     "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn", "fg_flash_attn_workspace_size",
-    "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_bcast_add",
+    "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
 )
 
@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
     l.fg_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_unpatchify.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     l.fg_bcast_add.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    l.fg_geglu.argtypes = [vp, i64, i32, i32, vp, i64, vp]
+    l.fg_cast_resample.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_strided_copy.argtypes = [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32, vp]
     l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
@@ -149,7 +151,7 @@ def lib() -> C.CDLL:
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",
                  "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
-                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero"):
+                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero", "fg_geglu", "fg_cast_resample"):
         getattr(l, name).restype = C.c_int
     _lib = l
     return l

@@ -288,6 +288,37 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK 
   }
 }
 
+// y = bf16(x) for a channels-last tensor, optionally nearest-upsampled 2x: the raw (un-normalised) conv operands of the
+// SDXL UNet's Downsample2D / Upsample2D (diffusers; wrapped by fastgen/networks/SDXL/network.py:210-230).
+template <typename T, bool UP>
+__global__ void __launch_bounds__(kGnThreads) cast_resample_kernel(const T* __restrict__ x, int64_t x_ld, int n, int h,
+                                                                   int w, int c, __nv_bfloat16* __restrict__ y,
+                                                                   int64_t y_ld) {
+  const int nvec = c >> 3;
+  const int64_t total = static_cast<int64_t>(n) * h * w * nvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kGnThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kGnThreads) {
+    const int64_t pix = i / nvec;
+    const int co = static_cast<int>(i % nvec) * 8;
+    float v[8];
+    load8<T>(x + pix * x_ld + co, v);
+    if constexpr (UP) {
+      const int ix = static_cast<int>(pix % w);
+      const int64_t t = pix / w;
+      const int iy = static_cast<int>(t % h);
+      const int64_t img = t / h;
+      const int W2 = 2 * w;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t o = (img * 2 * h + 2 * iy + (d >> 1)) * W2 + 2 * ix + (d & 1);
+        store8_bf16(y + o * y_ld + co, v);
+      }
+    } else {
+      store8_bf16(y + pix * y_ld + co, v);
+    }
+  }
+}
+
 // fg_gn_apply has no accumulation, so its slab may depend on the batch: large enough that the per-CTA prologue
 // (coefficients from the fp64 statistics) amortises, small enough that ~8 CTAs per SM exist.
 static int pick_slab_apply(int n, int pixels, int c, int* pix_per_slab) {
@@ -397,5 +428,36 @@ extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
 #undef FG_GN_DISPATCH
 #undef FG_GN_LAUNCH
   FG_CHECK_LAUNCH("gn_apply");
+  return FG_OK;
+}
+
+extern "C" int fg_cast_resample(const void* x, int32_t x_dtype, int64_t x_ld, int32_t n, int32_t h, int32_t w, int32_t c,
+                                int32_t resample, void* y, int64_t y_ld, fg_stream_t stream_) {
+  using namespace fg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FG_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0, "cast_resample: bad arguments");
+  FG_CHECK_ARG(x_dtype == FG_F32 || x_dtype == FG_BF16, "cast_resample: bad dtype %d", x_dtype);
+  FG_CHECK_ARG(resample == FG_RES_NONE || resample == FG_RES_UP2, "cast_resample: resample must be NONE or UP2");
+  FG_CHECK_ARG(c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+               "cast_resample: c=%d, x_ld=%lld, y_ld=%lld must be multiples of 8 and ld >= c", c, (long long)x_ld,
+               (long long)y_ld);
+  FG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
+               "cast_resample: pointers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
+  int64_t g = (total + kGnThreads - 1) / kGnThreads;
+  if (g > 148 * 16) g = 148 * 16;
+  const int grid = static_cast<int>(g);
+  auto* yo = static_cast<__nv_bfloat16*>(y);
+  const bool up = resample == FG_RES_UP2;
+  if (x_dtype == FG_F32) {
+    const float* xi = static_cast<const float*>(x);
+    if (up) cast_resample_kernel<float, true><<<grid, kGnThreads, 0, stream>>>(xi, x_ld, n, h, w, c, yo, y_ld);
+    else cast_resample_kernel<float, false><<<grid, kGnThreads, 0, stream>>>(xi, x_ld, n, h, w, c, yo, y_ld);
+  } else {
+    const __nv_bfloat16* xi = static_cast<const __nv_bfloat16*>(x);
+    if (up) cast_resample_kernel<__nv_bfloat16, true><<<grid, kGnThreads, 0, stream>>>(xi, x_ld, n, h, w, c, yo, y_ld);
+    else cast_resample_kernel<__nv_bfloat16, false><<<grid, kGnThreads, 0, stream>>>(xi, x_ld, n, h, w, c, yo, y_ld);
+  }
+  FG_CHECK_LAUNCH("cast_resample");
   return FG_OK;
 }

@@ -318,6 +318,29 @@ __global__ void strided_copy_kernel(const CopyK p) {
   }
 }
 
+// GEGLU: y[r][j] = h[r][j] * gelu(h[r][inner + j]) with the exact (erf) GELU of torch.nn.functional.gelu
+__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ h, int64_t h_ld, int rows,
+                                                    int inner, __nv_bfloat16* __restrict__ y, int64_t y_ld) {
+  const int vec_per_row = inner >> 3;
+  const int64_t total = static_cast<int64_t>(rows) * vec_per_row;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / vec_per_row;
+    const int v = static_cast<int>(idx % vec_per_row);
+    const __nv_bfloat16* hr = h + r * h_ld;
+    float a[8], g[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hr) + v), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hr + inner) + v), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // diffusers GEGLU: hidden * gelu(gate), the gelu evaluated and rounded in the activation dtype (bf16)
+      const float ge = bf16_round(0.5f * g[k] * (1.0f + erff(g[k] * 0.70710678118654752f)));
+      o[k] = a[k] * ge;
+    }
+    *(reinterpret_cast<uint4*>(y + r * y_ld) + v) = pack8(o);
+  }
+}
+
 __global__ void bcast_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int na, int nb, int d,
                                  float* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(na) * nb * d;
@@ -496,5 +519,17 @@ extern "C" int fg_strided_copy(const void* src, void* dst, const int32_t* n, con
   }
   strided_copy_kernel<<<ew_grid2(items * k.vec), 256, 0, static_cast<cudaStream_t>(stream_)>>>(k);
   FG_CHECK_LAUNCH("strided_copy");
+  return FG_OK;
+}
+
+extern "C" int fg_geglu(const void* h, int64_t h_ld, int32_t rows, int32_t inner, void* y, int64_t y_ld,
+                        fg_stream_t stream_) {
+  using namespace fg;
+  FG_CHECK_ARG(h && y && rows > 0 && inner > 0 && inner % 8 == 0, "geglu: bad arguments (inner %% 8 == 0)");
+  FG_CHECK_ARG(h_ld >= 2 * inner && h_ld % 8 == 0 && y_ld >= inner && y_ld % 8 == 0 && al16(h) && al16(y),
+               "geglu: rows must be 16-byte aligned, h_ld >= 2 * inner");
+  geglu_kernel<<<ew_grid2(static_cast<int64_t>(rows) * (inner / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(h), h_ld, rows, inner, static_cast<__nv_bfloat16*>(y), y_ld);
+  FG_CHECK_LAUNCH("geglu");
   return FG_OK;
 }

@@ -350,3 +350,19 @@ def strided_copy_args(src: torch.Tensor, dst: torch.Tensor, n: Sequence[int], sr
 def strided_copy(src, dst, n, src_strides, dst_strides, item_elems) -> None:
     args, _keep = strided_copy_args(src, dst, n, src_strides, dst_strides, item_elems)
     L.check(L.lib().fg_strided_copy(*args, _stream()), "fg_strided_copy")
+
+
+def geglu(h: torch.Tensor, rows: int, inner: int, y: torch.Tensor) -> None:
+    """y[r, j] = h[r, j] * gelu(h[r, inner + j]) (erf GELU, rounded to bf16 before the product like diffusers' GEGLU)."""
+    _need_cuda(h, y)
+    assert h.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+    L.check(L.lib().fg_geglu(h.data_ptr(), h.stride(0), rows, inner, y.data_ptr(), y.stride(0), _stream()), "fg_geglu")
+
+
+def cast_resample(x: torch.Tensor, x_ld: int, n: int, h: int, w: int, c: int, y: torch.Tensor, y_ld: int,
+                  up2: bool = False) -> None:
+    """y = bf16(x) for channels-last [n,h,w,c] (fp32 / bf16), optionally nearest-upsampled to [n,2h,2w,c]."""
+    _need_cuda(x, y)
+    assert y.dtype == torch.bfloat16
+    L.check(L.lib().fg_cast_resample(x.data_ptr(), _DT[x.dtype], x_ld, n, h, w, c, L.FG_RES_UP2 if up2 else L.FG_RES_NONE,
+                                     y.data_ptr(), y_ld, _stream()), "fg_cast_resample")

@@ -121,6 +121,13 @@ typedef struct {
 
 int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream);
 
+/* y = bf16(x) for a channels-last [n,h,w,c] tensor (fp32 or bf16), resample = FG_RES_NONE, or FG_RES_UP2 for the
+ * nearest 2x upsampling of diffusers Upsample2D (F.interpolate(scale_factor=2, mode="nearest"); output [n,2h,2w,c]):
+ * the raw conv operands of the SDXL UNet's down/upsamplers (UNet2DConditionModel, wrapped by the reference at
+ * fastgen/networks/SDXL/network.py:210-230 and driven by fastgen/networks/SD15/network.py:152-324). */
+int fg_cast_resample(const void* x, int32_t x_dtype, int64_t x_ld, int32_t n, int32_t h, int32_t w, int32_t c,
+                     int32_t resample, void* y, int64_t y_ld, fg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * UNet self-attention (softmax(q.k/sqrt(d)) v per head, fp32 softmax) -- replaces AttentionOp + the two
  * einsums (fastgen/networks/EDM/network.py:160-168, 290-296).  qkv is the 1x1-conv output in channels-last
@@ -218,6 +225,9 @@ int fg_unpatchify(const void* y, int64_t y_ld, int32_t b, int32_t c, int32_t f, 
  * unpack permutations around the Ulysses all-to-all (tokens <-> heads) and the head-sharded KV-cache append. */
 int fg_strided_copy(const void* src, void* dst, const int32_t* n, const int64_t* src_strides,
                     const int64_t* dst_strides, int32_t item_bytes, fg_stream_t stream);
+/* GEGLU feed-forward gate of the SDXL transformer blocks (diffusers GEGLU, used by UNet2DConditionModel which the
+ * reference wraps at fastgen/networks/SDXL/network.py:210-230): y[r][j] = h[r][j] * gelu_erf(h[r][inner + j]), bf16. */
+int fg_geglu(const void* h, int64_t h_ld, int32_t rows, int32_t inner, void* y, int64_t y_ld, fg_stream_t stream);
 /* out[i][g][:] = a[i][:] + b[g][:], fp32: scale_shift_table of every block + timestep projection of every frame. */
 int fg_bcast_add(const float* a, const float* b, int32_t na, int32_t nb, int32_t d, float* out, fg_stream_t stream);
 

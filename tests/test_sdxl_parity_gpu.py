@@ -1,0 +1,100 @@
+"""Parity of the CUDA SDXL UNet path against the CPU oracle (oracle/sdxl_oracle.py, PARITY UNPINNED: the layer
+arithmetic lives in diffusers 0.35.1 `UNet2DConditionModel`) on identical random bf16-representable weights and inputs;
+bf16 path tolerance rel-L2 <= 1e-2 on x0 / eps (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from oracle import sampler_oracle as SO
+from oracle import sdxl_oracle as XO
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _net(cfg, seed):
+    from fastgen_b200.sdxl import StableDiffusionXL
+
+    sd = {k: v.bfloat16().float() for k, v in XO.make_state_dict(cfg, seed).items()}
+    net = StableDiffusionXL(unet_config=cfg)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("unet.logvar_linear") for k in missing)
+    return net.cuda().eval(), sd
+
+
+def _inputs(cfg, B, S, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cfg["in_channels"], S, S, generator=g).to(dtype)
+    text = torch.randn(B, 77, cfg["cross_attention_dim"], generator=g).bfloat16().float()
+    pooled = torch.randn(B, cfg["pooled_dim"], generator=g).bfloat16().float()
+    return x, text, pooled
+
+
+@pytest.mark.parametrize("cfg,S", [(XO.tiny_config(), 32),
+                                   (XO.tiny_config(block_out_channels=(64, 192), down_attn=(False, True),
+                                                   transformer_layers=(1, 2), num_heads=(1, 3), layers_per_block=1), 16)],
+                         ids=["3level", "2level_d64x3"])
+def test_sdxl_forward_matches_oracle(cfg, S):
+    net, sd = _net(cfg, 0)
+    B = 2
+    x, text, pooled = _inputs(cfg, B, S, 1)
+    t = torch.tensor([0.999, 0.4], dtype=torch.float64)
+    for pred in ("eps", "x0"):
+        out = net(x.cuda(), t.cuda(), condition=[text.cuda(), pooled.cuda()], fwd_pred_type=pred)
+        ref = XO.sdxl_forward(sd, cfg, x, t, text, pooled, fwd_pred_type=pred)
+        assert out.shape == x.shape and out.dtype == x.dtype
+        assert _rel(out, ref) < 1e-2, (pred, _rel(out, ref))
+    # bf16 latents (the reference's SDXL configuration, experiments/SDXL/config_dmd2.py): same network, bf16 in / out
+    xb = x.bfloat16()
+    out = net(xb.cuda(), t.cuda(), condition=[text.cuda().bfloat16(), pooled.cuda().bfloat16()], fwd_pred_type="eps")
+    ref = XO.sdxl_forward(sd, cfg, xb.float(), t, text, pooled, fwd_pred_type="eps")
+    assert out.dtype == torch.bfloat16 and _rel(out, ref) < 1.5e-2, _rel(out, ref)
+    # a second prompt through the same plan: the text keys / values are recomputed, nothing else is rebuilt
+    x2, text2, pooled2 = _inputs(cfg, B, S, 5)
+    out2 = net(x2.cuda(), t.cuda(), condition=[text2.cuda(), pooled2.cuda()], fwd_pred_type="eps")
+    ref2 = XO.sdxl_forward(sd, cfg, x2, t, text2, pooled2, fwd_pred_type="eps")
+    assert _rel(out2, ref2) < 1e-2, _rel(out2, ref2)
+
+
+def test_sdxl_four_step_sampler_matches_oracle():
+    """config 3 of BASELINE.json at test size: DMD2 4-step SDE generation, t_list = linspace(0.999, 0, 5)"""
+    from fastgen_b200.sampler import FastGenModel
+
+    cfg = XO.tiny_config()
+    net, sd = _net(cfg, 2)
+    B, S = 2, 32
+    noise, text, pooled = _inputs(cfg, B, S, 3)
+    g = torch.Generator().manual_seed(4)
+    eps = [torch.randn(B, 4, S, S, generator=g) for _ in range(3)]
+    sched = SO.Schedule("alphas", XO.alphas_cumprod())
+    ref = SO.generator_fn(lambda x, tb, **kw: XO.sdxl_forward(sd, cfg, x, tb, text, pooled), sched, noise, 4, None, eps,
+                          "sde")
+    it = iter(eps)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, **kw: next(it).to(x.device, x.dtype)
+    try:
+        out = FastGenModel.generator_fn(net, noise.cuda(), condition=[text.cuda(), pooled.cuda()],
+                                        student_sample_steps=4)
+    finally:
+        torch.randn_like = orig
+    assert out.shape == noise.shape
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+def test_sdxl_argument_errors():
+    from fastgen_b200._lib import FastGenB200Error
+
+    cfg = XO.tiny_config()
+    net, _ = _net(cfg, 0)
+    x, text, pooled = _inputs(cfg, 1, 32, 0)
+    t = torch.tensor([0.5], dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        net(x.cuda(), t.cuda(), condition=[text.cuda(), pooled.cuda()], r=t.cuda())
+    with pytest.raises(FastGenB200Error):
+        net(x, t, condition=[text, pooled])
+    with pytest.raises(AssertionError):
+        net(x.cuda(), t.cuda(), condition=[text.cuda(), pooled.cuda()], fwd_pred_type="bogus")
+    assert net(x.cuda(), t.cuda(), condition=[text.cuda(), pooled.cuda()], return_features_early=True) == []

@@ -233,3 +233,38 @@ def test_bcast_add():
     ops.bcast_add(a, b, out)
     torch.cuda.synchronize()
     assert torch.equal(out, a[:, None] + b[None])
+
+
+@pytest.mark.parametrize("rows,inner", [(300, 256), (77, 40), (4096, 2560)])
+def test_geglu(rows, inner):
+    """diffusers GEGLU (SDXL feed-forward): hidden * gelu(gate), gelu evaluated and rounded in bf16"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(0)
+    h = (2 * torch.randn(rows, 2 * inner + 8, device=DEV)).bfloat16()   # ld > 2 * inner
+    y = torch.zeros(rows, inner, device=DEV, dtype=torch.bfloat16)
+    ops.geglu(h, rows, inner, y)
+    torch.cuda.synchronize()
+    hid, gate = h[:, :inner], h[:, inner:2 * inner]
+    ref = hid.float() * F.gelu(gate.float()).bfloat16().float()
+    assert _rel(y, ref) < 4e-3, _rel(y, ref)
+    assert torch.equal(y, ref.bfloat16()) or (y.float() - ref).abs().max() <= 2 ** -7 * ref.abs().max()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("up2", [False, True])
+def test_cast_resample(dt, up2):
+    from fastgen_b200 import ops
+
+    torch.manual_seed(1)
+    n, h, w, c, ld = 3, 8, 16, 40, 56
+    buf = torch.randn(n, h, w, ld, device=DEV).to(dt)
+    x = buf[..., 8:8 + c]                                             # a slice of a wider concat buffer
+    s = 2 if up2 else 1
+    y = torch.zeros(n, s * h, s * w, c, device=DEV, dtype=torch.bfloat16)
+    ops.cast_resample(x, ld, n, h, w, c, y, c, up2=up2)
+    torch.cuda.synchronize()
+    ref = x.bfloat16()
+    if up2:
+        ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(y, ref)
