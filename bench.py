@@ -296,25 +296,40 @@ WAN_TL = [0.999, 0.937, 0.833, 0.624, 0.0]
 WAN_TFLOP_PER_SAMPLE = 995.0  # causal AR sample, 7 chunks x 5 passes (upper bound)
 
 
+WAN14B_TFLOP_PER_SAMPLE = 4 * 6523.3  # bidirectional 14B forward at 720p (75 600 tokens) x 4 steps
+
+
 def run_wan(args):
     import torch.distributed as dist
 
-    from fastgen_b200.sampler import CausVidModel
-    from fastgen_b200.wan import CausalWan
+    from fastgen_b200.sampler import CausVidModel, FastGenModel
+    from fastgen_b200.wan import CausalWan, Wan
+
+    big = args.workload == "wan14b"   # BASELINE configs[4]: bidirectional 14B, 720p, 4-step ode, Ulysses over all ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    sp = min(world, 4)
+    sp = world if big else min(world, 4)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 0)
     frames = 21
+    lh, lw = (90, 160) if big else (60, 104)
     torch.manual_seed(0)
     with torch.device(dev):
-        net = CausalWan(total_num_frames=frames, chunk_size=3, use_wan_official_sinusoidal=True, enable_logvar_linear=False)
+        if big:
+            with torch.no_grad():
+                torch.set_default_dtype(torch.bfloat16)   # 14 B parameters: build them in bf16 straight away
+                try:
+                    net = Wan(model_id_or_local_path=Wan.MODEL_ID_14B, enable_logvar_linear=False)
+                finally:
+                    torch.set_default_dtype(torch.float32)
+        else:
+            net = CausalWan(total_num_frames=frames, chunk_size=3, use_wan_official_sinusoidal=True,
+                            enable_logvar_linear=False)
         torch.nn.init.normal_(net.transformer.proj_out.weight, std=0.02)
     net = net.to(torch.bfloat16).eval()
     replica = rank // sp
@@ -322,12 +337,15 @@ def run_wan(args):
         groups = [dist.new_group(list(range(g * sp, (g + 1) * sp))) for g in range(world // sp)]
         net.sp_group = groups[replica]
     torch.manual_seed(1 + replica)  # ranks of one sequence-parallel group draw identical noise
-    noise_h = torch.randn(1, 16, frames, 60, 104).bfloat16().pin_memory()
+    noise_h = torch.randn(1, 16, frames, lh, lw).bfloat16().pin_memory()
     text_h = torch.randn(1, 512, 4096).bfloat16().pin_memory()
-    out_h = torch.empty(1, 16, frames, 60, 104, dtype=torch.bfloat16).pin_memory()
+    out_h = torch.empty(1, 16, frames, lh, lw, dtype=torch.bfloat16).pin_memory()
     noise, text = noise_h.to(dev), text_h.to(dev)
 
     def gen(n_, c_):
+        if big:
+            return FastGenModel.generator_fn(net, n_, student_sample_steps=4, t_list=WAN_TL, condition=c_,
+                                             student_sample_type="ode")
         return CausVidModel.generator_fn(net, n_, student_sample_steps=4, t_list=WAN_TL, condition=c_,
                                          student_sample_type="sde")
 
@@ -381,12 +399,15 @@ def run_wan(args):
     gemm_fl = sum(d["flops"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
     if rank == 0:
         line = {
-            "metric": "samples/sec, 4-step self-forcing Wan 2.1 1.3B T2V 480p 81 frames", "value": value,
+            "metric": ("samples/sec, 4-step Wan 2.1 14B T2V 720p 81 frames" if big else
+                       "samples/sec, 4-step self-forcing Wan 2.1 1.3B T2V 480p 81 frames"), "value": value,
             "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong" if replicas == 1 else "strong within a group of 4, weak across groups",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Wan 2.1 1.3B T2V 480p 81-frame 4-step self-forcing, batch 1 per group (BASELINE configs[3])",
-                       "latent": [1, 16, frames, 60, 104], "t_list": WAN_TL, "chunk_size": 3,
+            "config": {"workload": ("Wan 2.1 14B T2V 720p 81-frame 4-step (ode), batch 1, Ulysses sequence parallel (BASELINE configs[4])"
+                                    if big else
+                                    "Wan 2.1 1.3B T2V 480p 81-frame 4-step self-forcing, batch 1 per group (BASELINE configs[3])"),
+                       "latent": [1, 16, frames, lh, lw], "t_list": WAN_TL, "chunk_size": None if big else 3,
                        "parallelism": f"Ulysses sequence parallel x{sp}, {replicas} replica(s)",
                        "l2": "inputs exceed L2: 2.8 GB of weights + up to 6 GB of KV cache streamed per sample"},
             "e2e": {"value": replicas * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
@@ -398,7 +419,8 @@ def run_wan(args):
                          "peak_source": peak_src + ", sustained bf16", "share_of_step": att["ms"] / tot_ms if tot_ms else None,
                          "gemm_tflops": gemm_fl / (gemm_ms / 1000.0) / 1e12 if gemm_ms else None,
                          "per_kernel_ms": {k: round(d["ms"], 2) for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]},
-                         "model_flops_utilisation": (value * WAN_TFLOP_PER_SAMPLE) / (world * tf_sus)},
+                         "model_flops_utilisation": (value * (WAN14B_TFLOP_PER_SAMPLE if big else WAN_TFLOP_PER_SAMPLE))
+                                                    / (world * tf_sus)},
             "cpu_baseline": None,
         }
         print(json.dumps(line))
@@ -518,7 +540,7 @@ def run_sdxl(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="in64", choices=["in64", "wan", "sdxl"],
+    ap.add_argument("--workload", default="in64", choices=["in64", "wan", "wan14b", "sdxl"],
                     help="in64 = the headline line the driver records; wan = secondary workload for profiles/")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -529,7 +551,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "wan":
+    elif args.workload in ("wan", "wan14b"):
         run_wan(args)
     elif args.workload == "sdxl":
         run_sdxl(args)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfastgen_b200.so")
 FG_MAX_SEG = 6
 FG_F32, FG_BF16, FG_F64 = 0, 1, 2
 FG_RES_NONE, FG_RES_SAME, FG_RES_UP2, FG_RES_DOWN2 = 0, 1, 2, 3
-FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU = 0, 1, 2
+FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU, FG_ACT_GEGLU = 0, 1, 2, 3
 
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
@@ -85,7 +85,7 @@ class LnModParams(C.Structure):
         ("x", C.c_void_p), ("x_ld", C.c_int64), ("rows", C.c_int32), ("d", C.c_int32), ("eps", C.c_float),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("mod_ld", C.c_int64), ("rows_per_group", C.c_int32),
-        ("y", C.c_void_p), ("y_ld", C.c_int64),
+        ("y", C.c_void_p), ("y_ld", C.c_int64), ("x_dtype", C.c_int32),
     ]
 
 

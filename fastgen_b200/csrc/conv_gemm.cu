@@ -39,6 +39,8 @@ constexpr int kResNone = 0;      // no residual, or one the TMA path cannot take
 constexpr int kResSame = 1;
 constexpr int kResUp2 = 2;
 __host__ __device__ constexpr int epi_mode(bool out_bf16, int res) { return (out_bf16 ? 1 : 0) | (res << 1); }
+// FG_ACT_GEGLU: bf16 output of half the accumulator width, out[j] = v[2j] * gelu_erf(v[2j+1]), no residual
+constexpr int kEpiGeglu = 8 | 1;
 
 template <int BLOCK_N>
 struct ConvCfg {
@@ -308,7 +310,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   using Cfg = ConvCfg<BLOCK_N>;
   constexpr bool kTmaStore = EPI != kEpiGeneric;
   constexpr bool kOutBf16 = kTmaStore && (EPI & 1);
-  constexpr int kRes = kTmaStore ? (EPI >> 1) : kResNone;
+  constexpr int kRes = kTmaStore ? ((EPI >> 1) & 3) : kResNone;
+  constexpr bool kGeglu = kTmaStore && (EPI & 8);
+  static_assert(!kGeglu || (kOutBf16 && kRes == kResNone && BLOCK_N % 128 == 0), "GEGLU tail: bf16, no residual");
   static_assert(!kTmaStore || BLOCK_N >= 64, "the TMA-store epilogue needs tiles of at least one bf16 slab");
 
   extern __shared__ uint8_t smem_raw[];
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     // slab ring bookkeeping (slab_idx counts the slabs of this CTA across all its tiles)
     constexpr uint32_t kResAhead = 2;  // residual slabs in flight ahead of the one being processed
-    constexpr int kSlabCols = kOutBf16 ? 64 : 32;
+    constexpr int kSlabCols = kGeglu ? 128 : kOutBf16 ? 64 : 32;  // accumulator columns behind one 128-byte slab row
     // FG_RES_UP2 prefetch: three output slabs, the fourth buffer holds the four quarter-size residual boxes
     constexpr uint32_t kOutRing = (kRes == kResUp2) ? Cfg::OUT_SLABS - 1 : Cfg::OUT_SLABS;
     const bool is_store_thread = (warp == 2 && lane == 0);
@@ -505,7 +509,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 32; ++j) a[j] = 1.0f;
             }
-            if constexpr (!kOutBf16) {
+            if constexpr (kGeglu) {
+              // columns (2j, 2j+1) = (hidden_j, gate_j): 32 accumulator columns -> 16 outputs = two 16-byte chunks
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float hid = a[16 * j + 2 * k], g = a[16 * j + 2 * k + 1];
+                  o[k] = hid * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f)));
+                }
+                const int chunk = (cc >> 4) + j;
+                uint4 u;
+                u.x = pack_bf16x2(o[0] * sc, o[1] * sc), u.y = pack_bf16x2(o[2] * sc, o[3] * sc);
+                u.z = pack_bf16x2(o[4] * sc, o[5] * sc), u.w = pack_bf16x2(o[6] * sc, o[7] * sc);
+                *reinterpret_cast<uint4*>(my_row + ((chunk ^ wkey) << 4)) = u;
+              }
+            } else if constexpr (!kOutBf16) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float4 o = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
@@ -538,7 +558,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (is_store_thread && !(p.dbg & 1)) {
-            tma_store_4d(&p.tmOut, slab, t.co0 + c0, t.w0, t.h0, t.img0);
+            tma_store_4d(&p.tmOut, slab, kGeglu ? ((t.co0 + c0) >> 1) : (t.co0 + c0), t.w0, t.h0, t.img0);
             tma_store_commit();
           }
           if constexpr (!kOutBf16) {
@@ -637,6 +657,9 @@ static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_
       case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame)>(kp, num_sms, stream);
       case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2)>(kp, num_sms, stream);
       case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2)>(kp, num_sms, stream);
+      case kEpiGeglu:
+        if constexpr (BLOCK_N % 128 == 0) return launch_conv<BLOCK_N, kEpiGeglu>(kp, num_sms, stream);
+        break;
       default: break;
     }
   }
@@ -645,15 +668,18 @@ static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_
 
 // Tile width: the candidate that minimises (waves of tiles over the SMs) x (tile cost ~ width), i.e. padding waste in
 // N and wave quantisation are weighed together; ties go to the wider tile (fewer A re-reads from L2).
-static int pick_block_n(int cout, int m_tiles, int num_sms) {
-  if (cout <= 16) return 16;
-  if (cout <= 64) return 64;
+static int pick_block_n(int cout, int m_tiles, int num_sms, bool geglu) {
+  if (!geglu) {
+    if (cout <= 16) return 16;
+    if (cout <= 64) return 64;
+  }
   if (cout <= 128) return 128;
   int best = 128;
   int64_t best_cost = INT64_MAX;
   const int cands[3] = {128, 192, 256};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
+    if (geglu && bn % 128) continue;  // a GEGLU slab is 128 accumulator columns
     const int64_t tiles = static_cast<int64_t>(m_tiles) * ((cout + bn - 1) / bn);
     const int64_t waves = (tiles + num_sms - 1) / num_sms;
     const int64_t cost = waves * (bn + 16);  // + fixed per-tile cost (pipeline fill, barriers)
@@ -679,8 +705,13 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   FG_CHECK_ARG(p->nseg >= 1 && p->nseg <= FG_MAX_SEG, "conv_gemm: nseg=%d out of range", p->nseg);
   FG_CHECK_ARG(p->out != nullptr, "conv_gemm: null output");
   FG_CHECK_ARG(p->out_dtype == FG_F32 || p->out_dtype == FG_BF16, "conv_gemm: bad out_dtype %d", p->out_dtype);
-  FG_CHECK_ARG(p->out_ld >= p->cout, "conv_gemm: out_ld %lld < cout %d", (long long)p->out_ld, p->cout);
-  FG_CHECK_ARG(p->act >= FG_ACT_NONE && p->act <= FG_ACT_SILU, "conv_gemm: bad act %d", p->act);
+  FG_CHECK_ARG(p->act >= FG_ACT_NONE && p->act <= FG_ACT_GEGLU, "conv_gemm: bad act %d", p->act);
+  const bool geglu = p->act == FG_ACT_GEGLU;
+  const int out_cols = geglu ? p->cout / 2 : p->cout;  // GEGLU writes one column per (hidden, gate) column pair
+  FG_CHECK_ARG(p->out_ld >= out_cols, "conv_gemm: out_ld %lld < %d output columns", (long long)p->out_ld, out_cols);
+  if (geglu)
+    FG_CHECK_ARG(p->cout % 16 == 0 && p->out_dtype == FG_BF16 && !p->res && !p->gate && !p->stats,
+                 "conv_gemm: FG_ACT_GEGLU needs cout %% 16 == 0, a bf16 output, no residual / gate / statistics");
   if (p->gate)
     FG_CHECK_ARG(p->gate_rows > 0 && p->gate_ld >= p->cout, "conv_gemm: gate needs gate_rows > 0 and gate_ld >= cout");
 
@@ -716,7 +747,7 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     cudaGetLastError();
     num_sms = 148;
   }
-  const int block_n = pick_block_n(p->cout, kp.tiles_w * kp.tiles_h * kp.tiles_img, num_sms);
+  const int block_n = pick_block_n(p->cout, kp.tiles_w * kp.tiles_h * kp.tiles_img, num_sms, geglu);
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_img * kp.tiles_n;
 
@@ -791,7 +822,7 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     const int esz = p->out_dtype == FG_F32 ? 4 : 2;
     static const bool allow_tma_store = !(getenv("FG_CONV_TMA_STORE") && getenv("FG_CONV_TMA_STORE")[0] == '0');
     if (allow_tma_store && kp.vec && block_n >= 64 && (p->out_ld * esz) % 16 == 0) {
-      const uint64_t dims[4] = {(uint64_t)p->cout, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
+      const uint64_t dims[4] = {(uint64_t)out_cols, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
       const uint64_t ldb = (uint64_t)p->out_ld * esz;
       const uint64_t strides[4] = {(uint64_t)esz, ldb, ldb * p->w, ldb * p->w * p->h};
       const uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
@@ -812,9 +843,10 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
         if (r != FG_OK) return r;
         res_kind = up ? kResUp2 : kResSame;
       }
-      epi = epi_mode(p->out_dtype == FG_BF16, res_kind);
+      epi = geglu ? kEpiGeglu : epi_mode(p->out_dtype == FG_BF16, res_kind);
     }
   }
+  if (geglu) FG_CHECK_ARG(epi == kEpiGeglu, "conv_gemm: FG_ACT_GEGLU needs the TMA-store epilogue (16-byte aligned bf16 output rows)");
   if (kp.stats) FG_CHECK_ARG(epi != kEpiGeneric, "conv_gemm: fused GroupNorm statistics need the TMA-store epilogue (cout %% 4 == 0, cout > 16, 16-byte aligned rows)");
 
   switch (block_n) {

@@ -43,7 +43,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // LayerNorm (+ modulate | + affine)
 // ---------------------------------------------------------------------------------------------------------
 struct LnK {
-  const __nv_bfloat16* x;
+  const void* x;  // bf16 or fp32 rows
   int64_t x_ld;
   int rows, d;
   float eps;
@@ -57,20 +57,27 @@ struct LnK {
   int64_t y_ld;
 };
 
-template <int NV>  // 16-byte vectors per lane: d <= NV * 256
+template <int NV, typename TX>  // NV 8-element vectors per lane: d <= NV * 256; TX = input row type
 __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const LnK p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = p.d >> 3;
   const float inv_d = 1.0f / static_cast<float>(p.d);
   for (int row = blockIdx.x * (kRowThreads / 32) + warp; row < p.rows; row += gridDim.x * (kRowThreads / 32)) {
-    const __nv_bfloat16* xr = p.x + static_cast<int64_t>(row) * p.x_ld;
+    const TX* xr = static_cast<const TX*>(p.x) + static_cast<int64_t>(row) * p.x_ld;
     float v[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+        if constexpr (sizeof(TX) == 2) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+        } else {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + 2 * vi);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 2 * vi + 1);
+          v[i][0] = a.x, v[i][1] = a.y, v[i][2] = a.z, v[i][3] = a.w;
+          v[i][4] = b.x, v[i][5] = b.y, v[i][6] = b.z, v[i][7] = b.w;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += v[i][k];
       }
@@ -382,20 +389,29 @@ extern "C" int fg_ln_modulate(const fg_ln_mod_params* p, fg_stream_t stream_) {
                  "ln_modulate: modulation needs rows_per_group > 0, mod_ld >= d, 16-byte aligned rows");
   if (p->gamma) FG_CHECK_ARG(al16(p->gamma) && al16(p->beta), "ln_modulate: gamma/beta must be 16-byte aligned");
   LnK k;
-  k.x = static_cast<const __nv_bfloat16*>(p->x), k.x_ld = p->x_ld, k.rows = p->rows, k.d = p->d, k.eps = p->eps;
+  FG_CHECK_ARG(p->x_dtype == FG_BF16 || p->x_dtype == FG_F32, "ln_modulate: x_dtype %d must be FG_BF16 or FG_F32", p->x_dtype);
+  k.x = p->x, k.x_ld = p->x_ld, k.rows = p->rows, k.d = p->d, k.eps = p->eps;
   k.gamma = p->gamma, k.beta = p->beta, k.scale = p->scale, k.shift = p->shift, k.mod_ld = p->mod_ld;
   k.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : p->rows;
   k.y = static_cast<__nv_bfloat16*>(p->y), k.y_ld = p->y_ld;
   const int grid = row_grid(p->rows);
   const int nv = (p->d / 8 + 31) / 32;
-  if (nv <= 6)
-    ln_modulate_kernel<6><<<grid, kRowThreads, 0, stream>>>(k);
-  else if (nv <= 12)
-    ln_modulate_kernel<12><<<grid, kRowThreads, 0, stream>>>(k);
-  else if (nv <= 20)
-    ln_modulate_kernel<20><<<grid, kRowThreads, 0, stream>>>(k);
+#define FG_LN_LAUNCH(TX)                                                \
+  do {                                                                  \
+    if (nv <= 6)                                                        \
+      ln_modulate_kernel<6, TX><<<grid, kRowThreads, 0, stream>>>(k);   \
+    else if (nv <= 12)                                                  \
+      ln_modulate_kernel<12, TX><<<grid, kRowThreads, 0, stream>>>(k);  \
+    else if (nv <= 20)                                                  \
+      ln_modulate_kernel<20, TX><<<grid, kRowThreads, 0, stream>>>(k);  \
+    else                                                                \
+      ln_modulate_kernel<32, TX><<<grid, kRowThreads, 0, stream>>>(k);  \
+  } while (0)
+  if (p->x_dtype == FG_BF16)
+    FG_LN_LAUNCH(__nv_bfloat16);
   else
-    ln_modulate_kernel<32><<<grid, kRowThreads, 0, stream>>>(k);
+    FG_LN_LAUNCH(float);
+#undef FG_LN_LAUNCH
   FG_CHECK_LAUNCH("ln_modulate");
   return FG_OK;
 }

@@ -261,10 +261,11 @@ def ln_mod_params(x: torch.Tensor, x_ld: int, rows: int, d: int, eps: float, y: 
                   scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, mod_ld: int = 0,
                   rows_per_group: int = 0) -> "L.LnModParams":
     _need_cuda(x, y, gamma, beta, scale, shift)
-    if x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
-        raise ValueError("ln_modulate: rows must be bfloat16")
+    if x.dtype not in (torch.bfloat16, torch.float32) or y.dtype != torch.bfloat16:
+        raise ValueError("ln_modulate: input rows must be bfloat16 or float32, output rows bfloat16")
     p = L.LnModParams()
     p.x, p.x_ld, p.rows, p.d, p.eps = x.data_ptr(), x_ld, rows, d, eps
+    p.x_dtype = _DT[x.dtype]
     p.gamma, p.beta, p.scale, p.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
     p.mod_ld, p.rows_per_group = mod_ld, rows_per_group
     p.y, p.y_ld = y.data_ptr(), y_ld

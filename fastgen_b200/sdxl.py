@@ -16,15 +16,16 @@ Forward (model-level ``classify_forward``, fastgen/networks/SD15/network.py:46-3
                     next norm fused)
   Transformer2D   = fg_gn_apply(norm) -> GEMM(proj_in) -> per block [fg_ln_modulate -> GEMM(q|k|v) -> fg_flash_attn ->
                     GEMM(to_out + residual) -> fg_ln_modulate -> GEMM(q) -> fg_flash_attn(77 text keys) -> GEMM(to_out +
-                    residual) -> fg_ln_modulate -> GEMM(ff.0) -> fg_geglu -> GEMM(ff.2 + residual)] -> GEMM(proj_out +
-                    the block input as residual)
+                    residual) -> fg_ln_modulate -> GEMM(ff.0 with the GEGLU gate in its tail) -> GEMM(ff.2 + residual)] ->
+                    GEMM(proj_out + the block input as residual)
   Downsample2D    = fg_cast_resample -> fg_conv_gemm (stride-1 taps) -> fg_strided_copy (keeps the even pixels: the
                     stride-2 / pad-1 convolution evaluated where its outputs are)
   Upsample2D      = fg_cast_resample(nearest 2x) -> fg_conv_gemm
   skip concatenations are zero-copy: the producer writes its slice of the consumer's channels-last buffer.
 
 The feature maps between layers are fp32 (GroupNorm statistics are accumulated by the producing GEMM), every tensor-core
-operand and the token stream inside the transformer blocks is bf16, accumulation / statistics / softmax are fp32.  The
+operand is bf16, the token (residual) stream inside the transformer blocks is fp32 like the feature maps, accumulation /
+statistics / softmax are fp32.  The
 text keys/values of all 70 cross-attention layers depend on the prompt only and are computed once per condition tensor.
 """
 from __future__ import annotations
@@ -348,7 +349,12 @@ class StableDiffusionXL(FastGenNetwork):
                 pk[q + ".q2.w"] = w(blk.attn2.to_q)
                 pk[q + ".kv2.w"] = torch.cat([blk.attn2.to_k.weight, blk.attn2.to_v.weight], 0).detach().to(bf).contiguous()
                 pk[q + ".o2.w"], pk[q + ".o2.b"] = w(blk.attn2.to_out[0]), b(blk.attn2.to_out[0])
-                pk[q + ".ff0.w"], pk[q + ".ff0.b"] = w(blk.ff.net[0].proj), b(blk.ff.net[0].proj)
+                # GEGLU fused into the ff.net.0 GEMM tail: rows interleaved to (hidden_j, gate_j) pairs (FG_ACT_GEGLU)
+                fp = blk.ff.net[0].proj
+                inner = fp.out_features // 2
+                perm = torch.stack([torch.arange(inner), torch.arange(inner) + inner], 1).reshape(-1).to(fp.weight.device)
+                pk[q + ".ff0.w"] = fp.weight.detach()[perm].to(bf).contiguous()
+                pk[q + ".ff0.b"] = fp.bias.detach()[perm].to(f32).contiguous()
                 pk[q + ".ff2.w"], pk[q + ".ff2.b"] = w(blk.ff.net[2]), b(blk.ff.net[2])
         for i, blk in enumerate(u.down_blocks):
             if hasattr(blk, "downsamplers"):
@@ -440,8 +446,8 @@ class StableDiffusionXL(FastGenNetwork):
             if kind == "res":
                 req("h0", px * ci), req("raw", px * ci), req("h1", px * co, f32), req("h2", px * co), req("mid", px * co, f32)
             elif kind == "tr":
-                req("nrm", px * ci), req("hs", px * ci), req("qkv", px * 3 * ci), req("att", px * ci)
-                req("ff", px * 8 * ci), req("gg", px * 4 * ci)
+                req("nrm", px * ci), req("hs", px * ci, f32), req("qkv", px * 3 * ci), req("att", px * ci)
+                req("gg", px * 4 * ci)
             elif kind == "ds":
                 req("h0", px * ci), req("full", px * co, f32)
             else:
@@ -560,9 +566,9 @@ class StableDiffusionXL(FastGenNetwork):
             d, N = c // heads, x.h * x.w
             rows = B * N
             k = "t." + key
-            nrm, hs = scratch("nrm", [rows, c]), scratch("hs", [rows, c])
+            nrm, hs = scratch("nrm", [rows, c]), scratch("hs", [rows, c], f32)     # fp32 token (residual) stream
             qkv, att = scratch("qkv", [rows, 3 * c]), scratch("att", [rows, c])
-            ff, gg = scratch("ff", [rows, 8 * c]), scratch("gg", [rows, 4 * c])
+            gg = scratch("gg", [rows, 4 * c])
             gn(x, pk[k + ".norm"], 1e-6, nrm.view(B, h, w, c), False, x_stats)
             gemm(nrm, c, pk[k + ".in.w"], rows, c, hs, c, "proj_in", bias=pk[k + ".in.b"])
             for li in range(len(a.transformer_blocks)):
@@ -579,12 +585,14 @@ class StableDiffusionXL(FastGenNetwork):
                 gemm(att, c, pk[q + ".o2.w"], rows, c, hs, c, "attn2_out", bias=pk[q + ".o2.b"], res=hs, res_ld=c,
                      res_mode=L.FG_RES_SAME)
                 ln(hs, rows, c, pk[q + ".norm3"], nrm, "ln3")
-                gemm(nrm, c, pk[q + ".ff0.w"], rows, 8 * c, ff, 8 * c, "ff0", bias=pk[q + ".ff0.b"])
-                plan.add(lib.fg_geglu, ff.data_ptr(), 8 * c, rows, 4 * c, gg.data_ptr(), 4 * c, desc="geglu")
+                gemm(nrm, c, pk[q + ".ff0.w"], rows, 8 * c, gg, 4 * c, "ff0_geglu", bias=pk[q + ".ff0.b"],
+                     act=L.FG_ACT_GEGLU)
                 gemm(gg, 4 * c, pk[q + ".ff2.w"], rows, c, hs, c, "ff2", bias=pk[q + ".ff2.b"], res=hs, res_ld=c,
                      res_mode=L.FG_RES_SAME)
+            plan.add(lib.fg_cast_resample, hs.data_ptr(), L.FG_F32, c, rows, 1, 1, c, L.FG_RES_NONE, nrm.data_ptr(), c,
+                     desc="cast_tokens")
             st = fused_stats(h, w, c, dst.ld, next_c)
-            conv([ops.Seg(hs.view(B, h, w, c), c, pk[k + ".out.w"], c, 1)], B, h, w, c, dst.t, dst.ld, "proj_out",
+            conv([ops.Seg(nrm.view(B, h, w, c), c, pk[k + ".out.w"], c, 1)], B, h, w, c, dst.t, dst.ld, "proj_out",
                  bias=pk[k + ".out.b"], res=x.t, res_ld=x.ld, res_mode=L.FG_RES_SAME, **(st or {}))
             return st["stats"] if st else None
 

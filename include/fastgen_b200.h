@@ -30,7 +30,9 @@ typedef void* fg_stream_t; /* cudaStream_t */
 typedef enum { FG_OK = 0, FG_ERR_INVALID = -1, FG_ERR_CUDA = -2, FG_ERR_UNSUPPORTED = -3 } fg_status;
 typedef enum { FG_F32 = 0, FG_BF16 = 1, FG_F64 = 2 } fg_dtype;
 typedef enum { FG_RES_NONE = 0, FG_RES_SAME = 1, FG_RES_UP2 = 2, FG_RES_DOWN2 = 3 } fg_resample;
-typedef enum { FG_ACT_NONE = 0, FG_ACT_GELU_TANH = 1, FG_ACT_SILU = 2 } fg_activation;
+/* FG_ACT_GEGLU: the accumulator columns are (hidden_j, gate_j) pairs (the caller interleaves the weight rows) and the
+ * output has cout / 2 columns, out[p, j] = v[p, 2j] * gelu_erf(v[p, 2j+1]) -- diffusers GEGLU of the SDXL feed-forward. */
+typedef enum { FG_ACT_NONE = 0, FG_ACT_GELU_TANH = 1, FG_ACT_SILU = 2, FG_ACT_GEGLU = 3 } fg_activation;
 
 const char* fg_last_error(void);
 int fg_version(void);
@@ -169,7 +171,7 @@ int64_t fg_flash_attn_workspace_size(const fg_flash_attn_params* p);
  * fastgen/networks/Wan/network.py:139,150, network_causal.py:503-507,538-542), or LayerNorm(x) * gamma + beta
  * (norm2, Wan/network.py:144); LayerNorm in fp32 without rounding in between (diffusers FP32LayerNorm). */
 typedef struct {
-  const void* x;        /* bf16 [rows][x_ld] */
+  const void* x;        /* [rows][x_ld], bf16 or fp32 (x_dtype) */
   int64_t x_ld;
   int32_t rows, d;
   float eps;
@@ -181,6 +183,7 @@ typedef struct {
   int32_t rows_per_group;
   void* y;              /* bf16 [rows][y_ld] */
   int64_t y_ld;
+  int32_t x_dtype;      /* FG_BF16 (Wan / DiT token rows) or FG_F32 (fp32 token stream of the SDXL transformer blocks) */
 } fg_ln_mod_params;
 
 int fg_ln_modulate(const fg_ln_mod_params* p, fg_stream_t stream);

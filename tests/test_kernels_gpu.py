@@ -485,3 +485,27 @@ def test_attention_large_logits_rescale():
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
     assert _rel(out, ref) < 1.5e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("rows,k,inner", [(300, 64, 128), (1000, 640, 2560), (77, 128, 200)])
+def test_conv_gemm_geglu_tail(rows, k, inner):
+    """FG_ACT_GEGLU: (hidden, gate) column pairs -> hidden * gelu_erf(gate), half-width bf16 output (SDXL ff.net.0)"""
+    import torch.nn.functional as F
+
+    from fastgen_b200 import _lib as L
+    from fastgen_b200 import ops
+
+    torch.manual_seed(0)
+    a = torch.randn(rows, k, device="cuda").bfloat16()
+    w = (torch.randn(2 * inner, k, device="cuda") * k ** -0.5).bfloat16()       # rows [0, inner) hidden, then gate
+    bias = 0.1 * torch.randn(2 * inner, device="cuda")
+    perm = torch.stack([torch.arange(inner), torch.arange(inner) + inner], 1).reshape(-1).cuda()
+    out = torch.zeros(rows, inner + 8, device="cuda", dtype=torch.bfloat16)       # ld > inner
+    ops.conv_gemm([ops.Seg(a, k, w[perm].contiguous(), k, 1)], rows, 1, 1, 2 * inner, out, inner + 8,
+                  bias=bias[perm].contiguous(), act=L.FG_ACT_GEGLU)
+    torch.cuda.synchronize()
+    v = a.float() @ w.float().t() + bias
+    ref = v[:, :inner] * F.gelu(v[:, inner:])
+    got = out[:, :inner].float()
+    assert ((got - ref).norm() / ref.norm()).item() < 4e-3
+    assert torch.all(out[:, inner:] == 0)

@@ -268,3 +268,21 @@ def test_cast_resample(dt, up2):
     if up2:
         ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).bfloat16()
     assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("rows,d", [(100, 640), (37, 1280), (9, 72)])
+def test_ln_affine_fp32_rows(rows, d):
+    """fp32 token stream of the SDXL transformer blocks: LayerNorm(x) * gamma + beta, fp32 in, bf16 out"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(2)
+    x = 3 * torch.randn(rows, d + 8, device=DEV) + 1.0
+    gamma, beta = 1 + 0.1 * torch.randn(d, device=DEV), 0.1 * torch.randn(d, device=DEV)
+    y = torch.zeros(rows, d, device=DEV, dtype=torch.bfloat16)
+    p = ops.ln_mod_params(x, d + 8, rows, d, 1e-5, y, d, gamma=gamma, beta=beta)
+    from fastgen_b200 import _lib as L
+    import ctypes
+    L.check(L.lib().fg_ln_modulate(ctypes.byref(p), torch.cuda.current_stream().cuda_stream), "fg_ln_modulate")
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x[:, :d], (d,), gamma, beta, 1e-5)
+    assert _rel(y, ref) < 3e-3, _rel(y, ref)
