@@ -131,6 +131,17 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// erf GELU through one MUFU: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with the odd polynomial fitted (minimax over
+// |x| <= 8, argument clamped there: tanh has saturated) to atanh(erf(x / sqrt 2)).  Max |error| against the exact
+// 0.5 x (1 + erf(x / sqrt 2)) is 2.5e-5 (the textbook tanh GELU: 4.7e-4), 80x below the bf16 rounding of the result;
+// erff() in this tail made the GEGLU GEMM epilogue-bound (834 vs 1314 TFLOP/s, profiles/sdxl_r01.md).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  const float u = xc * fmaf(x2, fmaf(x2, -0.000351519786667389f, 0.037005665847143085f), 0.7975078607596384f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_fast(u), hx);
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == FG_ACT_GELU_TANH) {
     const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                   const float hid = a[16 * j + 2 * k], g = a[16 * j + 2 * k + 1];
-                  o[k] = hid * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f)));
+                  o[k] = hid * gelu_erf_fast(g);
                 }
                 const int chunk = (cc >> 4) + j;
                 uint4 u;
