@@ -208,5 +208,108 @@ class CausVidModel(FastGenModel):
         net.clear_caches()
         return x
 
+    @classmethod
+    def generator_fn_extrapolation(cls, net, noise: torch.Tensor, condition: Any = None, *, num_segments: int,
+                                   overlap_frames: int, student_sample_steps: int = 1,
+                                   student_sample_type: str = "sde", t_list: Optional[List[float]] = None,
+                                   precision_amp: Optional[torch.dtype] = None, context_noise: Optional[float] = 0,
+                                   **kwargs) -> torch.Tensor:
+        """Multi-segment autoregressive generation with a VAE bridge between segments -- reference
+        ``CausVidModel.generator_fn_extrapolation`` (distribution_matching/causvid.py:187-397): same arguments, call
+        order, random draws and float32 ``t_list``.  ``net.vae`` (``decode`` / ``encode``) is the caller's; the VAE
+        itself is outside this path.  One deliberate difference: with ``t_list=None`` the reference
+        calls ``get_t_list(..., dtype=torch.float32)``, a keyword that method does not take (causvid.py:244 vs
+        noise_schedule.py:259), so only its explicit-``t_list`` branch runs; here the default list is
+        ``get_t_list(steps)`` cast to float32."""
+        with inference_mode(net, precision_amp=precision_amp, device_type=noise.device.type):
+            if num_segments < 1:
+                raise ValueError("num_segments must be >= 1")
+            if overlap_frames > 0 and getattr(net, "vae", None) is None:
+                raise ValueError("generator_fn_extrapolation requires a VAE instance via `vae` when overlap_frames > 0")
+            batch_size, _, segment_frames, _, _ = noise.shape
+            dtype, device = noise.dtype, noise.device
+            chunk_size = net.chunk_size
+            if segment_frames % chunk_size != 0:
+                raise ValueError(f"Segment length {segment_frames} must be divisible by chunk_size {chunk_size}")
+            if overlap_frames < 0 or overlap_frames >= segment_frames:
+                raise ValueError("overlap_frames must be in [0, segment_frames)")
+            if overlap_frames % chunk_size != 0:
+                raise ValueError("overlap_frames must be divisible by chunk_size")
+            sched = net.noise_scheduler
+            if t_list is None:
+                tl = sched.get_t_list(student_sample_steps, device=device).to(torch.float32)
+            else:
+                assert len(t_list) - 1 == student_sample_steps, (
+                    f"t_list length (excluding zero) != student_sample_steps: {len(t_list) - 1} != {student_sample_steps}")
+                tl = torch.tensor(t_list, device=device, dtype=torch.float32)
+            t_host = tl.detach().cpu()
+            assert t_host[-1].item() == 0, "t_list[-1] must be zero"
+            fwd = dict(condition=condition, fwd_pred_type="x0", cache_tag="pos", is_ar=True)
+
+            def prefill_caches(segment_latents: torch.Tensor, frames: int) -> None:
+                start = 0
+                t_zero = tl[-1].expand(batch_size)
+                while start < frames:
+                    end = min(start + chunk_size, frames)
+                    net(segment_latents[:, :, start:end, ...], t_zero, cur_start_frame=start, store_kv=True, **fwd, **kwargs)
+                    start = end
+
+            def run_segment(segment_latents: torch.Tensor, prefill_frames: int) -> torch.Tensor:
+                x = segment_latents.clone()
+                net.clear_caches()
+                if prefill_frames > 0:
+                    prefill_caches(x, prefill_frames)
+                    x[:, :, prefill_frames:, ...] = sched.latents(x[:, :, prefill_frames:, ...].contiguous(), t_init=tl[0])
+                else:
+                    x = sched.latents(x, t_init=tl[0])
+                start = prefill_frames
+                while start < segment_frames:
+                    end = min(start + chunk_size, segment_frames)
+                    x_next = x[:, :, start:end, ...]
+                    for step in range(len(t_host) - 1):
+                        t_cur = tl[step].expand(batch_size)
+                        x_cur = x_next
+                        x_next = net(x_cur, t_cur, cur_start_frame=start, store_kv=False, **fwd, **kwargs)
+                        if bool(t_host[step + 1] > 0):
+                            if student_sample_type == "sde":
+                                eps_infer = torch.randn_like(x_next)
+                            elif student_sample_type == "ode":
+                                eps_infer = sched.x0_to_eps(xt=x_cur.contiguous(), x0=x_next, t=t_cur)
+                            else:
+                                raise NotImplementedError(
+                                    f"student_sample_type must be one of 'sde', 'ode' but got {student_sample_type}")
+                            x_next = sched.forward_process(x_next, eps_infer, tl[step + 1].expand(batch_size))
+                    x[:, :, start:end, ...] = x_next
+                    x_cache, t_cache = x_next, tl[-1].expand(batch_size)
+                    if context_noise and context_noise > 0:
+                        t_cache = torch.full((batch_size,), context_noise, device=device, dtype=dtype)
+                        x_cache = sched.forward_process(x_next, torch.randn_like(x_next), t_cache)
+                    net(x_cache, t_cache, cur_start_frame=start, store_kv=True, **fwd, **kwargs)
+                    start = end
+                net.clear_caches()
+                return x
+
+            segments = []
+            current, prefill = noise, 0
+            for idx in range(num_segments):
+                seg = run_segment(current, prefill)
+                segments.append(seg if idx == 0 or overlap_frames == 0 else seg[:, :, overlap_frames:, :, :])
+                if idx == num_segments - 1:
+                    break
+                if overlap_frames == 0:
+                    current, prefill = torch.randn_like(noise), 0
+                    continue
+                # bridge through pixels: decode, keep the last frames, encode back; all but the first overlapped latent
+                # frame are reused directly
+                decoded = net.vae.decode(seg)
+                tail = net.vae.encode(decoded[:, :, -overlap_frames:, :, :]).to(dtype=dtype, device=device)
+                if overlap_frames > 1:
+                    tail = torch.cat([tail[:, :, :1, :, :], seg[:, :, -(overlap_frames - 1):, :, :]], dim=2)
+                nxt = torch.randn_like(seg)
+                nxt[:, :, :overlap_frames, :, :] = tail
+                current, prefill = nxt, overlap_frames
+            net.clear_caches()
+            return torch.cat(segments, dim=2).to(dtype=noise.dtype)
+
 
 SelfForcingModel = CausVidModel

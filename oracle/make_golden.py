@@ -231,6 +231,64 @@ def causal_trace_fixture():
     print("wrote causal trace:", len(trace), "calls")
 
 
+def extrapolation_fixture():
+    """CausVidModel.generator_fn_extrapolation (causvid.py:187-397) against a stub causal network with a stub VAE:
+    call trace, random draws and output of a 3-segment run with 3 overlapping frames and context noise"""
+    from fastgen.methods.distribution_matching.causvid import CausVidModel
+    from fastgen.networks.network import CausalFastGenNetwork
+
+    trace = []
+
+    class StubVAE:
+        def decode(self, z):
+            trace.append(["vae.decode", list(z.shape)])
+            return 2.0 * z
+
+        def encode(self, v):
+            trace.append(["vae.encode", list(v.shape)])
+            return 0.5 * v + 0.125
+
+    class Stub(CausalFastGenNetwork):
+        def __init__(self):
+            super().__init__(net_pred_type="flow", schedule_type="rf", chunk_size=3, total_num_frames=6)
+            self.vae = StubVAE()
+
+        def clear_caches(self):
+            trace.append(["clear_caches"])
+
+        def forward(self, x_t, t, condition=None, r=None, return_features_early=False, feature_indices=None,
+                    return_logvar=False, fwd_pred_type=None, **kw):
+            trace.append(["net", list(x_t.shape), float(t[0]), fwd_pred_type, kw.get("cache_tag"),
+                          int(kw.get("cur_start_frame")), bool(kw.get("store_kv")), bool(kw.get("is_ar")),
+                          sorted(k for k in kw if k not in ("cache_tag", "cur_start_frame", "store_kv", "is_ar"))])
+            return 0.5 * x_t + 0.25 * float(t[0])
+
+    net = Stub()
+    torch.manual_seed(SEED + 12)
+    noise = torch.randn(2, 4, 6, 4, 4)
+    with _Recorder(net) as rec:
+        out = CausVidModel.generator_fn_extrapolation(net, noise, condition=None, num_segments=3, overlap_frames=3,
+                                                      student_sample_steps=2, student_sample_type="sde",
+                                                      t_list=[0.999, 0.6, 0.0], context_noise=0.1)
+    fx = dict(trace=json.dumps(trace), noise=_np(noise), out=_np(out))
+    for i, e in enumerate(rec.eps):
+        fx[f"eps{i}"] = _np(e)
+    # the ode variant without overlap (fresh noise per segment)
+    trace2 = []
+    trace, trace_keep = trace2, trace
+    torch.manual_seed(SEED + 13)
+    with _Recorder(net) as rec2:
+        out2 = CausVidModel.generator_fn_extrapolation(net, noise, condition=None, num_segments=2, overlap_frames=0,
+                                                       student_sample_steps=2, student_sample_type="ode",
+                                                       t_list=[0.999, 0.6, 0.0], context_noise=0)
+    fx["out_ode"] = _np(out2)
+    for i, e in enumerate(rec2.eps):
+        fx[f"ode_eps{i}"] = _np(e)
+    np.savez_compressed(os.path.join(OUT, "extrapolation_trace.npz"), **fx)
+    print("wrote extrapolation trace:", len(trace_keep), "calls,", len(rec.eps), "draws; ode:", len(rec2.eps), "draws",
+          tuple(out.shape), tuple(out2.shape))
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -240,3 +298,4 @@ if __name__ == "__main__":
     edm_fixture("dhariwal_tiny")
     meanflow_fixture()
     causal_trace_fixture()
+    extrapolation_fixture()

@@ -189,3 +189,64 @@ def causvid_sample_loop(net: Callable[..., torch.Tensor], sched: Schedule, x: to
     if clear_caches:
         clear_caches()
     return x
+
+
+def causvid_extrapolation(net: Callable[..., torch.Tensor], sched: Schedule, noise: torch.Tensor, t_list: Sequence[float],
+                          chunk_size: int, num_segments: int, overlap_frames: int, draws: Sequence[torch.Tensor],
+                          sample_type: str = "sde", context_noise: float = 0.0,
+                          vae_decode: Optional[Callable] = None, vae_encode: Optional[Callable] = None,
+                          clear_caches: Optional[Callable[[], None]] = None) -> torch.Tensor:
+    """causvid.py:187-397 with every ``randn_like`` draw supplied in call order; ``t_list`` is float32 there (:247-249).
+    ``net(x_chunk, t_batch, cur_start_frame=..., store_kv=...) -> x0``."""
+    b, frames = noise.shape[0], noise.shape[2]
+    assert frames % chunk_size == 0 and 0 <= overlap_frames < frames and overlap_frames % chunk_size == 0
+    tl = torch.tensor(list(t_list), dtype=torch.float32)
+    assert tl[-1].item() == 0
+    it = iter(draws)
+    clear = clear_caches or (lambda: None)
+
+    def run_segment(lat: torch.Tensor, prefill: int) -> torch.Tensor:
+        x = lat.clone()
+        clear()
+        for s in range(0, prefill, chunk_size):
+            net(x[:, :, s:min(s + chunk_size, prefill)], tl[-1].expand(b), cur_start_frame=s, store_kv=True)
+        if prefill == 0:
+            x = sched.latents(x, tl[0])
+        else:
+            x[:, :, prefill:] = sched.latents(x[:, :, prefill:], tl[0])
+        for s in range(prefill, frames, chunk_size):
+            e = min(s + chunk_size, frames)
+            x_next = x[:, :, s:e]
+            for t_cur, t_next in zip(tl[:-1], tl[1:]):
+                tb = t_cur.expand(b)
+                x_cur = x_next
+                x_next = net(x_cur, tb, cur_start_frame=s, store_kv=False)
+                if t_next > 0:
+                    eps = next(it) if sample_type == "sde" else sched.x0_to_eps(x_cur, x_next, tb)
+                    x_next = sched.forward_process(x_next, eps, t_next.expand(b))
+            x[:, :, s:e] = x_next
+            x_cache, t_cache = x_next, tl[-1].expand(b)
+            if context_noise and context_noise > 0:
+                t_cache = torch.full((b,), context_noise, dtype=noise.dtype)
+                x_cache = sched.forward_process(x_next, next(it), t_cache)
+            net(x_cache, t_cache, cur_start_frame=s, store_kv=True)
+        clear()
+        return x
+
+    segs, cur, prefill = [], noise, 0
+    for i in range(num_segments):
+        seg = run_segment(cur, prefill)
+        segs.append(seg if i == 0 or overlap_frames == 0 else seg[:, :, overlap_frames:])
+        if i == num_segments - 1:
+            break
+        if overlap_frames == 0:
+            cur, prefill = next(it), 0
+            continue
+        tail = vae_encode(vae_decode(seg)[:, :, -overlap_frames:]).to(noise.dtype)
+        if overlap_frames > 1:
+            tail = torch.cat([tail[:, :, :1], seg[:, :, -(overlap_frames - 1):]], dim=2)
+        nxt = next(it).clone()
+        nxt[:, :, :overlap_frames] = tail
+        cur, prefill = nxt, overlap_frames
+    clear()
+    return torch.cat(segs, dim=2).to(noise.dtype)

@@ -148,3 +148,32 @@ def test_causal_chunking_matches_reference_trace():
             assert abs(c[2] - exp_t[k]) < 1e-12
             assert c[6] == (k == 4) and c[7] is True and c[3] == "x0" and c[4] == "pos"
             assert c[8] == ["neg_condition"]
+
+
+def test_extrapolation_matches_reference():
+    """generator_fn_extrapolation (causvid.py:187-397): the oracle restatement reproduces the reference's output and
+    call trace (stub network + stub VAE, recorded random draws) for the sde / overlap and the ode / no-overlap runs"""
+    g = _load("extrapolation_trace.npz")
+    noise = torch.from_numpy(g["noise"])
+    sched = SO.Schedule("rf")
+    calls = []
+
+    def net(x, t, cur_start_frame=0, store_kv=False):
+        calls.append(["net", list(x.shape), float(t[0]), "x0", "pos", int(cur_start_frame), bool(store_kv), True, []])
+        return 0.5 * x + 0.25 * float(t[0])
+
+    def dec(z):
+        calls.append(["vae.decode", list(z.shape)])
+        return 2.0 * z
+
+    def enc(v):
+        calls.append(["vae.encode", list(v.shape)])
+        return 0.5 * v + 0.125
+
+    draws = [torch.from_numpy(g[f"eps{i}"]) for i in range(10)]
+    out = SO.causvid_extrapolation(net, sched, noise, [0.999, 0.6, 0.0], 3, 3, 3, draws, "sde", 0.1, dec, enc,
+                                   clear_caches=lambda: calls.append(["clear_caches"]))
+    assert torch.equal(out, torch.from_numpy(g["out"]))
+    assert calls == json.loads(str(g["trace"]))
+    out2 = SO.causvid_extrapolation(net, sched, noise, [0.999, 0.6, 0.0], 3, 2, 0, [torch.from_numpy(g["ode_eps0"])], "ode")
+    assert torch.equal(out2, torch.from_numpy(g["out_ode"]))
