@@ -410,7 +410,8 @@ def run_wan(args):
                                     "Wan 2.1 1.3B T2V 480p 81-frame 4-step self-forcing, batch 1 per group (BASELINE configs[3])"),
                        "latent": [1, 16, frames, lh, lw], "t_list": WAN_TL, "chunk_size": None if big else 3,
                        "parallelism": f"Ulysses sequence parallel x{sp}, {replicas} replica(s)",
-                       "l2": "inputs exceed L2: 2.8 GB of weights + up to 6 GB of KV cache streamed per sample"},
+                       "l2": ("inputs exceed L2: 28 GB of bf16 weights and 75 600-token activations streamed per forward" if big
+                              else "inputs exceed L2: 2.8 GB of weights + up to 6 GB of KV cache streamed per sample")},
             "e2e": {"value": replicas * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": noise_h.numel() * 2 + text_h.numel() * 2, "d2h_bytes_per_step": out_h.numel() * 2},
             "gpu_launches": launches, "clocks": clk.summary(),
