@@ -244,7 +244,11 @@ def run_ours(args):
     roofline = {
         "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear)", "bound": "tensor",
         "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus if tf_sus else None,
-        "traffic": traffic, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+        "traffic": traffic,
+        "traffic_note": "DRAM read+write bytes per fg_conv_gemm launch (ncu, profiles/traffic.json); algorithmic bytes per "
+                        "launch at batch 256 = 610 MB of activations + ~5 MB of weights (DESIGN.md): the excess is < 0 "
+                        "because consumers hit the 126 MB L2",
+        "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
         "how": "sum of algorithmic conv/linear FLOPs of all fg_conv_gemm launches / sum of their CUDA-event durations, "
                f"separate measurement pass of the same {K} steps",
         "launches_per_step": conv["launches"] / K, "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
