@@ -120,6 +120,7 @@ struct GnApplyK {
   int64_t raw_ld;
   __nv_bfloat16* raw_lo;
   int pix_per_slab;  // in OUTPUT pixels for DOWN2, input pixels otherwise
+  int vpp;           // 4-channel vectors per pass over the channels (= threads per pixel row)
 };
 
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
@@ -148,45 +149,45 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
   Vec<__nv_bfloat16>::load(p, v);
 }
 
-// grid (slabs, n): coefficients a[c], b[c] with y = a*x + b are built once per CTA in shared memory.
+// grid (slabs, n).  A thread owns ONE 4-channel vector (its 8 coefficients of y = a*x + b live in registers, computed
+// by the thread itself from the fp64 statistics: no shared memory, no block barrier) and walks the pixels of the slab
+// with four independent 16-byte loads in flight.  Small register footprint (launch bounds: 4 blocks of up to 288 threads
+// per SM) so that enough warps are resident to hide the SiLU's MUFU latency -- profiles/ncu_r01.md has the capture of
+// the previous version (89 registers, 14 warps per SM, 2-4 waves of big blocks: 2.2-3.7 TB/s).
+constexpr int kGnApplyMaxThreads = 288;
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 f0 = unpack_bf16x2(a.x), f1 = unpack_bf16x2(a.y);
+  v[0] = f0.x, v[1] = f0.y, v[2] = f1.x, v[3] = f1.y;
+}
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void split4(const float (&v)[4], float (&lo)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) lo[k] = v[k] - __bfloat162float(__float2bfloat16_rn(v[k]));
+}
+
 template <typename T, int MODE, bool LO>  // MODE: FG_RES_NONE / FG_RES_UP2 / FG_RES_DOWN2; LO: split-precision outputs
-__global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK p) {
-  extern __shared__ float s_coef[];  // a[c] | b[c]
-  float* s_a = s_coef;
-  float* s_b = s_coef + p.c;
+__global__ void __launch_bounds__(kGnApplyMaxThreads, 4) gn_apply_kernel(const GnApplyK p) {
   const int n = blockIdx.y;
   const int hw = p.h * p.w;
-  {
-    const double cnt = static_cast<double>(hw) * p.cg;
-    for (int ch = threadIdx.x; ch < p.c; ch += blockDim.x) {
-      const int g = ch / p.cg;
-      const double s = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2];
-      const double ss = p.stats[(static_cast<int64_t>(n) * p.groups + g) * 2 + 1];
-      const double mean = s / cnt;
-      double var = ss / cnt - mean * mean;
-      var = var > 0.0 ? var : 0.0;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
-      const float meanf = static_cast<float>(mean);
-      float a = rstd * __ldg(p.gamma + ch);
-      float b = __ldg(p.beta + ch) - meanf * a;
-      if (p.scale) {
-        const float sc = 1.0f + __ldg(p.scale + n * p.mod_ld + ch);
-        a *= sc;
-        b *= sc;
-      }
-      if (p.shift) b += __ldg(p.shift + n * p.mod_ld + ch);
-      s_a[ch] = a;
-      s_b[ch] = b;
-    }
-  }
-  __syncthreads();
-
   const T* xb = static_cast<const T*>(p.x) + static_cast<int64_t>(n) * hw * p.x_ld;
-  const int nvec = p.c >> 3;
-  // thread -> (8-channel vector, pixel row): the vector index is FIXED per thread, so its 16 coefficients live
-  // in registers and the pixel loop has no div/mod; 4 pixels are in flight per thread.
-  const int vpp = min(nvec, static_cast<int>(blockDim.x));  // vectors per pass
-  const int ppi = blockDim.x / vpp;                         // pixels per iteration of the block
+  const int nvec = p.c >> 2;
+  const int vpp = p.vpp;             // vectors per pass (<= blockDim.x, host-chosen)
+  const int ppi = blockDim.x / vpp;  // pixels per iteration of the block
   const int prow = threadIdx.x / vpp;
   if (prow >= ppi) return;
   constexpr bool up = MODE == FG_RES_UP2;
@@ -195,58 +196,84 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK 
   const int npix = down ? (p.h >> 1) * ow : hw;  // pixels this kernel iterates over (output pixels for DOWN2)
   const int p0 = blockIdx.x * p.pix_per_slab;
   const int p1 = min(npix, p0 + p.pix_per_slab);
+  const double inv_cnt = 1.0 / (static_cast<double>(hw) * p.cg);
 
   for (int vi = threadIdx.x % vpp; vi < nvec; vi += vpp) {
-    float a8[8], b8[8];
+    const int co = vi * 4;
+    float a4[4], b4[4];
+    {
+      int g_prev = -1;
+      float meanf = 0.f, rstd = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a8[k] = s_a[vi * 8 + k], b8[k] = s_b[vi * 8 + k];
-    const int co = vi * 8;
+      for (int k = 0; k < 4; ++k) {
+        const int ch = co + k;
+        const int g = ch / p.cg;
+        if (g != g_prev) {  // (a 4-channel vector touches one or two groups, rarely more)
+          const double* st = p.stats + (static_cast<int64_t>(n) * p.groups + g) * 2;
+          const double mean = st[0] * inv_cnt;
+          double var = st[1] * inv_cnt - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+          meanf = static_cast<float>(mean);
+          g_prev = g;
+        }
+        float a = rstd * __ldg(p.gamma + ch);
+        float b = __ldg(p.beta + ch) - meanf * a;
+        if (p.scale) {
+          const float sc = 1.0f + __ldg(p.scale + n * p.mod_ld + ch);
+          a *= sc;
+          b *= sc;
+        }
+        if (p.shift) b += __ldg(p.shift + n * p.mod_ld + ch);
+        a4[k] = a, b4[k] = b;
+      }
+    }
 
     if constexpr (down) {
       for (int opix = p0 + prow; opix < p1; opix += ppi) {
         const int oy = opix / ow, ox = opix % ow;
-        float v[4][8];
+        float v[4][4];
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-          load8<T>(xb + static_cast<int64_t>((2 * oy + (d >> 1)) * p.w + 2 * ox + (d & 1)) * p.x_ld + co, v[d]);
-        float acc[8], racc[8];
+          load4<T>(xb + static_cast<int64_t>((2 * oy + (d >> 1)) * p.w + 2 * ox + (d & 1)) * p.x_ld + co, v[d]);
+        float acc[4], racc[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float y0 = fmaf(a8[k], v[0][k], b8[k]), y1 = fmaf(a8[k], v[1][k], b8[k]);
-          float y2 = fmaf(a8[k], v[2][k], b8[k]), y3 = fmaf(a8[k], v[3][k], b8[k]);
+        for (int k = 0; k < 4; ++k) {
+          float y0 = fmaf(a4[k], v[0][k], b4[k]), y1 = fmaf(a4[k], v[1][k], b4[k]);
+          float y2 = fmaf(a4[k], v[2][k], b4[k]), y3 = fmaf(a4[k], v[3][k], b4[k]);
           if (p.silu) y0 = silu_f(y0), y1 = silu_f(y1), y2 = silu_f(y2), y3 = silu_f(y3);
           acc[k] = 0.25f * ((y0 + y1) + (y2 + y3));
           racc[k] = 0.25f * ((v[0][k] + v[1][k]) + (v[2][k] + v[3][k]));
         }
         const int64_t o = static_cast<int64_t>(n) * npix + opix;
-        store8_bf16(p.y + o * p.y_ld + co, acc);
+        store4_bf16(p.y + o * p.y_ld + co, acc);
         if (LO && p.y_lo) {
-          float lo[8];
-          split8(acc, lo);
-          store8_bf16(p.y_lo + o * p.y_ld + co, lo);
+          float lo[4];
+          split4(acc, lo);
+          store4_bf16(p.y_lo + o * p.y_ld + co, lo);
         }
         if (p.raw) {
-          store8_bf16(p.raw + o * p.raw_ld + co, racc);
+          store4_bf16(p.raw + o * p.raw_ld + co, racc);
           if (LO && p.raw_lo) {
-            float lo[8];
-            split8(racc, lo);
-            store8_bf16(p.raw_lo + o * p.raw_ld + co, lo);
+            float lo[4];
+            split4(racc, lo);
+            store4_bf16(p.raw_lo + o * p.raw_ld + co, lo);
           }
         }
       }
       continue;
     }
 
-    auto emit = [&](int pix, const float (&v)[8]) {
-      float yv[8];
+    auto emit = [&](int pix, const float (&v)[4]) {
+      float yv[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float t = fmaf(a8[k], v[k], b8[k]);
+      for (int k = 0; k < 4; ++k) {
+        const float t = fmaf(a4[k], v[k], b4[k]);
         yv[k] = p.silu ? silu_f(t) : t;
       }
-      float ylo[8], rlo[8];
-      if (LO && p.y_lo) split8(yv, ylo);
-      if (LO && p.raw_lo) split8(v, rlo);
+      float ylo[4], rlo[4];
+      if (LO && p.y_lo) split4(yv, ylo);
+      if (LO && p.raw_lo) split4(v, rlo);
       if constexpr (up) {
         const int iy = pix / p.w, ix = pix % p.w;
         const int W2 = p.w * 2;
@@ -254,35 +281,35 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(const GnApplyK 
         for (int d = 0; d < 4; ++d) {
           const int64_t o =
               static_cast<int64_t>(n) * hw * 4 + static_cast<int64_t>(2 * iy + (d >> 1)) * W2 + 2 * ix + (d & 1);
-          store8_bf16(p.y + o * p.y_ld + co, yv);
-          if (LO && p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + co, ylo);
-          if (p.raw) store8_bf16(p.raw + o * p.raw_ld + co, v);
-          if (LO && p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
+          store4_bf16(p.y + o * p.y_ld + co, yv);
+          if (LO && p.y_lo) store4_bf16(p.y_lo + o * p.y_ld + co, ylo);
+          if (p.raw) store4_bf16(p.raw + o * p.raw_ld + co, v);
+          if (LO && p.raw_lo) store4_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
         }
       } else {
         const int64_t o = static_cast<int64_t>(n) * hw + pix;
-        store8_bf16(p.y + o * p.y_ld + co, yv);
-        if (LO && p.y_lo) store8_bf16(p.y_lo + o * p.y_ld + co, ylo);
-        if (p.raw) store8_bf16(p.raw + o * p.raw_ld + co, v);
-        if (LO && p.raw_lo) store8_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
+        store4_bf16(p.y + o * p.y_ld + co, yv);
+        if (LO && p.y_lo) store4_bf16(p.y_lo + o * p.y_ld + co, ylo);
+        if (p.raw) store4_bf16(p.raw + o * p.raw_ld + co, v);
+        if (LO && p.raw_lo) store4_bf16(p.raw_lo + o * p.raw_ld + co, rlo);
       }
     };
 
     int pix = p0 + prow;
     for (; pix + 3 * ppi < p1; pix += 4 * ppi) {
-      float v0[8], v1[8], v2[8], v3[8];
-      load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
-      load8<T>(xb + static_cast<int64_t>(pix + ppi) * p.x_ld + co, v1);
-      load8<T>(xb + static_cast<int64_t>(pix + 2 * ppi) * p.x_ld + co, v2);
-      load8<T>(xb + static_cast<int64_t>(pix + 3 * ppi) * p.x_ld + co, v3);
+      float v0[4], v1[4], v2[4], v3[4];
+      load4<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
+      load4<T>(xb + static_cast<int64_t>(pix + ppi) * p.x_ld + co, v1);
+      load4<T>(xb + static_cast<int64_t>(pix + 2 * ppi) * p.x_ld + co, v2);
+      load4<T>(xb + static_cast<int64_t>(pix + 3 * ppi) * p.x_ld + co, v3);
       emit(pix, v0);
       emit(pix + ppi, v1);
       emit(pix + 2 * ppi, v2);
       emit(pix + 3 * ppi, v3);
     }
     for (; pix < p1; pix += ppi) {
-      float v0[8];
-      load8<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
+      float v0[4];
+      load4<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
       emit(pix, v0);
     }
   }
@@ -319,13 +346,14 @@ __global__ void __launch_bounds__(kGnThreads) cast_resample_kernel(const T* __re
   }
 }
 
-// fg_gn_apply has no accumulation, so its slab may depend on the batch: large enough that the per-CTA prologue
-// (coefficients from the fp64 statistics) amortises, small enough that ~8 CTAs per SM exist.
+// fg_gn_apply has no accumulation, so its slab may depend on the batch.  ~24-96K elements per CTA keep the per-thread
+// prologue (coefficients from the fp64 statistics) at a few percent of the work and give ~8 waves of 4 blocks per SM
+// at the bench batch, so the tail is short.
 static int pick_slab_apply(int n, int pixels, int c, int* pix_per_slab) {
   const int64_t total = static_cast<int64_t>(n) * pixels * c;
-  int64_t per_cta = total / (148 * 8);
-  if (per_cta < 32768) per_cta = 32768;
-  if (per_cta > 262144) per_cta = 262144;
+  int64_t per_cta = total / (148 * 4 * 8);
+  if (per_cta < 24576) per_cta = 24576;
+  if (per_cta > 98304) per_cta = 98304;
   int64_t slabs = (static_cast<int64_t>(pixels) * c + per_cta - 1) / per_cta;
   if (slabs > pixels) slabs = pixels;
   if (slabs < 1) slabs = 1;
@@ -401,9 +429,15 @@ extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
   const int pixels = p->resample == FG_RES_DOWN2 ? (p->h / 2) * (p->w / 2) : p->h * p->w;
   const int slabs = pick_slab_apply(p->n, pixels, p->c, &k.pix_per_slab);
   const dim3 grid(slabs, p->n);
-  const size_t smem = sizeof(float) * 2 * p->c;
-  const int nvec = p->c / 8;
-  const int threads = nvec >= kGnThreads ? kGnThreads : nvec * (kGnThreads / nvec);
+  // threads: a multiple of the vectors-per-pass close to 256 (<= 288); very wide tensors take several passes per thread
+  const int nvec = p->c / 4;
+  const int passes = (nvec + kGnApplyMaxThreads - 1) / kGnApplyMaxThreads;
+  k.vpp = (nvec + passes - 1) / passes;
+  int rows_per_iter = (256 + k.vpp / 2) / k.vpp;
+  if (rows_per_iter < 1) rows_per_iter = 1;
+  while (rows_per_iter > 1 && rows_per_iter * k.vpp > kGnApplyMaxThreads) --rows_per_iter;
+  const int threads = rows_per_iter * k.vpp;
+  const size_t smem = 0;
   const bool lo = p->y_lo || p->raw_lo;
 #define FG_GN_LAUNCH(T, MODE)                                             \
   do {                                                                    \
