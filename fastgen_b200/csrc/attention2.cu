@@ -296,9 +296,17 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
         for (int c = 0; c < BKV; ++c)
           if (c >= kv_valid) sv[c] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      // four independent FMNMX3 chains (16 deep each instead of one of 64): only two softmax warps share a scheduler, so
+      // a serial dependency chain shows as issue bubbles
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < BKV; c += 2) mx = fmax3(mx, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+      for (int c = 0; c < BKV; c += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+      }
+      float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
       mx *= sc;  // scale > 0: max commutes with the scaling
       if (j > 0) {
         const bool need = mx > m_run + 8.0f;
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       }
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
-      uint64_t lsum2 = pack2(0.f, 0.f);
+      uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};  // independent chains
       // P = exp2(s * scale - m) as bf16, written over the S columns: 32 keys -> 16 packed columns per store.
       // kPolyOf8 of every 8 pairs take the polynomial, the rest the MUFU unit (balances MUFU time against issue slots)
 #pragma unroll
@@ -342,13 +350,13 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
             unpack2(x2, x0, x1);
             e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
           }
-          lsum2 = fadd2(lsum2, pack2(e0, e1));
+          lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
         tmem_st_32x16(s_addr + (c >> 1), pk);
       }
       float lsum0, lsum1;
-      unpack2(lsum2, lsum0, lsum1);
+      unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
       l_run += lsum0 + lsum1;
       tmem_st_wait();
       tc_fence_before();
