@@ -110,7 +110,11 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
-template <int DP, int POLY>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+// HALF: the key tile is processed as two 64-key halves with their own S/P columns and barriers.  While the softmax
+// warpgroup of a query tile works on one half, the tensor pipe runs O += P.V of the other half and the next
+// S = Q.K^T into the columns that product has released, so the softmax no longer idles for the MMA round trip
+// between key tiles (23 % of its time in the ncu capture of the full-tile pipeline, profiles/ncu_r01.md).
+template <int DP, int POLY, int HALF>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
 __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
   using Cfg = Attn2Cfg<DP>;
   constexpr int BKV = kA2BKV;
@@ -123,10 +127,12 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;        // [S]
   uint64_t* kv_empty = kv_full + S;    // [S]
-  uint64_t* s_full = kv_empty + S;     // [2]
-  uint64_t* p_full = s_full + 2;       // [2]
-  uint64_t* pv_done = p_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* v_full = kv_empty + S;     // [S]  half-tile pipeline: K and V slots are filled / released separately
+  uint64_t* v_empty = v_full + S;      // [S]  (kv_full / kv_empty then track K alone)
+  uint64_t* s_full = v_empty + S;      // [2 tiles][2 halves] (index t * 2 + h; the full-tile pipeline uses h = 0)
+  uint64_t* p_full = s_full + 4;       // [2][2]
+  uint64_t* pv_done = p_full + 4;      // [2][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_blocks = (p.Tq + 255) / 256;
@@ -159,8 +165,10 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       for (int i = 0; i < S; ++i) {
         mbar_init(&kv_full[i], 1);
         mbar_init(&kv_empty[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 4);
         mbar_init(&pv_done[i], 1);
@@ -188,13 +196,26 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       for (int j = 0; j < nkv; ++j) {
         const int seg = (jb + j) >= n0;
         const int row0 = (seg ? jb + j - n0 : jb + j) * BKV;
-        mbar_wait(&kv_empty[stage], phase ^ 1u);
         uint8_t* sk = sKV + stage * 2 * Cfg::KV_TILE_BYTES;
         uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * Cfg::KV_TILE_BYTES);
-        for (int dc = 0; dc < Cfg::DC; ++dc) {
-          tma_load_4d(sk + dc * BKV * 128, &p.tmK[seg], &kv_full[stage], dc * 64, head, row0, img);
-          tma_load_4d(sv + dc * BKV * 128, &p.tmV[seg], &kv_full[stage], dc * 64, head, row0, img);
+        if constexpr (HALF) {
+          // K_j is free once the S products of tile j - S have run (early in the previous iteration), V_j only after
+          // its P.V products: separate barriers let K_{j+1} arrive a full iteration before its first reader
+          mbar_wait(&kv_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[stage], Cfg::KV_TILE_BYTES);
+          for (int dc = 0; dc < Cfg::DC; ++dc)
+            tma_load_4d(sk + dc * BKV * 128, &p.tmK[seg], &kv_full[stage], dc * 64, head, row0, img);
+          mbar_wait(&v_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::KV_TILE_BYTES);
+          for (int dc = 0; dc < Cfg::DC; ++dc)
+            tma_load_4d(sv + dc * BKV * 128, &p.tmV[seg], &v_full[stage], dc * 64, head, row0, img);
+        } else {
+          mbar_wait(&kv_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[stage], 2 * Cfg::KV_TILE_BYTES);
+          for (int dc = 0; dc < Cfg::DC; ++dc) {
+            tma_load_4d(sk + dc * BKV * 128, &p.tmK[seg], &kv_full[stage], dc * 64, head, row0, img);
+            tma_load_4d(sv + dc * BKV * 128, &p.tmV[seg], &kv_full[stage], dc * 64, head, row0, img);
+          }
         }
         if (++stage == S) {
           stage = 0;
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
                          umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk, (dc | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[t]);
+        umma_commit(&s_full[2 * t]);
       };
       auto issue_pv = [&](int t, int stage, int j) {
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
@@ -228,8 +249,74 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
         for (int kk = 0; kk < BKV / 16; ++kk)
           umma_bf16_ts(o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv,
                        (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&pv_done[t]);
+        umma_commit(&pv_done[2 * t]);
       };
+      // half-tile pipeline: per key tile j and half h, O_t += P_th.V_j[h] then S_th <- Q_t.K_{j+1}[h]^T for both tiles
+      constexpr uint32_t idesc_qk_h = umma_idesc_bf16(128, 64, 0, 0);
+      auto issue_qk_h = [&](int t, int h, int stage) {
+        const uint32_t k_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES) + h * (64 * 128);
+        const uint32_t qa = q_addr + t * Cfg::Q_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128 + h * 64);
+#pragma unroll
+        for (int dc = 0; dc < Cfg::DC; ++dc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
+                         umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk_h, (dc | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[2 * t + h]);
+      };
+      auto issue_pv_h = [&](int t, int h, int stage, int j) {
+        const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
+        const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP);
+        const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128 + h * 64);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + (h * 4 + kk) * 2048, BKV * 128), idesc_pv,
+                       (j | h | kk) != 0 ? 1u : 0u);
+        umma_commit(&pv_done[2 * t + h]);
+      };
+      if constexpr (HALF) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_qk_h(0, 0, 0);
+        issue_qk_h(1, 0, 0);
+        issue_qk_h(0, 1, 0);
+        issue_qk_h(1, 1, 0);
+        umma_commit(&kv_empty[0]);  // K_0 has no further reader
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < nkv; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == S) {
+            nstage = 0;
+            nphase ^= 1u;
+          }
+          const bool more = j + 1 < nkv;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (h == 0 && t == 0) mbar_wait(&v_full[stage], phase);
+              mbar_wait(&p_full[2 * t + h], j & 1);
+              tc_fence_after();
+              issue_pv_h(t, h, stage, j);
+              if (h == 1 && t == 1) umma_commit(&v_empty[stage]);  // every reader of V_j has been issued
+              if (more) {
+                if (h == 0 && t == 0) {
+                  mbar_wait(&kv_full[nstage], nphase);
+                  tc_fence_after();
+                }
+                issue_qk_h(t, h, nstage);  // overwrites P_th: issued after the product that reads it
+                if (h == 1 && t == 1) umma_commit(&kv_empty[nstage]);  // every reader of K_{j+1} has been issued
+              }
+            }
+          }
+          stage = nstage;
+          phase = nphase;
+        }
+      } else {
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
@@ -255,7 +342,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
           issue_qk(0, nstage);
         }
         // query tile 1
-        mbar_wait(&p_full[1], j & 1);
+        mbar_wait(&p_full[2], j & 1);
         tc_fence_after();
         issue_pv(1, stage, j);
         umma_commit(&kv_empty[stage]);  // every reader of K_j / V_j has been issued before this commit
@@ -263,6 +350,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
         stage = nstage;
         phase = nphase;
       }
+      }  // !HALF
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -277,8 +365,96 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
     const float sc = p.scale_log2;
     float m_run = -INFINITY;  // running max in scaled (log2) units
     float l_run = 0.f;
+    if constexpr (HALF) {
+      constexpr int HK = BKV / 2;  // keys per half
+      for (int i = 0; i < 2 * nkv; ++i) {
+        const int j = i >> 1, h = i & 1;
+        mbar_wait(&s_full[2 * t + h], j & 1);
+        tc_fence_after();
+        const uint32_t sh_addr = s_addr + static_cast<uint32_t>(h * HK);
+        uint32_t sv[HK];
+#pragma unroll
+        for (int c = 0; c < HK; c += 32) {
+          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c]);
+          tmem_ld_32x32(sh_addr + c, chunk);
+        }
+        tmem_ld_wait();
+        const int seg = (jb + j) >= n0;
+        const int col0 = (seg ? jb + j - n0 : jb + j) * BKV + h * HK;
+        int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
+        if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
+        if (kv_valid < HK) {  // ragged end of a segment / causal limit inside this half (rare)
+#pragma unroll
+          for (int c = 0; c < HK; ++c)
+            if (c >= kv_valid) sv[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < HK; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+        }
+        float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
+        mx *= sc;  // scale > 0: max commutes with the scaling
+        if (i > 0) {
+          const bool need = mx > m_run + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // O must be stable: wait for the product of the previous half (the last one issued for this tile)
+            mbar_wait(&pv_done[2 * t + (h ^ 1)], (h ? j : j - 1) & 1);
+            tc_fence_after();
+            const float m_new = need ? mx : m_run;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+            m_run = m_new;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < DP; c += 32) {
+              uint32_t o[32];
+              tmem_ld_32x32(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+              tmem_st_32x32(o_addr + c, o);
+            }
+            tmem_st_wait();
+          }
+        } else {
+          m_run = mx;
+        }
+        const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+        const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
+        uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
+#pragma unroll
+        for (int c = 0; c < HK; c += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c + k]), __uint_as_float(sv[c + k + 1])), sc2, negm2);
+            float e0, e1;
+            if (((k >> 1) & 7) < POLY) {
+              exp2_poly2(x2, e0, e1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
+            }
+            lsum2[(k >> 1) & 3] = fadd2(lsum2[(k >> 1) & 3], pack2(e0, e1));
+            pk[k >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x16(sh_addr + (c >> 1), pk);  // P_th: bf16 pairs over the first 32 columns of this half's S
+        }
+        float lsum0, lsum1;
+        unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
+        l_run += lsum0 + lsum1;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + h]);
+      }
+    } else {
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+      mbar_wait(&s_full[2 * t], j & 1);
       tc_fence_after();
       uint32_t sv[BKV];
 #pragma unroll
@@ -311,7 +487,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       if (j > 0) {
         const bool need = mx > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(&pv_done[t], (j - 1) & 1);  // O stable until this tile's P is published
+          mbar_wait(&pv_done[2 * t], (j - 1) & 1);  // O stable until this tile's P is published
           tc_fence_after();
           const float m_new = need ? mx : m_run;
           const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
@@ -361,11 +537,12 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[2 * t]);
     }
+    }  // !HALF
     // ---- epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ----
     if (nkv) {
-      mbar_wait(&pv_done[t], (nkv - 1) & 1);
+      mbar_wait(&pv_done[2 * t + HALF], (nkv - 1) & 1);  // the last product issued for this tile
       tc_fence_after();
     }
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
@@ -487,12 +664,12 @@ size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256;  // up to 8 splits: bf16 O + (m, l)
 }
 
-template <int DP, int POLY>
+template <int DP, int POLY, int HALF = 0>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -554,7 +731,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
     if (r != FG_OK) return r;
   }
   const int grid = kp.B * kp.H * q_blocks * nsplit;
-  attention2_kernel<DP, POLY><<<grid, kA2Threads, Cfg::SMEM_BYTES, stream>>>(kp);
+  attention2_kernel<DP, POLY, HALF><<<grid, kA2Threads, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("flash_attn");
   if (nsplit > 1) {
     const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
@@ -569,6 +746,11 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
 // called by fg_flash_attn after argument validation
 int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   static const int poly = getenv("FG_ATTN_POLY") ? atoi(getenv("FG_ATTN_POLY")) : 2;  // (0|2|3|4: tuning experiments)
+  static const bool half = !(getenv("FG_ATTN_HALF") && getenv("FG_ATTN_HALF")[0] == '0');  // half-tile pipeline (default)
+  if (half && poly == 2) {
+    if (p->d <= 64) return launch_attention2<64, 2, 1>(p, scale, stream);
+    return launch_attention2<128, 2, 1>(p, scale, stream);
+  }
   if (p->d <= 64) {
     if (poly == 0) return launch_attention2<64, 0>(p, scale, stream);
     if (poly == 3) return launch_attention2<64, 3>(p, scale, stream);
