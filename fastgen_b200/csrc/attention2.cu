@@ -110,10 +110,10 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
-// HALF: the key tile is processed as two 64-key halves with their own S/P columns and barriers.  While the softmax
-// warpgroup of a query tile works on one half, the tensor pipe runs O += P.V of the other half and the next
-// S = Q.K^T into the columns that product has released, so the softmax no longer idles for the MMA round trip
-// between key tiles (23 % of its time in the ncu capture of the full-tile pipeline, profiles/ncu_r01.md).
+// HALF (experiment, off by default -- see flash_attn_v2): the key tile is processed as two 64-key halves with their
+// own S/P columns and barriers.  While the softmax warpgroup of a query tile works on one half, the tensor pipe runs
+// O += P.V of the other half and the next S = Q.K^T into the columns that product has released, so the softmax does
+// not idle for the MMA round trip between key tiles (23 % of its time in the ncu capture of the full-tile pipeline).
 template <int DP, int POLY, int HALF>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
 __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
   using Cfg = Attn2Cfg<DP>;
@@ -746,7 +746,10 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
 // called by fg_flash_attn after argument validation
 int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   static const int poly = getenv("FG_ATTN_POLY") ? atoi(getenv("FG_ATTN_POLY")) : 2;  // (0|2|3|4: tuning experiments)
-  static const bool half = !(getenv("FG_ATTN_HALF") && getenv("FG_ATTN_HALF")[0] == '0');  // half-tile pipeline (default)
+  // half-tile pipeline: opt-in experiment (FG_ATTN_HALF=1).  Measured on B200 it is SLOWER at d = 128 (816 vs 1017 TFLOP/s
+  // on the Wan chunk-6 shape: the N = 64 S products run at half the tensor-pipe efficiency) and equal at d = 64, where
+  // the softmax warps are bound by dependent-issue latency, not by the wait for S (profiles/attn_r01.md).
+  static const bool half = getenv("FG_ATTN_HALF") && getenv("FG_ATTN_HALF")[0] == '1';
   if (half && poly == 2) {
     if (p->d <= 64) return launch_attention2<64, 2, 1>(p, scale, stream);
     return launch_attention2<128, 2, 1>(p, scale, stream);
