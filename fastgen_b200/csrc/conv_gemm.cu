@@ -693,7 +693,11 @@ static int pick_block_n(int cout, int m_tiles, int num_sms, bool geglu) {
     if (geglu && bn % 128) continue;  // a GEGLU slab is 128 accumulator columns
     const int64_t tiles = static_cast<int64_t>(m_tiles) * ((cout + bn - 1) / bn);
     const int64_t waves = (tiles + num_sms - 1) / num_sms;
-    const int64_t cost = waves * (bn + 16);  // + fixed per-tile cost (pipeline fill, barriers)
+    // time of a tile ~ (bn + fixed per-tile cost) / efficiency: a 128-wide tile reads as many shared-memory bytes per
+    // MMA clock as the 128 B/clk port delivers (A 16 KB + B 16 KB per 256 clocks), wider tiles have headroom --
+    // measured 620-820 TFLOP/s on 128-wide tiles against 1200-1300 on 256-wide ones (profiles/sdxl_r01.md)
+    const int eff = bn == 128 ? 80 : bn == 192 ? 92 : 100;
+    const int64_t cost = waves * (bn + 16) * 100 / eff;
     if (cost <= best_cost) {
       best_cost = cost;
       best = bn;
