@@ -39,6 +39,7 @@ class ConvParams(C.Structure):
         ("out_scale", C.c_float),
         ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_ld", C.c_int64),
         ("stats", C.c_void_p), ("stats_groups", C.c_int32), ("stats_cg", C.c_int32), ("stats_ch0", C.c_int32),
+        ("stats2", C.c_void_p), ("stats2_groups", C.c_int32), ("stats2_cg", C.c_int32), ("stats2_ch0", C.c_int32),
     ]
 
 

@@ -94,6 +94,8 @@ struct ConvKParams {
   // fused GroupNorm statistics of the output (fp32 TMA-store path): per (image, group) sum / sum of squares
   double* stats;
   int32_t stats_groups, stats_cg, stats_ch0;
+  double* stats2;  // second consumer of the same output (the decoder GroupNorm that reads it inside a skip concatenation)
+  int32_t stats2_groups, stats2_cg, stats2_ch0;
 };
 
 struct TileCoord {
@@ -591,20 +593,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                   s2 = fmaf(v, v, s2);
                 }
               }
-              const int g = (ch < p.Cout) ? (p.stats_ch0 + ch) / p.stats_cg : -1 - col;  // invalid lanes: singleton runs
+              // the column sums feed up to two group layouts: this tensor's own next norm and, for a tensor that is also
+              // a skip connection, the decoder norm that reads it at channel offset stats2_ch0 of a concatenation
+              auto reduce_groups = [&](double* base, int groups, int cg, int ch0) {
+                float r1 = s1, r2 = s2;
+                const int g = (ch < p.Cout) ? (ch0 + ch) / cg : -1 - col;  // invalid lanes: singleton runs
 #pragma unroll
-              for (int off = 1; off < 32; off <<= 1) {
-                const float o1 = __shfl_down_sync(0xffffffffu, s1, off);
-                const float o2 = __shfl_down_sync(0xffffffffu, s2, off);
-                const int og = __shfl_down_sync(0xffffffffu, g, off);
-                if (lane + off < 32 && og == g) s1 += o1, s2 += o2;
-              }
-              const int pg = __shfl_up_sync(0xffffffffu, g, 1);
-              if ((lane == 0 || pg != g) && g >= 0 && simg < p.N) {
-                double* dst = p.stats + (static_cast<int64_t>(simg) * p.stats_groups + g) * 2;
-                atomicAdd(dst, static_cast<double>(s1));
-                atomicAdd(dst + 1, static_cast<double>(s2));
-              }
+                for (int off = 1; off < 32; off <<= 1) {
+                  const float o1 = __shfl_down_sync(0xffffffffu, r1, off);
+                  const float o2 = __shfl_down_sync(0xffffffffu, r2, off);
+                  const int og = __shfl_down_sync(0xffffffffu, g, off);
+                  if (lane + off < 32 && og == g) r1 += o1, r2 += o2;
+                }
+                const int pg = __shfl_up_sync(0xffffffffu, g, 1);
+                if ((lane == 0 || pg != g) && g >= 0 && simg < p.N) {
+                  double* dst = base + (static_cast<int64_t>(simg) * groups + g) * 2;
+                  atomicAdd(dst, static_cast<double>(r1));
+                  atomicAdd(dst + 1, static_cast<double>(r2));
+                }
+              };
+              reduce_groups(p.stats, p.stats_groups, p.stats_cg, p.stats_ch0);
+              if (p.stats2) reduce_groups(p.stats2, p.stats2_groups, p.stats2_cg, p.stats2_ch0);
             }
           }
         }
@@ -812,11 +821,17 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.out = p->out;
   kp.out_dtype = p->out_dtype;
   kp.out_ld = p->out_ld;
+  FG_CHECK_ARG(!p->stats2 || p->stats, "conv_gemm: stats2 without stats (use stats for a single consumer)");
   if (p->stats) {
     FG_CHECK_ARG(p->out_dtype == FG_F32 && p->stats_groups > 0 && p->stats_cg > 0 && p->stats_ch0 >= 0,
                  "conv_gemm: fused GroupNorm statistics need an fp32 output, stats_groups > 0, stats_cg > 0");
     FG_CHECK_ARG(kp.BW * kp.BH >= 32, "conv_gemm: fused GroupNorm statistics need images of at least 32 pixels");
     kp.stats = p->stats, kp.stats_groups = p->stats_groups, kp.stats_cg = p->stats_cg, kp.stats_ch0 = p->stats_ch0;
+    if (p->stats2) {
+      FG_CHECK_ARG(p->stats2_groups > 0 && p->stats2_cg > 0 && p->stats2_ch0 >= 0,
+                   "conv_gemm: stats2 needs stats2_groups > 0, stats2_cg > 0, stats2_ch0 >= 0");
+      kp.stats2 = p->stats2, kp.stats2_groups = p->stats2_groups, kp.stats2_cg = p->stats2_cg, kp.stats2_ch0 = p->stats2_ch0;
+    }
   }
   FG_CHECK_ARG(kp.res_mode >= FG_RES_NONE && kp.res_mode <= FG_RES_DOWN2, "conv_gemm: bad res_mode %d", kp.res_mode);
   if (kp.res_mode != FG_RES_NONE) {

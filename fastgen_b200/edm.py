@@ -497,10 +497,15 @@ class _Plan:
             return _Act(self._new([n, res, res, c], f32), 0, c)
 
         # ---------------- encoder / decoder ----------------
-        # entry list with look-ahead: the conv that writes a block's output also accumulates the GroupNorm statistics
-        # of the NEXT entry's norm0 when that norm sees exactly this tensor (not a skip concatenation)
+        # The conv that writes a tensor also accumulates the GroupNorm statistics of its consumers (fg_conv_gemm stats /
+        # stats2): the next entry's norm0 when that norm sees exactly this tensor, and -- for the two producers of a
+        # decoder skip concatenation torch.cat([x, skip]) (x at channel 0, the encoder skip at channel cx) -- the
+        # concatenation's norm0, each producer adding its channels' share to the same [n, 32, 2] slot.
         entries = [("enc", nm) for nm in enc_names] + [("dec", nm) for nm in dec_names]
         final_norm, final_conv = m.final_layers()
+
+        def can_fuse(px: int, cout: int, ld: int) -> bool:
+            return bool(self.net.fuse_gn_stats) and px >= 32 and cout % 4 == 0 and cout > 16 and ld % 4 == 0
 
         def next_norm(i: int):
             if i + 1 < len(entries):
@@ -509,6 +514,24 @@ class _Plan:
                     return None          # the next block normalises a concatenation
                 return m.enc[nm].norm0 if side == "enc" else m.dec[nm].norm0
             return final_norm
+
+        # which decoder block pops which encoder entry, and whether both producers of its input can fuse the statistics
+        popped_by: Dict[str, str] = {}
+        stack = list(enc_names)
+        for name in dec_names:
+            if name in m.concat_with_skip:
+                popped_by[stack.pop()] = name
+        cat_slot: Dict[str, torch.Tensor] = {}
+        for ei, (side, name) in enumerate(entries):
+            if side != "dec" or name not in x_home:
+                continue
+            blk = m.dec[name]
+            buf, _ = x_home[name]
+            px, ld = buf.shape[1] * buf.shape[2], buf.shape[3]
+            cs = m.concat_with_skip[name]
+            cx = blk.in_channels - cs
+            if can_fuse(px, cx, ld) and can_fuse(px, cs, ld) and blk.in_channels % blk.norm0.num_groups == 0:
+                cat_slot[name] = self.new_stats()
 
         x: Optional[_Act] = None
         x_stats: Optional[torch.Tensor] = None
@@ -522,12 +545,36 @@ class _Plan:
                     buf, _ = x_home[name]
                     assert x.buf is buf, "planner bug: decoder input was not written into its concat buffer"
                     x = _Act(buf, 0, mod.in_channels)
-                    x_stats = None
+                    x_stats = cat_slot.get(name)
                 di = dec_names.index(name)
                 nxt = dec_names[di + 1] if di + 1 < len(dec_names) else None
                 dst = out_act(mod.out_channels, res, x_home.get(nxt) if nxt is not None else None)
+            # statistics targets of this entry's output
+            targets: List[Tuple[torch.Tensor, int, int, int]] = []   # (slot, groups, channels per group, channel offset)
+            own_slot = None
+            cout = mod.out_channels
+            fusable = can_fuse(res * res, cout, dst.ld)
             nn_ = next_norm(i)
-            out_stats = self.fused_stats(res, res, mod.out_channels, dst.ld, nn_, mod.out_channels) if nn_ is not None else None
+            if nn_ is not None and fusable and cout % nn_.num_groups == 0:
+                own_slot = self.new_stats()
+                targets.append((own_slot, nn_.num_groups, cout // nn_.num_groups, 0))
+            nxt_entry = entries[i + 1] if i + 1 < len(entries) else None
+            if nxt_entry is not None and nxt_entry[0] == "dec" and nxt_entry[1] in cat_slot:
+                cblk = m.dec[nxt_entry[1]]
+                targets.append((cat_slot[nxt_entry[1]], cblk.norm0.num_groups, cblk.in_channels // cblk.norm0.num_groups, 0))
+            if side == "enc" and popped_by.get(name) in cat_slot:
+                cname = popped_by[name]
+                cblk = m.dec[cname]
+                targets.append((cat_slot[cname], cblk.norm0.num_groups, cblk.in_channels // cblk.norm0.num_groups,
+                                cblk.in_channels - m.concat_with_skip[cname]))
+            assert len(targets) <= 2, "planner bug: more than two statistics consumers"
+            out_stats = None
+            if targets:
+                t0 = targets[0]
+                out_stats = dict(stats=t0[0], stats_groups=t0[1], stats_cg=t0[2], stats_ch0=t0[3])
+                if len(targets) == 2:
+                    t1 = targets[1]
+                    out_stats.update(stats2=t1[0], stats2_groups=t1[1], stats2_cg=t1[2], stats2_ch0=t1[3])
             if isinstance(mod, _Conv):
                 w = pk[f"enc.{name}"]
                 self.conv(self.segs3(self.xin, self.xin_lo, cin_pad, w["hi"], w.get("lo"), cin_pad, 9), n, R, R,
@@ -535,7 +582,7 @@ class _Plan:
             else:
                 self._block(f"{side}.{name}", mod, x, dst, x_stats, out_stats)
             x = dst
-            x_stats = out_stats["stats"] if out_stats else None
+            x_stats = own_slot
         # ---------------- output head ----------------
         norm, conv = final_norm, final_conv
         key = "final"

@@ -52,6 +52,7 @@ def conv_gemm_params(
     act: int = L.FG_ACT_NONE,
     gate: Optional[torch.Tensor] = None, gate_ld: int = 0, gate_rows: int = 0,
     stats: Optional[torch.Tensor] = None, stats_groups: int = 0, stats_cg: int = 0, stats_ch0: int = 0,
+    stats2: Optional[torch.Tensor] = None, stats2_groups: int = 0, stats2_cg: int = 0, stats2_ch0: int = 0,
 ) -> "L.ConvParams":
     """Fill an ``fg_conv_params`` (the tensors must stay alive and in place while the struct is used)."""
     _need_cuda(out, bias, rowvec, res, gate, *[s.a for s in segs], *[s.w for s in segs])
@@ -75,6 +76,10 @@ def conv_gemm_params(
         _need_cuda(stats)
         assert stats.dtype == torch.float64
         p.stats, p.stats_groups, p.stats_cg, p.stats_ch0 = stats.data_ptr(), stats_groups, stats_cg, stats_ch0
+    if stats2 is not None:
+        _need_cuda(stats2)
+        assert stats is not None and stats2.dtype == torch.float64
+        p.stats2, p.stats2_groups, p.stats2_cg, p.stats2_ch0 = stats2.data_ptr(), stats2_groups, stats2_cg, stats2_ch0
     return p
 
 

@@ -472,10 +472,30 @@ class StableDiffusionXL(FastGenNetwork):
             assert i < arena.shape[0], "planner bug: statistics arena too small"
             return arena[i]
 
+        def can_fuse(px: int, cout: int, out_ld: int) -> bool:
+            return px >= 32 and cout % 4 == 0 and cout > 16 and out_ld % 4 == 0
+
         def fused_stats(h: int, w: int, cout: int, out_ld: int, c_norm: Optional[int]):
-            if c_norm is None or h * w < 32 or cout % 4 or cout <= 16 or out_ld % 4 or cout != c_norm:
+            """conv kwargs that accumulate the statistics of a norm over exactly this tensor, or None"""
+            if c_norm is None or cout != c_norm or not can_fuse(h * w, cout, out_ld):
                 return None
             return dict(stats=new_stats(), stats_groups=G, stats_cg=c_norm // G, stats_ch0=0)
+
+        def stats_kw(dst: "_Act", own_c: Optional[int], cat: Optional[Tuple[torch.Tensor, int, int]]):
+            """statistics targets of a layer output: its own next norm (over own_c == dst.c channels) and / or the norm
+            of the skip concatenation it is part of -- cat = (slot, channels per group, channel offset).  Returns
+            (conv kwargs, slot of the own norm or None)."""
+            kw: Dict[str, Any] = {}
+            own = fused_stats(dst.h, dst.w, dst.c, dst.ld, own_c)
+            if own:
+                kw.update(own)
+            if cat is not None:
+                slot, cg, ch0 = cat
+                if own:
+                    kw.update(stats2=slot, stats2_groups=G, stats2_cg=cg, stats2_ch0=ch0)
+                else:
+                    kw.update(stats=slot, stats_groups=G, stats_cg=cg, stats_ch0=ch0)
+            return kw, (own["stats"] if own else None)
 
         def conv(segs, n, h, w, cout, out, out_ld, desc, **kw):
             p = ops.conv_gemm_params(segs, n, h, w, cout, out, out_ld, **kw)
@@ -537,8 +557,8 @@ class StableDiffusionXL(FastGenNetwork):
         gemm(ws["emb_act"], T, pk["temb.w"], B, tl, ws["temb"], tl, "time_proj_all", bias=pk["temb.b"])
 
         # ---- layers -----------------------------------------------------------------------------------------------
-        def resnet(key: str, r: _Resnet, x: _Act, dst: _Act, x_stats, next_c: Optional[int]):
-            """ResnetBlock2D; returns the statistics slot the output conv accumulated for the next norm (or None)"""
+        def resnet(key: str, r: _Resnet, x: _Act, dst: _Act, x_stats, out_kw: Dict[str, Any]):
+            """ResnetBlock2D; out_kw: statistics kwargs of the output conv (see stats_kw)"""
             h, w, cin, cout = x.h, x.w, r.cin, r.cout
             assert x.c == cin and dst.c == cout
             short = (key + ".sc.w") in pk
@@ -557,11 +577,9 @@ class StableDiffusionXL(FastGenNetwork):
                 segs.append(ops.Seg(raw, cin, pk[key + ".sc.w"], cin, 1))
             else:
                 kw = dict(res=x.t, res_ld=x.ld, res_mode=L.FG_RES_SAME)
-            st2 = fused_stats(h, w, cout, dst.ld, next_c)
-            conv(segs, B, h, w, cout, dst.t, dst.ld, "res.conv2", bias=pk[key + ".c2.b"], **kw, **(st2 or {}))
-            return st2["stats"] if st2 else None
+            conv(segs, B, h, w, cout, dst.t, dst.ld, "res.conv2", bias=pk[key + ".c2.b"], **kw, **out_kw)
 
-        def transformer(key: str, a: _Transformer2D, x: _Act, dst: _Act, x_stats, next_c: Optional[int]):
+        def transformer(key: str, a: _Transformer2D, x: _Act, dst: _Act, x_stats, out_kw: Dict[str, Any]):
             h, w, c, heads = x.h, x.w, a.dim, a.heads
             d, N = c // heads, x.h * x.w
             rows = B * N
@@ -591,10 +609,8 @@ class StableDiffusionXL(FastGenNetwork):
                      res_mode=L.FG_RES_SAME)
             plan.add(lib.fg_cast_resample, hs.data_ptr(), L.FG_F32, c, rows, 1, 1, c, L.FG_RES_NONE, nrm.data_ptr(), c,
                      desc="cast_tokens")
-            st = fused_stats(h, w, c, dst.ld, next_c)
             conv([ops.Seg(nrm.view(B, h, w, c), c, pk[k + ".out.w"], c, 1)], B, h, w, c, dst.t, dst.ld, "proj_out",
-                 bias=pk[k + ".out.b"], res=x.t, res_ld=x.ld, res_mode=L.FG_RES_SAME, **(st or {}))
-            return st["stats"] if st else None
+                 bias=pk[k + ".out.b"], res=x.t, res_ld=x.ld, res_mode=L.FG_RES_SAME, **out_kw)
 
         def cast(x: _Act, up: bool) -> torch.Tensor:
             s = 2 if up else 1
@@ -617,6 +633,7 @@ class StableDiffusionXL(FastGenNetwork):
                 skip_shapes.append((h, w, d["c"]))
         pending = list(range(len(skip_shapes)))
         skip_home: Dict[int, _Act] = {}
+        skip_user: Dict[int, Tuple[int, int]] = {}       # skip index -> (up block, resnet) that concatenates it
         cat_of: Dict[Tuple[int, int], torch.Tensor] = {}
         for i, uu in enumerate(lay["up"]):
             for j, (rin, skip, co) in enumerate(uu["res"]):
@@ -626,30 +643,54 @@ class StableDiffusionXL(FastGenNetwork):
                 buf = new(B, sh, sw, rin + skip)
                 cat_of[(i, j)] = buf
                 skip_home[s] = _Act(buf, rin, skip)
+                skip_user[s] = (i, j)
         assert not pending
+        # GroupNorm statistics of a concatenation come from its two producers (fg_conv_gemm stats / stats2 with a channel
+        # offset) when both can fuse them; a skip written by a downsampler (stride-1 conv + subsampling) cannot
+        down_skips = set()
+        k_ = 0
+        for d in lay["down"]:
+            k_ += len(d["res"])
+            if d["down"]:
+                k_ += 1
+                down_skips.add(k_)
+        cat_slot: Dict[Tuple[int, int], torch.Tensor] = {}
+        for s_, (i, j) in skip_user.items():
+            buf = cat_of[(i, j)]
+            rin, skip, _ = lay["up"][i]["res"][j]
+            px, ld = buf.shape[1] * buf.shape[2], buf.shape[3]
+            if s_ not in down_skips and can_fuse(px, rin, ld) and can_fuse(px, skip, ld) and (rin + skip) % G == 0:
+                cat_slot[(i, j)] = new_stats()
+
+        def cat_target(key: Optional[Tuple[int, int]], part: str):
+            """(slot, channels per group, channel offset) of concat norm `key` for its x part / skip part, or None"""
+            if key is None or key not in cat_slot:
+                return None
+            rin, skip, _ = lay["up"][key[0]]["res"][key[1]]
+            return cat_slot[key], (rin + skip) // G, (0 if part == "x" else rin)
 
         # ---- down path --------------------------------------------------------------------------------------------
         si = 0
         x = skip_home[si]
-        st = fused_stats(H, W, c0, x.ld, c0)
-        conv([ops.Seg(ws["xin"], 8, pk["conv_in.w"], 8, 9)], B, H, W, c0, x.t, x.ld, "conv_in", bias=pk["conv_in.b"],
-             **(st or {}))
-        x_stats = st["stats"] if st else None
+        kw0, x_stats = stats_kw(x, c0, cat_target(skip_user[si], "skip"))
+        conv([ops.Seg(ws["xin"], 8, pk["conv_in.w"], 8, 9)], B, H, W, c0, x.t, x.ld, "conv_in", bias=pk["conv_in.b"], **kw0)
         si += 1
         for i, d in enumerate(lay["down"]):
             blk = u.down_blocks[i]
             for j in range(len(d["res"])):
                 dst = skip_home[si]
-                si += 1
                 last = j == len(d["res"]) - 1
                 after_c = (None if d["down"] else lay["mid_c"]) if last else d["c"]   # norm that reads dst next
+                okw, own = stats_kw(dst, after_c, cat_target(skip_user[si], "skip"))
+                si += 1
                 if d["attn"]:
                     mid = _Act(scratch("mid", [B, x.h, x.w, d["c"]], f32), 0, d["c"])
-                    s_mid = resnet(f"down.{i}.{j}", blk.resnets[j], x, mid, x_stats, d["c"])
-                    x_stats = transformer(f"down.{i}.{j}", blk.attentions[j], mid, dst, s_mid, after_c)
+                    mkw, s_mid = stats_kw(mid, d["c"], None)
+                    resnet(f"down.{i}.{j}", blk.resnets[j], x, mid, x_stats, mkw)
+                    transformer(f"down.{i}.{j}", blk.attentions[j], mid, dst, s_mid, okw)
                 else:
-                    x_stats = resnet(f"down.{i}.{j}", blk.resnets[j], x, dst, x_stats, after_c)
-                x = dst
+                    resnet(f"down.{i}.{j}", blk.resnets[j], x, dst, x_stats, okw)
+                x, x_stats = dst, own
             if d["down"]:
                 dst = skip_home[si]
                 si += 1
@@ -667,11 +708,14 @@ class StableDiffusionXL(FastGenNetwork):
         # ---- mid block --------------------------------------------------------------------------------------------
         mc = lay["mid_c"]
         m1 = _Act(new(B, x.h, x.w, mc), 0, mc)
-        s1 = resnet("mid.0", u.mid_block.resnets[0], x, m1, x_stats, mc)
+        kw1, s1 = stats_kw(m1, mc, None)
+        resnet("mid.0", u.mid_block.resnets[0], x, m1, x_stats, kw1)
         m2 = _Act(new(B, x.h, x.w, mc), 0, mc)
-        s2 = transformer("mid.0", u.mid_block.attentions[0], m1, m2, s1, mc)
+        kw2, s2 = stats_kw(m2, mc, None)
+        transformer("mid.0", u.mid_block.attentions[0], m1, m2, s1, kw2)
         x = _Act(cat_of[(0, 0)], 0, mc)
-        resnet("mid.1", u.mid_block.resnets[1], m2, x, s2, None)
+        kw3, _ = stats_kw(x, None, cat_target((0, 0), "x"))
+        resnet("mid.1", u.mid_block.resnets[1], m2, x, s2, kw3)
         # ---- up path ----------------------------------------------------------------------------------------------
         nb = len(lay["up"])
         for i, uu in enumerate(lay["up"]):
@@ -681,25 +725,31 @@ class StableDiffusionXL(FastGenNetwork):
                 cat = cat_of[(i, j)]
                 assert x.buf is cat and x.off == 0 and x.c == rin, "planner bug: up-path input is not in its concat buffer"
                 xin = _Act(cat, 0, rin + skip)
+                xin_stats = cat_slot.get((i, j))      # None: this norm runs its own fg_gn_stats pass
                 last = j == nres - 1
                 if not last:
-                    dst, after_c = _Act(cat_of[(i, j + 1)], 0, co), None
+                    dst = _Act(cat_of[(i, j + 1)], 0, co)
+                    okw, own = stats_kw(dst, None, cat_target((i, j + 1), "x"))
                 elif uu["up"]:
-                    dst, after_c = _Act(new(B, xin.h, xin.w, co), 0, co), None
+                    dst = _Act(new(B, xin.h, xin.w, co), 0, co)
+                    okw, own = {}, None
                 else:
-                    dst, after_c = _Act(new(B, xin.h, xin.w, co), 0, co), co       # conv_norm_out reads it
+                    dst = _Act(new(B, xin.h, xin.w, co), 0, co)
+                    okw, own = stats_kw(dst, co, None)                 # conv_norm_out reads it
                 if uu["attn"]:
                     mid = _Act(scratch("mid", [B, xin.h, xin.w, co], f32), 0, co)
-                    s_mid = resnet(f"up.{i}.{j}", blk.resnets[j], xin, mid, None, co)
-                    x_stats = transformer(f"up.{i}.{j}", blk.attentions[j], mid, dst, s_mid, after_c)
+                    mkw, s_mid = stats_kw(mid, co, None)
+                    resnet(f"up.{i}.{j}", blk.resnets[j], xin, mid, xin_stats, mkw)
+                    transformer(f"up.{i}.{j}", blk.attentions[j], mid, dst, s_mid, okw)
                 else:
-                    x_stats = resnet(f"up.{i}.{j}", blk.resnets[j], xin, dst, None, after_c)
-                x = dst
+                    resnet(f"up.{i}.{j}", blk.resnets[j], xin, dst, xin_stats, okw)
+                x, x_stats = dst, own
             if uu["up"]:
                 xu = cast(x, True)
                 dst = _Act(cat_of[(i + 1, 0)], 0, uu["c"])
+                ukw, _ = stats_kw(dst, None, cat_target((i + 1, 0), "x"))
                 conv([ops.Seg(xu, uu["c"], pk[f"us.{i}.w"], uu["c"], 9)], B, 2 * x.h, 2 * x.w, uu["c"], dst.t, dst.ld,
-                     "upsample", bias=pk[f"us.{i}.b"])
+                     "upsample", bias=pk[f"us.{i}.b"], **ukw)
                 x, x_stats = dst, None
         assert i == nb - 1
         # ---- output head --------------------------------------------------------------------------------------------

@@ -87,6 +87,10 @@ typedef struct {
   int32_t stats_groups; /* g = (stats_ch0 + co) / stats_cg -- the fg_gn_stats pass of the consumer fused into the      */
   int32_t stats_cg;     /* producer (the caller zeroes the buffer, e.g. fg_zero, before the launch)                     */
   int32_t stats_ch0;
+  double* stats2;        /* optional second statistics target [n][stats2_groups][2]: a tensor that is also a skip connection */
+  int32_t stats2_groups; /* feeds the decoder GroupNorm that reads it at channel offset stats2_ch0 of a concatenation       */
+  int32_t stats2_cg;     /* (torch.cat([x, skip]), EDM/network.py:559-561); with stats_ch0 on the producer of x, that norm  */
+  int32_t stats2_ch0;    /* needs no fg_gn_stats pass of its own                                                            */
 } fg_conv_params;
 
 int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream);

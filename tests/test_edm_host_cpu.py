@@ -1,0 +1,48 @@
+"""CPU dry run of the EDM launch lists (BASELINE.json configs[0] and [1] plus the tiny golden-fixture networks): every C-ABI
+call validates its arguments on the host (no kernel can run here: each must fail with FG_ERR_CUDA, never FG_ERR_INVALID),
+and the planner's bookkeeping is checked: every GroupNorm has exactly one statistics source, and the full-size networks
+need no separate fg_gn_stats pass (the producing convs accumulate the statistics, skip concatenations included)."""
+import collections
+
+import pytest
+
+CIFAR = dict(img_resolution=32, img_channels=3, label_dim=10, sigma_shift=0.0, sigma_data=0.5, model_type="SongUNet",
+             augment_dim=9, model_channels=128, channel_mult=[2, 2, 2], channel_mult_noise=1,
+             embedding_type="positional", encoder_type="standard", decoder_type="standard", resample_filter=[1, 1],
+             dropout=0.0, label_dropout=0, r_timestep=False, drop_precond=None)
+IN64 = dict(img_resolution=64, img_channels=3, label_dim=1000, sigma_shift=0.0, sigma_data=0.5,
+            model_type="DhariwalUNet", augment_dim=0, model_channels=192, channel_mult=[1, 2, 3, 4], channel_mult_emb=4,
+            num_blocks=3, attn_resolutions=[32, 16, 8], dropout=0.0, label_dropout=0, r_timestep=False,
+            drop_precond=None)
+
+
+def _cfgs():
+    from oracle.make_golden import CONFIGS
+
+    return [("cifar", CIFAR, "bf16", 0), ("in64", IN64, "bf16", 0), ("in64_x3", IN64, "bf16x3", 0),
+            ("song_tiny", CONFIGS["song_tiny"], "bf16", None), ("dhariwal_tiny", CONFIGS["dhariwal_tiny"], "bf16x3", None)]
+
+
+@pytest.mark.parametrize("name,cfg,compute,max_stats_passes", _cfgs(), ids=[c[0] for c in _cfgs()])
+def test_edm_launch_list_arguments_validate_on_the_host(monkeypatch, name, cfg, compute, max_stats_passes):
+    from fastgen_b200 import _lib as L
+    from fastgen_b200 import edm as E
+    from fastgen_b200 import ops
+
+    monkeypatch.setattr(E, "_ALLOW_HOST_PLANS", True)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *a, **k: None)
+    net = E.EDMPrecond(**cfg).eval()
+    net.set_compute(compute)
+    plan = net._plan(3)
+    counts = collections.Counter(fn.__name__ for fn, _ in plan.steps)
+    invalid, ok = [], 0
+    for fn, args in plan.steps:
+        st = fn(*args, None)
+        if st == -1:
+            invalid.append((fn.__name__, L.lib().fg_last_error().decode()))
+        ok += st == 0
+    assert not invalid, invalid[:5]
+    assert ok <= counts["fg_zero"], "a kernel launch succeeded without a GPU?"   # (cudaMemsetAsync may report success)
+    assert counts["fg_conv_gemm"] > 10 and counts["fg_gn_apply"] > 10
+    if max_stats_passes is not None:
+        assert counts["fg_gn_stats"] <= max_stats_passes, counts

@@ -225,6 +225,35 @@ def test_conv_gemm_fused_groupnorm_statistics(n, h, w, cin, cout, taps, groups, 
     assert torch.allclose(stats, ref, rtol=2e-5, atol=1e-3), (stats - ref).abs().max().item()
 
 
+def test_conv_gemm_two_statistics_targets():
+    """a tensor that is also a skip connection: the epilogue feeds its own next norm (stats) and, at a channel offset with
+    another group width and group count, the decoder norm that reads it inside a concatenation (stats2)"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(11)
+    dev = "cuda"
+    n, h, w, cin, cout = 5, 16, 16, 64, 192
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, device=dev) / math.sqrt(cin * 9)).bfloat16()
+    out = torch.empty(n, h, w, cout, device=dev)
+    g1, cg1 = 32, cout // 32                      # own norm: 32 groups of 6
+    g2, ctot, ch0 = 16, 576, 384                  # concat norm: 16 groups of 36 over 576 channels, ours are [384, 576)
+    cg2 = ctot // g2
+    s1 = torch.zeros(n, g1, 2, device=dev, dtype=torch.float64)
+    s2 = torch.full((n, g2, 2), 3.0, device=dev, dtype=torch.float64)   # the other producer has already added its share
+    ops.conv_gemm([ops.Seg(_nhwc(x), cin, wt.permute(0, 2, 3, 1).contiguous(), cin, 9)], n, h, w, cout, out, cout,
+                  stats=s1, stats_groups=g1, stats_cg=cg1, stats_ch0=0,
+                  stats2=s2, stats2_groups=g2, stats2_cg=cg2, stats2_ch0=ch0)
+    torch.cuda.synchronize()
+    o = out.double()
+    for st, groups, cg, c0, base in ((s1, g1, cg1, 0, 0.0), (s2, g2, cg2, ch0, 3.0)):
+        ref = torch.full((n, groups, 2), base, device=dev, dtype=torch.float64)
+        gidx = (c0 + torch.arange(cout, device=dev)) // cg
+        ref[:, :, 0].index_add_(1, gidx, o.sum(dim=(1, 2)))
+        ref[:, :, 1].index_add_(1, gidx, (o * o).sum(dim=(1, 2)))
+        assert torch.allclose(st, ref, rtol=2e-5, atol=1e-3), (st - ref).abs().max().item()
+
+
 def test_conv_gemm_split_precision_segments():
     """bf16x3 split products (hi*hi + lo*hi + hi*lo) reach ~fp32 accuracy: the 'fp32 path' of the network"""
     from fastgen_b200 import ops
