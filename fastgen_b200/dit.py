@@ -2,7 +2,8 @@
 
 Drop-in for ``fastgen.networks.DiT.network.DiT`` (reference DiT/network.py:228-574): same constructor keywords, same
 ``forward`` signature, same ``state_dict`` key names (``blocks.0.attention.qkv.weight`` ...) including the Facebook-DiT
-checkpoint key conversion (:346-401).  Inference only (no ``r`` embedder, no features / logvar outputs).
+checkpoint key conversion (:346-401), optional ``r`` embedder (MeanFlow-style second timestep).  Inference only (no
+features / logvar outputs).
 
 Forward = patchify -> GEMM (+pos_embed) -> per block [ln_modulate -> GEMM(qkv) -> flash attention -> GEMM(proj; gate*v +
 residual) -> ln_modulate -> GEMM(fc1, GELU-tanh) -> GEMM(fc2; gate*v + residual)] -> ln_modulate -> GEMM -> unpatchify;
@@ -92,8 +93,8 @@ class DiT(FastGenNetwork):
                  r_timestep=False, scale_t=True, time_cond_type="abs", net_pred_type="flow", schedule_type="rf",
                  enable_fused_attn=False, use_sit_convention=False, **model_kwargs):
         super().__init__(net_pred_type=net_pred_type, schedule_type=schedule_type, **model_kwargs)
-        if r_timestep:
-            raise NotImplementedError("the r-timestep embedder is not built")
+        if time_cond_type not in ("abs", "diff"):
+            raise ValueError(f"Invalid time_cond_type: {time_cond_type}")
         if hidden_size % num_heads or (hidden_size // num_heads) % 8 or hidden_size // num_heads > 128:
             raise ValueError("head dim must be a multiple of 8 and <= 128")
         self.use_sit_convention = use_sit_convention
@@ -104,7 +105,8 @@ class DiT(FastGenNetwork):
         self.img_resolution = input_size * 8
         self.x_embedder = _PatchEmbed(in_channels, hidden_size, patch_size)
         self.t_embedder = _TimeEmbedding(hidden_size)
-        self.r_embedder = None
+        self.r_timestep, self.time_cond_type = r_timestep, time_cond_type
+        self.r_embedder = _TimeEmbedding(hidden_size) if r_timestep else None      # reference DiT/network.py:274-279
         n_emb = num_classes + (1 if class_dropout_prob > 0 else 0)
         self.y_embedder = _ClassEmbedding(n_emb, hidden_size)
         self.num_patches = (input_size // patch_size) ** 2
@@ -132,6 +134,9 @@ class DiT(FastGenNetwork):
         nn.init.normal_(self.y_embedder.class_embeddings.weight, std=0.02)
         nn.init.normal_(self.t_embedder.proj_net[0].weight, std=0.02)
         nn.init.normal_(self.t_embedder.proj_net[2].weight, std=0.02)
+        if self.r_embedder is not None:
+            nn.init.normal_(self.r_embedder.proj_net[0].weight, std=0.02)
+            nn.init.normal_(self.r_embedder.proj_net[2].weight, std=0.02)
         for blk in self.blocks:
             nn.init.constant_(blk.conditioning_net[-1].weight, 0)
             nn.init.constant_(blk.conditioning_net[-1].bias, 0)
@@ -180,6 +185,9 @@ class DiT(FastGenNetwork):
         pk["patch.w"], pk["patch.b"] = pe.weight.detach().reshape(pe.weight.shape[0], -1).to(bf).contiguous(), b(pe)
         pk["t1.w"], pk["t1.b"] = w(self.t_embedder.proj_net[0]), b(self.t_embedder.proj_net[0])
         pk["t2.w"], pk["t2.b"] = w(self.t_embedder.proj_net[2]), b(self.t_embedder.proj_net[2])
+        if self.r_embedder is not None:
+            pk["r1.w"], pk["r1.b"] = w(self.r_embedder.proj_net[0]), b(self.r_embedder.proj_net[0])
+            pk["r2.w"], pk["r2.b"] = w(self.r_embedder.proj_net[2]), b(self.r_embedder.proj_net[2])
         cw = [blk.conditioning_net[1].weight for blk in self.blocks] + [self.final_layer.adaptive_params[1].weight]
         cb = [blk.conditioning_net[1].bias for blk in self.blocks] + [self.final_layer.adaptive_params[1].bias]
         pk["cond.w"] = torch.cat(cw, 0).detach().to(bf).contiguous()      # [(6L + 2) D, D]
@@ -192,8 +200,8 @@ class DiT(FastGenNetwork):
         pk["out.w"], pk["out.b"] = w(self.final_layer.projection), b(self.final_layer.projection)
         self._packed, self._plans = pk, {}
 
-    def _plan(self, B: int, x_dtype: torch.dtype):
-        key = (B, x_dtype)
+    def _plan(self, B: int, x_dtype: torch.dtype, has_r: bool = False):
+        key = (B, x_dtype, has_r)
         ent = self._plans.get(key)
         if ent is not None:
             return ent
@@ -210,6 +218,7 @@ class DiT(FastGenNetwork):
         ws = dict(x_in=z(B, Cc, 1, S, S, dt=x_dtype), tok=z(rows, kin_pad), pos=z(rows, D), hs=z(rows, D), nrm=z(rows, D),
                   qkv=z(rows, 3 * D), att=z(rows, D), f1=z(rows, Hd), tok_out=z(rows, kout),
                   out=z(B, Co, 1, S, S, dt=x_dtype), emb=z(B, 256), te1=z(B, D), yemb=z(B, D, dt=f32), c=z(B, D, dt=f32),
+                  emb_r=z(B, 256), re1=z(B, D), c0=z(B, D, dt=f32),
                   c_act=z(B, D), mod=z(B, (6 * Lb + 2) * D, dt=f32))
         ws["pos"].copy_(self.pos_embed.detach().to(bf).expand(B, N, D).reshape(rows, D))
         if kin_pad != kin:
@@ -241,8 +250,15 @@ class DiT(FastGenNetwork):
         gemm(ws["tok"], kin_pad, patch_w, rows, D, ws["hs"], D, "patch", bias=pk["patch.b"], res=ws["pos"], res_ld=D,
              res_mode=L.FG_RES_SAME)
         gemm(ws["emb"], 256, pk["t1.w"], B, D, ws["te1"], D, "time1", bias=pk["t1.b"], act=L.FG_ACT_SILU)
-        gemm(ws["te1"], D, pk["t2.w"], B, D, ws["c"], D, "time2", bias=pk["t2.b"], res=ws["yemb"], res_ld=D,
-             res_mode=L.FG_RES_SAME)                                    # c = t_emb + y
+        if not has_r:
+            gemm(ws["te1"], D, pk["t2.w"], B, D, ws["c"], D, "time2", bias=pk["t2.b"], res=ws["yemb"], res_ld=D,
+                 res_mode=L.FG_RES_SAME)                                # c = t_emb + y
+        else:                                                           # c = t_emb + y + r_emb (DiT/network.py:518-533)
+            gemm(ws["te1"], D, pk["t2.w"], B, D, ws["c0"], D, "time2", bias=pk["t2.b"], res=ws["yemb"], res_ld=D,
+                 res_mode=L.FG_RES_SAME)
+            gemm(ws["emb_r"], 256, pk["r1.w"], B, D, ws["re1"], D, "r_time1", bias=pk["r1.b"], act=L.FG_ACT_SILU)
+            gemm(ws["re1"], D, pk["r2.w"], B, D, ws["c"], D, "r_time2", bias=pk["r2.b"], res=ws["c0"], res_ld=D,
+                 res_mode=L.FG_RES_SAME)
         plan.add(lib.fg_split_bf16, ws["c"].data_ptr(), D, None, 0, B, D, 1, ws["c_act"].data_ptr(), None, D, None, 0,
                  desc="silu_c")
         gemm(ws["c_act"], D, pk["cond.w"], B, mod_ld, ws["mod"], mod_ld, "cond", bias=pk["cond.b"])
@@ -288,8 +304,6 @@ class DiT(FastGenNetwork):
             assert fwd_pred_type in NET_PRED_TYPES, f"{fwd_pred_type} is not supported as fwd_pred_type"
         if return_features_early or len(feature_indices) or return_logvar:
             raise NotImplementedError("feature / logvar outputs are training-time paths of the reference")
-        if r is not None:
-            raise NotImplementedError("the r-timestep embedder is not built")
         if not x_t.is_cuda:
             raise L.FastGenB200Error("DiT (B200) needs CUDA tensors: there is no CPU path")
         if x_t.dtype not in (torch.float32, torch.bfloat16):
@@ -309,12 +323,22 @@ class DiT(FastGenNetwork):
                 tt = tt.expand(B)
             if self.use_sit_convention:
                 tt = 1 - tt
-            plan, ws = self._plan(B, x_t.dtype)
+            has_r = self.r_embedder is not None and r is not None     # (r without an r embedder is ignored, like the reference)
+            plan, ws = self._plan(B, x_t.dtype, has_r)
             ws["x_in"].copy_(x_t.reshape(ws["x_in"].shape))
             half = 128
             freq = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=x_t.device) / half)
-            ang = tt[:, None].float() * freq[None, :]
-            ws["emb"].copy_(torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(tt.dtype))
+
+            def fourier(v):
+                ang = v[:, None].float() * freq[None, :]
+                return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(v.dtype)
+
+            ws["emb"].copy_(fourier(tt))
+            if has_r:
+                rr = self.prepare_t(torch.atleast_1d(r).to(x_t.device), dtype=x_t.dtype)
+                if rr.numel() == 1 and B > 1:
+                    rr = rr.expand(B)
+                ws["emb_r"].copy_(fourier(tt - rr if self.time_cond_type == "diff" else rr))
             ws["yemb"].copy_(self.y_embedder.class_embeddings.weight.detach()[condition.to(x_t.device)])
             plan.run(torch.cuda.current_stream().cuda_stream, self.profile)
             out = ws["out"].reshape(B, self.out_channels, self.input_size, self.input_size)

@@ -98,6 +98,15 @@ class _CondEmbedder(nn.Module):
         self.text_embedder = _TimeEmbedder(text_dim, dim)
 
 
+class _REmbedder(nn.Module):
+    """the reference's r embedder: a copy of condition_embedder without its text branch (Wan/network.py:799-834)"""
+
+    def __init__(self, dim: int, freq_dim: int):
+        super().__init__()
+        self.time_embedder = _TimeEmbedder(freq_dim, dim)
+        self.time_proj = nn.Linear(dim, 6 * dim)
+
+
 class _WanTransformer(nn.Module):
     def __init__(self, cfg: Dict[str, Any], logvar: bool):
         super().__init__()
@@ -149,6 +158,9 @@ class _Plan:
         self.keep: List[Any] = []
         self.runs = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.n_head = 0
+        self.has_r = False
+        self.mod_groups = (0, 0)
 
     def add(self, fn, *args, desc: str = "", flops: float = 0.0):
         self.steps.append((fn, args, desc, flops))
@@ -192,11 +204,11 @@ class _WanBase:
     """Shared implementation (mixed into the two public classes)."""
 
     def _init_wan(self, model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
-                  r_timestep, norm_temb, encoder_depth):
-        if r_timestep or encoder_depth is not None:
-            raise NotImplementedError("the r-timestep embedder (MeanFlow on Wan) is not built")
-        if norm_temb:
-            raise NotImplementedError("norm_temb (sCM AdaLN normalisation) is not built")
+                  r_timestep, norm_temb, encoder_depth, r_embedder_init="pretrained", time_cond_type="diff"):
+        if time_cond_type not in ("abs", "diff"):
+            raise ValueError(f"Invalid time condition: {time_cond_type}")
+        if r_embedder_init not in ("pretrained", "zero", "random"):
+            raise ValueError(f"Invalid embedder_init: {r_embedder_init}")
         cfg = dict(_DEFAULTS)
         if transformer_config is not None:
             cfg.update(transformer_config)
@@ -215,7 +227,11 @@ class _WanBase:
         self.expand_timesteps = False
         self._use_wan_official_sinusoidal = use_wan_official_sinusoidal
         self.transformer = _WanTransformer(cfg, enable_logvar_linear)
+        self.norm_temb, self.encoder_depth, self.time_cond_type = bool(norm_temb), encoder_depth, time_cond_type
+        if encoder_depth is not None and not 0 <= encoder_depth <= cfg["layers"]:
+            raise ValueError("encoder_depth must be in [0, layers]")
         self.reset_wan_parameters()
+        self.transformer.r_embedder = self._init_r_embedder(r_embedder_init) if r_timestep else None
         self._packed: Optional[Dict[str, Any]] = None
         self._plans: Dict[Any, _Plan] = {}
         self._ws: Dict[Any, Dict[str, torch.Tensor]] = {}
@@ -253,6 +269,30 @@ class _WanBase:
             if isinstance(m, nn.Linear):
                 nn.init.normal_(m.weight, std=0.02)
         nn.init.zeros_(self.transformer.proj_out.weight)
+
+    def _init_r_embedder(self, how: str) -> "_REmbedder":
+        """reference Wan.init_embedder (Wan/network.py:799-834)"""
+        ce = self.transformer.condition_embedder
+        emb = _REmbedder(self.cfg["dim"], self.cfg["freq_dim"]).to(ce.time_proj.weight.device, ce.time_proj.weight.dtype)
+        with torch.no_grad():
+            emb.time_embedder.load_state_dict(ce.time_embedder.state_dict())
+            emb.time_proj.load_state_dict(ce.time_proj.state_dict())
+            if how == "zero":
+                for prm in emb.parameters():
+                    prm.zero_()
+            elif how == "random":
+                for m in emb.modules():
+                    if isinstance(m, nn.Linear):
+                        nn.init.xavier_uniform_(m.weight)
+                        nn.init.zeros_(m.bias)
+                for m in emb.time_embedder.modules():
+                    if isinstance(m, nn.Linear):
+                        nn.init.normal_(m.weight, std=0.02)
+                nn.init.zeros_(emb.time_embedder.linear_2.weight)
+                nn.init.zeros_(emb.time_embedder.linear_2.bias)
+                nn.init.zeros_(emb.time_proj.weight)
+                nn.init.zeros_(emb.time_proj.bias)
+        return emb
 
     def _invalidate(self):
         self._packed = None
@@ -332,6 +372,10 @@ class _WanBase:
         for nm, lin in (("t1", ce.time_embedder.linear_1), ("t2", ce.time_embedder.linear_2), ("tp", ce.time_proj),
                         ("x1", ce.text_embedder.linear_1), ("x2", ce.text_embedder.linear_2), ("out", tr.proj_out)):
             pk[nm + ".w"], pk[nm + ".b"] = w(lin), b(lin)
+        if tr.r_embedder is not None:
+            re = tr.r_embedder
+            for nm, lin in (("r1", re.time_embedder.linear_1), ("r2", re.time_embedder.linear_2), ("rp", re.time_proj)):
+                pk[nm + ".w"], pk[nm + ".b"] = w(lin), b(lin)
         tables = []
         for i, blk in enumerate(tr.blocks):
             a1, a2 = blk.attn1, blk.attn2
@@ -388,6 +432,9 @@ class _WanBase:
             emb=z(groups, cfg["freq_dim"]), te1=z(groups, D), temb=z(groups, D), temb_act=z(groups, D),
             tproj=z(groups, 6 * D, dt=f32), mod=z(cfg["layers"], groups, 6 * D, dt=f32), head_mod=z(groups, 2 * D, dt=f32),
         )
+        if self.transformer.r_embedder is not None:
+            ws.update(emb_r=z(groups, cfg["freq_dim"]), re1=z(groups, D), remb=z(groups, D), remb_act=z(groups, D),
+                      rtproj=z(groups, 6 * D, dt=f32))
         if P > 1:
             # Ulysses exchange buffers (per sample b: [P][n/P][3][H/P*d] for q,k,v and [P][n/P][H/P*d] for the output)
             ws.update(hs_full=z(rows, D), a2a_s=z(B, P, n // P, 3 * Dl), qkv_full=z(B, n, 3 * Dl), att_full=z(B, n, Dl),
@@ -498,7 +545,8 @@ class _WanBase:
                    dsc["ds"], dsc["item"], desc)
 
     def _build_plan(self, B, F, Hh, Ww, x_dtype, per_frame: bool, kv: Optional[Dict[str, Any]], cache_start: int,
-                    store_kv: bool, frame0: int, mask: Optional[Tuple[int, int]], cross: Dict[str, Any]) -> _Plan:
+                    store_kv: bool, frame0: int, mask: Optional[Tuple[int, int]], cross: Dict[str, Any],
+                    has_r: bool = False) -> _Plan:
         """Launch list of one forward.  With sequence parallelism (P ranks) a rank owns tokens
         [rank * fs/P, (rank+1) * fs/P) of EVERY frame (so modulation groups stay contiguous), all heads; around each
         self-attention q/k/v are exchanged to (all tokens, H/P heads) and the output back (Ulysses); the KV cache holds
@@ -537,8 +585,37 @@ class _WanBase:
         self._gemm(plan, ws["te1"], D, pk["t2.w"], groups, D, ws["temb_act"], D, "time2s", bias=pk["t2.b"],
                    act=L.FG_ACT_SILU)
         self._gemm(plan, ws["temb_act"], D, pk["tp.w"], groups, 6 * D, ws["tproj"], 6 * D, "tproj", bias=pk["tp.b"])
-        plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["tproj"].data_ptr(), cfg["layers"], groups, 6 * D,
-                 ws["mod"].data_ptr(), desc="mod")
+        nl = cfg["layers"]
+        if not has_r:
+            plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["tproj"].data_ptr(), nl, groups, 6 * D,
+                     ws["mod"].data_ptr(), desc="mod")
+        else:
+            # r embedder (MeanFlow-style second timestep, Wan/network.py:330-352): same three linears on the embedding
+            # of r (or t - r); its projection is added to the time projection, or replaces it from block
+            # `encoder_depth` on
+            self._gemm(plan, ws["emb_r"], cfg["freq_dim"], pk["r1.w"], groups, D, ws["re1"], D, "r_time1", bias=pk["r1.b"],
+                       act=L.FG_ACT_SILU)
+            self._gemm(plan, ws["re1"], D, pk["r2.w"], groups, D, ws["remb"], D, "r_time2", bias=pk["r2.b"])
+            self._gemm(plan, ws["re1"], D, pk["r2.w"], groups, D, ws["remb_act"], D, "r_time2s", bias=pk["r2.b"],
+                       act=L.FG_ACT_SILU)
+            k = self.encoder_depth
+            if k is None:
+                self._gemm(plan, ws["remb_act"], D, pk["rp.w"], groups, 6 * D, ws["rtproj"], 6 * D, "r_tproj",
+                           bias=pk["rp.b"], res=ws["tproj"], res_ld=6 * D, res_mode=L.FG_RES_SAME)
+                plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["rtproj"].data_ptr(), nl, groups, 6 * D,
+                         ws["mod"].data_ptr(), desc="mod")
+            else:
+                self._gemm(plan, ws["remb_act"], D, pk["rp.w"], groups, 6 * D, ws["rtproj"], 6 * D, "r_tproj",
+                           bias=pk["rp.b"])
+                if k > 0:
+                    plan.add(lib.fg_bcast_add, pk["tables"].data_ptr(), ws["tproj"].data_ptr(), k, groups, 6 * D,
+                             ws["mod"].data_ptr(), desc="mod")
+                if k < nl:
+                    plan.add(lib.fg_bcast_add, pk["tables"][k:].data_ptr(), ws["rtproj"].data_ptr(), nl - k, groups, 6 * D,
+                             ws["mod"][k:].data_ptr(), desc="mod_r")
+        plan.n_head = len(plan.steps)           # embedding launches: _run_split runs them, then the host-side tail
+        plan.has_r = has_r
+        plan.mod_groups = (B, F if per_frame else 1)
         hs, nrm, qkv, att, q2, f1 = ws["hs"], ws["nrm"], ws["qkv"], ws["att"], ws["q2"], ws["f1"]
         if P > 1:
             # this rank's token rows (b, f, i) <- global rows (b, f, rank*fs_l + i)
@@ -631,7 +708,7 @@ class _WanBase:
     def _run_transformer(self, x_t: torch.Tensor, timestep: torch.Tensor, condition: torch.Tensor, per_frame: bool,
                          cache_tag: str = "pos", use_cache: bool = False, cur_start_frame: int = 0,
                          store_kv: bool = False, total_num_frames: int = 21,
-                         mask: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                         mask: Optional[Tuple[int, int]] = None, r_timestep: Optional[torch.Tensor] = None) -> torch.Tensor:
         """timestep: rescaled (1000 t), [B] (global AdaLN) or [B, F] (per frame).  Returns the raw output [B,C,F,H,W]."""
         if not x_t.is_cuda:
             raise L.FastGenB200Error("Wan (B200) needs CUDA tensors: there is no CPU path")
@@ -664,10 +741,14 @@ class _WanBase:
                 frame0 = kv["len"] // fs
             if store_kv:
                 kv["len"] = cache_start + F * fs
-        key = (B, F, Hh, Ww, x_t.dtype, per_frame, use_cache, cache_start, store_kv, frame0, mask, cache_tag)
+        has_r = r_timestep is not None
+        if has_r and self.transformer.r_embedder is None:
+            raise ValueError("r_timestep provided but no r_embedder is present")
+        key = (B, F, Hh, Ww, x_t.dtype, per_frame, use_cache, cache_start, store_kv, frame0, mask, cache_tag, has_r)
         plan = self._plans.get(key)
         if plan is None:
-            plan = self._build_plan(B, F, Hh, Ww, x_t.dtype, per_frame, kv, cache_start, store_kv, frame0, mask, cross)
+            plan = self._build_plan(B, F, Hh, Ww, x_t.dtype, per_frame, kv, cache_start, store_kv, frame0, mask, cross,
+                                    has_r=has_r)
             if len(self._plans) > 64:
                 self._plans.clear()
             self._plans[key] = plan
@@ -683,6 +764,17 @@ class _WanBase:
         else:
             ws["emb"].zero_()
             ws["emb"][:B].copy_(emb)   # rows [0, B): one modulation group per sample (rows_per_group = n)
+        if has_r:
+            rs = r_timestep.reshape(B, -1)
+            rsf = (rs.expand(B, F) if rs.shape[1] != F else rs).reshape(-1) if per_frame else rs[:, 0]
+            if self.time_cond_type == "diff":
+                rsf = tsf - rsf
+            emb_r = _sinusoid(rsf, cfg["freq_dim"], self._use_wan_official_sinusoidal).to(torch.bfloat16)
+            if per_frame:
+                ws["emb_r"].copy_(emb_r)
+            else:
+                ws["emb_r"].zero_()
+                ws["emb_r"][:B].copy_(emb_r)
         # the head adds table + temb in bf16 (reference Wan/network.py:229,250): needs temb, so run the embedding
         # launches first, then that one tiny add, then the rest of the plan
         # (not under sequence parallelism: capturing the NCCL all-to-all into a graph deadlocked the NCCL watchdog)
@@ -704,12 +796,25 @@ class _WanBase:
     def _run_split(self, plan: _Plan, ws, stream: int) -> None:
         D = self.cfg["dim"]
         pk = self._packed
-        # steps 0..6 are patchify, patch, time1, time2, time2s, tproj, mod
+        # the first plan.n_head steps are the embedding launches (patchify, patch, time1, time2, time2s, tproj[, r...], mod)
         head = _Plan()
-        head.steps, rest = plan.steps[:7], plan.steps[7:]
+        head.steps, rest = plan.steps[:plan.n_head], plan.steps[plan.n_head:]
         head.run(stream, self.profile)
-        hm = (pk["head_table"][None] + ws["temb"][:, None, :]).reshape(ws["temb"].shape[0], 2 * D)
+        # the head adds table + temb in bf16 (reference Wan/network.py:229,250); with an r embedder temb is temb + remb,
+        # or remb alone when encoder_depth is set (:349-353)
+        temb = ws["temb"]
+        if plan.has_r:
+            temb = ws["remb"] if self.encoder_depth is not None else ws["temb"] + ws["remb"]
+        hm = (pk["head_table"][None] + temb[:, None, :]).reshape(temb.shape[0], 2 * D)
         ws["head_mod"].copy_(hm)
+        if self.norm_temb:
+            # sCM-style normalisation of the AdaLN shift / scale vectors (Wan/network.py:72-78, 132-136): x / (1e-4 + |x|)
+            # with the norm over all dims but the batch one, i.e. (frames, D) for per-frame modulation
+            b_, f_ = plan.mod_groups
+            m = ws["mod"][:, :b_ * f_].view(-1, b_, f_, 6, D)
+            for j in (0, 1, 3, 4):
+                x = m[:, :, :, j, :]
+                x.div_(torch.linalg.vector_norm(x, dim=(2, 3), keepdim=True, dtype=torch.float32) + 1e-4)
         tail = _Plan()
         tail.steps = rest
         tail.run(stream, self.profile)
@@ -725,7 +830,7 @@ class _WanBase:
             assert fwd_pred_type in NET_PRED_TYPES, f"{fwd_pred_type} is not supported as fwd_pred_type"
         if return_features_early or len(feature_indices) or return_logvar:
             raise NotImplementedError("feature / logvar outputs are training-time paths of the reference")
-        if r is not None:
+        if r is not None and self.transformer.r_embedder is None:
             raise ValueError("r_timestep provided but no r_embedder is present")
         return fwd_pred_type, False
 
@@ -747,7 +852,7 @@ class Wan(_WanBase, FastGenNetwork):
         if load_pretrained:
             raise NotImplementedError("no hub access: build with load_pretrained=False and call load_state_dict")
         self._init_wan(model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
-                       r_timestep, norm_temb, encoder_depth)
+                       r_timestep, norm_temb, encoder_depth, r_embedder_init, time_cond_type)
 
     def forward(self, x_t: torch.Tensor, t: torch.Tensor, condition: Any = None, r: Optional[torch.Tensor] = None,
                 return_features_early: bool = False, feature_indices: Optional[Set[int]] = None,
@@ -764,7 +869,12 @@ class Wan(_WanBase, FastGenNetwork):
             if t.numel() == 1 and x_t.shape[0] > 1:
                 t = t.expand(x_t.shape[0])
             timestep = self.noise_scheduler.rescale_t(t)
-            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False, cache_tag="__bidir__")
+            r_timestep = None
+            if r is not None:
+                r = torch.atleast_1d(r).to(x_t.device)
+                r_timestep = self.noise_scheduler.rescale_t(r.expand(x_t.shape[0]) if r.numel() == 1 else r)
+            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False, cache_tag="__bidir__",
+                                        r_timestep=r_timestep)
             return self.noise_scheduler.convert_model_output(x_t, out, t, src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)
 
@@ -789,7 +899,7 @@ class CausalWan(_WanBase, CausalFastGenNetwork):
             raise NotImplementedError("no hub access: build with load_pretrained=False and call load_state_dict")
         self._delete_cache_on_clear = delete_cache_on_clear
         self._init_wan(model_id_or_local_path, transformer_config, enable_logvar_linear, use_wan_official_sinusoidal,
-                       r_timestep, norm_temb, encoder_depth)
+                       r_timestep, norm_temb, encoder_depth, r_embedder_init, time_cond_type)
 
     def clear_caches(self) -> None:
         if self._delete_cache_on_clear:
@@ -826,9 +936,17 @@ class CausalWan(_WanBase, CausalFastGenNetwork):
                 nc, rem = F // self.chunk_size, F % self.chunk_size
                 first = (self.chunk_size + rem) * fs if nc else rem * fs
                 mask = (first, self.chunk_size * fs)
+            r_timestep = None
+            if r is not None:
+                r = torch.atleast_1d(r).to(x_t.device)
+                if r.ndim == 1 and r.numel() == 1 and B > 1:
+                    r = r.expand(B)
+                r_timestep = self.noise_scheduler.rescale_t(r)
+                r_timestep = r_timestep.view(-1, 1) if r_timestep.ndim == 1 else r_timestep
+                r_timestep = r_timestep.expand(B, F) if r_timestep.shape[1] != F else r_timestep
             out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=True, cache_tag=cache_tag,
                                         use_cache=use_cache, cur_start_frame=cur_start_frame, store_kv=store_kv,
-                                        total_num_frames=self.total_num_frames, mask=mask)
+                                        total_num_frames=self.total_num_frames, mask=mask, r_timestep=r_timestep)
             t_conv = t[:, None, :, None, None] if t.ndim == 2 else t
             return self.noise_scheduler.convert_model_output(x_t, out, t_conv, src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)

@@ -82,6 +82,9 @@ def make_state_dict(cfg: Dict[str, Any], seed: int) -> Dict[str, torch.Tensor]:
     lin("final_layer.adaptive_params.1", 2 * D, D, std=0.5 * D ** -0.5)
     lin("final_layer.projection", p * p * C, D)
     lin("logvar_linear", 1, D)
+    if cfg.get("r_timestep"):     # drawn last: the other weights do not depend on this option
+        lin("r_embedder.proj_net.0", D, 256)
+        lin("r_embedder.proj_net.2", D, D)
     return sd
 
 
@@ -94,7 +97,7 @@ def _modulate(x, shift, scale):
 
 
 def dit_forward(sd, cfg, x_t: torch.Tensor, t: torch.Tensor, condition: torch.Tensor, fwd_pred_type: str = "x0",
-                net_pred_type: str = "flow") -> torch.Tensor:
+                net_pred_type: str = "flow", r: torch.Tensor = None, time_cond_type: str = "abs") -> torch.Tensor:
     """DiT.forward (DiT/network.py:464-574) with the RF schedule; dtype of x_t is the compute dtype."""
     D, p, heads = cfg["hidden_size"], cfg["patch_size"], cfg["num_heads"]
     x_in, t_in = x_t, t
@@ -109,11 +112,18 @@ def dit_forward(sd, cfg, x_t: torch.Tensor, t: torch.Tensor, condition: torch.Te
     x = x.flatten(2).transpose(1, 2) + sd["pos_embed"].to(x_t.dtype)
     half = 128
     freq = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
-    ang = tt[:, None].float() * freq[None, :]
-    four = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(tt.dtype)
-    t_emb = _lin(sd, "t_embedder.proj_net.2", F.silu(_lin(sd, "t_embedder.proj_net.0", four)))
+
+    def fourier(v):
+        ang = v[:, None].float() * freq[None, :]
+        return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(v.dtype)
+
+    t_emb = _lin(sd, "t_embedder.proj_net.2", F.silu(_lin(sd, "t_embedder.proj_net.0", fourier(tt))))
     y = sd["y_embedder.class_embeddings.weight"].to(x_t.dtype)[condition]
     c = t_emb + y
+    if r is not None and "r_embedder.proj_net.0.weight" in sd:     # DiT/network.py:518-533 (r is NOT flipped for SiT)
+        rr = ((r.double() * 1000.0).to(r.dtype) if cfg["scale_t"] else r).to(x_t.dtype)
+        rin = tt - rr if time_cond_type == "diff" else rr
+        c = c + _lin(sd, "r_embedder.proj_net.2", F.silu(_lin(sd, "r_embedder.proj_net.0", fourier(rin))))
     B, N, _ = x.shape
     d = D // heads
     for i in range(cfg["depth"]):

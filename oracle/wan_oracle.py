@@ -48,7 +48,8 @@ def tiny_config(**kw) -> Dict[str, Any]:
     return cfg
 
 
-def make_state_dict(cfg: Dict[str, Any], seed: int, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+def make_state_dict(cfg: Dict[str, Any], seed: int, dtype: torch.dtype = torch.float32,
+                    r_embedder: bool = False) -> Dict[str, torch.Tensor]:
     """Random, non-degenerate weights under the diffusers key names (proj_out is NOT zero, unlike reset_parameters)."""
     g = torch.Generator().manual_seed(seed)
     D, Fd, T = cfg["dim"], cfg["ffn_dim"], cfg["text_dim"]
@@ -83,6 +84,10 @@ def make_state_dict(cfg: Dict[str, Any], seed: int, dtype: torch.dtype = torch.f
         lin(b + "ffn.net.2", D, Fd)
     sd[p + "scale_shift_table"] = torch.randn(1, 2, D, generator=g) / D ** 0.5
     lin(p + "proj_out", cfg["out_channels"] * pt * ph * pw, D)
+    if r_embedder:   # drawn last: the other weights do not depend on this option
+        lin(p + "r_embedder.time_embedder.linear_1", D, cfg["freq_dim"])
+        lin(p + "r_embedder.time_embedder.linear_2", D, D)
+        lin(p + "r_embedder.time_proj", 6 * D, D)
     return {k: v.to(dtype) for k, v in sd.items()}
 
 
@@ -238,7 +243,14 @@ def block_causal_mask(num_frames: int, frame_seqlen: int, chunk_size: int) -> to
     return (idx[None, :] < ends[:, None]) | (idx[None, :] == idx[:, None])
 
 
-def block(sd, i, cfg, hs, temb, enc, rotary, per_frame: bool, cache=None, cache_start=None, store_kv=False, mask=None):
+def normalize(x: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
+    """fastgen/networks/Wan/network.py:72-78 with dim=None: the norm runs over every dim but the first"""
+    norm = torch.linalg.vector_norm(x, dim=list(range(1, x.ndim)), keepdim=True, dtype=torch.float32)
+    return x / (eps + norm).to(x.dtype)
+
+
+def block(sd, i, cfg, hs, temb, enc, rotary, per_frame: bool, cache=None, cache_start=None, store_kv=False, mask=None,
+          norm_temb: bool = False):
     """block_forward (Wan/network.py:106-153) / _wan_block_forward_inline_cache (network_causal.py:467-548)."""
     b = f"transformer.blocks.{i}."
     table = sd[b + "scale_shift_table"].float()
@@ -261,6 +273,11 @@ def block(sd, i, cfg, hs, temb, enc, rotary, per_frame: bool, cache=None, cache_
         def gated(x, gate):
             return x * gate
     shift_msa, scale_msa, gate_msa, c_shift, c_scale, c_gate = mods
+    if norm_temb:   # Wan/network.py:131-136 (the per-frame variant normalises after squeeze(2): over frames and channels)
+        sq = (lambda v: v.squeeze(2)) if per_frame else (lambda v: v)
+        un = (lambda v: v.unsqueeze(2)) if per_frame else (lambda v: v)
+        shift_msa, scale_msa = un(normalize(sq(shift_msa))), un(normalize(sq(scale_msa)))
+        c_shift, c_scale = un(normalize(sq(c_shift))), un(normalize(sq(c_scale)))
     eps = cfg["eps"]
     n1 = modulate(fp32_layer_norm(hs.float(), None, None, eps), scale_msa, shift_msa).type_as(hs)
     a = attention(sd, b + "attn1.", cfg, n1, rotary=rotary, cache=cache, layer=i, cache_start=cache_start,
@@ -276,8 +293,11 @@ def block(sd, i, cfg, hs, temb, enc, rotary, per_frame: bool, cache=None, cache_
 
 def transformer_forward(sd, cfg, x: torch.Tensor, timestep: torch.Tensor, text: torch.Tensor, *,
                         official_sinusoidal: bool = False, cache: Optional[KVCache] = None, cur_start_frame: int = 0,
-                        store_kv: bool = False, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """classify_forward (Wan/network.py:156-279) with either prepare / block-forward flavour.
+                        store_kv: bool = False, mask: Optional[torch.Tensor] = None,
+                        r_timestep: Optional[torch.Tensor] = None, time_cond_type: str = "diff",
+                        encoder_depth: Optional[int] = None, norm_temb: bool = False) -> torch.Tensor:
+    """classify_forward (Wan/network.py:156-279) with either prepare / block-forward flavour; r_timestep (same shape as
+    timestep, rescaled) goes through the r embedder of classify_forward_prepare (:330-353).
 
     x [B, C, F, H, W] in the compute dtype; timestep already rescaled (1000 t): [B] (bidirectional, global AdaLN) or
     [B, F] (causal, per-frame AdaLN); text [B, L, text_dim].  Returns the raw network output [B, C, F, H, W]."""
@@ -302,10 +322,32 @@ def transformer_forward(sd, cfg, x: torch.Tensor, timestep: torch.Tensor, text: 
     tproj = tproj.unflatten(2, (6, -1)) if per_frame else tproj.unflatten(1, (6, -1))
     enc = _linear(sd, p + "condition_embedder.text_embedder.linear_2",
                   F.gelu(_linear(sd, p + "condition_embedder.text_embedder.linear_1", text.to(dt)), approximate="tanh"))
+    rproj = None
+    if r_timestep is not None:
+        if p + "r_embedder.time_proj.weight" not in sd:
+            raise ValueError("r_timestep provided but no r_embedder is present")
+        rt = r_timestep.flatten()
+        if time_cond_type == "diff":
+            rt = ts - rt
+        remb_in = (sinusoidal_embedding_1d_wan(cfg["freq_dim"], rt) if official_sinusoidal
+                   else timesteps_diffusers(rt, cfg["freq_dim"]))
+        if per_frame:
+            remb_in = remb_in.unflatten(0, (B, -1))
+        remb = _linear(sd, p + "r_embedder.time_embedder.linear_2",
+                       F.silu(_linear(sd, p + "r_embedder.time_embedder.linear_1", remb_in.to(dt)))).type_as(text.to(dt))
+        rproj = _linear(sd, p + "r_embedder.time_proj", F.silu(remb))
+        rproj = rproj.unflatten(2, (6, -1)) if per_frame else rproj.unflatten(1, (6, -1))
+        if encoder_depth is None:
+            tproj = tproj + rproj
+            temb = temb + remb
+        else:
+            temb = remb
     cache_start = cur_start_frame * (pph * ppw) if cache is not None else None
     for i in range(cfg["layers"]):
+        if encoder_depth is not None and i == encoder_depth and rproj is not None:
+            tproj = rproj
         hs = block(sd, i, cfg, hs, tproj, enc, rotary, per_frame, cache=cache, cache_start=cache_start,
-                   store_kv=store_kv, mask=mask)
+                   store_kv=store_kv, mask=mask, norm_temb=norm_temb)
     table = sd[p + "scale_shift_table"]  # head: table + temb in the parameter dtype (no .float(), Wan/network.py:229,250)
     if temb.dim() == 3:   # per frame
         shift, scale = (table.unsqueeze(0) + temb.unsqueeze(2)).chunk(2, dim=2)
@@ -337,11 +379,14 @@ def _flow_to(x_t, flow, t, target: str):
     raise NotImplementedError(target)
 
 
-def wan_forward(sd, cfg, x_t, t, text, fwd_pred_type="x0", dtype=torch.bfloat16, official_sinusoidal=False):
+def wan_forward(sd, cfg, x_t, t, text, fwd_pred_type="x0", dtype=torch.bfloat16, official_sinusoidal=False, r=None,
+                time_cond_type="diff", encoder_depth=None, norm_temb=False):
     """Wan.forward (Wan/network.py:1077-1163), net_pred_type='flow', schedule 'rf'."""
     timestep = (t.double() * 1000.0).to(t.dtype)            # rescale_t (noise_schedule.py:1337-1341)
+    r_timestep = None if r is None else (r.double() * 1000.0).to(r.dtype)
     out = transformer_forward({k: v for k, v in sd.items()}, cfg, x_t.to(dtype), timestep, text.to(dtype),
-                              official_sinusoidal=official_sinusoidal)
+                              official_sinusoidal=official_sinusoidal, r_timestep=r_timestep,
+                              time_cond_type=time_cond_type, encoder_depth=encoder_depth, norm_temb=norm_temb)
     return _flow_to(x_t, out.to(x_t.dtype), t, fwd_pred_type)
 
 

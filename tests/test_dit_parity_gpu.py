@@ -60,3 +60,22 @@ def test_dit_two_step_sampler_matches_oracle():
     finally:
         torch.randn_like = orig
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("tct", ["abs", "diff"])
+def test_dit_r_embedder_matches_oracle(tct):
+    """second timestep r (MeanFlow-style): c = t_emb + y + r_embedder(r | t - r), reference DiT/network.py:518-533"""
+    cfg = DO.tiny_config(r_timestep=True, time_cond_type=tct)
+    net, sd = _net(cfg, 3)
+    g = torch.Generator().manual_seed(5)
+    B, S = 2, cfg["input_size"]
+    x = torch.randn(B, cfg["in_channels"], S, S, generator=g)
+    t = torch.tensor([0.9, 0.6], dtype=torch.float64)
+    r = torch.tensor([0.2, 0.6], dtype=torch.float64)
+    lab = torch.eye(cfg["num_classes"])[torch.tensor([4, 0])]
+    out = net(x.cuda(), t.cuda(), condition=lab.cuda(), r=r.cuda(), fwd_pred_type="flow")
+    ref = DO.dit_forward(sd, cfg, x, t, lab, fwd_pred_type="flow", r=r, time_cond_type=tct)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    out0 = net(x.cuda(), t.cuda(), condition=lab.cuda(), fwd_pred_type="flow")
+    ref0 = DO.dit_forward(sd, cfg, x, t, lab, fwd_pred_type="flow")
+    assert _rel(out0, ref0) < 1e-2 and _rel(out0, ref) > 3e-2

@@ -59,8 +59,15 @@ def test_networks_refuse_cpu_tensors_and_training_outputs():
         wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64), fwd_pred_type="nope")
     with pytest.raises(ValueError):
         wan(torch.zeros(1, 16, 2, 8, 8), torch.full((1,), 0.5), condition=torch.zeros(1, 8, 64), r=torch.ones(1))
-    with pytest.raises(NotImplementedError):
-        Wan(transformer_config=cfg, r_timestep=True)
+    wr = Wan(transformer_config=cfg, r_timestep=True, r_embedder_init="random")      # reference Wan.init_embedder
+    keys = set(wr.state_dict().keys())
+    assert {"transformer.r_embedder.time_embedder.linear_1.weight", "transformer.r_embedder.time_proj.bias"} <= keys
+    assert not any("r_embedder.text_embedder" in k for k in keys)
+    assert float(wr.transformer.r_embedder.time_proj.weight.abs().max()) == 0.0        # zero r projection initially
+    wp = Wan(transformer_config=cfg, r_timestep=True)                                  # "pretrained": a copy
+    assert torch.equal(wp.transformer.r_embedder.time_proj.weight, wp.transformer.condition_embedder.time_proj.weight)
+    with pytest.raises(ValueError):
+        Wan(transformer_config=cfg, r_timestep=True, time_cond_type="bogus")
     cw = CausalWan(transformer_config=cfg, chunk_size=2, total_num_frames=5)
     assert cw.chunk_size == 2 and cw.total_num_frames == 5 and cw.net_pred_type == "flow" and cw.schedule_type == "rf"
     cw.clear_caches()  # no caches yet: a no-op

@@ -5,8 +5,8 @@ import pytest
 import torch
 
 
-@pytest.mark.parametrize("P,rank", [(1, 0), (4, 1)])
-def test_wan14b_720p_launch_list_arguments_validate_on_the_host(monkeypatch, P, rank):
+@pytest.mark.parametrize("P,rank,with_r", [(1, 0, False), (4, 1, False), (1, 0, True)])
+def test_wan14b_720p_launch_list_arguments_validate_on_the_host(monkeypatch, P, rank, with_r):
     from fastgen_b200 import _lib as L
     from fastgen_b200 import ops
     from fastgen_b200 import wan as W
@@ -16,7 +16,7 @@ def test_wan14b_720p_launch_list_arguments_validate_on_the_host(monkeypatch, P, 
     cfg = dict(W.WAN_CONFIGS[W.Wan.MODEL_ID_14B], layers=1)
     torch.set_default_dtype(torch.bfloat16)
     try:
-        net = W.Wan(transformer_config=cfg, enable_logvar_linear=False).eval()
+        net = W.Wan(transformer_config=cfg, enable_logvar_linear=False, r_timestep=with_r, encoder_depth=None).eval()
     finally:
         torch.set_default_dtype(torch.float32)
     monkeypatch.setattr(net, "_sp_size", lambda: P)
@@ -37,7 +37,8 @@ def test_wan14b_720p_launch_list_arguments_validate_on_the_host(monkeypatch, P, 
     import types
     monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace(cuda_stream=0))
     cross = net._cross_kv(torch.zeros(B, 512, 4096, dtype=torch.bfloat16), "__bidir__")
-    plan = net._build_plan(B, F, Hh, Ww, torch.bfloat16, False, None, 0, False, 0, None, cross)
+    plan = net._build_plan(B, F, Hh, Ww, torch.bfloat16, False, None, 0, False, 0, None, cross, has_r=with_r)
+    assert plan.n_head == (11 if with_r else 7)
     dry_run(plan)
     assert len(statuses) > 20
     invalid = [s for s in statuses if s[2] == -1]

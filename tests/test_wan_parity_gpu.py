@@ -21,7 +21,7 @@ def _rel(a, b):
 def _nets(cfg, seed, cls_name, **kw):
     import fastgen_b200.wan as W
 
-    sd = {k: v.bfloat16() for k, v in WO.make_state_dict(cfg, seed).items()}
+    sd = {k: v.bfloat16() for k, v in WO.make_state_dict(cfg, seed, r_embedder=bool(kw.get("r_timestep"))).items()}
     net = getattr(W, cls_name)(transformer_config=cfg, enable_logvar_linear=False, **kw)
     missing, unexpected = net.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
@@ -50,6 +50,44 @@ def test_bidirectional_forward_matches_oracle(official):
         assert _rel(out, ref16) < 2 * TOL, (pred, _rel(out, ref16))
         # and the CUDA path is at least as close to the exact value as the bf16 reference arithmetic is
         assert _rel(out, ref32) < 1.5 * _rel(ref16, ref32) + 1e-3
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(time_cond_type="abs"), dict(encoder_depth=1), dict(norm_temb=True),
+                                dict(encoder_depth=0, norm_temb=True)],
+                         ids=["diff", "abs", "encoder_depth1", "norm_temb", "encoder_depth0_norm_temb"])
+def test_r_embedder_variants_match_oracle(kw):
+    """second timestep r (MeanFlow on Wan): r embedder added to / replacing the time projection, sCM-style normalised
+    AdaLN vectors -- reference classify_forward_prepare (Wan/network.py:330-353) and block_forward (:131-136)"""
+    cfg = WO.tiny_config(layers=3)
+    net, sd = _nets(cfg, 4, "Wan", r_timestep=True, **kw)
+    x, text = _inputs(cfg, 2, 3, 8, 12)
+    t = torch.tensor([0.8, 0.5], dtype=torch.float64)
+    r = torch.tensor([0.3, 0.5], dtype=torch.float64)
+    out = net(x.cuda(), t.cuda(), condition=text.cuda(), r=r.cuda(), fwd_pred_type="flow")
+    ref32 = WO.wan_forward(sd, cfg, x, t, text, fwd_pred_type="flow", dtype=torch.float32, r=r, **kw)
+    assert _rel(out, ref32) < TOL, _rel(out, ref32)
+    # without r the r embedder is not used at all (norm_temb still is)
+    out0 = net(x.cuda(), t.cuda(), condition=text.cuda(), fwd_pred_type="flow")
+    ref0 = WO.wan_forward(sd, cfg, x, t, text, fwd_pred_type="flow", dtype=torch.float32,
+                          norm_temb=kw.get("norm_temb", False))
+    assert _rel(out0, ref0) < TOL, _rel(out0, ref0)
+    assert _rel(out0, ref32) > 5 * TOL      # ... and r does change the prediction
+
+
+def test_causal_r_embedder_per_frame():
+    """CausalWan with r (network_causal.py:641-665): per-frame r embedding, normalised per-frame AdaLN vectors"""
+    cfg = WO.tiny_config(layers=2)
+    total = 4
+    net, sd = _nets(cfg, 5, "CausalWan", total_num_frames=total, chunk_size=2, r_timestep=True, norm_temb=True)
+    x, text = _inputs(cfg, 2, total, 8, 8)
+    t = torch.tensor([0.7, 0.4], dtype=torch.float64)
+    r = torch.tensor([0.2, 0.1], dtype=torch.float64)
+    out = net(x.cuda(), t.cuda(), condition=text.cuda(), r=r.cuda(), fwd_pred_type="flow", is_ar=True)
+    B = x.shape[0]
+    ts = (t * 1000.0).view(-1, 1).expand(B, total)
+    rs = (r * 1000.0).view(-1, 1).expand(B, total)
+    ref = WO.transformer_forward(sd, cfg, x.float(), ts, text.float(), r_timestep=rs, norm_temb=True)
+    assert _rel(out, ref) < TOL, _rel(out, ref)
 
 
 def test_causal_chunks_with_kv_cache_match_oracle():
