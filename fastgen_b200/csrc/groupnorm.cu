@@ -366,7 +366,9 @@ static int pick_slab(int n, int pixels, int c, int* pix_per_slab) {
   // accumulated in the same order whatever batch it is part of.
   (void)n;
   int64_t slabs = (static_cast<int64_t>(pixels) * c + 32767) / 32768;
-  if (slabs > pixels) slabs = pixels;
+  // at least 64 pixels per CTA (8 per warp): with very wide tensors (SDXL concatenations, c = 1920) a 32K-element slab
+  // is only 17 pixels and the per-vector merges into shared memory dominate (measured 1.1 TB/s)
+  if (slabs > (pixels + 63) / 64) slabs = (pixels + 63) / 64;
   if (slabs < 1) slabs = 1;
   *pix_per_slab = static_cast<int>((pixels + slabs - 1) / slabs);
   return static_cast<int>((pixels + *pix_per_slab - 1) / *pix_per_slab);

@@ -12,6 +12,8 @@
 // Replaces: FP32LayerNorm + the modulate / type_as chains of fastgen/networks/Wan/network.py:116-151 and
 // network_causal.py:503-545, torch.nn.RMSNorm + apply_rotary_emb of network_causal.py:262-291, the KV-cache slice
 // assignments of :365-368, Conv3d patch embedding / unpatchify permutes of Wan/network.py:300-301, 262-266.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -127,6 +129,97 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const LnK p) {
         }
         *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
       }
+    }
+  }
+}
+
+// Streaming variant: one warp per row, nothing of the row kept in registers.  Pass 1 accumulates the sum and the sum of
+// squares of (x - K) with K = the row's first element (shifted single-pass variance: no cancellation unless the row mean is
+// far from x[0] in units of the row's spread), pass 2 re-reads the row (L1 / L2: it was just read) and writes the output.
+// <= 64 registers, so 8+ CTAs (32+ warps) per SM are resident; the register-resident kernel above needs 101-255 registers (2-5 CTAs) and
+// measured 0.25 (d = 5120) to 0.65 of the copy bandwidth (profiles/membound_micro_r01.txt).
+template <typename TX>
+__device__ __forceinline__ void ln_load8(const TX* xr, int vi, float (&v)[8]) {
+  if constexpr (sizeof(TX) == 2) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v);
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + 2 * vi);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 2 * vi + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+}
+
+template <typename TX>
+__global__ void __launch_bounds__(kRowThreads, 8) ln_modulate_stream_kernel(const LnK p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = p.d >> 3;
+  const float inv_d = 1.0f / static_cast<float>(p.d);
+  for (int row = blockIdx.x * (kRowThreads / 32) + warp; row < p.rows; row += gridDim.x * (kRowThreads / 32)) {
+    const TX* xr = static_cast<const TX*>(p.x) + static_cast<int64_t>(row) * p.x_ld;
+    float kshift;
+    if constexpr (sizeof(TX) == 2)
+      kshift = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(xr)));
+    else
+      kshift = __ldg(reinterpret_cast<const float*>(xr));
+    float s = 0.f, ss = 0.f;
+    int vi = lane;
+    for (; vi + 96 < nvec; vi += 128) {  // four independent 16/32-byte loads in flight per lane
+      float v0[8], v1[8], v2[8], v3[8];
+      ln_load8<TX>(xr, vi, v0);
+      ln_load8<TX>(xr, vi + 32, v1);
+      ln_load8<TX>(xr, vi + 64, v2);
+      ln_load8<TX>(xr, vi + 96, v3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d0 = v0[k] - kshift, d1 = v1[k] - kshift, d2 = v2[k] - kshift, d3 = v3[k] - kshift;
+        s += (d0 + d1) + (d2 + d3);
+        ss = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, ss))));
+      }
+    }
+    for (; vi < nvec; vi += 32) {
+      float v0[8];
+      ln_load8<TX>(xr, vi, v0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d0 = v0[k] - kshift;
+        s += d0;
+        ss = fmaf(d0, d0, ss);
+      }
+    }
+    const float ms = warp_sum(s) * inv_d;  // mean - K
+    float var = warp_sum(ss) * inv_d - ms * ms;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + p.eps);
+    const float mean = kshift + ms;
+    const int g = row / p.rows_per_group;
+    const float* sc = p.scale ? p.scale + static_cast<int64_t>(g) * p.mod_ld : nullptr;
+    const float* sh = p.shift ? p.shift + static_cast<int64_t>(g) * p.mod_ld : nullptr;
+    __nv_bfloat16* yr = p.y + static_cast<int64_t>(row) * p.y_ld;
+    for (vi = lane; vi < nvec; vi += 32) {
+      float o[8];
+      ln_load8<TX>(xr, vi, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (o[k] - mean) * rstd;
+      if (p.gamma) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vi);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vi + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vi);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vi + 1);
+        o[0] = fmaf(o[0], g0.x, b0.x), o[1] = fmaf(o[1], g0.y, b0.y), o[2] = fmaf(o[2], g0.z, b0.z);
+        o[3] = fmaf(o[3], g0.w, b0.w), o[4] = fmaf(o[4], g1.x, b1.x), o[5] = fmaf(o[5], g1.y, b1.y);
+        o[6] = fmaf(o[6], g1.z, b1.z), o[7] = fmaf(o[7], g1.w, b1.w);
+      }
+      if (sc) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc) + 2 * vi);
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc) + 2 * vi + 1);
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh) + 2 * vi);
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(sh) + 2 * vi + 1);
+        o[0] = fmaf(o[0], 1.0f + s0.x, h0.x), o[1] = fmaf(o[1], 1.0f + s0.y, h0.y);
+        o[2] = fmaf(o[2], 1.0f + s0.z, h0.z), o[3] = fmaf(o[3], 1.0f + s0.w, h0.w);
+        o[4] = fmaf(o[4], 1.0f + s1.x, h1.x), o[5] = fmaf(o[5], 1.0f + s1.y, h1.y);
+        o[6] = fmaf(o[6], 1.0f + s1.z, h1.z), o[7] = fmaf(o[7], 1.0f + s1.w, h1.w);
+      }
+      *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
     }
   }
 }
@@ -396,6 +489,19 @@ extern "C" int fg_ln_modulate(const fg_ln_mod_params* p, fg_stream_t stream_) {
   k.y = static_cast<__nv_bfloat16*>(p->y), k.y_ld = p->y_ld;
   const int grid = row_grid(p->rows);
   const int nv = (p->d / 8 + 31) / 32;
+  // rows wider than 1536 elements stream (the register-resident kernel would need 168-255 registers); FG_LN_STREAM=0|1
+  // forces one kernel for A/B runs
+  static const int stream_mode = getenv("FG_LN_STREAM") ? atoi(getenv("FG_LN_STREAM")) : -1;
+  const bool use_stream = stream_mode >= 0 ? stream_mode != 0 : true;
+  if (use_stream) {
+    const int sgrid = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(p->rows) + 3) / 4, 148 * 8 * 4));
+    if (p->x_dtype == FG_BF16)
+      ln_modulate_stream_kernel<__nv_bfloat16><<<sgrid, kRowThreads, 0, stream>>>(k);
+    else
+      ln_modulate_stream_kernel<float><<<sgrid, kRowThreads, 0, stream>>>(k);
+    FG_CHECK_LAUNCH("ln_modulate");
+    return FG_OK;
+  }
 #define FG_LN_LAUNCH(TX)                                                \
   do {                                                                  \
     if (nv <= 6)                                                        \
