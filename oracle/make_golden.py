@@ -289,6 +289,34 @@ def extrapolation_fixture():
           tuple(out.shape), tuple(out2.shape))
 
 
+def checkpoint_fixture():
+    """a `.pth` in the layout of the reference Checkpointer (utils/checkpointer.py:84-96: one torch.save dict) holding the
+    state_dict of a real reference EDMPrecond (net + an EMA copy), with one forward of that network for parity"""
+    from fastgen.networks.EDM.network import EDMPrecond
+
+    cfg = dict(img_resolution=8, img_channels=3, label_dim=4, model_type="DhariwalUNet", model_channels=32,
+               channel_mult=[1], num_blocks=1, attn_resolutions=[8], augment_dim=0, dropout=0.0, label_dropout=0)
+    torch.manual_seed(SEED + 21)
+    net = EDMPrecond(**cfg).eval()
+    with torch.no_grad():
+        for prm in net.parameters():       # the reference zero-initialises some layers: make every tensor informative
+            if float(prm.abs().max()) < 1e-4:
+                prm.normal_(0, 0.05)
+    # the EMA entry holds only a few tensors: the reference loads with strict=False (checkpointer.py:157-158)
+    ema = {k: v * 0.5 for k, v in list(net.state_dict().items())[:4]}
+    save_dict = {"model": {"net": net.state_dict(), "ema": ema}, "optimizer": None, "scheduler": None,
+                 "grad_scaler": None, "callbacks": None, "iteration": 7}
+    torch.save(save_dict, os.path.join(OUT, "ref_checkpoint_tiny.pth"))
+    x = torch.randn(2, 3, 8, 8) * 3
+    t = torch.tensor([2.5, 0.3], dtype=torch.float64)
+    lab = torch.eye(4)[torch.tensor([1, 3])]
+    with torch.no_grad():
+        out = net(x, t, condition=lab, fwd_pred_type="x0")
+    np.savez_compressed(os.path.join(OUT, "ref_checkpoint_tiny_io.npz"), x=_np(x), t=_np(t), lab=_np(lab), out=_np(out),
+                        cfg=json.dumps(cfg))
+    print("wrote checkpoint fixture:", sum(p.numel() for p in net.parameters()), "parameters")
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -299,3 +327,4 @@ if __name__ == "__main__":
     meanflow_fixture()
     causal_trace_fixture()
     extrapolation_fixture()
+    checkpoint_fixture()

@@ -219,3 +219,26 @@ def test_batch_independence_at_bench_batch():
     # and the network is a deterministic function of its inputs run to run
     again = net(x, t, condition=lab, fwd_pred_type="x0")
     assert _rel(again, big) < 1e-2
+
+
+@pytest.mark.parametrize("compute,tol", [("bf16", 1e-2), ("bf16x3", 2e-3)])
+def test_reference_checkpoint_drives_our_network(compute, tol):
+    """a `.pth` in the reference Checkpointer's layout (written from a real reference EDMPrecond,
+    oracle/make_golden.py:checkpoint_fixture) loaded by fastgen_b200.checkpoint reproduces the reference's forward"""
+    import json
+    import os
+
+    import numpy as np
+
+    from fastgen_b200.checkpoint import load_checkpoint
+    from fastgen_b200.edm import EDMPrecond
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    io = np.load(os.path.join(gold, "ref_checkpoint_tiny_io.npz"))
+    net = EDMPrecond(**json.loads(str(io["cfg"])))
+    assert load_checkpoint({"net": net}, os.path.join(gold, "ref_checkpoint_tiny.pth")) == 7
+    net = net.cuda().eval()
+    net.set_compute(compute)
+    out = net(torch.from_numpy(io["x"]).cuda(), torch.from_numpy(io["t"]).cuda(),
+              condition=torch.from_numpy(io["lab"]).cuda(), fwd_pred_type="x0")
+    assert _rel(out, torch.from_numpy(io["out"])) < tol, _rel(out, torch.from_numpy(io["out"]))
