@@ -941,5 +941,36 @@ class EDMPrecond(FastGenNetwork):
             return self.noise_scheduler.convert_model_output(x_t, out, tt, src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)
 
+    def sample(self, noise: torch.Tensor, condition: Optional[torch.Tensor] = None,
+               neg_condition: Optional[torch.Tensor] = None, guidance_scale: Optional[float] = 5.0, num_steps: int = 50,
+               **kwargs) -> torch.Tensor:
+        """Teacher sampling: EDM's deterministic Euler sampler with optional classifier-free guidance -- reference
+        ``EDMPrecond.sample`` (EDM/network.py:976-1026): same sigma list, same batched [negative | positive] network call,
+        same update ``x <- x + (sigma_next - sigma) (x - x0) / sigma``.  The two elementwise passes of a step are
+        ``fg_axpby`` launches with fp64 coefficients and one rounding: ``x0 = (1 - g) x0_uncond + g x0_cond`` and
+        ``x <- (sigma_next / sigma) x + (1 - sigma_next / sigma) x0`` (the reference rounds after each fp32 operation)."""
+        assert self.schedule_type == "edm", f"{self.schedule_type} is not supported"
+        with torch.no_grad():
+            sched = self.noise_scheduler
+            sigmas = sched.get_t_list(num_steps, device=noise.device)
+            x = sched.latents(noise=noise, t_init=sigmas[0])
+            B = x.shape[0]
+            cfg = guidance_scale is not None and guidance_scale > 1.0 and neg_condition is not None
+            if cfg:
+                cond_input = torch.cat([neg_condition, condition], dim=0)
+                g = torch.full((B,), float(guidance_scale), dtype=torch.float64, device=x.device)
+            for sigma, sigma_next in zip(sigmas[:-1], sigmas[1:]):
+                t = sigma.expand(B)
+                if cfg:
+                    x0_pred = self(torch.cat([x, x], dim=0), torch.cat([t, t], dim=0), condition=cond_input,
+                                   fwd_pred_type="x0")
+                    x0_uncond, x0_cond = x0_pred.chunk(2)
+                    x0_pred = ops.axpby(x0_uncond.contiguous(), 1.0 - g, x0_cond.contiguous(), g)
+                else:
+                    x0_pred = self(x, t, condition=condition, fwd_pred_type="x0")
+                ratio = (sigma_next.to(torch.float64) / sigma.to(torch.float64)).expand(B).contiguous()
+                x = ops.axpby(x.contiguous(), ratio, x0_pred.contiguous(), 1.0 - ratio)
+            return x
+
 
 EDMPrecondB200 = EDMPrecond

@@ -312,8 +312,14 @@ def checkpoint_fixture():
     lab = torch.eye(4)[torch.tensor([1, 3])]
     with torch.no_grad():
         out = net(x, t, condition=lab, fwd_pred_type="x0")
+    # teacher sampling with classifier-free guidance (EDM/network.py:976-1026): 6 Euler steps, guidance 2.0 / none
+    noise = torch.randn(2, 3, 8, 8)
+    neg = torch.zeros(2, 4)
+    with torch.no_grad():
+        samp_cfg = net.sample(noise, condition=lab, neg_condition=neg, guidance_scale=2.0, num_steps=6)
+        samp = net.sample(noise, condition=lab, neg_condition=None, guidance_scale=None, num_steps=6)
     np.savez_compressed(os.path.join(OUT, "ref_checkpoint_tiny_io.npz"), x=_np(x), t=_np(t), lab=_np(lab), out=_np(out),
-                        cfg=json.dumps(cfg))
+                        cfg=json.dumps(cfg), noise=_np(noise), neg=_np(neg), sample_cfg=_np(samp_cfg), sample=_np(samp))
     print("wrote checkpoint fixture:", sum(p.numel() for p in net.parameters()), "parameters")
 
 

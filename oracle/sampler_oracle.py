@@ -250,3 +250,22 @@ def causvid_extrapolation(net: Callable[..., torch.Tensor], sched: Schedule, noi
         cur, prefill = nxt, overlap_frames
     clear()
     return torch.cat(segs, dim=2).to(noise.dtype)
+
+
+def edm_teacher_sample(net: NetFn, sched: Schedule, noise: torch.Tensor, condition, neg_condition,
+                       guidance_scale: Optional[float] = 5.0, num_steps: int = 50) -> torch.Tensor:
+    """EDMPrecond.sample (EDM/network.py:976-1026): deterministic Euler steps on the EDM sigma list with optional CFG;
+    ``net(x, t, condition=...) -> x0``; arithmetic in the tensor dtype like the reference."""
+    sigmas = sched.get_t_list(num_steps)
+    x = sched.latents(noise, sigmas[0])
+    for sigma, sigma_next in zip(sigmas[:-1], sigmas[1:]):
+        t = sigma.expand(x.shape[0])
+        if guidance_scale is not None and guidance_scale > 1.0 and neg_condition is not None:
+            x0 = net(torch.cat([x, x], 0), torch.cat([t, t], 0), condition=torch.cat([neg_condition, condition], 0))
+            x0_uncond, x0_cond = x0.chunk(2)
+            x0 = x0_uncond + guidance_scale * (x0_cond - x0_uncond)
+        else:
+            x0 = net(x, t, condition=condition)
+        d = (x - x0) / _bc(t, x).to(x.dtype)
+        x = x + (sigma_next - sigma).to(x.dtype) * d
+    return x

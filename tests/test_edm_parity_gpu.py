@@ -242,3 +242,28 @@ def test_reference_checkpoint_drives_our_network(compute, tol):
     out = net(torch.from_numpy(io["x"]).cuda(), torch.from_numpy(io["t"]).cuda(),
               condition=torch.from_numpy(io["lab"]).cuda(), fwd_pred_type="x0")
     assert _rel(out, torch.from_numpy(io["out"])) < tol, _rel(out, torch.from_numpy(io["out"]))
+
+
+@pytest.mark.parametrize("compute,tol", [("bf16", 1e-2), ("bf16x3", 2e-3)])
+def test_teacher_sample_with_cfg_matches_reference(compute, tol):
+    """EDMPrecond.sample (EDM/network.py:976-1026) -- 6 Euler steps with classifier-free guidance 2.0
+    (batched [negative | positive] forward) and without guidance, against samples of the real reference network"""
+    import json
+    import os
+
+    import numpy as np
+
+    from fastgen_b200.checkpoint import load_checkpoint
+    from fastgen_b200.edm import EDMPrecond
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    io = np.load(os.path.join(gold, "ref_checkpoint_tiny_io.npz"))
+    net = EDMPrecond(**json.loads(str(io["cfg"])))
+    load_checkpoint({"net": net}, os.path.join(gold, "ref_checkpoint_tiny.pth"))
+    net = net.cuda().eval()
+    net.set_compute(compute)
+    noise, lab, neg = (torch.from_numpy(io[k]).cuda() for k in ("noise", "lab", "neg"))
+    out = net.sample(noise, condition=lab, neg_condition=neg, guidance_scale=2.0, num_steps=6)
+    assert out.shape == noise.shape and _rel(out, torch.from_numpy(io["sample_cfg"])) < tol
+    out = net.sample(noise, condition=lab, neg_condition=None, guidance_scale=None, num_steps=6)
+    assert _rel(out, torch.from_numpy(io["sample"])) < tol

@@ -177,3 +177,28 @@ def test_extrapolation_matches_reference():
     assert calls == json.loads(str(g["trace"]))
     out2 = SO.causvid_extrapolation(net, sched, noise, [0.999, 0.6, 0.0], 3, 2, 0, [torch.from_numpy(g["ode_eps0"])], "ode")
     assert torch.equal(out2, torch.from_numpy(g["out_ode"]))
+
+
+def test_teacher_sampler_matches_reference():
+    """EDMPrecond.sample (EDM/network.py:976-1026, Euler + classifier-free guidance) on the reference network stored in
+    the checkpoint fixture: the restated network + restated sampler reproduce the reference's samples"""
+    import json
+    import os
+
+    io = _load("ref_checkpoint_tiny_io.npz")
+    cfg = dict(sigma_shift=0.0, sigma_data=0.5, r_timestep=False, drop_precond=None, channel_mult_emb=4)
+    cfg.update(json.loads(str(io["cfg"])))
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sd = torch.load(os.path.join(gold, "ref_checkpoint_tiny.pth"), weights_only=False)["model"]["net"]
+    lab, noise, neg = (torch.from_numpy(io[k]) for k in ("lab", "noise", "neg"))
+
+    def net(x, t, condition=None, **kw):
+        return EO.edm_precond_forward(sd, cfg, x, t, condition)
+
+    with torch.no_grad():
+        out = net(torch.from_numpy(io["x"]), torch.from_numpy(io["t"]), lab)
+        s_cfg = SO.edm_teacher_sample(net, SO.Schedule("edm"), noise, lab, neg, 2.0, 6)
+        s_raw = SO.edm_teacher_sample(net, SO.Schedule("edm"), noise, lab, None, None, 6)
+    for got, key in ((out, "out"), (s_cfg, "sample_cfg"), (s_raw, "sample")):
+        ref = torch.from_numpy(io[key])
+        assert ((got - ref).norm() / ref.norm()).item() < 1e-5, key
