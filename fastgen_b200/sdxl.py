@@ -815,3 +815,33 @@ class StableDiffusionXL(FastGenNetwork):
             return self.noise_scheduler.convert_model_output(x_t, out, torch.atleast_1d(t).to(dev),
                                                              src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)
+
+    def sample(self, noise: torch.Tensor, condition: Optional[List[torch.Tensor]] = None,
+               neg_condition: Optional[List[torch.Tensor]] = None, guidance_scale: Optional[float] = 7.5,
+               num_steps: int = 50, **kwargs) -> torch.Tensor:
+        """Teacher sampling: DDIM-style steps with optional classifier-free guidance -- reference
+        ``StableDiffusionXL.sample`` (SDXL/network.py:418-473): same t list, same batched [negative | positive] eps
+        prediction, ``x0 = eps_to_x0(x, eps, t)``, ``x <- alpha(t_next) x0 + sigma(t_next) eps``.  The elementwise passes
+        are ``fg_axpby`` / ``fg_sub_div`` launches (fp64 coefficients, one rounding each)."""
+        with torch.no_grad():
+            sched = self.noise_scheduler
+            t_list = sched.get_t_list(num_steps, device=noise.device)
+            x = sched.latents(noise=noise, t_init=t_list[0])
+            B = x.shape[0]
+            cfg = guidance_scale is not None and guidance_scale > 1.0 and neg_condition is not None
+            if cfg:
+                cond_input = [torch.cat([neg_condition[0], condition[0]], dim=0),
+                              torch.cat([neg_condition[1], condition[1]], dim=0)]
+                g = torch.full((B,), float(guidance_scale), dtype=torch.float64, device=x.device)
+            for t, t_next in zip(t_list[:-1], t_list[1:]):
+                t_batch = t.expand(B)
+                if cfg:
+                    eps_pred = self(torch.cat([x, x], dim=0), torch.cat([t_batch, t_batch], dim=0), condition=cond_input,
+                                    fwd_pred_type="eps")
+                    eps_uncond, eps_cond = eps_pred.chunk(2)
+                    eps_pred = ops.axpby(eps_uncond.contiguous(), 1.0 - g, eps_cond.contiguous(), g)
+                else:
+                    eps_pred = self(x, t_batch, condition=condition, fwd_pred_type="eps")
+                x0_pred = sched.eps_to_x0(x, eps_pred, t_batch)
+                x = sched.forward_process(x0_pred, eps_pred, t_next.expand(B))
+            return x

@@ -269,3 +269,28 @@ def edm_teacher_sample(net: NetFn, sched: Schedule, noise: torch.Tensor, conditi
         d = (x - x0) / _bc(t, x).to(x.dtype)
         x = x + (sigma_next - sigma).to(x.dtype) * d
     return x
+
+
+def ddim_teacher_sample(net_eps: NetFn, sched: Schedule, noise: torch.Tensor, condition, neg_condition,
+                        guidance_scale: Optional[float] = 7.5, num_steps: int = 50) -> torch.Tensor:
+    """StableDiffusionXL.sample / StableDiffusion15.sample (SDXL/network.py:418-473): DDIM-style steps on the alphas
+    schedule with optional CFG.  ``net_eps(x, t, condition) -> eps``; ``condition`` is a list of tensors that is batched
+    [negative | positive] for guidance; arithmetic in the tensor dtype like the reference."""
+    t_list = sched.get_t_list(num_steps)
+    x = sched.latents(noise, t_list[0])
+    b = x.shape[0]
+    for t, t_next in zip(t_list[:-1], t_list[1:]):
+        tb = t.expand(b)
+        if guidance_scale is not None and guidance_scale > 1.0 and neg_condition is not None:
+            cond = [torch.cat([n, c], 0) for n, c in zip(neg_condition, condition)]
+            eps = net_eps(torch.cat([x, x], 0), torch.cat([tb, tb], 0), cond)
+            eps_u, eps_c = eps.chunk(2)
+            eps = eps_u + guidance_scale * (eps_c - eps_u)
+        else:
+            eps = net_eps(x, tb, condition)
+        a, s_ = sched.alpha(tb), sched.sigma(tb)
+        x0 = ((x.double() - eps.double() * _bc(s_, x)) / _bc(sched._nz(a), x)).to(x.dtype)    # eps_to_x0 (:576-608)
+        an = sched.alpha(t_next.expand(b)).view(-1, 1, 1, 1).to(x.dtype)
+        sn = sched.sigma(t_next.expand(b)).view(-1, 1, 1, 1).to(x.dtype)
+        x = an * x0 + sn * eps
+    return x

@@ -84,6 +84,28 @@ def test_sdxl_four_step_sampler_matches_oracle():
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
+def test_sdxl_teacher_sample_with_cfg_matches_oracle():
+    """StableDiffusionXL.sample (SDXL/network.py:418-473): 4 DDIM steps with classifier-free guidance 3.0 (batched
+    [negative | positive] eps prediction).  Guidance multiplies the difference of two predictions by 3, and with it
+    their independent bf16 noise: the bound is 2e-2 here, 1e-2 without guidance."""
+    cfg = XO.tiny_config()
+    net, sd = _net(cfg, 6)
+    B, S = 2, 32
+    noise, text, pooled = _inputs(cfg, B, S, 8)
+    _, ntext, npooled = _inputs(cfg, B, S, 9)
+    sched = SO.Schedule("alphas", XO.alphas_cumprod())
+
+    def eps_fn(x, tb, cond):
+        return XO.sdxl_forward(sd, cfg, x, tb, cond[0], cond[1], fwd_pred_type="eps")
+
+    for g, tol in ((3.0, 2e-2), (None, 1e-2)):
+        ref = SO.ddim_teacher_sample(eps_fn, sched, noise, [text, pooled], [ntext, npooled], g, 4)
+        out = net.sample(noise.cuda(), condition=[text.cuda(), pooled.cuda()],
+                         neg_condition=[ntext.cuda(), npooled.cuda()], guidance_scale=g, num_steps=4)
+        assert out.shape == noise.shape
+        assert _rel(out, ref) < tol, (g, _rel(out, ref))
+
+
 def test_sdxl_argument_errors():
     from fastgen_b200._lib import FastGenB200Error
 
