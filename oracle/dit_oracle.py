@@ -23,7 +23,7 @@ Mlp = Linear -> GELU(tanh) -> Linear.
 from __future__ import annotations
 
 import math
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 import numpy as np
 import torch

@@ -8,7 +8,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/edm_oracle.py).  Restates, with the random 
 """
 from __future__ import annotations
 
-from typing import Any, Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -3,7 +3,6 @@ of the Wan path (pack -> all_to_all -> attention over (all tokens, local heads) 
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

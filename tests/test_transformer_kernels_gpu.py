@@ -1,5 +1,4 @@
 """GPU unit tests of the transformer (Wan / DiT) C-ABI kernels against plain PyTorch restatements of the same op."""
-import math
 
 import pytest
 import torch
