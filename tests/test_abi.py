@@ -93,3 +93,45 @@ def test_invalid_arguments_map_to_value_error_without_a_gpu():
     assert st == -1
     with pytest.raises(ValueError, match="conv_gemm"):
         _lib.check(st, "fg_conv_gemm")
+
+
+def test_header_is_self_contained_c(tmp_path):
+    """include/fastgen_b200.h is the drop-in boundary: plain C99 (no CUDA / torch headers), usable from C++ as well"""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "fastgen_b200.h"\n'
+                   "int main(void) { fg_conv_params p; fg_flash_attn_params a; (void)p; (void)a; return FG_OK; }\n")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                   check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+
+
+def test_c_program_links_against_the_library(tmp_path):
+    """a C caller (what a cgo / JNI / FFI binding would be) links libfastgen_b200.so and gets FG_ERR_INVALID with a message
+    for an empty problem -- no GPU needed, argument validation is host-side"""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from fastgen_b200 import _lib
+
+    _lib.lib()  # built?
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    src = tmp_path / "caller.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "fastgen_b200.h"\n'
+                   "int main(void) {\n"
+                   "  fg_conv_params p; memset(&p, 0, sizeof p);\n"
+                   "  int st = fg_conv_gemm(&p, (fg_stream_t)0);\n"
+                   '  printf("%d %d %s\\n", fg_version() >= 100, st, fg_last_error());\n'
+                   "  return st == FG_ERR_INVALID ? 0 : 1;\n}\n")
+    exe = tmp_path / "caller"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lfastgen_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("1 -1 ") and "conv_gemm" in out
