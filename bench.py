@@ -544,9 +544,83 @@ def run_sdxl(args):
         dist.destroy_process_group()
 
 
+CIFAR = dict(img_resolution=32, img_channels=3, label_dim=10, sigma_shift=0.0, sigma_data=0.5, model_type="SongUNet",
+             augment_dim=9, model_channels=128, channel_mult=[2, 2, 2], channel_mult_noise=1,
+             embedding_type="positional", encoder_type="standard", decoder_type="standard", resample_filter=[1, 1],
+             dropout=0.0, label_dropout=0, r_timestep=False, drop_precond=None)
+CIFAR_GFLOP_PER_SAMPLE_FORWARD = 42.38
+
+
+def run_cifar(args):
+    """BASELINE configs[0]: EDM CIFAR-10 32x32 DMD2 one-step generator, batch 64 (the reference's CPU-runnable case)."""
+    from fastgen_b200 import ops
+    from fastgen_b200.edm import EDMPrecond
+    from fastgen_b200.sampler import FastGenModel
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    K, W = args.steps, max(args.warmup, 0)
+    B = args.batch if args.batch != BATCH else 64
+    torch.manual_seed(0)
+    net = EDMPrecond(**CIFAR)
+    _randomize_zero_init_(net, 0)
+    net = net.to(dev).eval()
+    torch.manual_seed(1)
+    noise_h = torch.randn(B, 3, 32, 32).pin_memory()
+    labels_h = torch.eye(10)[torch.randint(10, (B,))].pin_memory()
+    out_h = torch.empty(B, 3, 32, 32).pin_memory()
+    noise, labels = noise_h.to(dev), labels_h.to(dev)
+
+    def gen(n_, l_):
+        return FastGenModel.generator_fn(net, n_, condition=l_, student_sample_steps=1)
+
+    def timed(fn, iters):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(W):
+        gen(noise, labels)
+    iters = K * 20     # a step is ~3 ms: time 20 generations per "step" so that the events see a long region
+    ops.launch_count_reset()
+    with ClockSampler(0) as clk:
+        ms = timed(lambda: gen(noise, labels), iters)
+    launches = ops.launch_count()
+
+    def e2e_step():
+        out_h.copy_(gen(noise_h.to(dev, non_blocking=True), labels_h.to(dev, non_blocking=True)), non_blocking=True)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, iters)
+    hbm, tf_sus, tf_burst, peak_src = _peaks()
+    value = B * iters / (ms / 1000.0)
+    line = {
+        "metric": "samples/sec, 1-step CIFAR-10 EDM DMD2 generator", "value": value, "unit": "samples/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"EDM CIFAR-10 32x32 DMD2 one-step generator, batch {B} (BASELINE configs[0])",
+                   "generations_timed": iters, "t_list": "get_t_list(1) = [79.56, 0]",
+                   "l2": "the whole working set (223 MB of fp32 weights as bf16 = 111 MB, ~100 MB of activations) is of the "
+                         "order of the 126 MB L2: this configuration is launch-latency bound, not bandwidth bound"},
+        "e2e": {"value": B * iters / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / iters,
+                "h2d_bytes_per_step": 4 * (noise_h.numel() + labels_h.numel()), "d2h_bytes_per_step": 4 * out_h.numel()},
+        "gpu_launches": launches, "launches_per_generation": launches / iters, "clocks": clk.summary(),
+        "roofline": {"kernel": "conv_gemm_kernel", "bound": "tensor", "achieved": None, "peak": tf_sus, "unit": "TFLOP/s",
+                     "frac": None, "traffic": None,
+                     "model_flops_utilisation": value * CIFAR_GFLOP_PER_SAMPLE_FORWARD * 1e9 / 1e12 / tf_sus},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="in64", choices=["in64", "wan", "wan14b", "sdxl"],
+    ap.add_argument("--workload", default="in64", choices=["in64", "cifar", "wan", "wan14b", "sdxl"],
                     help="in64 = the headline line the driver records; wan = secondary workload for profiles/")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -561,6 +635,8 @@ def main():
         run_wan(args)
     elif args.workload == "sdxl":
         run_sdxl(args)
+    elif args.workload == "cifar":
+        run_cifar(args)
     else:
         run_ours(args)
 
