@@ -565,6 +565,7 @@ def run_cifar(args):
     net = EDMPrecond(**CIFAR)
     _randomize_zero_init_(net, 0)
     net = net.to(dev).eval()
+    net.use_cuda_graphs = not args.no_graphs   # 174 launches of 10-30 us: replay them as one CUDA graph
     torch.manual_seed(1)
     noise_h = torch.randn(B, 3, 32, 32).pin_memory()
     labels_h = torch.eye(10)[torch.randint(10, (B,))].pin_memory()
@@ -588,9 +589,10 @@ def run_cifar(args):
         gen(noise, labels)
     iters = K * 20     # a step is ~3 ms: time 20 generations per "step" so that the events see a long region
     ops.launch_count_reset()
+    net.graph_launches = 0
     with ClockSampler(0) as clk:
         ms = timed(lambda: gen(noise, labels), iters)
-    launches = ops.launch_count()
+    launches = ops.launch_count() + net.graph_launches   # direct launches + launches replayed through the CUDA graph
 
     def e2e_step():
         out_h.copy_(gen(noise_h.to(dev, non_blocking=True), labels_h.to(dev, non_blocking=True)), non_blocking=True)
@@ -604,7 +606,7 @@ def run_cifar(args):
         "steps": K, "warmup": W, "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"EDM CIFAR-10 32x32 DMD2 one-step generator, batch {B} (BASELINE configs[0])",
-                   "generations_timed": iters, "t_list": "get_t_list(1) = [79.56, 0]",
+                   "generations_timed": iters, "t_list": "get_t_list(1) = [79.56, 0]", "cuda_graph": bool(net.use_cuda_graphs),
                    "l2": "the whole working set (223 MB of fp32 weights as bf16 = 111 MB, ~100 MB of activations) is of the "
                          "order of the 126 MB L2: this configuration is launch-latency bound, not bandwidth bound"},
         "e2e": {"value": B * iters / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / iters,
@@ -628,6 +630,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="cifar workload: launch every kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -267,3 +267,20 @@ def test_teacher_sample_with_cfg_matches_reference(compute, tol):
     assert out.shape == noise.shape and _rel(out, torch.from_numpy(io["sample_cfg"])) < tol
     out = net.sample(noise, condition=lab, neg_condition=None, guidance_scale=None, num_steps=6)
     assert _rel(out, torch.from_numpy(io["sample"])) < tol
+
+
+def test_cuda_graph_replay_matches_eager_launches():
+    """opt-in EDMPrecond.use_cuda_graphs: from its second use a batch size's launch list replays as one CUDA graph; the
+    outputs equal the eager path's (to the fp64-atomic noise floor) for new inputs, new t and new labels"""
+    net, _ = _net(IN64, 0, "bf16")
+    torch.manual_seed(5)
+    xs = [torch.randn(2, 3, 64, 64, device="cuda") * s for s in (80.0, 1.1, 5.0)]
+    ts = [torch.full((2,), v, device="cuda", dtype=torch.float64) for v in (80.0, 1.1, 5.0)]
+    labs = [torch.eye(1000, device="cuda")[torch.randint(1000, (2,), device="cuda")] for _ in range(3)]
+    eager = [net(x, t, condition=lab, fwd_pred_type="x0").clone() for x, t, lab in zip(xs, ts, labs)]
+    net.use_cuda_graphs = True
+    net._plans.clear()
+    replay = [net(x, t, condition=lab, fwd_pred_type="x0").clone() for x, t, lab in zip(xs, ts, labs)]
+    assert net.graph_launches > 0 and net._plans[2].graph is not None
+    for a, b in zip(eager, replay):
+        assert _rel(b, a) < 2e-3, _rel(b, a)
