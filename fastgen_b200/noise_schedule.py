@@ -385,6 +385,70 @@ class AlphasNoiseSchedule(BaseNoiseSchedule):
         raise NotImplementedError("flow prediction is not defined for table schedules in the sampler path")
 
 
+class TrigNoiseSchedule(BaseNoiseSchedule):
+    """TrigFlow: x_t = cos(t) x_0 + sin(t) eps, t in [0, pi/2]  (reference :1489-1652; the sCM parameterisation)."""
+
+    def __init__(self, min_t: float = 0.0, max_t: float = torch.pi / 2, num_steps: int = 1000, **kwargs):
+        super().__init__(min_t, max_t, num_steps, **kwargs)
+        assert 0 <= min_t < max_t, "Trig min_t must be non-negative and less than max_t"
+        self._sigmas = torch.sin(torch.linspace(min_t, max_t, num_steps, dtype=self.t_precision))
+
+    def _rescale_t(self, t):
+        return t
+
+    @property
+    def max_sigma(self) -> float:
+        return torch.sin(torch.tensor(self.max_t)).item()
+
+    @property
+    def sigmas(self):
+        return self._sigmas
+
+    def _alpha(self, t):
+        return torch.cos(t)
+
+    def _sigma(self, t):
+        return torch.sin(t)
+
+    def _alpha_prime(self, t):
+        return -torch.sin(t)
+
+    def _sigma_prime(self, t):
+        return torch.cos(t)
+
+    def sigma_idx_to_t(self, sigma_idx: torch.Tensor) -> torch.Tensor:
+        assert sigma_idx.dtype == torch.long
+        return sigma_idx.to(self.t_precision) / (self.num_steps - 1) * (self.max_t - self.min_t) + self.min_t
+
+    def sqrt_snr(self, t: torch.Tensor) -> torch.Tensor:
+        """cot(t) with tan(t) clamped away from zero (reference :1547-1557)"""
+        assert self.is_t_valid(t)
+        return 1.0 / self.non_zero_clamp(torch.tan(t.to(torch.float64)))
+
+    def sqrt_snr_to_t(self, sqrt_snr_t: torch.Tensor) -> torch.Tensor:
+        x = sqrt_snr_t.to(torch.float64)
+        return torch.atan2(torch.ones_like(x), x).to(sqrt_snr_t.dtype)
+
+    def flow_to_x0(self, xt, v, t):
+        """x0 = cos(t) x_t - sin(t) v in float64, one rounding (reference :1617-1634)"""
+        from . import ops
+
+        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        t64 = t.to(torch.float64)
+        return ops.axpby(xt.contiguous(), _coef(torch.cos(t64).reshape(-1), xt), v.contiguous(),
+                         _coef(-torch.sin(t64).reshape(-1), xt))
+
+    def x0_to_flow(self, xt, x0, t):
+        """v = (cos(t) x_t - x_0) / clamp(sin(t)) in float64, one rounding (reference :1636-1652): evaluated as
+        (x_0 - x_t cos(t)) / (-clamp(sin(t))), the same float64 operations up to two exact sign flips"""
+        from . import ops
+
+        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        t64 = t.to(torch.float64)
+        return ops.sub_div(x0.contiguous(), xt.contiguous(), _coef(torch.cos(t64).reshape(-1), xt),
+                           _coef(-self.non_zero_clamp(torch.sin(t64)).reshape(-1), xt))
+
+
 def scaled_linear_alphas_cumprod(num_steps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012) -> torch.Tensor:
     """DDIM `scaled_linear` betas of SD/SDXL (diffusers scheduler_config: 0.00085 -> 0.012, 1000 steps), computed
     locally in float32 like diffusers' DDIMScheduler so that no hub download is needed."""
@@ -408,6 +472,7 @@ NOISE_SCHEDULES = {
     "sdxl": SDXLNoiseSchedule,
     "rf": RFNoiseSchedule,
     "rectified_flow": RFNoiseSchedule,
+    "trig": TrigNoiseSchedule,
 }
 
 

@@ -323,6 +323,30 @@ def checkpoint_fixture():
     print("wrote checkpoint fixture:", sum(p.numel() for p in net.parameters()), "parameters")
 
 
+def trig_fixture():
+    """TrigNoiseSchedule (noise_schedule.py:1489-1652): scalar functions and the latent conversions, fp32 and bf16"""
+    from fastgen.networks.noise_schedule import get_noise_schedule
+
+    ns = get_noise_schedule("trig")
+    torch.manual_seed(SEED + 31)
+    t = torch.tensor([0.0, 1e-7, 0.3, 0.785, 1.2, torch.pi / 2], dtype=torch.float64)
+    fx = dict(t=_np(t), alpha=_np(ns.alpha(t)), sigma=_np(ns.sigma(t)), sqrt_snr=_np(ns.sqrt_snr(t)),
+              t_list4=_np(ns.get_t_list(4)), max_sigma=np.float64(ns.max_sigma),
+              idx_t=_np(ns.sigma_idx_to_t(torch.tensor([0, 17, 999]))),
+              snr_t=_np(ns.sqrt_snr_to_t(torch.tensor([0.1, 1.0, 30.0], dtype=torch.float64))))
+    tb = torch.tensor([1.3, 0.4, 1e-9], dtype=torch.float64)
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        xt = torch.randn(3, 4, 8, 8).to(dt)
+        v = torch.randn(3, 4, 8, 8).to(dt)
+        fx[f"xt_{name}"], fx[f"v_{name}"] = _np(xt), _np(v)
+        fx[f"x0_{name}"] = _np(ns.flow_to_x0(xt, v, tb))
+        fx[f"flow_{name}"] = _np(ns.x0_to_flow(xt, v, tb))          # (v reused as an x0 input)
+        fx[f"fwd_{name}"] = _np(ns.forward_process(xt, v, tb))
+    fx["tb"] = _np(tb)
+    np.savez_compressed(os.path.join(OUT, "schedule_trig.npz"), **fx)
+    print("wrote trig schedule fixture")
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -334,3 +358,4 @@ if __name__ == "__main__":
     causal_trace_fixture()
     extrapolation_fixture()
     checkpoint_fixture()
+    trig_fixture()

@@ -92,3 +92,24 @@ def test_sinusoid_variants_match_oracle():
     t = torch.tensor([999.0, 937.0, 0.0], dtype=torch.float64)
     assert torch.equal(_sinusoid(t, 256, True), WO.sinusoidal_embedding_1d_wan(256, t))
     assert torch.equal(_sinusoid(t, 256, False), WO.timesteps_diffusers(t, 256))
+
+
+def test_trig_schedule_scalars_match_reference_fixture():
+    """TrigNoiseSchedule host logic against values of the unmodified reference (oracle/make_golden.py:trig_fixture)"""
+    import os
+
+    import numpy as np
+
+    from fastgen_b200.noise_schedule import get_noise_schedule
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schedule_trig.npz"))
+    ns = get_noise_schedule("trig")
+    t = torch.from_numpy(g["t"])
+    assert torch.equal(ns.alpha(t), torch.from_numpy(g["alpha"])) and torch.equal(ns.sigma(t), torch.from_numpy(g["sigma"]))
+    assert torch.equal(ns.sqrt_snr(t), torch.from_numpy(g["sqrt_snr"]))
+    assert torch.equal(ns.get_t_list(4), torch.from_numpy(g["t_list4"])) and ns.max_sigma == float(g["max_sigma"])
+    assert torch.equal(ns.sigma_idx_to_t(torch.tensor([0, 17, 999])), torch.from_numpy(g["idx_t"]))
+    assert torch.equal(ns.sqrt_snr_to_t(torch.tensor([0.1, 1.0, 30.0], dtype=torch.float64)), torch.from_numpy(g["snr_t"]))
+    assert torch.equal(ns.rescale_t(t), t)
+    with pytest.raises(AssertionError):
+        ns.alpha(torch.tensor([1.7], dtype=torch.float64))
