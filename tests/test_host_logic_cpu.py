@@ -113,3 +113,12 @@ def test_trig_schedule_scalars_match_reference_fixture():
     assert torch.equal(ns.rescale_t(t), t)
     with pytest.raises(AssertionError):
         ns.alpha(torch.tensor([1.7], dtype=torch.float64))
+
+
+def test_package_root_exports_resolve():
+    import fastgen_b200 as F
+
+    for name in F.__all__:
+        assert getattr(F, name) is not None
+    with pytest.raises(AttributeError):
+        F.no_such_thing
