@@ -347,6 +347,62 @@ def trig_fixture():
     print("wrote trig schedule fixture")
 
 
+def wan_glue_fixture():
+    """Outputs of the UNMODIFIED reference Wan glue code (fastgen/networks/Wan/network.py + network_causal.py) run on
+    stand-in diffusers modules (oracle/ref_wan_harness.py): bidirectional forward with every r-embedder / norm_temb /
+    sinusoid variant, causal KV-cached chunks, the block-causal mask (eager FlexAttention)."""
+    os.environ["FASTGEN_DISABLE_FLEX_ATTENTION"] = "0"
+    os.environ["FASTGEN_FLEX_COMPILE"] = "0"
+    from oracle import ref_wan_harness as H
+    from oracle import wan_oracle as WO
+
+    cfg = WO.tiny_config(layers=2)
+    sd = WO.make_state_dict(cfg, 11, r_embedder=True)
+    g = torch.Generator().manual_seed(SEED + 41)
+    B, total, cs, Hh, Ww = 2, 7, 3, 8, 8
+    x = torch.randn(B, 16, total, Hh, Ww, generator=g)
+    text = torch.randn(B, 24, cfg["text_dim"], generator=g)
+    t = torch.tensor([800.0, 500.0], dtype=torch.float64)
+    r = torch.tensor([300.0, 500.0], dtype=torch.float64)
+    fx = dict(cfg=json.dumps(cfg), seed=np.int64(11), x=_np(x), text=_np(text), t=_np(t), r=_np(r))
+    variants = {"plain": {}, "r_diff": dict(r=True), "r_abs": dict(r=True, time_cond_type="abs"),
+                "r_enc1": dict(r=True, encoder_depth=1), "norm_temb": dict(norm_temb=True),
+                "r_enc0_norm": dict(r=True, encoder_depth=0, norm_temb=True), "official": dict(official_sinusoidal=True)}
+    xb = x[:, :, :3]
+    with torch.no_grad():
+        for name, kw in variants.items():
+            kw = dict(kw)
+            use_r = kw.pop("r", False)
+            tr = H.build_bidirectional(cfg, sd, r_timestep=True, **kw)
+            fx["bidir_" + name] = _np(tr(hidden_states=xb, timestep=t, encoder_hidden_states=text,
+                                         r_timestep=r if use_r else None, feature_indices=set()))
+        sd16 = {k: v.bfloat16() for k, v in sd.items()}
+        tr = H.build_bidirectional(cfg, sd16, r_timestep=True, norm_temb=True).to(torch.bfloat16)
+        fx["bidir_bf16_r_norm"] = _np(tr(hidden_states=xb.bfloat16(), timestep=t, encoder_hidden_states=text.bfloat16(),
+                                         r_timestep=r, feature_indices=set()))
+        # causal: chunk 0 = frames 0..3 (remainder absorbed), chunk 1 = frames 4..6; denoise pass then cache-fill pass
+        trc = H.build_causal(cfg, sd)
+        for ci, (s_, e_) in enumerate(((0, 4), (4, 7))):
+            xs = x[:, :, s_:e_]
+            ts = torch.full((B, e_ - s_), 937.0, dtype=torch.float64)
+            fx[f"causal_c{ci}_denoise"] = _np(H.causal_call(trc, xs, ts, text, chunk_size=cs, total_num_frames=total,
+                                                            cur_start_frame=s_, store_kv=False, is_ar=True))
+            fx[f"causal_c{ci}_store"] = _np(H.causal_call(trc, xs, torch.zeros(B, e_ - s_, dtype=torch.float64), text,
+                                                          chunk_size=cs, total_num_frames=total, cur_start_frame=s_,
+                                                          store_kv=True, is_ar=True))
+        trm = H.build_causal(cfg, sd)
+        fx["causal_block_mask"] = _np(H.causal_call(trm, x, torch.full((B, total), 500.0, dtype=torch.float64), text,
+                                                    chunk_size=cs, total_num_frames=total, is_ar=False))
+        trn = H.build_causal(cfg, sd16, norm_temb=True).to(torch.bfloat16)
+        ts = torch.full((B, 3), 937.0, dtype=torch.float64)
+        fx["causal_bf16_norm_store"] = _np(H.causal_call(trn, x[:, :, :3].bfloat16(), ts, text.bfloat16(), chunk_size=cs,
+                                                         total_num_frames=6, cur_start_frame=0, store_kv=True, is_ar=True))
+        fx["causal_bf16_norm_c1"] = _np(H.causal_call(trn, x[:, :, 3:6].bfloat16(), ts, text.bfloat16(), chunk_size=cs,
+                                                      total_num_frames=6, cur_start_frame=3, store_kv=False, is_ar=True))
+    np.savez_compressed(os.path.join(OUT, "wan_reference_glue.npz"), **fx)
+    print("wrote Wan reference-glue fixture:", len(fx), "arrays")
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -359,3 +415,4 @@ if __name__ == "__main__":
     extrapolation_fixture()
     checkpoint_fixture()
     trig_fixture()
+    wan_glue_fixture()

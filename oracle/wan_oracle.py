@@ -3,12 +3,25 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg, never by the
 product path (fastgen_b200/ has no import of this package and raises if the CUDA library is missing).
 
-PARITY UNPINNED.  The layer arithmetic of the reference's Wan networks lives in the third-party dependency
-diffusers==0.35.1 (reference requirements.txt:6; `WanTransformer3DModel`, `WanTransformerBlock`, `WanAttention`,
-`WanRotaryPosEmbed`, `WanTimeTextImageEmbedding`, imported at fastgen/networks/Wan/network.py:33-35 and
-network_causal.py:31-38), which is not under /root/reference and not installed in this image, and the reference's own
-tests for these networks assert shapes/dtypes only (tests/test_network.py:617-685, 933-1057).  So there is no golden
-vector to pin this file against.  What IS followed line by line is the reference's own code around that dependency:
+PARITY: the REFERENCE'S OWN CODE IS PINNED, THE THIRD-PARTY MODULE INTERNALS ARE NOT.  The layer arithmetic of the
+reference's Wan networks lives in the third-party dependency diffusers==0.35.1 (reference requirements.txt:6;
+`WanTransformer3DModel`, `WanTransformerBlock`, `WanAttention`, `WanRotaryPosEmbed`, `WanTimeTextImageEmbedding`,
+imported at fastgen/networks/Wan/network.py:33-35 and network_causal.py:31-38), which is not under /root/reference and
+not installed in this image, and the reference's own tests for these networks assert shapes/dtypes only
+(tests/test_network.py:617-685, 933-1057): there is no golden vector for the diffusers modules themselves.  But the
+functions the reference wrote around that dependency run unmodified on stand-in modules (oracle/ref_wan_harness.py), and
+tests/test_oracle_golden.py::test_wan_oracle_matches_reference_glue checks this file against their outputs
+(tests/golden/wan_reference_glue.npz): bidirectional forward incl. every r-embedder / encoder_depth / norm_temb /
+official-sinusoid variant (fp32 and bf16), causal KV-cached chunks (denoise and cache-fill passes, rotary frame offset),
+the block-causal mask through eager FlexAttention -- bit-exact, resp. 3e-7 for FlexAttention.  Reference behaviours found
+that way and NOT reproduced: (1) with FlexAttention available, a full-length `is_ar=True` call pads q/k/v with zero rows to
+a multiple of 128 and attends to the zero keys because no block mask is passed (network_causal.py:414-441; 8 zero keys
+next to 32 760 real ones at 480p) -- this file and the CUDA path use plain attention, which is also what the reference
+does without FlexAttention; (2) the causal network's r embedder cannot run with per-frame timesteps (`timestep -
+r_timestep` mixes the flattened [B*F] with [B, F], :645, and the flattened r projection is unflattened as if it were 3-D,
+:657) -- implemented here as the bidirectional code does it; (3) if diffusers does not keep the rotary tables in fp32
+under `.to(bfloat16)`, a bf16 reference rotates with bf16-rounded cos / sin (4e-3 on a block output); fp32 tables here.
+The lines followed:
 
   fastgen/networks/Wan/network.py:81-103        sinusoidal_embedding_1d_wan (official Wan sinusoid, fp64)
   fastgen/networks/Wan/network.py:106-153       block_forward (AdaLN modulate / gate / residual dtype chain)

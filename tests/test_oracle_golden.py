@@ -202,3 +202,57 @@ def test_teacher_sampler_matches_reference():
     for got, key in ((out, "out"), (s_cfg, "sample_cfg"), (s_raw, "sample")):
         ref = torch.from_numpy(io[key])
         assert ((got - ref).norm() / ref.norm()).item() < 1e-5, key
+
+
+def test_wan_oracle_matches_reference_glue():
+    """oracle/wan_oracle.py against outputs of the UNMODIFIED reference Wan code (classify_forward / prepare / block_forward,
+    CausalWanAttnProcessor, inline KV caches, rotary time offset, block-causal mask) run on stand-in diffusers modules
+    (oracle/ref_wan_harness.py -> tests/golden/wan_reference_glue.npz).  On the machine that wrote the fixture every
+    case but the FlexAttention one is bit-exact; the bounds below only leave room for another host's BLAS summation order
+    (fp32: 1e-5; bf16: isolated last-bit flips)."""
+    from oracle import wan_oracle as WO
+
+    def close(a, b):
+        return torch.equal(a, b) or _rel(a, b) < (2e-3 if a.dtype == torch.bfloat16 else 1e-5)
+
+    g = _load("wan_reference_glue.npz")
+    cfg = json.loads(str(g["cfg"]))
+    cfg["patch"] = tuple(cfg["patch"])
+    sd = WO.make_state_dict(cfg, int(g["seed"]), r_embedder=True)
+    x, text, t, r = (torch.from_numpy(g[k]) for k in ("x", "text", "t", "r"))
+    B, total, cs = x.shape[0], x.shape[2], 3
+    xb = x[:, :, :3]
+    variants = {"plain": {}, "r_diff": dict(r=True), "r_abs": dict(r=True, time_cond_type="abs"),
+                "r_enc1": dict(r=True, encoder_depth=1), "norm_temb": dict(norm_temb=True),
+                "r_enc0_norm": dict(r=True, encoder_depth=0, norm_temb=True), "official": dict(official_sinusoidal=True)}
+    with torch.no_grad():
+        for name, kw in variants.items():
+            kw = dict(kw)
+            use_r = kw.pop("r", False)
+            out = WO.transformer_forward(sd, cfg, xb, t, text, r_timestep=r if use_r else None, **kw)
+            assert close(out, torch.from_numpy(g["bidir_" + name])), name
+        sd16 = {k: v.bfloat16() for k, v in sd.items()}
+        out = WO.transformer_forward(sd16, cfg, xb.bfloat16(), t, text.bfloat16(), r_timestep=r, norm_temb=True)
+        assert close(out, _t(g["bidir_bf16_r_norm"], bf16=True))
+        fs = (x.shape[3] // 2) * (x.shape[4] // 2)
+        cache = WO.KVCache(cfg, B, total * fs, text.shape[1], torch.float32)
+        for ci, (s_, e_) in enumerate(((0, 4), (4, 7))):
+            xs = x[:, :, s_:e_]
+            ts = torch.full((B, e_ - s_), 937.0, dtype=torch.float64)
+            out = WO.transformer_forward(sd, cfg, xs, ts, text, cache=cache, cur_start_frame=s_, store_kv=False)
+            assert close(out, torch.from_numpy(g[f"causal_c{ci}_denoise"])), ci
+            out = WO.transformer_forward(sd, cfg, xs, torch.zeros(B, e_ - s_, dtype=torch.float64), text, cache=cache,
+                                         cur_start_frame=s_, store_kv=True)
+            assert close(out, torch.from_numpy(g[f"causal_c{ci}_store"])), ci
+        out = WO.transformer_forward(sd, cfg, x, torch.full((B, total), 500.0, dtype=torch.float64), text,
+                                     mask=WO.block_causal_mask(total, fs, cs))
+        ref = torch.from_numpy(g["causal_block_mask"])
+        assert ((out - ref).norm() / ref.norm()).item() < 1e-5
+        cache16 = WO.KVCache(cfg, B, 6 * fs, text.shape[1], torch.bfloat16)
+        ts = torch.full((B, 3), 937.0, dtype=torch.float64)
+        out = WO.transformer_forward(sd16, cfg, x[:, :, :3].bfloat16(), ts, text.bfloat16(), cache=cache16,
+                                     cur_start_frame=0, store_kv=True, norm_temb=True)
+        assert close(out, _t(g["causal_bf16_norm_store"], bf16=True))
+        out = WO.transformer_forward(sd16, cfg, x[:, :, 3:6].bfloat16(), ts, text.bfloat16(), cache=cache16,
+                                     cur_start_frame=3, store_kv=False, norm_temb=True)
+        assert close(out, _t(g["causal_bf16_norm_c1"], bf16=True))
