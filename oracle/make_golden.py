@@ -403,6 +403,29 @@ def wan_glue_fixture():
     print("wrote Wan reference-glue fixture:", len(fx), "arrays")
 
 
+def sdxl_glue_fixture():
+    """Outputs of the UNMODIFIED reference `StableDiffusionXL.forward` + `classify_forward` (SDXL/network.py:334-416,
+    SD15/network.py:46-341) on a stand-in diffusers UNet (oracle/ref_sdxl_harness.py), fp32 and bf16, eps and x0"""
+    from oracle import ref_sdxl_harness as H
+    from oracle import sdxl_oracle as XO
+
+    cfg = XO.tiny_config()
+    sd = XO.make_state_dict(cfg, 21)
+    g = torch.Generator().manual_seed(SEED + 51)
+    x = torch.randn(2, 4, 32, 32, generator=g)
+    text = torch.randn(2, 77, cfg["cross_attention_dim"], generator=g)
+    pooled = torch.randn(2, cfg["pooled_dim"], generator=g)
+    t = torch.tensor([0.999, 0.4], dtype=torch.float64)
+    fx = dict(seed=np.int64(21), x=_np(x), text=_np(text), pooled=_np(pooled), t=_np(t))
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    with torch.no_grad():
+        for pred in ("eps", "x0"):
+            fx[f"f32_{pred}"] = _np(H.reference_sdxl_forward(cfg, sd, x, t, text, pooled, pred))
+            fx[f"bf16_{pred}"] = _np(H.reference_sdxl_forward(cfg, sd16, x.bfloat16(), t, text.bfloat16(), pooled.bfloat16(), pred))
+    np.savez_compressed(os.path.join(OUT, "sdxl_reference_glue.npz"), **fx)
+    print("wrote SDXL reference-glue fixture")
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -416,3 +439,4 @@ if __name__ == "__main__":
     checkpoint_fixture()
     trig_fixture()
     wan_glue_fixture()
+    sdxl_glue_fixture()

@@ -2,18 +2,22 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/edm_oracle.py): never imported by the product path.
 
-PARITY UNPINNED.  The reference's SDXL network (fastgen/networks/SDXL/network.py:159-416) wraps the third-party
-`diffusers==0.35.1` `UNet2DConditionModel` (imports at SDXL/network.py:29-36, construction at :210-230 from the hub
-config `stabilityai/stable-diffusion-xl-base-1.0`), absent from /root/reference and from this image, and the reference has
-no test that pins SDXL outputs.  Followed line by line from the reference: the model-level forward
-`classify_forward` (fastgen/networks/SD15/network.py:46-341, bound to the SDXL UNet at SDXL/network.py:192), the
-conditioning inputs of `StableDiffusionXL.forward` (:379-393: `time_ids = [1024, 1024, 0, 0, 1024, 1024]`, pooled text
-embeddings, `timestep = rescale_t(t) = 1000 t`) and the eps -> x0 conversion.  Restated from the published diffusers
-sources: Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0), TimestepEmbedding, the "text_time" addition embedding,
-ResnetBlock2D (GroupNorm 32 / eps 1e-5, SiLU, time_emb_proj added after conv1, 1x1 conv_shortcut), Downsample2D (3x3
-stride 2 pad 1), Upsample2D (nearest x2 + 3x3), Transformer2DModel with linear projections (GroupNorm eps 1e-6),
-BasicTransformerBlock (LayerNorm, self-attention, cross-attention, GEGLU feed-forward), DownBlock2D /
-CrossAttnDownBlock2D / UNetMidBlock2DCrossAttn / CrossAttnUpBlock2D / UpBlock2D and the skip-connection order.
+PARITY: the reference's own SDXL code is pinned, the diffusers block internals are not.  The reference's SDXL network
+(fastgen/networks/SDXL/network.py:159-416) wraps the third-party `diffusers==0.35.1` `UNet2DConditionModel` (imports at
+SDXL/network.py:29-36, construction at :210-230 from the hub config `stabilityai/stable-diffusion-xl-base-1.0`), absent
+from /root/reference and from this image, and the reference has no test that pins SDXL outputs.  What the
+reference itself wrote runs unmodified on a stand-in UNet (oracle/ref_sdxl_harness.py): `StableDiffusionXL.forward`
+(:334-416: `time_ids = [1024, 1024, 0, 0, 1024, 1024]`, pooled text embeddings, `timestep = rescale_t(t) = 1000 t`, the eps
+-> x0 conversion through its own noise schedule) and the model-level `classify_forward` bound onto the UNet
+(fastgen/networks/SD15/network.py:46-341: embedding sums, the skip tensors each up block receives, the output head);
+tests/test_oracle_golden.py::test_sdxl_oracle_matches_reference_glue checks this file against their outputs
+(tests/golden/sdxl_reference_glue.npz), bit-exact in fp32 and bf16.  Restated from the published diffusers sources, i.e.
+NOT pinned: Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0), TimestepEmbedding, the "text_time" addition
+embedding, ResnetBlock2D (GroupNorm 32 / eps 1e-5, SiLU, time_emb_proj added after conv1, 1x1 conv_shortcut),
+Downsample2D (3x3 stride 2 pad 1), Upsample2D (nearest x2 + 3x3), Transformer2DModel with linear projections (GroupNorm
+eps 1e-6), BasicTransformerBlock (LayerNorm, self-attention, cross-attention, GEGLU feed-forward) and the
+`torch.cat([hidden_states, res_hidden_states])` order inside an up block.  One independent anchor for the architecture:
+the parameter count of the SDXL-base configuration equals the published 2 567 463 684 (tests/test_sdxl_host_cpu.py).
 State-dict keys are the diffusers ones under the reference's `unet.` prefix.
 """
 from __future__ import annotations

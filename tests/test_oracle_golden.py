@@ -256,3 +256,25 @@ def test_wan_oracle_matches_reference_glue():
         out = WO.transformer_forward(sd16, cfg, x[:, :, 3:6].bfloat16(), ts, text.bfloat16(), cache=cache16,
                                      cur_start_frame=3, store_kv=False, norm_temb=True)
         assert close(out, _t(g["causal_bf16_norm_c1"], bf16=True))
+
+
+def test_sdxl_oracle_matches_reference_glue():
+    """oracle/sdxl_oracle.py against the UNMODIFIED reference `StableDiffusionXL.forward` + `classify_forward` run on a
+    stand-in diffusers UNet (oracle/ref_sdxl_harness.py -> tests/golden/sdxl_reference_glue.npz): conditioning inputs,
+    embedding sums, skip routing of the up blocks, output head, eps -> x0 through the reference's noise schedule"""
+    from oracle import sdxl_oracle as XO
+
+    g = _load("sdxl_reference_glue.npz")
+    cfg = XO.tiny_config()
+    sd = XO.make_state_dict(cfg, int(g["seed"]))
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    x, text, pooled, t = (torch.from_numpy(g[k]) for k in ("x", "text", "pooled", "t"))
+    with torch.no_grad():
+        for pred in ("eps", "x0"):
+            out = XO.sdxl_forward(sd, cfg, x, t, text, pooled, fwd_pred_type=pred)
+            ref = torch.from_numpy(g[f"f32_{pred}"])
+            assert torch.equal(out, ref) or _rel(out, ref) < 1e-5, pred
+            out = XO.sdxl_forward(sd16, cfg, x.bfloat16(), t, text.bfloat16(), pooled.bfloat16(), fwd_pred_type=pred,
+                                  dtype=torch.bfloat16)
+            ref = _t(g[f"bf16_{pred}"], bf16=True)
+            assert torch.equal(out, ref) or _rel(out, ref) < 2e-3, pred
