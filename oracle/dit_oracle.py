@@ -2,10 +2,14 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/edm_oracle.py): never imported by the product path.
 
-PARITY UNPINNED.  The reference's DiT (fastgen/networks/DiT/network.py) builds its blocks from the third-party `timm`
-package (`timm.models.vision_transformer.{PatchEmbed, Attention, Mlp}`, imported at DiT/network.py:15-16; un-pinned in
+PARITY: PINNED to the reference's own DiT code; only timm's three classes are restated.  The reference's DiT
+(fastgen/networks/DiT/network.py) builds its blocks from the third-party `timm` package
+(`timm.models.vision_transformer.{PatchEmbed, Attention, Mlp}`, imported at DiT/network.py:15-16; un-pinned in
 requirements.txt:20), which is neither under /root/reference nor installed here, and the reference's own test
-(tests/test_network.py:362-410) asserts shapes only.  Followed line by line from the reference:
+(tests/test_network.py:362-410) asserts shapes only.  The UNMODIFIED reference `DiT` class runs with stand-ins for just those
+three classes (oracle/ref_dit_harness.py) and tests/test_oracle_golden.py::test_dit_oracle_matches_reference checks this
+file against its outputs (tests/golden/dit_reference.npz: plain, 72-wide heads, SiT convention, r embedder diff / abs, x0
+and flow, the position table) -- bit-exact.  Followed line by line from the reference:
 
   DiT/network.py:29-41     apply_adaptive_modulation
   DiT/network.py:49-101    FourierTimeEmbedding ([cos | sin], exp(-ln(1e4) i / half), proj_net Linear-SiLU-Linear)

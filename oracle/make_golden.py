@@ -426,6 +426,37 @@ def sdxl_glue_fixture():
     print("wrote SDXL reference-glue fixture")
 
 
+DIT_VARIANTS = {"d64": {}, "d72": dict(hidden_size=144, num_heads=2, depth=3), "sit": dict(use_sit_convention=True),
+                "r_diff": dict(r_timestep=True, time_cond_type="diff"), "r_abs": dict(r_timestep=True, time_cond_type="abs")}
+
+
+def dit_fixture():
+    """Outputs of the UNMODIFIED reference DiT (fastgen/networks/DiT/network.py) with stand-ins for timm's PatchEmbed /
+    Attention / Mlp (oracle/ref_dit_harness.py): plain, 72-wide heads, SiT convention, r embedder (diff / abs)"""
+    from oracle import dit_oracle as DO
+    from oracle import ref_dit_harness as H
+
+    g = torch.Generator().manual_seed(SEED + 61)
+    cfg0 = DO.tiny_config()
+    x = torch.randn(3, cfg0["in_channels"], cfg0["input_size"], cfg0["input_size"], generator=g)
+    t = torch.tensor([0.9, 0.5, 0.1], dtype=torch.float64)
+    r = torch.tensor([0.2, 0.5, 0.05], dtype=torch.float64)
+    lab = torch.eye(cfg0["num_classes"])[torch.tensor([1, 7, 3])]
+    lab[2] = 0          # all-zero row -> the null class
+    fx = dict(x=_np(x), t=_np(t), r=_np(r), lab=_np(lab), seed=np.int64(31))
+    with torch.no_grad():
+        for name, kw in DIT_VARIANTS.items():
+            cfg = DO.tiny_config(**kw)
+            net = H.build_reference_dit(cfg, DO.make_state_dict(cfg, 31))
+            rr = r if kw.get("r_timestep") else None
+            for pred in ("x0", "flow"):
+                fx[f"{name}_{pred}"] = _np(net(x, t, condition=lab, r=rr, fwd_pred_type=pred))
+            if name == "d64":
+                fx["pos_embed"] = _np(net.pos_embed)
+    np.savez_compressed(os.path.join(OUT, "dit_reference.npz"), **fx)
+    print("wrote DiT reference fixture:", len(fx), "arrays")
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -440,3 +471,4 @@ if __name__ == "__main__":
     trig_fixture()
     wan_glue_fixture()
     sdxl_glue_fixture()
+    dit_fixture()

@@ -1,5 +1,6 @@
-"""Parity of the CUDA DiT path against the CPU oracle (oracle/dit_oracle.py, PARITY UNPINNED: the block arithmetic
-lives in timm) on identical random weights and inputs; bf16 path tolerance rel-L2 <= 1e-2 on x0."""
+"""Parity of the CUDA DiT path against the CPU oracle (oracle/dit_oracle.py, itself pinned bit-exactly to the unmodified
+reference DiT run with stand-ins for timm's three classes: tests/golden/dit_reference.npz) on identical random weights
+and inputs; bf16 path tolerance rel-L2 <= 1e-2 on x0."""
 import pytest
 import torch
 

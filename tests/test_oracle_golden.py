@@ -278,3 +278,25 @@ def test_sdxl_oracle_matches_reference_glue():
                                   dtype=torch.bfloat16)
             ref = _t(g[f"bf16_{pred}"], bf16=True)
             assert torch.equal(out, ref) or _rel(out, ref) < 2e-3, pred
+
+
+def test_dit_oracle_matches_reference():
+    """oracle/dit_oracle.py against the UNMODIFIED reference DiT (its own __init__, blocks, embedders, modulation, unpatchify,
+    SiT convention, r embedder) run with stand-ins for timm's PatchEmbed / Attention / Mlp only
+    (oracle/ref_dit_harness.py -> tests/golden/dit_reference.npz)"""
+    from oracle import dit_oracle as DO
+    from oracle.make_golden import DIT_VARIANTS
+
+    g = _load("dit_reference.npz")
+    x, t, r, lab = (torch.from_numpy(g[k]) for k in ("x", "t", "r", "lab"))
+    assert torch.equal(DO.pos_embed_2d(128, 4), torch.from_numpy(g["pos_embed"]))
+    with torch.no_grad():
+        for name, kw in DIT_VARIANTS.items():
+            cfg = DO.tiny_config(**kw)
+            sd = DO.make_state_dict(cfg, int(g["seed"]))
+            rr = r if kw.get("r_timestep") else None
+            for pred in ("x0", "flow"):
+                out = DO.dit_forward(sd, cfg, x, t, lab, fwd_pred_type=pred, r=rr,
+                                     time_cond_type=cfg.get("time_cond_type", "abs"))
+                ref = torch.from_numpy(g[f"{name}_{pred}"])
+                assert torch.equal(out, ref) or _rel(out, ref) < 1e-5, (name, pred)

@@ -1,5 +1,6 @@
-"""Parity of the CUDA SDXL UNet path against the CPU oracle (oracle/sdxl_oracle.py, PARITY UNPINNED: the layer
-arithmetic lives in diffusers 0.35.1 `UNet2DConditionModel`) on identical random bf16-representable weights and inputs;
+"""Parity of the CUDA SDXL UNet path against the CPU oracle (oracle/sdxl_oracle.py: pinned to the reference's own
+`StableDiffusionXL.forward` + `classify_forward` run on a stand-in UNet, tests/golden/sdxl_reference_glue.npz; the blocks of
+diffusers 0.35.1 `UNet2DConditionModel` are restated) on identical random bf16-representable weights and inputs;
 bf16 path tolerance rel-L2 <= 1e-2 on x0 / eps (BASELINE.json north_star)."""
 import pytest
 import torch
