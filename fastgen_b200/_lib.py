@@ -19,7 +19,8 @@ FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU, FG_ACT_GEGLU = 0, 1, 2, 3
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
-    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_flash_attn", "fg_flash_attn_workspace_size",
+    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_flash_attn",
+    "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
 )
@@ -132,6 +133,7 @@ def lib() -> C.CDLL:
     l.fg_gn_stats.argtypes = [vp, i32, i64, i32, i32, i32, i32, vp, vp]
     l.fg_gn_apply.argtypes = [C.POINTER(GnApplyParams), vp]
     l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
+    l.fg_attention_f32.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, i64, vp]
     l.fg_flash_attn.argtypes = [C.POINTER(FlashAttnParams), vp]
     l.fg_flash_attn_workspace_size.argtypes = [C.POINTER(FlashAttnParams)]
     l.fg_flash_attn_workspace_size.restype = C.c_int64
@@ -150,7 +152,7 @@ def lib() -> C.CDLL:
     l.fg_zero.argtypes = [vp, i64, vp]
     l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
-    for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_edm_input", "fg_edm_step",
+    for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_edm_input", "fg_edm_step",
                  "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
                  "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero", "fg_geglu", "fg_cast_resample"):
         getattr(l, name).restype = C.c_int

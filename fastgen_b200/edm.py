@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 
@@ -262,6 +263,10 @@ def _split(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return hi.contiguous(), lo.contiguous()
 
 
+_X3_ATTENTION_DEFAULT = os.environ.get("FASTGEN_B200_X3_ATTENTION", "f32")
+_F32_ATTENTION_WIDTHS = (64, 128, 192, 256)   # head widths fg_attention_f32 is instantiated for
+
+
 class _Plan:
     """Buffers + the flat launch list for one (batch size, dtype of x_t is irrelevant) forward."""
 
@@ -269,6 +274,7 @@ class _Plan:
         self.net, self.n = net, n
         self.dev = next(net.parameters()).device
         self.x3 = net.compute == "bf16x3"
+        self.attn_f32 = self.x3 and net.x3_attention == "f32"   # fp32 CUDA-core attention on the fp32-parity path
         self.steps: List[Tuple[Any, tuple]] = []
         self.step_flops: List[float] = []
         self.step_desc: List[Tuple[str, float]] = []
@@ -306,19 +312,26 @@ class _Plan:
                 if b.num_heads:
                     req("mid", px * b.out_channels)
                     req("h3", px * b.out_channels)
-                    req("qkv", px * 3 * b.out_channels)
+                    req("qkv_f32" if self._f32_attention(b) else "qkv", px * 3 * b.out_channels)
                     req("att", px * b.out_channels)
+                    if self._f32_attention(b):
+                        req("att_lo", px * b.out_channels)
         R = m.img_resolution
         last = list(m.dec.values())
         c_last = [b for b in last if isinstance(b, _Block)][-1].out_channels
         req("h0", n * R * R * c_last)
-        f32_roles = ("h1", "mid")
+        f32_roles = ("h1", "mid", "qkv_f32")
         self._scratch_buf: Dict[str, torch.Tensor] = {}
         for name, numel in need.items():
             dt = torch.float32 if name in f32_roles else torch.bfloat16
             self._scratch_buf[name] = self._new([numel], dt)
             if self.x3 and name in ("h0", "raw", "h2", "h3"):
                 self._scratch_buf[name + "_lo"] = self._new([numel], dt)
+
+    def _f32_attention(self, b: "_Block") -> bool:
+        """fp32 CUDA-core attention for this block: the split-precision path, unless switched off or the head width has
+        no fg_attention_f32 instance (then the bf16 tensor-core kernel runs, ~1e-3 instead of ~1e-5)"""
+        return bool(self.attn_f32 and b.num_heads and b.out_channels // b.num_heads in _F32_ATTENTION_WIDTHS)
 
     def _scratch(self, name: str, shape) -> torch.Tensor:
         numel = int(np.prod(shape))
@@ -658,17 +671,26 @@ class _Plan:
         h3 = self._scratch("h3", [n, ho, wo, cout])
         h3_lo = self._scratch("h3_lo", [n, ho, wo, cout]) if self.x3 else None
         self.gn(mid, b.norm2, pk[key + ".norm2"], h3, silu=False, y_lo=h3_lo, stats=st2["stats"] if st2 else None)
-        qkv = self._scratch("qkv", [n, ho, wo, 3 * cout])
+        f32_attn = self._f32_attention(b)
+        qkv = self._scratch("qkv_f32" if f32_attn else "qkv", [n, ho, wo, 3 * cout])
         wq = pk[key + ".qkv"]
         self.conv(self.segs3(h3, h3_lo, cout, wq["hi"], wq.get("lo"), cout, 1), n, ho, wo, 3 * cout, qkv, 3 * cout,
                   bias=wq["bias"])
         att = self._scratch("att", [n, ho, wo, cout])
-        self._launch(L.lib().fg_attention, qkv.data_ptr(), 3 * cout, n, ho * wo, b.num_heads, cout // b.num_heads,
-                     att.data_ptr(), cout, flops=4.0 * n * (ho * wo) ** 2 * cout)
         wp = pk[key + ".proj"]
-        segs = [ops.Seg(att, cout, wp["hi"], cout, 1)]
-        if self.x3:
-            segs.append(ops.Seg(att, cout, wp["lo"], cout, 1, alg=False))
+        if f32_attn:
+            # fp32 qkv (the three-segment GEMM above wrote it unrounded) -> fp32 softmax(q.k) v -> bf16 hi + lo
+            att_lo = self._scratch("att_lo", [n, ho, wo, cout])
+            self._launch(L.lib().fg_attention_f32, qkv.data_ptr(), 3 * cout, n, ho * wo, b.num_heads,
+                         cout // b.num_heads, att.data_ptr(), att_lo.data_ptr(), cout,
+                         flops=4.0 * n * (ho * wo) ** 2 * cout)
+            segs = self.segs3(att, att_lo, cout, wp["hi"], wp["lo"], cout, 1)
+        else:
+            self._launch(L.lib().fg_attention, qkv.data_ptr(), 3 * cout, n, ho * wo, b.num_heads,
+                         cout // b.num_heads, att.data_ptr(), cout, flops=4.0 * n * (ho * wo) ** 2 * cout)
+            segs = [ops.Seg(att, cout, wp["hi"], cout, 1)]
+            if self.x3:
+                segs.append(ops.Seg(att, cout, wp["lo"], cout, 1, alg=False))
         self.conv(segs, n, ho, wo, cout, dst.t, dst.ld, bias=wp["bias"], res=mid.t, res_ld=mid.ld,
                   res_mode=L.FG_RES_SAME, out_scale=float(b.skip_scale), **(out_stats or {}))
 
@@ -723,6 +745,9 @@ class EDMPrecond(FastGenNetwork):
         self.sigma_data, self.sigma_shift, self.drop_precond = sigma_data, sigma_shift, drop_precond
         self.compute = compute
         self.fuse_gn_stats = True   # GroupNorm statistics accumulated by the conv that writes the tensor
+        # attention of the "bf16x3" path: "bf16" = the tensor-core kernel (q, k, v, softmax weights rounded to bf16:
+        # ~1e-3 of the fp32 reference), "f32" = fg_attention_f32 (CUDA cores; profiles/x3_emulation.py predicts ~1e-5)
+        self.x3_attention = _X3_ATTENTION_DEFAULT
         self.model = _UNet(model_type, img_resolution=img_resolution, in_channels=img_channels,
                            out_channels=img_channels, label_dim=label_dim, **model_kwargs)
         self._packed: Optional[Dict[str, Any]] = None
@@ -750,6 +775,14 @@ class EDMPrecond(FastGenNetwork):
         if compute != self.compute:
             self.compute = compute
             self._invalidate()
+
+    def set_x3_attention(self, mode: str) -> None:
+        """attention of the "bf16x3" path: "f32" (fg_attention_f32, default) or "bf16" (the tensor-core kernel)"""
+        if mode not in ("f32", "bf16"):
+            raise ValueError(f"x3_attention must be 'f32' or 'bf16', got {mode}")
+        if mode != self.x3_attention:
+            self.x3_attention = mode
+            self._plans = {}
 
     @torch.no_grad()
     def repack(self) -> None:

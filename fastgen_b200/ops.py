@@ -130,6 +130,16 @@ def attention(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d
             "fg_attention")
 
 
+def attention_f32(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d: int,
+                  out_hi: torch.Tensor, out_lo: Optional[torch.Tensor], out_ld: int) -> None:
+    """fp32 softmax(q.k / sqrt(d)) v of a packed fp32 qkv tensor, written as a bf16 hi (+ lo) pair."""
+    _need_cuda(qkv, out_hi, out_lo)
+    if qkv.dtype != torch.float32 or out_hi.dtype != torch.bfloat16 or (out_lo is not None and out_lo.dtype != torch.bfloat16):
+        raise ValueError("attention_f32: qkv must be float32, the outputs bfloat16")
+    L.check(L.lib().fg_attention_f32(qkv.data_ptr(), qkv_ld, n, tokens, heads, d, out_hi.data_ptr(), _ptr(out_lo), out_ld,
+                                     _stream()), "fg_attention_f32")
+
+
 def edm_input(x: torch.Tensor, c_in: Optional[torch.Tensor], xin: torch.Tensor, c_pad: int,
               xin_lo: Optional[torch.Tensor] = None) -> None:
     _need_cuda(x, c_in, xin, xin_lo)

@@ -142,6 +142,14 @@ int fg_cast_resample(const void* x, int32_t x_dtype, int64_t x_ld, int32_t n, in
 int fg_attention(const void* qkv /* bf16 */, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
                  void* out /* bf16 [N,T,heads*d] */, int64_t out_ld, fg_stream_t stream);
 
+/* The same attention evaluated entirely in fp32 on the CUDA cores (no bf16 rounding of q, k, v, the softmax weights or
+ * the output), for the split-precision "fp32 path" of the EDM networks: the reference's AttentionOp is fp32 whatever the
+ * activation dtype (fastgen/networks/EDM/network.py:160-168).  qkv is fp32 [N, T, 3*heads*d] (q|k|v, head, d), rows
+ * 16-byte aligned; the output is the bf16 pair out_hi + out_lo (~16 mantissa bits; out_lo may be NULL), the operand
+ * format of a three-segment fg_conv_gemm projection.  d in {64, 128, 192, 256}. */
+int fg_attention_f32(const float* qkv, int64_t qkv_ld, int32_t n, int32_t tokens, int32_t heads, int32_t d,
+                     void* out_hi /* bf16 [N,T,heads*d] */, void* out_lo, int64_t out_ld, fg_stream_t stream);
+
 /* General flash attention (bf16 operands, fp32 softmax): out[b, t, h, :] = softmax(q.k^T * scale) v.
  * q / k / v are separate strided views [batch][tokens][heads*d] (row stride *_ld, batch stride *_bs, in elements);
  * the keys are the concatenation of up to two segments -- KV-cache prefix then current chunk -- which replaces the

@@ -19,12 +19,16 @@ IN64 = dict(img_resolution=64, img_channels=3, label_dim=1000, sigma_shift=0.0, 
 def _cfgs():
     from oracle.make_golden import CONFIGS
 
-    return [("cifar", CIFAR, "bf16", 0), ("in64", IN64, "bf16", 0), ("in64_x3", IN64, "bf16x3", 0),
-            ("song_tiny", CONFIGS["song_tiny"], "bf16", None), ("dhariwal_tiny", CONFIGS["dhariwal_tiny"], "bf16x3", None)]
+    return [("cifar", CIFAR, "bf16", 0, "bf16"), ("in64", IN64, "bf16", 0, "bf16"), ("in64_x3", IN64, "bf16x3", 0, "bf16"),
+            ("song_tiny", CONFIGS["song_tiny"], "bf16", None, "bf16"),
+            ("dhariwal_tiny", CONFIGS["dhariwal_tiny"], "bf16x3", None, "bf16"),
+            # fp32 CUDA-core attention on the split-precision path: head widths 256 (CIFAR), 64 (IN-64, tiny)
+            ("cifar_x3_f32attn", CIFAR, "bf16x3", 0, "f32"), ("in64_x3_f32attn", IN64, "bf16x3", 0, "f32"),
+            ("dhariwal_tiny_x3_f32attn", CONFIGS["dhariwal_tiny"], "bf16x3", None, "f32")]
 
 
-@pytest.mark.parametrize("name,cfg,compute,max_stats_passes", _cfgs(), ids=[c[0] for c in _cfgs()])
-def test_edm_launch_list_arguments_validate_on_the_host(monkeypatch, name, cfg, compute, max_stats_passes):
+@pytest.mark.parametrize("name,cfg,compute,max_stats_passes,x3_attention", _cfgs(), ids=[c[0] for c in _cfgs()])
+def test_edm_launch_list_arguments_validate_on_the_host(monkeypatch, name, cfg, compute, max_stats_passes, x3_attention):
     from fastgen_b200 import _lib as L
     from fastgen_b200 import edm as E
     from fastgen_b200 import ops
@@ -33,8 +37,13 @@ def test_edm_launch_list_arguments_validate_on_the_host(monkeypatch, name, cfg, 
     monkeypatch.setattr(ops, "_need_cuda", lambda *a, **k: None)
     net = E.EDMPrecond(**cfg).eval()
     net.set_compute(compute)
+    net.set_x3_attention(x3_attention)
     plan = net._plan(3)
     counts = collections.Counter(fn.__name__ for fn, _ in plan.steps)
+    n_attn = sum(1 for md in (net.model.enc, net.model.dec) for b in md.values() if getattr(b, "num_heads", 0))
+    f32 = compute == "bf16x3" and x3_attention == "f32"
+    assert counts["fg_attention_f32" if f32 else "fg_attention"] == n_attn > 0
+    assert counts["fg_attention" if f32 else "fg_attention_f32"] == 0
     invalid, ok = [], 0
     for fn, args in plan.steps:
         st = fn(*args, None)

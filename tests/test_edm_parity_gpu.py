@@ -14,7 +14,10 @@ from oracle import sampler_oracle as SO
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-TOL = {"bf16": 1e-2, "bf16x3": 2e-3}  # TODO(x3 attention): 1e-4 once attention is split-precision too
+# bf16x3: convolutions with three bf16 products + fp32 CUDA-core attention (fg_attention_f32).  Measured on B200: forward
+# 1.0e-5 / 1.4e-5 on the two tiny networks (gpurun_out/x3_f32_attention.txt, profiles/x3_f32_attention_r01.md); the CPU
+# emulation of the rounding points predicts <= 1.6e-5 for every quantity asserted below (profiles/x3_emulation.py --golden)
+TOL = {"bf16": 1e-2, "bf16x3": 1e-4}
 
 
 def _load(name):
