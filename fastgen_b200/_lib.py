@@ -22,6 +22,7 @@ SYMBOLS = (
     "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_flash_attn",
     "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
+    "fg_peer_put", "fg_peer_wait",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
 )
 
@@ -79,6 +80,18 @@ class FlashAttnParams(C.Structure):
         ("scale", C.c_float), ("mask_first", C.c_int32), ("mask_chunk", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+FG_MAX_PEERS = 8
+
+
+class PeerPutParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p * FG_MAX_PEERS), ("peers", C.c_int32), ("rank", C.c_int32),
+        ("n", C.c_int32 * 4), ("src_strides", C.c_int64 * 4), ("dst_strides", C.c_int64 * 4),
+        ("src_peer_stride", C.c_int64), ("dst_offset", C.c_int64), ("item_bytes", C.c_int32),
+        ("flags", C.c_void_p * FG_MAX_PEERS), ("state", C.c_void_p),
     ]
 
 
@@ -145,6 +158,8 @@ def lib() -> C.CDLL:
     l.fg_geglu.argtypes = [vp, i64, i32, i32, vp, i64, vp]
     l.fg_cast_resample.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_strided_copy.argtypes = [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32, vp]
+    l.fg_peer_put.argtypes = [C.POINTER(PeerPutParams), vp]
+    l.fg_peer_wait.argtypes = [vp, i32, vp, i64, vp]
     l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     l.fg_edm_step.argtypes = [C.POINTER(EdmStepParams), vp]
     l.fg_axpby.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
@@ -154,7 +169,8 @@ def lib() -> C.CDLL:
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_edm_input", "fg_edm_step",
                  "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
-                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero", "fg_geglu", "fg_cast_resample"):
+                 "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero", "fg_geglu", "fg_cast_resample",
+                 "fg_peer_put", "fg_peer_wait"):
         getattr(l, name).restype = C.c_int
     _lib = l
     return l

@@ -1,0 +1,160 @@
+// Ulysses all-to-all as ONE pass over the data: the pack permutation and the exchange are the same kernel, which stores
+// this rank's slices straight into the peers' buffers over NVLink (peer-mapped / symmetric memory), then raises a flag on
+// every peer; a one-CTA wait kernel, stream-ordered before the consumer, spins on the local flags.  No NCCL call, no
+// host round trip, no staging buffers (the NCCL path needs pack -> send buffer -> all_to_all -> recv buffer -> unpack),
+// and nothing in it changes from call to call, so a launch list containing it can be replayed or graph-captured.
+//
+// Replaces the sequence-parallel exchange around the self-attention of the Wan blocks (the reference reaches it through
+// diffusers' context-parallel attention dispatch / torch all_to_all_single; call sites fastgen/networks/Wan/network.py:
+// 106-153, network_causal.py:199-464).
+//
+// Protocol (per channel = one direction of the exchange; every rank runs the same sequence of put / wait pairs):
+//   put : CTA (x, dst) copies 16-byte vectors of the 4-D item set of destination `dst` to dst_base[dst] + dst_offset;
+//         every thread fences at system scope, the CTA counts itself done; the last CTA of the launch advances the local
+//         put epoch e and writes e with release.sys to flags[dst][rank] of every peer (its own included).
+//   wait: advances the local wait epoch e' (equal to the peers' put epoch, all ranks being in lockstep) and spins with
+//         ld.acquire.sys until every local flag >= e'.  A timeout (no peer progress) sets state[3] and returns instead of
+//         hanging the GPU; the host reads state[3] after synchronising and raises.
+// Epochs only grow, so flags are never reset and a fast peer that is one put ahead is harmless (>= comparison).
+// Write-after-read safety of the destination buffers comes from the two channels alternating: a peer can only issue
+// its put of exchange k+1 after its wait of exchange k on the other channel, i.e. after this rank finished the kernel
+// that consumed exchange k-1's data.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fg {
+
+constexpr int kPeerThreads = 256;
+
+struct PeerPutK {
+  const uint4* src;
+  uint4* dst[FG_MAX_PEERS];
+  unsigned long long* flags[FG_MAX_PEERS];
+  unsigned long long* state;  // [0] put epoch, [1] CTA counter, [2] wait epoch, [3] timeout flag
+  int n[4];
+  int64_t ss[4], ds[4];       // strides in 16-byte units
+  int64_t src_peer_stride;    // 16-byte units
+  int vec;                    // 16-byte vectors per item
+  int peers, rank;
+  unsigned total_ctas;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k) {
+  const int dst = blockIdx.y;
+  const uint4* __restrict__ src = k.src + dst * k.src_peer_stride;
+  uint4* __restrict__ out = k.dst[dst];
+  const int64_t total = static_cast<int64_t>(k.n[0]) * k.n[1] * k.n[2] * k.n[3] * k.vec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kPeerThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kPeerThreads) {
+    const int v = static_cast<int>(i % k.vec);
+    int64_t item = i / k.vec;
+    const int i3 = static_cast<int>(item % k.n[3]);
+    item /= k.n[3];
+    const int i2 = static_cast<int>(item % k.n[2]);
+    item /= k.n[2];
+    const int i1 = static_cast<int>(item % k.n[1]);
+    const int i0 = static_cast<int>(item / k.n[1]);
+    out[i0 * k.ds[0] + i1 * k.ds[1] + i2 * k.ds[2] + i3 * k.ds[3] + v] =
+        __ldg(src + i0 * k.ss[0] + i1 * k.ss[1] + i2 * k.ss[2] + i3 * k.ss[3] + v);
+  }
+  __threadfence_system();  // this thread's peer stores are ordered before the counter / flag writes below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(k.state + 1), 1u);
+    if (done == k.total_ctas - 1) {  // every other CTA fenced before it counted itself
+      __threadfence_system();
+      *reinterpret_cast<unsigned*>(k.state + 1) = 0u;
+      const unsigned long long e = k.state[0] + 1ull;
+      k.state[0] = e;
+      for (int p = 0; p < k.peers; ++p) st_release_sys(k.flags[p] + k.rank, e);
+    }
+  }
+}
+
+__global__ void peer_wait_kernel(const unsigned long long* __restrict__ flags, int peers, unsigned long long* state,
+                                 long long timeout_ns) {
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) {
+    epoch = state[2] + 1ull;
+    state[2] = epoch;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < peers) {
+    const unsigned long long e = epoch;
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < e) {
+      __nanosleep(64);
+      if (timeout_ns > 0 && static_cast<long long>(globaltimer_ns() - t0) > timeout_ns) {
+        state[3] = 1ull;  // the host raises on it after the next synchronisation; the consumer reads stale data, nothing hangs
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+}  // namespace fg
+
+extern "C" int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream_) {
+  using namespace fg;
+  set_error("");
+  FG_CHECK_ARG(p && p->src && p->state, "peer_put: null pointer");
+  FG_CHECK_ARG(p->peers >= 1 && p->peers <= FG_MAX_PEERS && p->rank >= 0 && p->rank < p->peers,
+               "peer_put: peers %d (max %d), rank %d", p->peers, FG_MAX_PEERS, p->rank);
+  FG_CHECK_ARG(p->item_bytes > 0 && p->item_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p->src) & 15) == 0 &&
+                   p->src_peer_stride % 16 == 0 && p->dst_offset % 16 == 0 && p->dst_offset >= 0,
+               "peer_put: items, offsets and the source must be 16-byte multiples / aligned");
+  PeerPutK k;
+  k.src = static_cast<const uint4*>(p->src);
+  k.state = reinterpret_cast<unsigned long long*>(p->state);
+  k.vec = p->item_bytes / 16, k.peers = p->peers, k.rank = p->rank;
+  k.src_peer_stride = p->src_peer_stride / 16;
+  int64_t items = 1;
+  for (int i = 0; i < 4; ++i) {
+    FG_CHECK_ARG(p->n[i] > 0 && p->src_strides[i] % 16 == 0 && p->dst_strides[i] % 16 == 0,
+                 "peer_put: extents must be positive, strides (bytes) multiples of 16");
+    k.n[i] = p->n[i], k.ss[i] = p->src_strides[i] / 16, k.ds[i] = p->dst_strides[i] / 16;
+    items *= p->n[i];
+  }
+  for (int q = 0; q < FG_MAX_PEERS; ++q) {
+    k.dst[q] = nullptr, k.flags[q] = nullptr;
+    if (q >= p->peers) continue;
+    FG_CHECK_ARG(p->dst[q] && p->flags[q] && (reinterpret_cast<uintptr_t>(p->dst[q]) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(p->flags[q]) & 7) == 0,
+                 "peer_put: destination / flag pointer of peer %d missing or misaligned", q);
+    k.dst[q] = reinterpret_cast<uint4*>(static_cast<char*>(p->dst[q]) + p->dst_offset);
+    k.flags[q] = reinterpret_cast<unsigned long long*>(p->flags[q]);
+  }
+  const int64_t vecs = items * k.vec;
+  // enough CTAs per destination to fill the machine with all destinations in flight, 4 vectors per thread at least
+  int64_t bx = (vecs + 4ll * kPeerThreads - 1) / (4ll * kPeerThreads);
+  const int64_t cap = (148ll * 8 + p->peers - 1) / p->peers;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  k.total_ctas = static_cast<unsigned>(bx * p->peers);
+  peer_put_kernel<<<dim3(static_cast<unsigned>(bx), p->peers), kPeerThreads, 0, static_cast<cudaStream_t>(stream_)>>>(k);
+  FG_CHECK_LAUNCH("peer_put");
+  return FG_OK;
+}
+
+extern "C" int fg_peer_wait(const uint64_t* flags, int32_t peers, uint64_t* state, int64_t timeout_ns,
+                            fg_stream_t stream_) {
+  using namespace fg;
+  set_error("");
+  FG_CHECK_ARG(flags && state && peers >= 1 && peers <= FG_MAX_PEERS, "peer_wait: bad arguments (peers %d)", peers);
+  FG_CHECK_ARG((reinterpret_cast<uintptr_t>(flags) & 7) == 0 && (reinterpret_cast<uintptr_t>(state) & 7) == 0,
+               "peer_wait: flags / state must be 8-byte aligned");
+  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const unsigned long long*>(flags), peers, reinterpret_cast<unsigned long long*>(state), timeout_ns);
+  FG_CHECK_LAUNCH("peer_wait");
+  return FG_OK;
+}

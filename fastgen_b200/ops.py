@@ -368,6 +368,30 @@ def strided_copy(src, dst, n, src_strides, dst_strides, item_elems) -> None:
     L.check(L.lib().fg_strided_copy(*args, _stream()), "fg_strided_copy")
 
 
+def peer_put_params(src: torch.Tensor, desc, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], rank: int,
+                    state: torch.Tensor) -> "L.PeerPutParams":
+    """``fg_peer_put`` parameters from a ``parallel.peer_put_*_desc`` descriptor (strides / offsets in elements of
+    ``src``'s dtype).  ``dst_ptrs[q]`` / ``flag_ptrs[q]``: device-mapped addresses of rank q's destination buffer and of
+    its flag array for this channel (symmetric memory); ``state``: this channel's 4 local int64 words."""
+    _need_cuda(src, state)
+    P = len(dst_ptrs)
+    if not 1 <= P <= L.FG_MAX_PEERS or len(flag_ptrs) != P or not 0 <= rank < P:
+        raise ValueError(f"peer_put: {P} peers (max {L.FG_MAX_PEERS}), rank {rank}")
+    if state.dtype != torch.int64 or state.numel() < 4 or not state.is_contiguous():
+        raise ValueError("peer_put: state must be 4 contiguous int64 words")
+    es = src.element_size()
+    p = L.PeerPutParams()
+    p.src = src.data_ptr()
+    p.peers, p.rank = P, rank
+    for q in range(P):
+        p.dst[q], p.flags[q] = dst_ptrs[q], flag_ptrs[q]
+    for i in range(4):
+        p.n[i], p.src_strides[i], p.dst_strides[i] = desc["n"][i], desc["ss"][i] * es, desc["ds"][i] * es
+    p.src_peer_stride, p.dst_offset, p.item_bytes = desc["src_peer_stride"] * es, desc["dst_off"] * es, desc["item"] * es
+    p.state = state.data_ptr()
+    return p
+
+
 def geglu(h: torch.Tensor, rows: int, inner: int, y: torch.Tensor) -> None:
     """y[r, j] = h[r, j] * gelu(h[r, inner + j]) (erf GELU, rounded to bf16 before the product like diffusers' GEGLU)."""
     _need_cuda(h, y)

@@ -50,6 +50,32 @@ def unshard_desc(P: int, B: int, F: int, fs: int, kout: int) -> Dict[str, Any]:
                 ds=[fs_l * kout, fs * kout, kout, 0], item=kout, src_off=0, dst_off=0)
 
 
+def peer_put_qkv_desc(B: int, n: int, P: int, rank: int, D: int, Dl: int) -> Dict[str, Any]:
+    """pack + exchange in one pass (``fg_peer_put``): this rank's qkv[b][r][j][dst][Dl] -> rank dst's
+    full[b][rank*n/P + r][j][Dl].  Same result as a2a_pack_desc + all_to_all_single on every destination."""
+    n_l = n // P
+    return dict(n=[B, n_l, 3, 1], ss=[n_l * 3 * D, 3 * D, D, 0], ds=[n * 3 * Dl, 3 * Dl, Dl, 0], item=Dl,
+                src_peer_stride=Dl, dst_off=rank * n_l * 3 * Dl)
+
+
+def peer_put_out_desc(B: int, n: int, P: int, rank: int, D: int, Dl: int) -> Dict[str, Any]:
+    """exchange + unpack in one pass: this rank's att_full[b][dst*n/P + r][Dl] (its heads, all tokens) -> rank dst's
+    att[b][r][rank*Dl : (rank+1)*Dl].  Same result as all_to_all_single + a2a_unpack_desc on every destination."""
+    n_l = n // P
+    return dict(n=[B, n_l, 1, 1], ss=[n * Dl, Dl, 0, 0], ds=[n_l * D, D, 0, 0], item=Dl, src_peer_stride=n_l * Dl,
+                dst_off=rank * Dl)
+
+
+def apply_peer_put_cpu(desc: Dict[str, Any], src: torch.Tensor, dsts: Sequence[torch.Tensor]) -> None:
+    """Reference execution of a peer-put descriptor: ``dsts[q]`` is rank q's destination buffer."""
+    n, item = desc["n"], desc["item"]
+    for q, dst in enumerate(dsts):
+        assert src.is_contiguous() and dst.is_contiguous()
+        sv = torch.as_strided(src, n + [item], desc["ss"] + [1], storage_offset=src.storage_offset() + q * desc["src_peer_stride"])
+        dv = torch.as_strided(dst, n + [item], desc["ds"] + [1], storage_offset=dst.storage_offset() + desc["dst_off"])
+        dv.copy_(sv)
+
+
 def apply_desc_cpu(desc: Dict[str, Any], src: torch.Tensor, dst: torch.Tensor) -> None:
     """Reference execution of a descriptor with torch.as_strided (CPU tests of the layout; the product path runs the
     same descriptor through ``fg_strided_copy``)."""

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Any, Dict, List, Mapping, Optional, Set, Tuple
 
 import torch
@@ -243,6 +244,12 @@ class _WanBase:
         self.use_cuda_graphs = True
         self.graph_launches = 0                        # kernel launches replayed through graphs (bench bookkeeping)
         self.sp_group = None                           # torch.distributed group for Ulysses sequence parallelism
+        # how the sequence-parallel exchange around the self-attention runs: "nccl" = pack kernel + all_to_all_single +
+        # unpack kernel (measured, profiles/wan*_scaling_r01.md); "peer" = fg_peer_put / fg_peer_wait over symmetric
+        # memory: pack and exchange are one kernel storing into the peers' buffers over NVLink, no NCCL call in the
+        # layer loop (opt-in: written after the round's GPU budget ended, layout checked on CPU only)
+        self.sp_exchange = os.environ.get("FASTGEN_B200_SP_EXCHANGE", "nccl")
+        self.peer_timeout_s = 20.0
 
     # ---- reference helpers ------------------------------------------------------------------------------
     @classmethod
@@ -435,7 +442,13 @@ class _WanBase:
         if self.transformer.r_embedder is not None:
             ws.update(emb_r=z(groups, cfg["freq_dim"]), re1=z(groups, D), remb=z(groups, D), remb_act=z(groups, D),
                       rtproj=z(groups, 6 * D, dt=f32))
-        if P > 1:
+        if P > 1 and self.sp_exchange == "peer":
+            # one-pass exchange: qkv_full and att are the DESTINATIONS the peers store into (symmetric memory)
+            ws.update(hs_full=z(rows, D), att_full=z(B, n, Dl), tok_out_l=z(lrows, kout), tok_out_g=z(P, lrows, kout))
+            ws.update(self._peer_buffers(B, n, D, Dl, P, dev))
+        elif P > 1:
+            if self.sp_exchange != "nccl":
+                raise ValueError(f"sp_exchange must be 'nccl' or 'peer', got {self.sp_exchange}")
             # Ulysses exchange buffers (per sample b: [P][n/P][3][H/P*d] for q,k,v and [P][n/P][H/P*d] for the output)
             ws.update(hs_full=z(rows, D), a2a_s=z(B, P, n // P, 3 * Dl), qkv_full=z(B, n, 3 * Dl), att_full=z(B, n, Dl),
                       a2a_r=z(B, P, n // P, Dl), tok_out_l=z(lrows, kout), tok_out_g=z(P, lrows, kout))
@@ -445,6 +458,40 @@ class _WanBase:
         ws["attn_ws"] = torch.empty(max(ops.flash_attn_workspace_size(probe), 16), device=dev, dtype=torch.uint8)
         self._ws[key] = ws
         return ws
+
+    def _peer_buffers(self, B: int, n: int, D: int, Dl: int, P: int, dev) -> Dict[str, Any]:
+        """Symmetric-memory destinations of the one-pass exchange: [ qkv_full [B, n, 3 Dl] | att [B n/P, D] | flags of the two
+        channels ], the same layout on every rank, so a peer's region is its mapped base pointer + the same offset."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        al = lambda v: (v + 255) // 256 * 256  # noqa: E731
+        full_b, att_b = B * n * 3 * Dl * 2, B * (n // P) * D * 2
+        off_att = al(full_b)
+        off_flags = al(off_att + att_b)
+        total = off_flags + al(2 * L.FG_MAX_PEERS * 8)
+        buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.sp_group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.sp_group)      # every rank's flags are zero before anybody's first put
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != P or ptrs[self._sp_rank()] != buf.data_ptr():
+            raise L.FastGenB200Error("symmetric memory rendezvous returned an unexpected pointer table")
+        bf = torch.bfloat16
+        return dict(
+            qkv_full=buf[:full_b].view(bf).view(B, n, 3 * Dl), att=buf[off_att:off_att + att_b].view(bf).view(B * (n // P), D),
+            peer=dict(buf=buf, hdl=hdl, full_ptrs=ptrs, att_ptrs=[p + off_att for p in ptrs],
+                      flag_ptrs=[[p + off_flags + c * L.FG_MAX_PEERS * 8 for p in ptrs] for c in range(2)],
+                      state=torch.zeros(2, 4, dtype=torch.int64, device=dev)))
+
+    def check_peer_exchange(self) -> None:
+        """Synchronise and raise if a wait of the one-pass exchange ever timed out (a peer stopped making progress)."""
+        for ws in self._ws.values():
+            px = ws.get("peer")
+            if px is not None and bool(px["state"][:, 3].any().item()):
+                raise L.FastGenB200Error(f"sequence-parallel peer exchange timed out after {self.peer_timeout_s} s: a rank "
+                                         "of the group did not reach the matching put")
 
     def _sp_size(self) -> int:
         if self.sp_group is None:
@@ -649,6 +696,32 @@ class _WanBase:
                 p = ops.flash_attn_params(qkv, 3 * D, n * 3 * D, segs, B, H, d, n, att, D, n * D, workspace=ws["attn_ws"], **mk)
                 plan.keep.append(p)
                 plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * D)
+            elif self.sp_exchange == "peer":
+                px, full, attf = ws["peer"], ws["qkv_full"], ws["att_full"]
+                tmo = int(self.peer_timeout_s * 1e9)
+                # qkv[b][r][j][dst][Dl] -> rank dst's full[b][rank*n_l + r][j][Dl], then wait for everybody's slices
+                p = ops.peer_put_params(qkv, PL.peer_put_qkv_desc(B, n, P, rank, D, Dl), px["full_ptrs"], px["flag_ptrs"][0],
+                                        rank, px["state"][0])
+                plan.keep.append(p)
+                plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_qkv")
+                plan.add(lib.fg_peer_wait, px["flag_ptrs"][0][rank], P, px["state"][0].data_ptr(), tmo, desc="peer_wait_qkv")
+                if kv is not None and store_kv:
+                    self._copy(plan, full[:, :, Dl:], kv["k"][i][:, cache_start:], [B, n, 1, 1], [n * 3 * Dl, 3 * Dl, 0, 0],
+                               [cap * Dl, Dl, 0, 0], Dl, "k_append")
+                    self._copy(plan, full[:, :, 2 * Dl:], kv["v"][i][:, cache_start:], [B, n, 1, 1],
+                               [n * 3 * Dl, 3 * Dl, 0, 0], [cap * Dl, Dl, 0, 0], Dl, "v_append")
+                cur = (full[:, :, Dl:], full[:, :, 2 * Dl:], 3 * Dl, n * 3 * Dl, n)
+                segs = [(kv["k"][i], kv["v"][i], Dl, cap * Dl, cache_start), cur] if kv is not None and cache_start > 0 else [cur]
+                p = ops.flash_attn_params(full, 3 * Dl, n * 3 * Dl, segs, B, Hl, d, n, attf, Dl, n * Dl,
+                                          workspace=ws["attn_ws"])
+                plan.keep.append(p)
+                plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * Dl)
+                # att_full[b][dst*n_l + r][Dl] -> rank dst's att[b][r][rank*Dl ...]: exchange + unpack in one pass
+                p = ops.peer_put_params(attf, PL.peer_put_out_desc(B, n, P, rank, D, Dl), px["att_ptrs"], px["flag_ptrs"][1],
+                                        rank, px["state"][1])
+                plan.keep.append(p)
+                plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_out")
+                plan.add(lib.fg_peer_wait, px["flag_ptrs"][1][rank], P, px["state"][1].data_ptr(), tmo, desc="peer_wait_out")
             else:
                 send, full, attf, recv = ws["a2a_s"], ws["qkv_full"], ws["att_full"], ws["a2a_r"]
                 # pack: qkv[b][r][j][dst][Dl] -> send[b][dst][r][j][Dl]   (one launch per sample keeps it 4-D)

@@ -240,6 +240,37 @@ int fg_unpatchify(const void* y, int64_t y_ld, int32_t b, int32_t c, int32_t f, 
  * unpack permutations around the Ulysses all-to-all (tokens <-> heads) and the head-sharded KV-cache append. */
 int fg_strided_copy(const void* src, void* dst, const int32_t* n, const int64_t* src_strides,
                     const int64_t* dst_strides, int32_t item_bytes, fg_stream_t stream);
+/* ------------------------------------------------------------------------------------------------------
+ * Sequence-parallel (Ulysses) exchange over NVLink peer memory: pack + all-to-all as one kernel, no NCCL.
+ * Replaces the all_to_all_single pair (plus its pack / unpack copies) around the self-attention of the Wan blocks under
+ * sequence parallelism (fastgen/networks/Wan/network.py:106-153, network_causal.py:199-464).
+ * fg_peer_put copies, for every destination q, the 4-D item set at src + q * src_peer_stride into dst[q] + dst_offset
+ * (dst[q] / flags[q] are the device-mapped addresses of rank q's buffer / flag array: CUDA IPC or symmetric memory; the
+ * own rank is a destination like any other), then writes its put epoch to flags[q][rank] of every rank.  fg_peer_wait
+ * spins (on the device, stream-ordered) until all `peers` local flags reached the local wait epoch.  `state` is 4
+ * zero-initialised uint64 of local device memory per channel {put epoch, CTA counter, wait epoch, timeout flag}; all
+ * ranks issue the same put / wait sequence per channel, which keeps the epochs in lockstep without host involvement.
+ * ---------------------------------------------------------------------------------------------------- */
+#define FG_MAX_PEERS 8
+
+typedef struct {
+  const void* src;
+  void* dst[FG_MAX_PEERS];
+  int32_t peers, rank;
+  int32_t n[4];             /* extents of the item set of ONE destination */
+  int64_t src_strides[4];   /* bytes, multiples of 16 */
+  int64_t dst_strides[4];
+  int64_t src_peer_stride;  /* bytes between the item sets of consecutive destinations */
+  int64_t dst_offset;       /* bytes: where this rank's contribution starts in every destination buffer */
+  int32_t item_bytes;       /* multiple of 16 */
+  uint64_t* flags[FG_MAX_PEERS];
+  uint64_t* state;
+} fg_peer_put_params;
+
+int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream);
+/* timeout_ns > 0: give up after that long without the flags arriving and set state[3] = 1 (nothing hangs) */
+int fg_peer_wait(const uint64_t* flags, int32_t peers, uint64_t* state, int64_t timeout_ns, fg_stream_t stream);
+
 /* GEGLU feed-forward gate of the SDXL transformer blocks (diffusers GEGLU, used by UNet2DConditionModel which the
  * reference wraps at fastgen/networks/SDXL/network.py:210-230): y[r][j] = h[r][j] * gelu_erf(h[r][inner + j]), bf16. */
 int fg_geglu(const void* h, int64_t h_ld, int32_t rows, int32_t inner, void* y, int64_t y_ld, fg_stream_t stream);

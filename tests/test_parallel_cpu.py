@@ -86,3 +86,46 @@ def test_ulysses_layout_world_size_2():
         ret = mgr.dict()
         mp.spawn(_ulysses_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
         assert all(ret.get(r) for r in range(world))
+
+
+def test_peer_put_descriptors_equal_pack_all_to_all_unpack():
+    """the one-pass exchange (fg_peer_put: every rank stores its slices straight into the peers' buffers) must leave
+    exactly what pack -> all_to_all_single -> (attention) -> all_to_all_single -> unpack leaves; all P ranks are
+    simulated in one process, the all-to-all being the block transpose send[src][dst] -> recv[dst][src]"""
+    import pytest
+
+    for P in (2, 4, 8):
+        torch.manual_seed(P)
+        B, Fr, fs, H, d = 2, 3, 16, 8, 8
+        D = H * d
+        n, n_l, Dl = Fr * fs, Fr * fs // P, (H // P) * d
+        qkv = [torch.randn(B * n_l, 3 * D) for _ in range(P)]            # local rows x all heads, per rank
+        # NCCL path: pack, exchange, and for the way back exchange, unpack
+        send = [torch.zeros(B, P, n_l, 3 * Dl) for _ in range(P)]
+        for r in range(P):
+            for b in range(B):
+                PL.apply_desc_cpu(PL.a2a_pack_desc(n_l, P, D, Dl), qkv[r][b * n_l:(b + 1) * n_l], send[r][b])
+        full_ref = [torch.stack([torch.cat([send[src][b, dst] for src in range(P)], 0) for b in range(B)], 0)
+                    for dst in range(P)]                                   # [B, n, 3*Dl] per rank
+        # peer path, direction 1
+        full = [torch.full((B, n, 3 * Dl), float("nan")) for _ in range(P)]
+        for r in range(P):
+            PL.apply_peer_put_cpu(PL.peer_put_qkv_desc(B, n, P, r, D, Dl), qkv[r], full)
+        for r in range(P):
+            assert torch.equal(full[r], full_ref[r]), (P, r)
+        # direction 2: some per-rank attention output over (all tokens, local heads)
+        attf = [torch.randn(B, n, Dl) for _ in range(P)]
+        att_ref = []
+        for dst in range(P):
+            recv = torch.stack([torch.stack([attf[src][b, dst * n_l:(dst + 1) * n_l] for src in range(P)], 0)
+                                for b in range(B)], 0)                     # [B, P, n_l, Dl]
+            a = torch.zeros(B * n_l, D)
+            PL.apply_desc_cpu(PL.a2a_unpack_desc(B, P, n_l, D, Dl), recv.contiguous(), a)
+            att_ref.append(a)
+        att = [torch.full((B * n_l, D), float("nan")) for _ in range(P)]
+        for r in range(P):
+            PL.apply_peer_put_cpu(PL.peer_put_out_desc(B, n, P, r, D, Dl), attf[r], att)
+        for r in range(P):
+            assert torch.equal(att[r], att_ref[r]), (P, r)
+    with pytest.raises(AssertionError):
+        PL.apply_peer_put_cpu(PL.peer_put_out_desc(1, 8, 2, 0, 16, 8), torch.zeros(4, 8).t(), [torch.zeros(4, 16)] * 2)
