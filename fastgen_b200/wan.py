@@ -470,6 +470,13 @@ class _WanBase:
         off_att = al(full_b)
         off_flags = al(off_att + att_b)
         total = off_flags + al(2 * L.FG_MAX_PEERS * 8)
+        import warnings
+
+        enable = getattr(symm, "enable_symm_mem_for_group", None)
+        if enable is not None:       # registers the group's store with the allocator (a no-op where rendezvous does it)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                enable(self.sp_group.group_name)
         buf = symm.empty(total, dtype=torch.uint8, device=dev)
         buf.zero_()
         hdl = symm.rendezvous(buf, self.sp_group)
