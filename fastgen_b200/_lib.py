@@ -22,7 +22,7 @@ SYMBOLS = (
     "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_flash_attn",
     "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
-    "fg_peer_put", "fg_peer_wait",
+    "fg_peer_put", "fg_peer_wait", "fg_sampler_vec",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
 )
 
@@ -158,6 +158,8 @@ def lib() -> C.CDLL:
     l.fg_geglu.argtypes = [vp, i64, i32, i32, vp, i64, vp]
     l.fg_cast_resample.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_strided_copy.argtypes = [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32, vp]
+    l.fg_sampler_vec.argtypes = [C.c_int]
+    l.fg_sampler_vec.restype = C.c_int
     l.fg_peer_put.argtypes = [C.POINTER(PeerPutParams), vp]
     l.fg_peer_wait.argtypes = [vp, i32, vp, i64, vp]
     l.fg_edm_input.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]

@@ -8,12 +8,45 @@
 //     FMA contraction (EDM/network.py:803-805  `c_skip * x_t + c_out * out`);
 //   * everything the reference evaluates in float64 (noise_schedule.py:441-449, 559-574, 992-1004) is evaluated
 //     in float64 here with __dmul_rn/__dadd_rn/__ddiv_rn and rounded once to the tensor dtype.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
+#include "sampler_vec.cuh"
 
 namespace fg {
 
 constexpr int kEwThreads = 256;
+
+// vectorised bodies (sampler_vec.cuh; index arithmetic and alignment checked on the host by
+// tests/test_sampler_vec_host_cpu.py): 4 pixels x all channels per thread for the EDM step, 16 bytes per thread and
+// iteration for the fp64-coefficient helpers
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads) edm_step_vec_kernel(const vec::EdmStepV p) {
+  vec::edm_step_vec_body<T>(p, blockIdx.x * static_cast<int64_t>(kEwThreads) + threadIdx.x,
+                            static_cast<int64_t>(gridDim.x) * kEwThreads);
+}
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kEwThreads) coef_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t total,
+                                                              int64_t outer, int64_t mid, int64_t inner,
+                                                              const double* __restrict__ c0,
+                                                              const double* __restrict__ c1, T* __restrict__ out) {
+  vec::coef_vec_body<T, MODE>(a, b, total, outer, mid, inner, c0, c1, out,
+                              blockIdx.x * static_cast<int64_t>(kEwThreads) + threadIdx.x,
+                              static_cast<int64_t>(gridDim.x) * kEwThreads);
+}
+
+// The vector kernels are opt-in until they have run on hardware once (FASTGEN_B200_SAMPLER_VEC=1): they were written
+// after round 1's GPU budget ended.  The scalar kernels below are the measured, bit-exact-tested default.
+static int g_sampler_vec = -1;  // -1: not yet read from the environment
+static bool sampler_vec_enabled() {
+  if (g_sampler_vec < 0) {
+    const char* e = getenv("FASTGEN_B200_SAMPLER_VEC");
+    g_sampler_vec = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_sampler_vec != 0;
+}
+static bool aligned_to(const void* p, uintptr_t bytes) { return (reinterpret_cast<uintptr_t>(p) & (bytes - 1)) == 0; }
 
 template <typename T>
 struct Cast;
@@ -230,6 +263,12 @@ static int ew_grid(int64_t total) {
 
 }  // namespace fg
 
+extern "C" int fg_sampler_vec(int enable) {
+  const int prev = fg::sampler_vec_enabled() ? 1 : 0;
+  if (enable >= 0) fg::g_sampler_vec = enable ? 1 : 0;
+  return prev;
+}
+
 extern "C" int fg_edm_input(const void* x, int32_t x_dtype, int32_t n, int32_t c, int32_t hw, const double* c_in,
                             void* xin, void* xin_lo, int32_t c_pad, fg_stream_t stream_) {
   using namespace fg;
@@ -269,6 +308,22 @@ extern "C" int fg_edm_step(const fg_edm_step_params* p, fg_stream_t stream_) {
   k.n = p->n, k.c = p->c, k.hw = p->hw, k.c_skip = p->c_skip, k.c_out = p->c_out, k.ode = p->ode;
   k.alpha_cur = p->alpha_cur, k.sigma_cur = p->sigma_cur, k.alpha_next = p->alpha_next, k.sigma_next = p->sigma_next;
   k.x0 = p->x0, k.x_next = p->x_next;
+  if (p->x_dtype != FG_F32 && p->x_dtype != FG_BF16) FG_CHECK_ARG(false, "edm_step: unsupported dtype %d", p->x_dtype);
+  const uintptr_t xa = p->x_dtype == FG_F32 ? 16 : 8;  // four elements of the latent dtype
+  if (sampler_vec_enabled() && p->hw % 4 == 0 && p->c <= 4 && p->f_ld == 4 && aligned_to(p->f, 16) && aligned_to(p->x_t, xa) &&
+      aligned_to(p->x0, xa) && aligned_to(p->eps, xa) && aligned_to(p->x_next, xa)) {
+    vec::EdmStepV v;
+    v.f = k.f, v.x_t = k.x_t, v.eps = k.eps, v.n = k.n, v.c = k.c, v.hw = k.hw, v.c_skip = k.c_skip, v.c_out = k.c_out;
+    v.ode = k.ode, v.alpha_cur = k.alpha_cur, v.sigma_cur = k.sigma_cur, v.alpha_next = k.alpha_next;
+    v.sigma_next = k.sigma_next, v.x0 = k.x0, v.x_next = k.x_next;
+    const int vgrid = ew_grid(static_cast<int64_t>(p->n) * p->hw / 4);
+    if (p->x_dtype == FG_F32)
+      edm_step_vec_kernel<float><<<vgrid, kEwThreads, 0, stream>>>(v);
+    else
+      edm_step_vec_kernel<__nv_bfloat16><<<vgrid, kEwThreads, 0, stream>>>(v);
+    FG_CHECK_LAUNCH("edm_step");
+    return FG_OK;
+  }
   const int grid = ew_grid(static_cast<int64_t>(p->n) * p->hw);
   if (p->x_dtype == FG_F32)
     edm_step_kernel<float><<<grid, kEwThreads, 0, stream>>>(k);
@@ -291,6 +346,24 @@ static int launch_coef(const void* a, const void* b, int32_t dtype, int64_t tota
                (long long)mid, (long long)inner);
   if (MODE == 0) FG_CHECK_ARG((b == nullptr) || c1, "%s: b given without its coefficient", name);
   if (MODE == 1) FG_CHECK_ARG(b && c1, "%s: null pointer", name);
+  const int64_t esz = dtype == FG_F32 ? 4 : dtype == FG_BF16 ? 2 : 8;
+  if (sampler_vec_enabled() && (dtype == FG_F32 || dtype == FG_BF16 || dtype == FG_F64) && inner % (16 / esz) == 0 &&
+      aligned_to(a, 16) && aligned_to(b, 16) && aligned_to(out, 16)) {
+    const int vgrid = ew_grid(total / (16 / esz));
+    if (dtype == FG_F32)
+      coef_vec_kernel<float, MODE><<<vgrid, kEwThreads, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+                                                                     total, outer, mid, inner, c0, c1, static_cast<float*>(out));
+    else if (dtype == FG_BF16)
+      coef_vec_kernel<__nv_bfloat16, MODE><<<vgrid, kEwThreads, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), total, outer, mid, inner, c0, c1,
+          static_cast<__nv_bfloat16*>(out));
+    else
+      coef_vec_kernel<double, MODE><<<vgrid, kEwThreads, 0, stream>>>(static_cast<const double*>(a),
+                                                                      static_cast<const double*>(b), total, outer, mid,
+                                                                      inner, c0, c1, static_cast<double*>(out));
+    FG_CHECK_LAUNCH(name);
+    return FG_OK;
+  }
   const int grid = ew_grid(total);
   if (dtype == FG_F32)
     coef_kernel<float, MODE><<<grid, kEwThreads, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b),

@@ -130,6 +130,12 @@ def attention(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d
             "fg_attention")
 
 
+def sampler_vec(enable: Optional[bool] = None) -> bool:
+    """Select (True / False) or query (None) the vectorised forms of the sampler-step kernels; returns the previous
+    setting.  Opt-in (default off, or FASTGEN_B200_SAMPLER_VEC=1) until they have run on hardware: see ``fg_sampler_vec``."""
+    return bool(L.lib().fg_sampler_vec(-1 if enable is None else int(bool(enable))))
+
+
 def attention_f32(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d: int,
                   out_hi: torch.Tensor, out_lo: Optional[torch.Tensor], out_ld: int) -> None:
     """fp32 softmax(q.k / sqrt(d)) v of a packed fp32 qkv tensor, written as a bf16 hi (+ lo) pair."""

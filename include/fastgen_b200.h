@@ -322,6 +322,12 @@ int fg_axpby(const void* a, const void* b, int32_t dtype, int64_t total, int64_t
 int fg_sub_div(const void* a, const void* b, int32_t dtype, int64_t total, int64_t outer, int64_t mid, int64_t inner,
                const double* cb, const double* cd, void* out, fg_stream_t stream);
 
+/* Select the vectorised forms of fg_edm_step / fg_axpby / fg_sub_div (4 pixels x all channels, resp. 16 bytes, per thread
+ * and iteration; same arithmetic, bit-identical results) where shapes and alignment allow: enable = 1 / 0, or -1 to only
+ * query.  Returns the previous setting.  Default: the environment variable FASTGEN_B200_SAMPLER_VEC (unset = 0: opt-in
+ * until the vector forms have been run on hardware). */
+int fg_sampler_vec(int enable);
+
 /* cudaMemsetAsync(ptr, 0, bytes) as a plan step (statistics arenas) */
 int fg_zero(void* ptr, int64_t bytes, fg_stream_t stream);
 

@@ -117,3 +117,14 @@ x = torch.randn(16, 64, 64, 640, device=dev)
 yb = torch.empty(16, 128, 128, 640, device=dev, dtype=torch.bfloat16)
 report("cast_resample up2 SDXL b16 64x64x640 fp32 -> 128x128 bf16", 16 * 64 * 64 * 640 * (4 + 8),
        lambda: ops.cast_resample(x, 640, 16, 64, 64, 640, yb, 640, up2=True))
+# vectorised sampler-step kernels (opt-in until run on hardware; `--vec` measures them next to the scalar forms)
+import sys  # noqa: E402
+
+if "--vec" in sys.argv:
+    ops.sampler_vec(True)
+    step("[vec] IN-64 b256 [256,3,64,64] fp32", 256, 3, 64, 64, torch.float32)
+    step("[vec] [4096,3,64,64] fp32 (asymptote)", 4096, 3, 64, 64, torch.float32)
+    step("[vec] SDXL b16 [16,4,128,128] bf16", 16, 4, 128, 128, torch.bfloat16)
+    axpby("[vec] Wan 720p [1,16,21,90,160] bf16 (10 MB)", (1, 16, 21, 90, 160), torch.bfloat16)
+    axpby("[vec] [64,16,21,60,104] bf16 (asymptote)", (64, 16, 21, 60, 104), torch.bfloat16)
+    ops.sampler_vec(False)
