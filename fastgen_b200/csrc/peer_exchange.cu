@@ -21,23 +21,11 @@
 // that consumed exchange k-1's data.
 #include "common.cuh"
 #include "host_util.h"
+#include "peer_exchange_body.cuh"
 
 namespace fg {
 
 constexpr int kPeerThreads = 256;
-
-struct PeerPutK {
-  const uint4* src;
-  uint4* dst[FG_MAX_PEERS];
-  unsigned long long* flags[FG_MAX_PEERS];
-  unsigned long long* state;  // [0] put epoch, [1] CTA counter, [2] wait epoch, [3] timeout flag
-  int n[4];
-  int64_t ss[4], ds[4];       // strides in 16-byte units
-  int64_t src_peer_stride;    // 16-byte units
-  int vec;                    // 16-byte vectors per item
-  int peers, rank;
-  unsigned total_ctas;
-};
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -49,23 +37,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k) {
-  const int dst = blockIdx.y;
-  const uint4* __restrict__ src = k.src + dst * k.src_peer_stride;
-  uint4* __restrict__ out = k.dst[dst];
-  const int64_t total = static_cast<int64_t>(k.n[0]) * k.n[1] * k.n[2] * k.n[3] * k.vec;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(kPeerThreads) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kPeerThreads) {
-    const int v = static_cast<int>(i % k.vec);
-    int64_t item = i / k.vec;
-    const int i3 = static_cast<int>(item % k.n[3]);
-    item /= k.n[3];
-    const int i2 = static_cast<int>(item % k.n[2]);
-    item /= k.n[2];
-    const int i1 = static_cast<int>(item % k.n[1]);
-    const int i0 = static_cast<int>(item / k.n[1]);
-    out[i0 * k.ds[0] + i1 * k.ds[1] + i2 * k.ds[2] + i3 * k.ds[3] + v] =
-        __ldg(src + i0 * k.ss[0] + i1 * k.ss[1] + i2 * k.ss[2] + i3 * k.ss[3] + v);
-  }
+  peer_put_copy(k, blockIdx.y, blockIdx.x * static_cast<int64_t>(kPeerThreads) + threadIdx.x,
+                static_cast<int64_t>(gridDim.x) * kPeerThreads, [](const Vec16* p) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+                  return Vec16{u.x, u.y, u.z, u.w};
+                });
   __threadfence_system();  // this thread's peer stores are ordered before the counter / flag writes below
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -114,7 +90,7 @@ extern "C" int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream_) {
                    p->src_peer_stride % 16 == 0 && p->dst_offset % 16 == 0 && p->dst_offset >= 0,
                "peer_put: items, offsets and the source must be 16-byte multiples / aligned");
   PeerPutK k;
-  k.src = static_cast<const uint4*>(p->src);
+  k.src = static_cast<const Vec16*>(p->src);
   k.state = reinterpret_cast<unsigned long long*>(p->state);
   k.vec = p->item_bytes / 16, k.peers = p->peers, k.rank = p->rank;
   k.src_peer_stride = p->src_peer_stride / 16;
@@ -131,7 +107,7 @@ extern "C" int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream_) {
     FG_CHECK_ARG(p->dst[q] && p->flags[q] && (reinterpret_cast<uintptr_t>(p->dst[q]) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(p->flags[q]) & 7) == 0,
                  "peer_put: destination / flag pointer of peer %d missing or misaligned", q);
-    k.dst[q] = reinterpret_cast<uint4*>(static_cast<char*>(p->dst[q]) + p->dst_offset);
+    k.dst[q] = reinterpret_cast<Vec16*>(static_cast<char*>(p->dst[q]) + p->dst_offset);
     k.flags[q] = reinterpret_cast<unsigned long long*>(p->flags[q]);
   }
   const int64_t vecs = items * k.vec;

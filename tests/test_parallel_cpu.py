@@ -129,3 +129,45 @@ def test_peer_put_descriptors_equal_pack_all_to_all_unpack():
             assert torch.equal(att[r], att_ref[r]), (P, r)
     with pytest.raises(AssertionError):
         PL.apply_peer_put_cpu(PL.peer_put_out_desc(1, 8, 2, 0, 16, 8), torch.zeros(4, 8).t(), [torch.zeros(4, 16)] * 2)
+
+
+def test_peer_put_kernel_copy_loop_on_the_host_equals_the_descriptor_reference():
+    """the index arithmetic of peer_put_kernel itself: its copy loop (csrc/peer_exchange_body.cuh, shared source) is
+    compiled with g++ and run for every (destination, thread id) of an emulated launch against host buffers standing in
+    for the peers; the result must equal the descriptor reference checked above (test infrastructure only)"""
+    import ctypes as C
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = os.path.join(here, "host_emu", "build", "libpeer_emu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-fPIC", "-shared",
+                    os.path.join(here, "host_emu", "peer_emu.cpp"), "-o", out], check=True)
+    lib = C.CDLL(out)
+    lib.emu_peer_put.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_int, C.c_int64]
+
+    def run(desc, src, dsts, threads):
+        es = src.element_size()
+        ptrs = (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+        st = lib.emu_peer_put(src.data_ptr(), ptrs, len(dsts), (C.c_int * 4)(*desc["n"]),
+                              (C.c_int64 * 4)(*[s * es for s in desc["ss"]]), (C.c_int64 * 4)(*[s * es for s in desc["ds"]]),
+                              desc["src_peer_stride"] * es, desc["dst_off"] * es, desc["item"] * es, threads)
+        assert st == 0
+
+    for P, threads in ((2, 7), (4, 1000), (8, 64)):
+        torch.manual_seed(P)
+        B, Fr, fs, H, d = 2, 3, 16, 8, 8
+        D = H * d
+        n, n_l, Dl = Fr * fs, Fr * fs // P, (H // P) * d
+        for r in range(P):
+            qkv = torch.randn(B * n_l, 3 * D).bfloat16()
+            attf = torch.randn(B, n, Dl).bfloat16()
+            for desc, src, shape in ((PL.peer_put_qkv_desc(B, n, P, r, D, Dl), qkv, (B, n, 3 * Dl)),
+                                     (PL.peer_put_out_desc(B, n, P, r, D, Dl), attf, (B * n_l, D))):
+                ref = [torch.zeros(shape, dtype=torch.bfloat16) for _ in range(P)]
+                got = [torch.zeros(shape, dtype=torch.bfloat16) for _ in range(P)]
+                PL.apply_peer_put_cpu(desc, src, ref)
+                run(desc, src, got, threads)
+                for q in range(P):
+                    assert torch.equal(got[q], ref[q]), (P, r, q)
