@@ -66,6 +66,13 @@ def peer_put_out_desc(B: int, n: int, P: int, rank: int, D: int, Dl: int) -> Dic
                 dst_off=rank * Dl)
 
 
+def peer_gather_desc(lrows: int, kout: int, rank: int) -> Dict[str, Any]:
+    """all-gather as a put: this rank's [lrows, kout] rows -> slot ``rank`` of every rank's gathered [P, lrows, kout]
+    (the same source for every destination: src_peer_stride = 0)."""
+    return dict(n=[lrows, 1, 1, 1], ss=[kout, 0, 0, 0], ds=[kout, 0, 0, 0], item=kout, src_peer_stride=0,
+                dst_off=rank * lrows * kout)
+
+
 def apply_peer_put_cpu(desc: Dict[str, Any], src: torch.Tensor, dsts: Sequence[torch.Tensor]) -> None:
     """Reference execution of a peer-put descriptor: ``dsts[q]`` is rank q's destination buffer."""
     n, item = desc["n"], desc["item"]

@@ -250,6 +250,9 @@ class _WanBase:
         # layer loop (opt-in: written after the round's GPU budget ended, layout checked on CPU only)
         self.sp_exchange = os.environ.get("FASTGEN_B200_SP_EXCHANGE", "nccl")
         self.peer_timeout_s = 20.0
+        # with the peer exchange no NCCL call is left in a launch list, so it could replay as a CUDA graph under sequence
+        # parallelism too (36 k launches per sample); off until the exchange itself has run on hardware
+        self.sp_graphs = False
 
     # ---- reference helpers ------------------------------------------------------------------------------
     @classmethod
@@ -444,8 +447,8 @@ class _WanBase:
                       rtproj=z(groups, 6 * D, dt=f32))
         if P > 1 and self.sp_exchange == "peer":
             # one-pass exchange: qkv_full and att are the DESTINATIONS the peers store into (symmetric memory)
-            ws.update(hs_full=z(rows, D), att_full=z(B, n, Dl), tok_out_l=z(lrows, kout), tok_out_g=z(P, lrows, kout))
-            ws.update(self._peer_buffers(B, n, D, Dl, P, dev))
+            ws.update(hs_full=z(rows, D), att_full=z(B, n, Dl), tok_out_l=z(lrows, kout))
+            ws.update(self._peer_buffers(B, n, D, Dl, P, dev, kout))
         elif P > 1:
             if self.sp_exchange != "nccl":
                 raise ValueError(f"sp_exchange must be 'nccl' or 'peer', got {self.sp_exchange}")
@@ -459,17 +462,20 @@ class _WanBase:
         self._ws[key] = ws
         return ws
 
-    def _peer_buffers(self, B: int, n: int, D: int, Dl: int, P: int, dev) -> Dict[str, Any]:
-        """Symmetric-memory destinations of the one-pass exchange: [ qkv_full [B, n, 3 Dl] | att [B n/P, D] | flags of the two
-        channels ], the same layout on every rank, so a peer's region is its mapped base pointer + the same offset."""
+    def _peer_buffers(self, B: int, n: int, D: int, Dl: int, P: int, dev, kout: int) -> Dict[str, Any]:
+        """Symmetric-memory destinations of the one-pass exchange: [ qkv_full [B, n, 3 Dl] | att [B n/P, D] | tok_out_g
+        [P, B n/P, kout] | flags of the three channels ], the same layout on every rank, so a peer's region is its mapped
+        base pointer + the same offset."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
         al = lambda v: (v + 255) // 256 * 256  # noqa: E731
         full_b, att_b = B * n * 3 * Dl * 2, B * (n // P) * D * 2
+        gat_b = P * B * (n // P) * kout * 2
         off_att = al(full_b)
-        off_flags = al(off_att + att_b)
-        total = off_flags + al(2 * L.FG_MAX_PEERS * 8)
+        off_gat = al(off_att + att_b)
+        off_flags = al(off_gat + gat_b)
+        total = off_flags + al(3 * L.FG_MAX_PEERS * 8)
         import warnings
 
         enable = getattr(symm, "enable_symm_mem_for_group", None)
@@ -488,9 +494,11 @@ class _WanBase:
         bf = torch.bfloat16
         return dict(
             qkv_full=buf[:full_b].view(bf).view(B, n, 3 * Dl), att=buf[off_att:off_att + att_b].view(bf).view(B * (n // P), D),
+            tok_out_g=buf[off_gat:off_gat + gat_b].view(bf).view(P, B * (n // P), kout),
             peer=dict(buf=buf, hdl=hdl, full_ptrs=ptrs, att_ptrs=[p + off_att for p in ptrs],
-                      flag_ptrs=[[p + off_flags + c * L.FG_MAX_PEERS * 8 for p in ptrs] for c in range(2)],
-                      state=torch.zeros(2, 4, dtype=torch.int64, device=dev)))
+                      gat_ptrs=[p + off_gat for p in ptrs],
+                      flag_ptrs=[[p + off_flags + c * L.FG_MAX_PEERS * 8 for p in ptrs] for c in range(3)],
+                      state=torch.zeros(3, 4, dtype=torch.int64, device=dev)))
 
     def check_peer_exchange(self) -> None:
         """Synchronise and raise if a wait of the one-pass exchange ever timed out (a peer stopped making progress)."""
@@ -778,7 +786,17 @@ class _WanBase:
             self._gemm(plan, nrm, D, pk["out.w"], rows, kout, ws["tok_out"], kout, "proj_out", bias=pk["out.b"])
         else:
             self._gemm(plan, nrm, D, pk["out.w"], lrows, kout, ws["tok_out_l"], kout, "proj_out", bias=pk["out.b"])
-            plan.add_py(lambda: dist.all_gather_into_tensor(ws["tok_out_g"], ws["tok_out_l"], group=group), "gather_out")
+            if self.sp_exchange == "peer":
+                # all-gather as a put of this rank's rows into slot `rank` of every rank's tok_out_g (third channel)
+                px = ws["peer"]
+                p = ops.peer_put_params(ws["tok_out_l"], PL.peer_gather_desc(lrows, kout, rank), px["gat_ptrs"],
+                                        px["flag_ptrs"][2], rank, px["state"][2])
+                plan.keep.append(p)
+                plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_gather")
+                plan.add(lib.fg_peer_wait, px["flag_ptrs"][2][rank], P, px["state"][2].data_ptr(),
+                         int(self.peer_timeout_s * 1e9), desc="peer_wait_gather")
+            else:
+                plan.add_py(lambda: dist.all_gather_into_tensor(ws["tok_out_g"], ws["tok_out_l"], group=group), "gather_out")
             # gathered[src][(b, f)][i] -> natural token order [(b, f)][src * fs_l + i]
             self._copy_desc(plan, ws["tok_out_g"], ws["tok_out"], PL.unshard_desc(P, B, F, fs, kout), "unshard")
         plan.add(lib.fg_unpatchify, ws["tok_out"].data_ptr(), kout, B, cfg["out_channels"], F, Hh, Ww, ph, pw,
@@ -858,7 +876,7 @@ class _WanBase:
         # the head adds table + temb in bf16 (reference Wan/network.py:229,250): needs temb, so run the embedding
         # launches first, then that one tiny add, then the rest of the plan
         # (not under sequence parallelism: capturing the NCCL all-to-all into a graph deadlocked the NCCL watchdog)
-        if self.use_cuda_graphs and self.profile is None and self.sp_group is None:
+        if self.use_cuda_graphs and self.profile is None and (self.sp_group is None or (self.sp_graphs and self.sp_exchange == "peer")):
             if plan.graph is None and plan.runs >= 1:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):

@@ -127,6 +127,14 @@ def test_peer_put_descriptors_equal_pack_all_to_all_unpack():
             PL.apply_peer_put_cpu(PL.peer_put_out_desc(B, n, P, r, D, Dl), attf[r], att)
         for r in range(P):
             assert torch.equal(att[r], att_ref[r]), (P, r)
+        # the final all-gather as a put: slot r of every rank's gathered buffer = rank r's rows
+        lrows, kout = B * n_l, 16
+        outs = [torch.randn(lrows, kout) for _ in range(P)]
+        gathered = [torch.full((P, lrows, kout), float("nan")) for _ in range(P)]
+        for r in range(P):
+            PL.apply_peer_put_cpu(PL.peer_gather_desc(lrows, kout, r), outs[r], gathered)
+        for r in range(P):
+            assert torch.equal(gathered[r], torch.stack(outs, 0)), (P, r)
     with pytest.raises(AssertionError):
         PL.apply_peer_put_cpu(PL.peer_put_out_desc(1, 8, 2, 0, 16, 8), torch.zeros(4, 8).t(), [torch.zeros(4, 16)] * 2)
 

@@ -72,17 +72,19 @@ def test_wan14b_peer_exchange_launch_list_validates_on_the_host(monkeypatch):
     net.sp_group = object()
     net.sp_exchange = "peer"
 
-    def host_peer_buffers(B, n, D, Dl, P_, dev):
+    def host_peer_buffers(B, n, D, Dl, P_, dev, kout):
         # stand-in for the symmetric-memory rendezvous: every "peer" is a region of host memory
-        bufs = [torch.zeros(B * n * 3 * Dl + B * (n // P_) * D + 64, dtype=torch.bfloat16) for _ in range(P_)]
-        off_att, off_flags = B * n * 3 * Dl * 2, (B * n * 3 * Dl + B * (n // P_) * D) * 2
+        e_full, e_att, e_gat = B * n * 3 * Dl, B * (n // P_) * D, P_ * B * (n // P_) * kout
+        bufs = [torch.zeros(e_full + e_att + e_gat + 96, dtype=torch.bfloat16) for _ in range(P_)]
+        off_att, off_gat, off_flags = e_full * 2, (e_full + e_att) * 2, (e_full + e_att + e_gat) * 2
         ptrs = [b.data_ptr() for b in bufs]
         mine = bufs[rank]
-        return dict(qkv_full=mine[:B * n * 3 * Dl].view(B, n, 3 * Dl),
-                    att=mine[B * n * 3 * Dl:B * n * 3 * Dl + B * (n // P_) * D].view(B * (n // P_), D),
+        return dict(qkv_full=mine[:e_full].view(B, n, 3 * Dl), att=mine[e_full:e_full + e_att].view(B * (n // P_), D),
+                    tok_out_g=mine[e_full + e_att:e_full + e_att + e_gat].view(P_, B * (n // P_), kout),
                     peer=dict(buf=bufs, hdl=None, full_ptrs=ptrs, att_ptrs=[p + off_att for p in ptrs],
-                              flag_ptrs=[[p + off_flags + c * 64 for p in ptrs] for c in range(2)],
-                              state=torch.zeros(2, 4, dtype=torch.int64)))
+                              gat_ptrs=[p + off_gat for p in ptrs],
+                              flag_ptrs=[[p + off_flags + c * 64 for p in ptrs] for c in range(3)],
+                              state=torch.zeros(3, 4, dtype=torch.int64)))
 
     monkeypatch.setattr(net, "_peer_buffers", host_peer_buffers)
     net.repack()
@@ -107,6 +109,10 @@ def test_wan14b_peer_exchange_launch_list_validates_on_the_host(monkeypatch):
     assert descs.count("peer_put_qkv") == descs.count("peer_wait_qkv") == 2
     assert descs.count("peer_put_out") == descs.count("peer_wait_out") == 2
     assert "a2a_pack" not in descs and "a2a_unpack" not in descs and "a2a_qkv" not in descs and "a2a_out" not in descs
+    # no torch.distributed call is left anywhere in the launch list: the final gather is a put + wait as well
+    assert not any(s[0] == "collective" for s in statuses)
+    j = descs.index("peer_put_gather")
+    assert descs[j - 1:j + 4] == ["proj_out", "peer_put_gather", "peer_wait_gather", "unshard", "unpatchify"]
     # put -> wait -> attention -> put -> wait -> output projection, in that order inside a block
     i = descs.index("peer_put_qkv")
     assert descs[i:i + 6] == ["peer_put_qkv", "peer_wait_qkv", "self_attn", "peer_put_out", "peer_wait_out", "o1"]
