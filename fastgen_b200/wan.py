@@ -252,7 +252,7 @@ class _WanBase:
         self.peer_timeout_s = 20.0
         # with the peer exchange no NCCL call is left in a launch list, so it could replay as a CUDA graph under sequence
         # parallelism too (36 k launches per sample); off until the exchange itself has run on hardware
-        self.sp_graphs = False
+        self.sp_graphs = os.environ.get("FASTGEN_B200_SP_GRAPHS") == "1"
 
     # ---- reference helpers ------------------------------------------------------------------------------
     @classmethod
