@@ -917,6 +917,22 @@ class _WanBase:
         tail.steps = rest
         tail.run(stream, self.profile)
 
+    # ---- teacher sampling ---------------------------------------------------------------
+    @property
+    def unipc_scheduler(self):
+        """The multistep scheduler of ``sample()``.  The reference builds diffusers' ``UniPCMultistepScheduler`` from the
+        model's scheduler folder (Wan/network.py:635-639); here it defaults to the restated flow-matching UniPC of
+        ``fastgen_b200/unipc.py`` and can be assigned any object with the same interface (e.g. the diffusers one)."""
+        if getattr(self, "_unipc_scheduler", None) is None:
+            from .unipc import FlowUniPCMultistepScheduler
+
+            self._unipc_scheduler = FlowUniPCMultistepScheduler()
+        return self._unipc_scheduler
+
+    @unipc_scheduler.setter
+    def unipc_scheduler(self, scheduler) -> None:
+        self._unipc_scheduler = scheduler
+
     def _check_fwd_args(self, feature_indices, return_features_early, return_logvar, fwd_pred_type, r):
         if feature_indices is None:
             feature_indices = {}
@@ -973,8 +989,39 @@ class Wan(_WanBase, FastGenNetwork):
                 r_timestep = self.noise_scheduler.rescale_t(r.expand(x_t.shape[0]) if r.numel() == 1 else r)
             out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False, cache_tag="__bidir__",
                                         r_timestep=r_timestep)
+            if fwd_pred_type == self.net_pred_type:
+                out = out.clone()   # the caller owns what it gets back (reference: a fresh tensor); `out` is the plan's buffer
             return self.noise_scheduler.convert_model_output(x_t, out, t, src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)
+
+
+    def sample(self, noise: torch.Tensor, condition: Any = None, neg_condition: Any = None,
+               guidance_scale: Optional[float] = 5.0, num_steps: int = 50, shift: float = 5.0,
+               skip_layers: Optional[List[int]] = None, skip_layers_start_percent: float = 0.0, **kwargs) -> torch.Tensor:
+        """Teacher multistep sampling with classifier-free guidance: the loop of reference ``Wan.sample``
+        (Wan/network.py:919-988) around ``self.unipc_scheduler``.  Two forwards per step (condition, negative
+        condition), ``flow = uncond + g (cond - uncond)``, one scheduler step.  ``skip_layers`` (skip-layer guidance) is
+        handed to the forward like the reference does, and is not implemented there."""
+        assert self.schedule_type == "rf", f"{self.schedule_type} is not supported"
+        sch = self.unipc_scheduler
+        sch.config.flow_shift = shift
+        sch.set_timesteps(num_inference_steps=num_steps, device=noise.device)
+        timesteps = sch.timesteps
+        t_init = timesteps[0] / sch.config.num_train_timesteps
+        latents = self.noise_scheduler.latents(noise=noise, t_init=t_init)
+        ns = self.noise_scheduler
+        for idx, timestep in enumerate(timesteps):
+            t = (timestep / sch.config.num_train_timesteps).expand(latents.shape[0])
+            t = ns.safe_clamp(t, min=ns.min_t, max=ns.max_t).to(latents.dtype)
+            flow_pred = self(latents, t, condition=condition, r=None, return_features_early=False, feature_indices={},
+                             return_logvar=False)
+            if guidance_scale is not None:
+                flow_uncond = self(latents, t, condition=neg_condition, r=None, return_features_early=False,
+                                   feature_indices={}, return_logvar=False,
+                                   skip_layers=skip_layers if idx >= skip_layers_start_percent * num_steps else None)
+                flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
+            latents = sch.step(flow_pred, timestep, latents, return_dict=False)[0]
+        return latents
 
 
 class CausalWan(_WanBase, CausalFastGenNetwork):
@@ -1045,6 +1092,58 @@ class CausalWan(_WanBase, CausalFastGenNetwork):
             out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=True, cache_tag=cache_tag,
                                         use_cache=use_cache, cur_start_frame=cur_start_frame, store_kv=store_kv,
                                         total_num_frames=self.total_num_frames, mask=mask, r_timestep=r_timestep)
+            if fwd_pred_type == self.net_pred_type:
+                out = out.clone()   # the caller owns what it gets back (reference: a fresh tensor); `out` is the plan's buffer
             t_conv = t[:, None, :, None, None] if t.ndim == 2 else t
             return self.noise_scheduler.convert_model_output(x_t, out, t_conv, src_pred_type=self.net_pred_type,
                                                              target_pred_type=fwd_pred_type)
+
+    def sample(self, noise: torch.Tensor, condition: Any = None, neg_condition: Any = None,
+               guidance_scale: Optional[float] = 5.0, sample_steps: Optional[int] = 50, shift: float = 5.0,
+               context_noise: float = 0, **kwargs) -> torch.Tensor:
+        """Autoregressive teacher sampling with classifier-free guidance: the loop of reference ``CausalWan.sample``
+        (Wan/network_causal.py:1186-1295).  Per chunk (the first one absorbs the remainder frames) a full multistep
+        trajectory with two KV-cached forwards per step (cache tags "pos" / "neg"), the chunk written back into ``noise``
+        in place like the reference, then one cache-fill forward per tag at t = 0 (or ``context_noise``)."""
+        assert self.schedule_type == "rf", f"{self.schedule_type} is not supported"
+        was_training = self.training
+        self.eval()
+        self.clear_caches()
+        x = noise
+        batch_size, num_frames = x.shape[0], x.shape[2]
+        num_chunks, remaining_size = num_frames // self.chunk_size, num_frames % self.chunk_size
+        sch = self.unipc_scheduler
+        time_rescale_factor = sch.config.num_train_timesteps
+        for i in range(max(1, num_chunks)):
+            if num_chunks == 0:
+                start, end = 0, remaining_size
+            else:
+                start = 0 if i == 0 else self.chunk_size * i + remaining_size
+                end = self.chunk_size * (i + 1) + remaining_size
+            x_next = x[:, :, start:end]
+            sch.config.flow_shift = shift
+            sch.set_timesteps(num_inference_steps=sample_steps, device=noise.device)
+            for timestep in sch.timesteps:
+                t = (timestep / time_rescale_factor).expand(batch_size)
+                x_cur = x_next
+                flow_pred = self(x_cur, t, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=False,
+                                 is_ar=True)
+                if guidance_scale is not None:
+                    flow_uncond = self(x_cur, t, condition=neg_condition, cache_tag="neg", cur_start_frame=start,
+                                       store_kv=False, is_ar=True)
+                    flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
+                x_next = sch.step(flow_pred, timestep, x_next, return_dict=False)[0]
+            x[:, :, start:end] = x_next
+            # rerun at t = 0 (or with context noise) to write this chunk's keys / values into the caches
+            x_cache = x_next
+            t_cache = torch.full((batch_size,), 0, device=x.device, dtype=x.dtype)
+            if context_noise > 0:
+                t_cache = torch.full((batch_size,), context_noise, device=x.device, dtype=x.dtype)
+                x_cache = self.noise_scheduler.forward_process(x_next, torch.randn_like(x_next), t_cache)
+            _ = self(x_cache, t_cache, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=True, is_ar=True)
+            if guidance_scale is not None:
+                _ = self(x_cache, t_cache, condition=neg_condition, cache_tag="neg", cur_start_frame=start, store_kv=True,
+                         is_ar=True)
+        self.clear_caches()
+        self.train(was_training)
+        return x

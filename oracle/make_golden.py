@@ -457,6 +457,96 @@ def dit_fixture():
     print("wrote DiT reference fixture:", len(fx), "arrays")
 
 
+def wan_sample_stub_flow(x, t, condition, cur_start_frame=0, store_kv=False, cache_state=0.0):
+    """deterministic stand-in for a Wan forward (flow prediction): depends on the latent, the timestep, the condition, the
+    chunk position and on what the cache held -- so a wrong call order, cache tag or argument shows in the samples.
+    Shared by the fixture generator, the oracle restatement and the CPU test of the product loop."""
+    tt = t.float().reshape(t.shape[0], *([1] * (x.dim() - 1)))
+    c = condition.float().mean(dim=tuple(range(1, condition.dim()))).reshape(-1, *([1] * (x.dim() - 1)))
+    out = 0.6 * x.float() + 0.25 * torch.sin(3.0 * tt) + 0.5 * c + 0.01 * cur_start_frame + 0.05 * cache_state
+    return out.to(x.dtype)
+
+
+def wan_sample_fixture():
+    """Traces and samples of the UNMODIFIED reference teacher samplers `Wan.sample` (Wan/network.py:919-988) and
+    `CausalWan.sample` (network_causal.py:1186-1295), called as plain functions on a stand-in `self`: a stub network
+    (wan_sample_stub_flow), the reference's own rf noise schedule, and fastgen_b200.unipc.FlowUniPCMultistepScheduler
+    standing in for the diffusers scheduler object (the loop only uses its interface; the scheduler arithmetic is not
+    what this fixture pins)."""
+    from fastgen.networks.noise_schedule import get_noise_schedule
+    from fastgen_b200.unipc import FlowUniPCMultistepScheduler
+    from oracle import ref_wan_harness as H
+
+    RW, RC = H.load_reference_wan()
+
+    class Stub:
+        schedule_type = "rf"
+        training = False
+
+        def __init__(self, chunk_size=3):
+            self.noise_scheduler = get_noise_schedule("rf")
+            self.unipc_scheduler = FlowUniPCMultistepScheduler()
+            self.chunk_size = chunk_size
+            self.trace, self.cache = [], {}
+
+        def eval(self):
+            self.trace.append(("eval",))
+
+        def train(self, mode=True):
+            self.trace.append(("train", bool(mode)))
+
+        def clear_caches(self):
+            self.trace.append(("clear_caches",))
+            self.cache = {}
+
+        def __call__(self, x, t, condition=None, cache_tag=None, cur_start_frame=0, store_kv=False, is_ar=None, **kw):
+            extra = {k: v for k, v in kw.items() if v not in (None, False) and v != {}}
+            self.trace.append(("fwd", [float(v) for v in t.float().flatten()], str(t.dtype), float(condition.flatten()[0]),
+                               cache_tag, int(cur_start_frame), bool(store_kv), is_ar, sorted(extra)))
+            state = self.cache.get(cache_tag, 0.0)
+            if store_kv:
+                self.cache[cache_tag] = state + float(x.float().mean())
+            return wan_sample_stub_flow(x, t, condition, cur_start_frame, store_kv, state)
+
+    g = torch.Generator().manual_seed(SEED + 77)
+    fx = {}
+    cond, neg = torch.randn(2, 5, 8, generator=g), torch.randn(2, 5, 8, generator=g)
+    fx["cond"], fx["neg"] = _np(cond), _np(neg)
+    with torch.no_grad():
+        for tag, dtype, kw in (("bidir_cfg", torch.float32, dict(guidance_scale=5.0, num_steps=6, shift=5.0)),
+                               ("bidir_nocfg", torch.float32, dict(guidance_scale=None, num_steps=4, shift=3.0)),
+                               ("bidir_bf16", torch.bfloat16, dict(guidance_scale=3.0, num_steps=5, shift=5.0))):
+            noise = torch.randn(2, 4, 3, 4, 4, generator=g).to(dtype)
+            st = Stub()
+            out = RW.Wan.sample(st, noise.clone(), condition=cond.to(dtype), neg_condition=neg.to(dtype), **kw)
+            fx[tag + "_noise"], fx[tag + "_out"], fx[tag + "_trace"] = _np(noise), _np(out), json.dumps(st.trace)
+            fx[tag + "_kw"] = json.dumps(kw)
+        for tag, frames, kw in (("causal_cfg", 7, dict(guidance_scale=4.0, sample_steps=4, shift=5.0)),
+                                ("causal_ctx", 6, dict(guidance_scale=None, sample_steps=3, shift=3.0, context_noise=0.1)),
+                                ("causal_short", 2, dict(guidance_scale=2.0, sample_steps=3, shift=5.0))):
+            noise = torch.randn(2, 4, frames, 4, 4, generator=g)
+            draws = []
+            orig = torch.randn_like
+
+            def rl(x, **k2):
+                e = torch.randn(x.shape, generator=g).to(x.dtype)
+                draws.append(e)
+                return e
+
+            torch.randn_like = rl
+            try:
+                st = Stub()
+                out = RC.CausalWan.sample(st, noise.clone(), condition=cond, neg_condition=neg, **kw)
+            finally:
+                torch.randn_like = orig
+            fx[tag + "_noise"], fx[tag + "_out"], fx[tag + "_trace"] = _np(noise), _np(out), json.dumps(st.trace)
+            fx[tag + "_kw"] = json.dumps(kw)
+            for i, e in enumerate(draws):
+                fx[f"{tag}_eps{i}"] = _np(e)
+    np.savez_compressed(os.path.join(OUT, "wan_sample_trace.npz"), **fx)
+    print("wan_sample_trace.npz", {k: v.shape for k, v in fx.items() if hasattr(v, "shape") and v.ndim > 0 and "out" in k})
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -472,3 +562,4 @@ if __name__ == "__main__":
     wan_glue_fixture()
     sdxl_glue_fixture()
     dit_fixture()
+    wan_sample_fixture()

@@ -1,5 +1,6 @@
-"""Parity of the CUDA Wan path (through the C ABI) against the CPU oracle (oracle/wan_oracle.py, PARITY UNPINNED: the
-layer arithmetic lives in diffusers, see the oracle header) on identical random-init weights, seeds and inputs.
+"""Parity of the CUDA Wan path (through the C ABI) against the CPU oracle (oracle/wan_oracle.py: pinned bit-exactly to the
+reference's own Wan code run on stand-in diffusers modules, tests/golden/wan_reference_glue.npz; the diffusers module
+internals are restated, see the oracle header) on identical random-init weights, seeds and inputs.
 
 Tolerance (BASELINE.json north star): per-step x0 relative L2 <= 1e-2 on the bf16 path.  The oracle is evaluated both
 in bfloat16 (what the reference network computes) and in float32 on the same bf16-rounded weights (the exact value)."""
