@@ -92,6 +92,11 @@ def test_sequence_parallel_matches_single_gpu():
             assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
 
 
+_UNVERIFIED = pytest.mark.skipif(os.environ.get("FASTGEN_B200_TEST_UNVERIFIED") != "1",
+                                 reason="never run on hardware yet: set FASTGEN_B200_TEST_UNVERIFIED=1")
+
+
+@_UNVERIFIED
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_matches_single_gpu():
@@ -107,6 +112,7 @@ def test_sequence_parallel_peer_exchange_matches_single_gpu():
             assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
 
 
+@_UNVERIFIED
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_replays_as_cuda_graphs():
