@@ -24,7 +24,10 @@ def _cfgs():
             ("dhariwal_tiny", CONFIGS["dhariwal_tiny"], "bf16x3", None, "bf16"),
             # fp32 CUDA-core attention on the split-precision path: head widths 256 (CIFAR), 64 (IN-64, tiny)
             ("cifar_x3_f32attn", CIFAR, "bf16x3", 0, "f32"), ("in64_x3_f32attn", IN64, "bf16x3", 0, "f32"),
-            ("dhariwal_tiny_x3_f32attn", CONFIGS["dhariwal_tiny"], "bf16x3", None, "f32")]
+            ("dhariwal_tiny_x3_f32attn", CONFIGS["dhariwal_tiny"], "bf16x3", None, "f32"),
+            ("song_tiny_x3_f32attn", CONFIGS["song_tiny"], "bf16x3", None, "f32"),
+            # head width 32 has no fg_attention_f32 instance: that block keeps the bf16 tensor-core kernel
+            ("narrow_heads_x3", dict(CONFIGS["song_tiny"], model_channels=32, channel_mult=[1, 1]), "bf16x3", None, "f32")]
 
 
 @pytest.mark.parametrize("name,cfg,compute,max_stats_passes,x3_attention", _cfgs(), ids=[c[0] for c in _cfgs()])
@@ -41,7 +44,7 @@ def test_edm_launch_list_arguments_validate_on_the_host(monkeypatch, name, cfg, 
     plan = net._plan(3)
     counts = collections.Counter(fn.__name__ for fn, _ in plan.steps)
     n_attn = sum(1 for md in (net.model.enc, net.model.dec) for b in md.values() if getattr(b, "num_heads", 0))
-    f32 = compute == "bf16x3" and x3_attention == "f32"
+    f32 = compute == "bf16x3" and x3_attention == "f32" and name != "narrow_heads_x3"
     assert counts["fg_attention_f32" if f32 else "fg_attention"] == n_attn > 0
     assert counts["fg_attention" if f32 else "fg_attention_f32"] == 0
     invalid, ok = [], 0
