@@ -125,3 +125,63 @@ def test_sequence_parallel_peer_exchange_replays_as_cuda_graphs():
         for r in range(world):
             errs = ret[r]
             assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
+
+
+def _peer_kernel_worker(rank, world, port, ret):
+    """fg_peer_put / fg_peer_wait alone: every rank stores a rank-specific pattern into slot `rank` of every rank's buffer
+    (the all-gather descriptor), three rounds on one channel, and checks what arrived after the device-side wait."""
+    import ctypes as C
+
+    import torch.distributed._symmetric_memory as symm
+
+    from fastgen_b200 import _lib as L
+    from fastgen_b200 import ops
+    from fastgen_b200 import parallel as PL
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        rows, cols = 300, 64
+        data_b = world * rows * cols * 2
+        enable = getattr(symm, "enable_symm_mem_for_group", None)
+        if enable is not None:
+            enable(dist.group.WORLD.group_name)
+        buf = symm.empty(data_b + 256, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        gathered = buf[:data_b].view(torch.bfloat16).view(world, rows, cols)
+        state = torch.zeros(4, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        ok = True
+        for rnd in range(3):
+            src = torch.full((rows, cols), float(10 * rnd + rank + 1), device=dev, dtype=torch.bfloat16)
+            p = ops.peer_put_params(src, PL.peer_gather_desc(rows, cols, rank), ptrs, [q + data_b for q in ptrs], rank, state)
+            L.check(L.lib().fg_peer_put(C.byref(p), stream), "fg_peer_put")
+            L.check(L.lib().fg_peer_wait(ptrs[rank] + data_b, world, state.data_ptr(), int(5e9), stream), "fg_peer_wait")
+            torch.cuda.synchronize()
+            want = torch.stack([torch.full((rows, cols), float(10 * rnd + r + 1)) for r in range(world)]).bfloat16()
+            ok = ok and torch.equal(gathered.cpu(), want)
+            dist.barrier()      # (test only) nobody overwrites a slot before everybody has checked it
+        ret[rank] = (ok, state.cpu().tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+@_UNVERIFIED
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(300)
+def test_peer_put_and_wait_kernels_alone():
+    """run this one FIRST when bringing the peer exchange up on hardware: it isolates the two kernels and the symmetric-
+    memory rendezvous from the Wan plan"""
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_peer_kernel_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        for r in range(world):
+            ok, state = ret[r]
+            assert ok and state == [3, 0, 3, 0], (r, ok, state)     # 3 puts, counter reset, 3 waits, no timeout
