@@ -547,6 +547,56 @@ def wan_sample_fixture():
     print("wan_sample_trace.npz", {k: v.shape for k, v in fx.items() if hasattr(v, "shape") and v.ndim > 0 and "out" in k})
 
 
+def original_wan_keys(layers: int = 2):
+    """key names of an original-format (Wan-AI/Wan2.1 `*.pth`-style) checkpoint of a T2V model"""
+    keys = ["patch_embedding.weight", "patch_embedding.bias", "head.head.weight", "head.head.bias", "head.modulation"]
+    for i in (0, 2):
+        keys += [f"text_embedding.{i}.weight", f"text_embedding.{i}.bias", f"time_embedding.{i}.weight",
+                 f"time_embedding.{i}.bias"]
+    keys += ["time_projection.1.weight", "time_projection.1.bias"]
+    for b in range(layers):
+        p = f"blocks.{b}."
+        keys += [p + "modulation", p + "norm3.weight", p + "norm3.bias", p + "ffn.0.weight", p + "ffn.0.bias",
+                 p + "ffn.2.weight", p + "ffn.2.bias"]
+        for a in ("self_attn", "cross_attn"):
+            for part in ("q", "k", "v", "o"):
+                keys += [f"{p}{a}.{part}.weight", f"{p}{a}.{part}.bias"]
+            keys += [f"{p}{a}.norm_q.weight", f"{p}{a}.norm_k.weight"]
+    return keys
+
+
+def wan_remap_fixture():
+    """What the UNMODIFIED reference `Wan.load_state_dict` (Wan/network.py:990-1075) hands to nn.Module.load_state_dict for
+    original-format checkpoints: flat or nested under 'generator' / 'state_dict' / 'model', keys with and without the
+    'model.' / 'module.' prefixes.  The instance is created without __init__ (no diffusers model is needed for the key
+    logic) and nn.Module.load_state_dict is replaced by a recorder for the call."""
+    from oracle import ref_wan_harness as H
+
+    RW, _ = H.load_reference_wan()
+    obj = RW.Wan.__new__(RW.Wan)
+    torch.nn.Module.__init__(obj)
+    obj._use_wan_official_sinusoidal = True
+    got = {}
+    orig = torch.nn.Module.load_state_dict
+    torch.nn.Module.load_state_dict = lambda self, sd, **kw: got.update(keys=list(sd.keys()), kw=sorted(kw))
+    fx = {}
+    try:
+        for tag, nest, prefix in (("flat", None, ""), ("generator_model", "generator", "model."),
+                                  ("state_dict_module", "state_dict", "module."), ("model_plain", "model", "")):
+            src = {prefix + k: torch.zeros(1) for k in original_wan_keys()}
+            RW.Wan.load_state_dict(obj, {nest: src} if nest else src, strict=False)
+            fx[tag] = dict(nest=nest, src=list(src.keys()), dst=got["keys"], kw=got["kw"])
+        # a checkpoint that already carries diffusers names passes through untouched
+        src = {"transformer.blocks.0.attn1.to_q.weight": torch.zeros(1), "transformer.scale_shift_table": torch.zeros(1)}
+        RW.Wan.load_state_dict(obj, src)
+        fx["diffusers_names"] = dict(nest=None, src=list(src.keys()), dst=got["keys"], kw=got["kw"])
+    finally:
+        torch.nn.Module.load_state_dict = orig
+    with open(os.path.join(OUT, "wan_original_key_remap.json"), "w") as f:
+        json.dump(fx, f, indent=0)
+    print("wan_original_key_remap.json", {k: len(v["dst"]) for k, v in fx.items()})
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -563,3 +613,4 @@ if __name__ == "__main__":
     sdxl_glue_fixture()
     dit_fixture()
     wan_sample_fixture()
+    wan_remap_fixture()

@@ -122,3 +122,31 @@ def test_package_root_exports_resolve():
         assert getattr(F, name) is not None
     with pytest.raises(AttributeError):
         F.no_such_thing
+
+
+def test_original_wan_checkpoint_key_remap_matches_the_reference(monkeypatch):
+    """`Wan.load_state_dict` on original-format checkpoints (flat / nested under 'generator', 'state_dict', 'model'; keys
+    with 'model.' / 'module.' prefixes) hands nn.Module.load_state_dict exactly the keys the UNMODIFIED reference does
+    (tests/golden/wan_original_key_remap.json, oracle/make_golden.py:wan_remap_fixture); every remapped key exists in the
+    network, and diffusers-named checkpoints pass through untouched."""
+    import json
+    import os
+
+    import torch
+
+    import fastgen_b200.wan as W
+    from oracle import wan_oracle as WO
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wan_original_key_remap.json")))
+    net = W.Wan(transformer_config=WO.tiny_config(layers=2), use_wan_official_sinusoidal=True, enable_logvar_linear=False)
+    own = set(net.state_dict().keys())
+    got = {}
+    monkeypatch.setattr(torch.nn.Module, "load_state_dict", lambda self, sd, **kw: got.update(keys=list(sd.keys()), kw=sorted(kw)))
+    for tag, rec in fx.items():
+        src = {k: torch.zeros(1) for k in rec["src"]}
+        kw = {"strict": False} if rec["kw"] else {}
+        net.load_state_dict({rec["nest"]: src} if rec["nest"] else src, **kw)
+        assert got["keys"] == rec["dst"], tag
+        assert got["kw"] == rec["kw"], tag
+        assert set(got["keys"]) <= own, (tag, sorted(set(got["keys"]) - own)[:5])
+    assert len(fx["flat"]["dst"]) == len(own)      # the original T2V key list covers every parameter of the network
