@@ -457,6 +457,44 @@ def dit_fixture():
     print("wrote DiT reference fixture:", len(fx), "arrays")
 
 
+def facebook_dit_keys(sd):
+    """a Facebook-DiT-named view of a state dict in the reference's naming (the inverse of DiT/network.py:375-385)"""
+    fb = {}
+    for k, v in sd.items():
+        k = k.replace("t_embedder.proj_net", "t_embedder.mlp").replace(".attention.", ".attn.")
+        k = k.replace(".feed_forward.", ".mlp.").replace("y_embedder.class_embeddings", "y_embedder.embedding_table")
+        k = k.replace("final_layer.projection", "final_layer.linear")
+        k = k.replace("final_layer.adaptive_params", "final_layer.adaLN_modulation")
+        k = k.replace(".conditioning_net.", ".adaLN_modulation.")
+        fb[k] = v
+    return fb
+
+
+def dit_remap_fixture():
+    """The UNMODIFIED reference `DiT.load_state_dict` (DiT/network.py:346-401) on a Facebook-DiT-named checkpoint whose
+    tensors are tagged with their own index: which tensor ends up under which reference key, the returned missing /
+    unexpected lists, and the pos_embed buffer handling (matching and mismatching shape)."""
+    from oracle import dit_oracle as DO
+    from oracle import ref_dit_harness as H
+
+    cfg = DO.tiny_config()
+    net = H.build_reference_dit(cfg, DO.make_state_dict(cfg, 31))
+    ref_sd = net.state_dict()
+    fb = facebook_dit_keys(ref_sd)
+    tagged = {k: torch.full_like(v, float(i + 1)) for i, (k, v) in enumerate(fb.items())}
+    res = net.load_state_dict(tagged, strict=False)
+    after = net.state_dict()
+    fx = dict(src=list(tagged.keys()), missing=list(res.missing_keys), unexpected=list(res.unexpected_keys),
+              tag_of={k: float(v.flatten()[0]) for k, v in after.items()})
+    bad = dict(tagged)
+    bad["pos_embed"] = torch.full((1, 3, 5), 99.0)
+    res2 = net.load_state_dict(bad, strict=False)
+    fx["bad_pos_missing"], fx["bad_pos_tag"] = list(res2.missing_keys), float(net.pos_embed.flatten()[0])
+    with open(os.path.join(OUT, "dit_facebook_key_remap.json"), "w") as f:
+        json.dump(fx, f, indent=0)
+    print("dit_facebook_key_remap.json", len(fx["src"]), "keys, missing", fx["missing"], fx["bad_pos_missing"], fx["bad_pos_tag"])
+
+
 def wan_sample_stub_flow(x, t, condition, cur_start_frame=0, store_kv=False, cache_state=0.0):
     """deterministic stand-in for a Wan forward (flow prediction): depends on the latent, the timestep, the condition, the
     chunk position and on what the cache held -- so a wrong call order, cache tag or argument shows in the samples.
@@ -614,3 +652,4 @@ if __name__ == "__main__":
     dit_fixture()
     wan_sample_fixture()
     wan_remap_fixture()
+    dit_remap_fixture()

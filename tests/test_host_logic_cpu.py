@@ -150,3 +150,31 @@ def test_original_wan_checkpoint_key_remap_matches_the_reference(monkeypatch):
         assert got["kw"] == rec["kw"], tag
         assert set(got["keys"]) <= own, (tag, sorted(set(got["keys"]) - own)[:5])
     assert len(fx["flat"]["dst"]) == len(own)      # the original T2V key list covers every parameter of the network
+
+
+def test_dit_facebook_key_conversion_matches_the_reference_record():
+    """same tagged Facebook-DiT checkpoint through our `DiT.load_state_dict`: every tensor lands under the key the
+    UNMODIFIED reference put it (tests/golden/dit_facebook_key_remap.json, oracle/make_golden.py:dit_remap_fixture), the
+    returned missing / unexpected lists agree, a pos_embed of the wrong shape is ignored like the reference does"""
+    import json
+    import os
+
+    from fastgen_b200.dit import DiT
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dit_facebook_key_remap.json")))
+    net = DiT(**DO.tiny_config())
+    own = net.state_dict()
+    assert set(own.keys()) == set(fx["tag_of"].keys())
+    from oracle.make_golden import facebook_dit_keys
+
+    fb_shapes = facebook_dit_keys(own)
+    assert list(fb_shapes.keys()) == fx["src"]
+    tagged = {k: torch.full_like(fb_shapes[k], float(i + 1)) for i, k in enumerate(fx["src"])}
+    res = net.load_state_dict(tagged, strict=False)
+    assert list(res.missing_keys) == fx["missing"] and list(res.unexpected_keys) == fx["unexpected"]
+    after = net.state_dict()
+    assert {k: float(v.flatten()[0]) for k, v in after.items()} == fx["tag_of"]
+    bad = dict(tagged)
+    bad["pos_embed"] = torch.full((1, 3, 5), 99.0)
+    res2 = net.load_state_dict(bad, strict=False)
+    assert list(res2.missing_keys) == fx["bad_pos_missing"] and float(net.pos_embed.flatten()[0]) == fx["bad_pos_tag"]
