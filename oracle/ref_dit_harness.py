@@ -15,7 +15,6 @@ import os
 import sys
 import types
 
-import torch
 from torch import nn
 
 from oracle.ref_shims import REF_ROOT, install_shims
