@@ -24,6 +24,9 @@ def attn(q, k, v, mode, share=1.0):
     p32 = torch.exp2(x)
     if mode == "current":
         p, den = p32.bfloat16().float(), p32.sum(-1, keepdim=True)
+    elif mode == "ones_column":      # row sum taken by the P.V product itself (a ones column in V): sum of the ROUNDED p
+        p = p32.bfloat16().float()
+        den = p.sum(-1, keepdim=True)
     else:
         pb = torch.exp2(x.bfloat16().float()).bfloat16().float()
         if share < 1.0:
@@ -40,7 +43,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
-print(f"{'case':44s} {'current':>10s} {'bf16x2 all':>11s} {'bf16x2 1/2':>11s} {'bf16x2 1/4':>11s}")
+print(f"{'case':44s} {'current':>10s} {'bf16x2 all':>11s} {'bf16x2 1/2':>11s} {'bf16x2 1/4':>11s} {'ones col.':>11s}")
 for name, T, d, qs in [("N(0,1) q,k  T=1024 d=64 (EDM 32x32)", 1024, 64, 1.0), ("sharp (q,k x2) T=1024 d=64", 1024, 64, 2.0),
                        ("very sharp (x4) T=1024 d=64", 1024, 64, 4.0), ("N(0,1) T=4096 d=64 (SDXL 64x64)", 4096, 64, 1.0),
                        ("N(0,1) T=4680 d=128 (Wan chunk)", 4680, 128, 1.0)]:
@@ -49,5 +52,5 @@ for name, T, d, qs in [("N(0,1) q,k  T=1024 d=64 (EDM 32x32)", 1024, 64, 1.0), (
     v = torch.randn(4, T, d).bfloat16()
     r = attn(q, k, v, "ref")
     row = [rel(attn(q, k, v, "current"), r), rel(attn(q, k, v, "bf16x2"), r), rel(attn(q, k, v, "bf16x2", 0.5), r),
-           rel(attn(q, k, v, "bf16x2", 0.25), r)]
+           rel(attn(q, k, v, "bf16x2", 0.25), r), rel(attn(q, k, v, "ones_column"), r)]
     print(f"{name:44s} " + " ".join(f"{e:11.3e}" for e in row))
