@@ -747,6 +747,8 @@ class EDMPrecond(FastGenNetwork):
         self.fuse_gn_stats = True   # GroupNorm statistics accumulated by the conv that writes the tensor
         # attention of the "bf16x3" path: "bf16" = the tensor-core kernel (q, k, v, softmax weights rounded to bf16:
         # ~1e-3 of the fp32 reference), "f32" = fg_attention_f32 (CUDA cores; profiles/x3_emulation.py predicts ~1e-5)
+        if _X3_ATTENTION_DEFAULT not in ("f32", "bf16"):
+            raise ValueError(f"FASTGEN_B200_X3_ATTENTION must be 'f32' or 'bf16', got {_X3_ATTENTION_DEFAULT}")
         self.x3_attention = _X3_ATTENTION_DEFAULT
         self.model = _UNet(model_type, img_resolution=img_resolution, in_channels=img_channels,
                            out_channels=img_channels, label_dim=label_dim, **model_kwargs)

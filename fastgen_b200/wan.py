@@ -249,6 +249,8 @@ class _WanBase:
         # memory: pack and exchange are one kernel storing into the peers' buffers over NVLink, no NCCL call in the
         # layer loop (opt-in: written after the round's GPU budget ended, layout checked on CPU only)
         self.sp_exchange = os.environ.get("FASTGEN_B200_SP_EXCHANGE", "nccl")
+        if self.sp_exchange not in ("nccl", "peer"):
+            raise ValueError(f"FASTGEN_B200_SP_EXCHANGE must be 'nccl' or 'peer', got {self.sp_exchange}")
         self.peer_timeout_s = 20.0
         # with the peer exchange no NCCL call is left in a launch list, so it could replay as a CUDA graph under sequence
         # parallelism too (36 k launches per sample); off until the exchange itself has run on hardware
