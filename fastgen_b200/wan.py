@@ -635,9 +635,8 @@ class _WanBase:
         Hl, Dl = H // P, (H // P) * d   # heads this rank attends with
         if P > 1 and mask:
             raise NotImplementedError("the block-causal mask (full-sequence causal forward) is not sequence-parallel")
-        if P > 1 and not per_frame:
-            # global AdaLN: one group per sample; local rows of a sample are contiguous, so nothing else changes
-            pass
+        # (global AdaLN under sequence parallelism: one group per sample, and the local rows of a sample are contiguous,
+        #  so the modulation-group arithmetic below is the same as on one GPU)
         # ---- embeddings (steps 0..6: see _run_split) ----
         plan.add(lib.fg_patchify, ws["x_in"].data_ptr(), ops._DT[x_dtype], B, cfg["in_channels"], F, Hh, Ww, ph, pw,
                  ws["tok"].data_ptr(), kin, desc="patchify")
