@@ -12,8 +12,9 @@
  *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated otherwise;
  *   - activations are channels-last: a "pixel row" is `C` contiguous elements, consecutive pixels of a
  *     [N,H,W,C] tensor are `ld` elements apart (ld >= C lets a tensor live inside a wider concat buffer);
- *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, keeps no global state
- *     besides a cached driver entry point, and is CUDA-graph capturable;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing and is CUDA-graph capturable; the only
+ *     process-wide state is a cached driver entry point, the one-time shared-memory attribute of each kernel, and the
+ *     fg_sampler_vec switch;
  *   - return value: FG_OK (0) or a negative fg_status; fg_last_error() gives a thread-local message.
  */
 #ifndef FASTGEN_B200_H_
