@@ -178,6 +178,12 @@ def main():
         lab = torch.eye(10)[torch.randint(10, (2,))]
         cases.append(("cifar10 full", CIFAR, 0, torch.randn(2, 3, 32, 32) * 80.0, torch.full((2,), 80.0, dtype=torch.float64),
                       lab))
+    if "--in64" in sys.argv:
+        from bench import IN64  # the BASELINE configs[1] network (295.9 M parameters); one sample, t = 1.1 (second step)
+        torch.manual_seed(2)
+        lab = torch.eye(1000)[torch.randint(1000, (1,))]
+        cases.append(("imagenet64 full", IN64, 0, torch.randn(1, 3, 64, 64) * 1.2, torch.full((1,), 1.1, dtype=torch.float64),
+                      lab))
     print(f"{'network':16s} {'fp32 oracle':>12s} {'x3 + bf16 attn':>15s} {'x3 + f32 attn':>14s}   (rel-L2 of x0 vs the float64 oracle)")
     for name, cfg, seed, x_t, t, labels in cases:
         r = ref64(cfg, seed, x_t, t, labels)
