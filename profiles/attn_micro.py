@@ -48,3 +48,29 @@ run("wan SP4 chunk6 (3 heads)", 1, 4680, 3, 128, 28080, 4680)
 run("wan bidir full tq32760", 1, 32760, 12, 128, 0, 32760, iters=2)
 run("edm 32x32 B256 H6 d64", 256, 1024, 6, 64, 0, 1024)
 run("edm 16x16 B256 H9 d64", 256, 256, 9, 64, 0, 256)
+
+
+def run_f32(tag, b, tq, heads, d, iters=5):
+    """fg_attention_f32 (the fp32 CUDA-core attention of the compute="bf16x3" parity path): `--f32` adds these lines"""
+    dm = heads * d
+    qkv = torch.randn(b, tq, 3 * dm, device=dev)
+    hi = torch.empty(b, tq, dm, device=dev, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    f = lambda: ops.attention_f32(qkv, 3 * dm, b, tq, heads, d, hi, lo, dm)  # noqa: E731
+    f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{tag:44s} {ms:8.3f} ms {4.0 * b * tq * tq * dm / ms / 1e9:8.1f} TFLOP/s (fp32 FMA)", flush=True)
+
+
+if "--f32" in sys.argv:
+    run_f32("f32 edm 32x32 B256 H6 d64", 256, 1024, 6, 64)
+    run_f32("f32 edm 16x16 B256 H9 d64", 256, 256, 9, 64)
+    run_f32("f32 edm 8x8 B256 H12 d64", 256, 64, 12, 64)
+    run_f32("f32 cifar 16x16 B64 H1 d256", 64, 256, 1, 256)
