@@ -591,6 +591,8 @@ class _WanBase:
 
     def clear_caches(self) -> None:
         """reference network_causal.py:1030-1056: lengths to 0, buffers zeroed (here: in place, no re-allocation)"""
+        if self.sp_group is not None and self.sp_exchange == "peer":
+            self.check_peer_exchange()     # a timed-out device-side wait must not pass silently (synchronises)
         for ent in self._kv.values():
             ent["k"].zero_()
             ent["v"].zero_()
