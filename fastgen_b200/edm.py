@@ -22,6 +22,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import warnings
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 
@@ -275,6 +276,7 @@ class _Plan:
         self.dev = next(net.parameters()).device
         self.x3 = net.compute == "bf16x3"
         self.attn_f32 = self.x3 and net.x3_attention == "f32"   # fp32 CUDA-core attention on the fp32-parity path
+        self._warned_widths: Set[int] = set()
         self.steps: List[Tuple[Any, tuple]] = []
         self.step_flops: List[float] = []
         self.step_desc: List[Tuple[str, float]] = []
@@ -331,7 +333,17 @@ class _Plan:
     def _f32_attention(self, b: "_Block") -> bool:
         """fp32 CUDA-core attention for this block: the split-precision path, unless switched off or the head width has
         no fg_attention_f32 instance (then the bf16 tensor-core kernel runs, ~1e-3 instead of ~1e-5)"""
-        return bool(self.attn_f32 and b.num_heads and b.out_channels // b.num_heads in _F32_ATTENTION_WIDTHS)
+        if not (self.attn_f32 and b.num_heads):
+            return False
+        d = b.out_channels // b.num_heads
+        if d not in _F32_ATTENTION_WIDTHS:
+            if d not in self._warned_widths:
+                self._warned_widths.add(d)
+                warnings.warn(f"compute='bf16x3': no fp32 attention kernel for head width {d} (instances: "
+                              f"{_F32_ATTENTION_WIDTHS}); this block uses the bf16 tensor-core attention (~1e-3 instead of "
+                              "~1e-5 of the fp32 reference)")
+            return False
+        return True
 
     def _scratch(self, name: str, shape) -> torch.Tensor:
         numel = int(np.prod(shape))
