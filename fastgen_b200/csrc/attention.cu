@@ -300,15 +300,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 template <int DP, int BKV>
 static int launch_attention(AttnKParams& kp, const fg_flash_attn_params* p, cudaStream_t stream) {
   using Cfg = AttnCfg<DP, BKV>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  const int cfg_dev = current_device();
+  if (!configured.test(cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
-    configured = true;
+    configured.set(cfg_dev);
   }
   {
     const uint64_t dims[4] = {(uint64_t)kp.d, (uint64_t)kp.H, (uint64_t)kp.Tq, (uint64_t)kp.B};

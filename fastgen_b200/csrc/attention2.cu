@@ -661,21 +661,23 @@ static int pick_nsplit(int ctas, int kv_tiles, int num_sms) {
 size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   const int dp = p->d <= 64 ? 64 : 128;
   const size_t rows = static_cast<size_t>(p->batch) * p->heads * p->tq;
-  return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256;  // up to 8 splits: bf16 O + (m, l)
+  // up to 8 splits: bf16 O + (m, l); slack for the 256-byte alignment of (m, l) and the 128-byte alignment of O
+  return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256 + 128;
 }
 
 template <int DP, int POLY, int HALF = 0>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  const int cfg_dev = current_device();
+  if (!configured.test(cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
-    configured = true;
+    configured.set(cfg_dev);
   }
   Attn2KParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -691,9 +693,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
   int nsplit = 1;
   __nv_bfloat16* part_o = nullptr;
   if (p->workspace && static_cast<size_t>(p->workspace_bytes) >= flash_attn_v2_workspace(p) && p->mask_chunk == 0) {
-    int dev = 0, num_sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int num_sms = device_sm_count(cfg_dev);
     static const int force = getenv("FG_ATTN_SPLIT") ? atoi(getenv("FG_ATTN_SPLIT")) : 0;
     const int tiles = (kp.kv_len[0] + kA2BKV - 1) / kA2BKV + (kp.kv_len[1] + kA2BKV - 1) / kA2BKV;
     nsplit = force > 0 ? (force < tiles ? force : tiles) : pick_nsplit(kp.B * kp.H * q_blocks, tiles, num_sms);

@@ -190,14 +190,15 @@ template <int D>
 static int launch_attention_f32(const float* qkv, int64_t qkv_ld, int n, int tokens, int heads, void* out_hi, void* out_lo,
                                 int64_t out_ld, cudaStream_t stream) {
   using Cfg = AttnF32Cfg<D>;
-  static bool configured = false;  // per process; the attribute is per function, setting it twice is harmless
-  if (!configured) {
+  static PerDeviceFlag configured;
+  const int cfg_dev = current_device();
+  if (!configured.test(cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("attention_f32: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
-    configured = true;
+    configured.set(cfg_dev);
   }
   const dim3 grid((tokens + kF32Tile - 1) / kF32Tile, heads, n);
   const float scale_log2e = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(D)));

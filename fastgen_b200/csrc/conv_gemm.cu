@@ -651,15 +651,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 template <int BLOCK_N, int EPI>
 static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  const int cfg_dev = current_device();
+  if (!configured.test(cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
-    configured = true;
+    configured.set(cfg_dev);
   }
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
   conv_gemm_kernel<BLOCK_N, EPI><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
@@ -764,13 +765,9 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   kp.tiles_w = p->w / kp.BW;
   kp.tiles_h = p->h / kp.BH;
   kp.tiles_img = (p->n + kp.BNI - 1) / kp.BNI;
-  int dev = 0, num_sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    // no device (argument checking on a CPU-only host): the tile choice does not matter
-    cudaGetLastError();
-    num_sms = 148;
-  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();  // no device (CPU-only argument check)
+  const int num_sms = device_sm_count(dev);
   const int block_n = pick_block_n(p->cout, kp.tiles_w * kp.tiles_h * kp.tiles_img, num_sms, geglu);
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_img * kp.tiles_n;

@@ -17,6 +17,19 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+int device_sm_count(int dev) {
+  static std::atomic<int> cache[64];
+  if (dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+    cudaGetLastError();  // no device (argument checking on a CPU-only host): callers only size grids with it
+    return 148;
+  }
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

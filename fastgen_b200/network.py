@@ -15,6 +15,17 @@ import torch
 from .noise_schedule import NET_PRED_TYPES, get_noise_schedule
 
 
+def tensor_identity(t: torch.Tensor):
+    """Key under which results derived from a conditioning tensor (text keys / values) may be reused: storage pointer,
+    version counter, shape, dtype.  ``None`` -- never reuse -- for tensors without a version counter: inference tensors
+    (created under ``torch.inference_mode``, as the reference's ``video_model_inference.py`` does for its prompt
+    embeddings, or by ``torch.stack`` of a list condition inside ``generator_fn``) cannot reveal an in-place update or a
+    recycled allocation, so their derived values are recomputed on every call, like the reference does."""
+    if t.is_inference():
+        return None
+    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+
 class FastGenNetwork(ABC, torch.nn.Module):
     def __init__(self, net_pred_type: str = "x0", schedule_type: str = "edm", **net_kwargs):
         super().__init__()

@@ -132,7 +132,7 @@ def attention(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d
 
 def sampler_vec(enable: Optional[bool] = None) -> bool:
     """Select (True / False) or query (None) the vectorised forms of the sampler-step kernels; returns the previous
-    setting.  Opt-in (default off, or FASTGEN_B200_SAMPLER_VEC=1) until they have run on hardware: see ``fg_sampler_vec``."""
+    setting.  Default on (FASTGEN_B200_SAMPLER_VEC=0 turns them off): see ``fg_sampler_vec``."""
     return bool(L.lib().fg_sampler_vec(-1 if enable is None else int(bool(enable))))
 
 

@@ -39,7 +39,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from .network import FastGenNetwork
+from .network import FastGenNetwork, tensor_identity
 from .noise_schedule import NET_PRED_TYPES
 from .wan import _Plan
 
@@ -368,7 +368,7 @@ class StableDiffusionXL(FastGenNetwork):
 
     # ---- text keys / values of every cross-attention layer (static per prompt) ------------------------------
     def _context(self, text: torch.Tensor) -> Dict[str, Any]:
-        key = (text.data_ptr(), text._version, tuple(text.shape), text.dtype)
+        key = tensor_identity(text)
         B, Lt, X = text.shape
         if X != self.cfg["cross_attention_dim"]:
             raise ValueError(f"text embedding width {X} != cross_attention_dim {self.cfg['cross_attention_dim']}")
@@ -389,7 +389,7 @@ class StableDiffusionXL(FastGenNetwork):
             ent["plan"] = plan
             self._ctx = ent
             self._plans = {}     # forward plans point into the previous buffers
-        if ent["key"] != key:
+        if key is None or ent["key"] != key:
             ent["text"].copy_(text.reshape(B * Lt, X))
             ent["plan"].run(torch.cuda.current_stream().cuda_stream, self.profile)
             ent["key"], ent["keep"] = key, text

@@ -35,7 +35,7 @@ from torch import nn
 from . import _lib as L
 from . import ops
 from . import parallel as PL
-from .network import CausalFastGenNetwork, FastGenNetwork
+from .network import CausalFastGenNetwork, FastGenNetwork, tensor_identity
 from .noise_schedule import NET_PRED_TYPES
 
 __all__ = ["Wan", "CausalWan", "WAN_CONFIGS"]
@@ -543,7 +543,7 @@ class _WanBase:
         persistent (forward plans point into them); their contents are recomputed when the condition tensor changes
         or after clear_caches() -- the reference recomputes them per call until the first store_kv pass
         (network_causal.py:326-345), with identical values."""
-        key = (condition.data_ptr(), condition._version, tuple(condition.shape), condition.dtype)
+        key = tensor_identity(condition)
         cfg, pk = self.cfg, self._packed
         D, Ln, Td = cfg["dim"], condition.shape[1], cfg["text_dim"]
         B = condition.shape[0]
@@ -569,7 +569,7 @@ class _WanBase:
             ent["plan"] = plan
             self._cross[cache_tag] = ent
             self._plans = {}   # forward plans hold pointers into the previous buffers
-        if ent["key"] != key:
+        if key is None or ent["key"] != key:
             ent["text"].copy_(condition.reshape(B * Ln, Td))
             ent["plan"].run(torch.cuda.current_stream().cuda_stream, self.profile)
             ent["key"] = key

@@ -325,8 +325,8 @@ int fg_sub_div(const void* a, const void* b, int32_t dtype, int64_t total, int64
 
 /* Select the vectorised forms of fg_edm_step / fg_axpby / fg_sub_div (4 pixels x all channels, resp. 16 bytes, per thread
  * and iteration; same arithmetic, bit-identical results) where shapes and alignment allow: enable = 1 / 0, or -1 to only
- * query.  Returns the previous setting.  Default: the environment variable FASTGEN_B200_SAMPLER_VEC (unset = 0: opt-in
- * until the vector forms have been run on hardware). */
+ * query.  Returns the previous setting.  Default: on (the environment variable FASTGEN_B200_SAMPLER_VEC=0 turns
+ * them off); the scalar forms remain for shapes the vector forms cannot take and for the equality tests. */
 int fg_sampler_vec(int enable);
 
 /* cudaMemsetAsync(ptr, 0, bytes) as a plan step (statistics arenas) */

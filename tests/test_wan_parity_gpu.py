@@ -207,3 +207,42 @@ def test_state_dict_keys_and_original_wan_remap():
     assert not unexpected and all("logvar" in m for m in missing), (missing, unexpected)
     for k, v in sd.items():
         assert torch.equal(net.state_dict()[k], v), k
+
+
+def test_wan_teacher_sampler_runs_on_the_gpu_and_tracks_the_oracle():
+    """`Wan.sample` end to end on the GPU (the loop itself is pinned to the reference on the CPU,
+    tests/test_wan_sample_cpu.py; the forward by tests/test_wan_parity_gpu.py): 4 UniPC steps with guidance 2 against the
+    same loop driven by the fp32 oracle forward.  Also checks that two consecutive flow predictions do not alias."""
+    import fastgen_b200.wan as W
+    from fastgen_b200.unipc import FlowUniPCMultistepScheduler
+    from oracle import wan_oracle as WO
+
+    cfg = WO.tiny_config()
+    sd = {k: v.bfloat16() for k, v in WO.make_state_dict(cfg, 0).items()}
+    net = W.Wan(transformer_config=cfg, enable_logvar_linear=False)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(torch.bfloat16).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    noise = torch.randn(2, 16, 3, 8, 12, generator=g).bfloat16()
+    text, neg = (torch.randn(2, 24, cfg["text_dim"], generator=g).bfloat16() for _ in range(2))
+    t = torch.tensor([0.8, 0.3], dtype=torch.float64, device="cuda")
+    a = net(noise.cuda(), t, condition=text.cuda())
+    a_copy = a.clone()
+    b = net(noise.cuda(), t, condition=neg.cuda())
+    assert a.data_ptr() != b.data_ptr() and torch.equal(a, a_copy)
+    out = net.sample(noise.cuda(), condition=text.cuda(), neg_condition=neg.cuda(), guidance_scale=2.0, num_steps=4, shift=5.0)
+    # the same loop on the CPU with the oracle forward (fp32 arithmetic on the same bf16 weights)
+    sch = FlowUniPCMultistepScheduler()
+    sch.config.flow_shift = 5.0
+    sch.set_timesteps(4)
+    # (latents, flow predictions and the guidance combination stay in the noise dtype, bf16, exactly as in the loop under
+    # test and in the reference: only the network arithmetic differs)
+    lat = (noise.double() * (sch.timesteps[0] / 1000).double()).bfloat16()
+    for ts in sch.timesteps:
+        tt = (ts / 1000).expand(2).bfloat16().double()
+        fc = WO.wan_forward(sd, cfg, lat, tt, text, fwd_pred_type="flow", dtype=torch.float32).bfloat16()
+        fu = WO.wan_forward(sd, cfg, lat, tt, neg, fwd_pred_type="flow", dtype=torch.float32).bfloat16()
+        lat = sch.step(fu + 2.0 * (fc - fu), ts, lat)[0]
+    assert lat.dtype == torch.bfloat16
+    rel = ((out.float().cpu().double() - lat.double()).norm() / lat.double().norm()).item()
+    assert out.dtype == torch.bfloat16 and rel < 5e-2, rel

@@ -92,11 +92,9 @@ def test_sequence_parallel_matches_single_gpu():
             assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
 
 
-_UNVERIFIED = pytest.mark.skipif(os.environ.get("FASTGEN_B200_TEST_UNVERIFIED") != "1",
-                                 reason="never run on hardware yet: set FASTGEN_B200_TEST_UNVERIFIED=1")
 
 
-@_UNVERIFIED
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_matches_single_gpu():
@@ -112,7 +110,6 @@ def test_sequence_parallel_peer_exchange_matches_single_gpu():
             assert len(errs) == 4 and max(errs) < 5e-3, (r, errs)
 
 
-@_UNVERIFIED
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_replays_as_cuda_graphs():
@@ -172,7 +169,6 @@ def _peer_kernel_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@_UNVERIFIED
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(300)
 def test_peer_put_and_wait_kernels_alone():
