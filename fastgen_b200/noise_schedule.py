@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+from contextlib import contextmanager
+
 import torch
 
 NET_PRED_TYPES = {"x0", "eps", "v", "flow"}
@@ -47,6 +49,7 @@ class BaseNoiseSchedule(torch.nn.Module):
         self.num_steps = num_steps
         self.clamp_min = clamp_min
         self.t_precision = _PRECISION[t_precision]
+        self._trusted_depth = 0
 
     # ---- scalar properties -------------------------------------------------------------------------
     @property
@@ -79,16 +82,41 @@ class BaseNoiseSchedule(torch.nn.Module):
         raise NotImplementedError
 
     def alpha(self, t: torch.Tensor) -> torch.Tensor:
-        assert self.is_t_valid(t), f"t must be in range [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         return self._alpha(t)
 
     def sigma(self, t: torch.Tensor) -> torch.Tensor:
-        assert self.is_t_valid(t), f"t must be in range [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         return self._sigma(t)
 
     def rescale_t(self, t: torch.Tensor) -> torch.Tensor:
-        assert self.is_t_valid(t), f"t must be in range [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         return self._rescale_t(t)
+
+    # ---- validity of t --------------------------------------------------------------------------------
+    def _check_t(self, t: torch.Tensor, name: str = "t") -> None:
+        """The reference's ``assert self.is_t_valid(t)`` at the top of every schedule call (:86, :436, ...).  On a device
+        tensor that assert costs a device->host synchronisation per call; inside :meth:`validated_t` -- entered by the
+        sampler loops of ``fastgen_b200.sampler`` after checking the whole t list once on the host -- it is skipped, so the
+        host can queue all the forwards of a sample ahead of the GPU."""
+        if self._trusted_depth > 0:
+            return
+        assert self.is_t_valid(t), f"{name} must be in [{self.min_t}, {self.max_t}], but got {t}"
+
+    @contextmanager
+    def validated_t(self, *t_host: torch.Tensor):
+        """Validate the CPU tensors ``t_host`` (together: every t the enclosed calls will pass, each in the dtype it will
+        be passed in -- the validity slack is one ulp of that dtype) once, then skip the per-call device-side checks inside
+        the block.  Raises the same AssertionError as the per-call check."""
+        for th in t_host:
+            th = torch.as_tensor(th)
+            assert not th.is_cuda, "validated_t takes the host copy of the t list"
+            assert self.is_t_valid(th), f"t must be in [{self.min_t}, {self.max_t}], but got {th}"
+        self._trusted_depth += 1
+        try:
+            yield
+        finally:
+            self._trusted_depth -= 1
 
     # ---- t helpers (reference :90-129, 259-272, 409-423) ---------------------------------------------
     @staticmethod
@@ -127,7 +155,7 @@ class BaseNoiseSchedule(torch.nn.Module):
 
         if t_init is None:
             t_init = torch.as_tensor(self.max_t, dtype=self.t_precision, device=noise.device)
-        assert self.is_t_valid(t_init), f"t_init must be in [{self.min_t}, {self.max_t}], but got {t_init}"
+        self._check_t(t_init, "t_init")
         return self._latents(noise, t_init)
 
     def _latents(self, noise: torch.Tensor, t_init: torch.Tensor) -> torch.Tensor:
@@ -138,7 +166,7 @@ class BaseNoiseSchedule(torch.nn.Module):
 
     def forward_process(self, x: torch.Tensor, eps: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """x*alpha(t) + eps*sigma(t) in float64, one rounding to x.dtype (reference :425-449)."""
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         return self._forward_process(x, eps, t)
 
     def _forward_process(self, x: torch.Tensor, eps: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
@@ -152,7 +180,7 @@ class BaseNoiseSchedule(torch.nn.Module):
         """(xt - x0*alpha) / clamp(sigma)  (reference :544-574)."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.sub_div(xt.contiguous(), x0.contiguous(), _coef(self._alpha(t64).reshape(-1), xt),
                            _coef(self.non_zero_clamp(self._sigma(t64)).reshape(-1), xt))
@@ -161,7 +189,7 @@ class BaseNoiseSchedule(torch.nn.Module):
         """(xt - eps*sigma) / clamp(alpha)  (reference :576-608)."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.sub_div(xt.contiguous(), eps.contiguous(), _coef(self._sigma(t64).reshape(-1), xt),
                            _coef(self.non_zero_clamp(self._alpha(t64)).reshape(-1), xt))
@@ -171,7 +199,7 @@ class BaseNoiseSchedule(torch.nn.Module):
         Evaluated as ((xt*c + v*(-1)) then / d) so each step is one fp64 op like the reference."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         xt_coeff = self._sigma_prime(t64) / self.non_zero_clamp(self._sigma(t64))
         x0_coeff = self.non_zero_clamp(xt_coeff * self._alpha(t64) - self._alpha_prime(t64))
@@ -269,7 +297,7 @@ class EDMNoiseSchedule(BaseNoiseSchedule):
         """x0 = xt - v*t  (reference :975-1004)."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.axpby(xt.contiguous(), _coef(torch.ones_like(t64).reshape(-1), xt), v.contiguous(),
                          _coef((-t64).reshape(-1), xt))
@@ -278,7 +306,7 @@ class EDMNoiseSchedule(BaseNoiseSchedule):
         """(xt - x0) / clamp(t)  (reference :1006-1034)."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.sub_div(xt.contiguous(), x0.contiguous(), _coef(torch.ones_like(t64).reshape(-1), xt),
                            _coef(self.non_zero_clamp(t64).reshape(-1), xt))
@@ -365,7 +393,7 @@ class AlphasNoiseSchedule(BaseNoiseSchedule):
         """x0 = alpha*xt - sigma*v  (reference :1161-1202)."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         self._check_vp(t64, xt.dtype)
         return ops.axpby(xt.contiguous(), _coef(self._alpha(t64).reshape(-1), xt), v.contiguous(),
@@ -375,7 +403,7 @@ class AlphasNoiseSchedule(BaseNoiseSchedule):
         """v = (alpha*xt - x0) / clamp(sigma)  (reference :1204-1233), i.e. -(x0 - xt*alpha)/sigma."""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         self._check_vp(t64, xt.dtype)
         return ops.sub_div(x0.contiguous(), xt.contiguous(), _coef(self._alpha(t64).reshape(-1), xt),
@@ -422,7 +450,7 @@ class TrigNoiseSchedule(BaseNoiseSchedule):
 
     def sqrt_snr(self, t: torch.Tensor) -> torch.Tensor:
         """cot(t) with tan(t) clamped away from zero (reference :1547-1557)"""
-        assert self.is_t_valid(t)
+        self._check_t(t)
         return 1.0 / self.non_zero_clamp(torch.tan(t.to(torch.float64)))
 
     def sqrt_snr_to_t(self, sqrt_snr_t: torch.Tensor) -> torch.Tensor:
@@ -433,7 +461,7 @@ class TrigNoiseSchedule(BaseNoiseSchedule):
         """x0 = cos(t) x_t - sin(t) v in float64, one rounding (reference :1617-1634)"""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.axpby(xt.contiguous(), _coef(torch.cos(t64).reshape(-1), xt), v.contiguous(),
                          _coef(-torch.sin(t64).reshape(-1), xt))
@@ -443,7 +471,7 @@ class TrigNoiseSchedule(BaseNoiseSchedule):
         (x_0 - x_t cos(t)) / (-clamp(sin(t))), the same float64 operations up to two exact sign flips"""
         from . import ops
 
-        assert self.is_t_valid(t), f"t must be in [{self.min_t}, {self.max_t}], but got {t}"
+        self._check_t(t, "t")
         t64 = t.to(torch.float64)
         return ops.sub_div(x0.contiguous(), xt.contiguous(), _coef(torch.cos(t64).reshape(-1), xt),
                            _coef(-self.non_zero_clamp(torch.sin(t64)).reshape(-1), xt))

@@ -16,7 +16,7 @@ the host side and invisible to results:
 """
 from __future__ import annotations
 
-from contextlib import contextmanager
+from contextlib import ExitStack, contextmanager
 from typing import Any, List, Optional
 
 import torch
@@ -61,14 +61,17 @@ class FastGenModel:
     @classmethod
     def _student_sample_loop(cls, net, x: torch.Tensor, t_list: torch.Tensor, condition: Any = None,
                              student_sample_type: str = "sde", **kwargs) -> torch.Tensor:
-        batch_size = x.shape[0]
-        has_preserve_hook = hasattr(net, "preserve_conditioning")
         t_host = t_list.detach().cpu()
-        t_dev = t_list.to(x.device)
-        sched = net.noise_scheduler
         # validate every t that reaches a schedule call once, on the host (the reference asserts inside each call,
         # paying a device sync each time; the trailing 0 is never passed to the schedule)
-        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
+        with net.noise_scheduler.validated_t(t_host[:-1]):
+            return cls._sample_loop_validated(net, x, t_host, t_list.to(x.device), condition, student_sample_type)
+
+    @classmethod
+    def _sample_loop_validated(cls, net, x, t_host, t_dev, condition, student_sample_type):
+        batch_size = x.shape[0]
+        has_preserve_hook = hasattr(net, "preserve_conditioning")
+        sched = net.noise_scheduler
         fused = isinstance(net, EDMPrecond) and net.net_pred_type == "x0" and not has_preserve_hook
         x_pred = x
         for i in range(len(t_host) - 1):
@@ -136,11 +139,14 @@ class MeanFlowModel(FastGenModel):
     @classmethod
     def _student_sample_loop(cls, net, x: torch.Tensor, t_list: torch.Tensor, condition: Any = None,
                              student_sample_type: str = "sde", **kwargs) -> torch.Tensor:
-        batch_size = x.shape[0]
         t_host = t_list.detach().cpu()
-        t_dev = t_list.to(x.device)
+        with net.noise_scheduler.validated_t(t_host):   # r = t_next (0 included) reaches the schedule in ode mode
+            return cls._sample_loop_validated(net, x, t_host, t_list.to(x.device), condition, student_sample_type)
+
+    @classmethod
+    def _sample_loop_validated(cls, net, x, t_host, t_dev, condition, student_sample_type):
+        batch_size = x.shape[0]
         sched = net.noise_scheduler
-        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
         for i in range(len(t_host) - 1):
             t_cur_batch = t_dev[i].expand(batch_size)
             t_next_batch = t_dev[i + 1].expand(batch_size)
@@ -168,14 +174,21 @@ class CausVidModel(FastGenModel):
     def _student_sample_loop(cls, net, x: torch.Tensor, t_list: torch.Tensor, condition: Any = None,
                              student_sample_type: str = "sde", context_noise: Optional[float] = 0, **kwargs
                              ) -> torch.Tensor:
+        t_host = t_list.detach().cpu()
+        # every t a forward or a schedule call of the loop sees: the list (its trailing 0 is the cache-fill timestep) and
+        # the context-noise level rounded to the latent dtype -- validated once here, not per call on the device
+        seen = [t_host] + ([torch.tensor([context_noise], dtype=x.dtype)] if context_noise > 0 else [])
+        with net.noise_scheduler.validated_t(*seen):
+            return cls._sample_loop_validated(net, x, t_host, t_list.to(x.device), condition, student_sample_type,
+                                              context_noise, **kwargs)
+
+    @classmethod
+    def _sample_loop_validated(cls, net, x, t_host, t_dev, condition, student_sample_type, context_noise, **kwargs):
         net.clear_caches()
         batch_size, num_frames = x.shape[0], x.shape[2]
         chunk_size = net.chunk_size
         num_chunks, remaining = num_frames // chunk_size, num_frames % chunk_size
-        t_host = t_list.detach().cpu()
-        t_dev = t_list.to(x.device)
         sched = net.noise_scheduler
-        assert sched.is_t_valid(t_host[:-1]), f"t must be in [{sched.min_t}, {sched.max_t}], but got {t_host}"
         for i in range(max(1, num_chunks)):
             if num_chunks == 0:
                 start, end = 0, remaining
@@ -221,7 +234,7 @@ class CausVidModel(FastGenModel):
         calls ``get_t_list(..., dtype=torch.float32)``, a keyword that method does not take (causvid.py:244 vs
         noise_schedule.py:259), so only its explicit-``t_list`` branch runs; here the default list is
         ``get_t_list(steps)`` cast to float32."""
-        with inference_mode(net, precision_amp=precision_amp, device_type=noise.device.type):
+        with inference_mode(net, precision_amp=precision_amp, device_type=noise.device.type), ExitStack() as trusted:
             if num_segments < 1:
                 raise ValueError("num_segments must be >= 1")
             if overlap_frames > 0 and getattr(net, "vae", None) is None:
@@ -244,6 +257,8 @@ class CausVidModel(FastGenModel):
                 tl = torch.tensor(t_list, device=device, dtype=torch.float32)
             t_host = tl.detach().cpu()
             assert t_host[-1].item() == 0, "t_list[-1] must be zero"
+            seen = [t_host] + ([torch.tensor([context_noise], dtype=dtype)] if context_noise and context_noise > 0 else [])
+            trusted.enter_context(sched.validated_t(*seen))   # one host-side check instead of a device sync per call
             fwd = dict(condition=condition, fwd_pred_type="x0", cache_tag="pos", is_ar=True)
 
             def prefill_caches(segment_latents: torch.Tensor, frames: int) -> None:

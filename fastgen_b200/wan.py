@@ -990,8 +990,8 @@ class Wan(_WanBase, FastGenNetwork):
             if r is not None:
                 r = torch.atleast_1d(r).to(x_t.device)
                 r_timestep = self.noise_scheduler.rescale_t(r.expand(x_t.shape[0]) if r.numel() == 1 else r)
-            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False, cache_tag="__bidir__",
-                                        r_timestep=r_timestep)
+            out = self._run_transformer(x_t.contiguous(), timestep, condition, per_frame=False,
+                                        cache_tag=getattr(self, "_bidir_cache_tag", "__bidir__"), r_timestep=r_timestep)
             if fwd_pred_type == self.net_pred_type:
                 out = out.clone()   # the caller owns what it gets back (reference: a fresh tensor); `out` is the plan's buffer
             return self.noise_scheduler.convert_model_output(x_t, out, t, src_pred_type=self.net_pred_type,
@@ -1013,17 +1013,28 @@ class Wan(_WanBase, FastGenNetwork):
         t_init = timesteps[0] / sch.config.num_train_timesteps
         latents = self.noise_scheduler.latents(noise=noise, t_init=t_init)
         ns = self.noise_scheduler
-        for idx, timestep in enumerate(timesteps):
-            t = (timestep / sch.config.num_train_timesteps).expand(latents.shape[0])
-            t = ns.safe_clamp(t, min=ns.min_t, max=ns.max_t).to(latents.dtype)
-            flow_pred = self(latents, t, condition=condition, r=None, return_features_early=False, feature_indices={},
-                             return_logvar=False)
-            if guidance_scale is not None:
-                flow_uncond = self(latents, t, condition=neg_condition, r=None, return_features_early=False,
-                                   feature_indices={}, return_logvar=False,
-                                   skip_layers=skip_layers if idx >= skip_layers_start_percent * num_steps else None)
-                flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
-            latents = sch.step(flow_pred, timestep, latents, return_dict=False)[0]
+        # every t of the trajectory checked once on the host (one copy), not per forward on the device
+        t_all = ns.safe_clamp(timesteps / sch.config.num_train_timesteps, min=ns.min_t, max=ns.max_t).to(latents.dtype)
+        with ns.validated_t(t_all.cpu()):
+            for idx, timestep in enumerate(timesteps):
+                t = (timestep / sch.config.num_train_timesteps).expand(latents.shape[0])
+                t = ns.safe_clamp(t, min=ns.min_t, max=ns.max_t).to(latents.dtype)
+                flow_pred = self(latents, t, condition=condition, r=None, return_features_early=False, feature_indices={},
+                                 return_logvar=False)
+                if guidance_scale is not None:
+                    # its own cache tag: the text keys / values of the negative prompt are computed once, not per step
+                    # (an attribute, not a keyword: the forward is called with exactly the reference's arguments)
+                    self._bidir_cache_tag = "__bidir_neg__"
+                    try:
+                        flow_uncond = self(latents, t, condition=neg_condition, r=None, return_features_early=False,
+                                           feature_indices={}, return_logvar=False,
+                                           skip_layers=skip_layers if idx >= skip_layers_start_percent * num_steps else None)
+                    finally:
+                        self._bidir_cache_tag = "__bidir__"
+                    flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
+                latents = sch.step(flow_pred, timestep, latents, return_dict=False)[0]
+        if self.sp_group is not None and self.sp_exchange == "peer":
+            self.check_peer_exchange()
         return latents
 
 
@@ -1117,36 +1128,41 @@ class CausalWan(_WanBase, CausalFastGenNetwork):
         num_chunks, remaining_size = num_frames // self.chunk_size, num_frames % self.chunk_size
         sch = self.unipc_scheduler
         time_rescale_factor = sch.config.num_train_timesteps
-        for i in range(max(1, num_chunks)):
-            if num_chunks == 0:
-                start, end = 0, remaining_size
-            else:
-                start = 0 if i == 0 else self.chunk_size * i + remaining_size
-                end = self.chunk_size * (i + 1) + remaining_size
-            x_next = x[:, :, start:end]
-            sch.config.flow_shift = shift
-            sch.set_timesteps(num_inference_steps=sample_steps, device=noise.device)
-            for timestep in sch.timesteps:
-                t = (timestep / time_rescale_factor).expand(batch_size)
-                x_cur = x_next
-                flow_pred = self(x_cur, t, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=False,
-                                 is_ar=True)
+        sch.config.flow_shift = shift
+        sch.set_timesteps(num_inference_steps=sample_steps, device=noise.device)
+        seen = [(sch.timesteps / time_rescale_factor).cpu(), torch.tensor([context_noise if context_noise > 0 else 0.0],
+                                                                          dtype=x.dtype)]
+        with self.noise_scheduler.validated_t(*seen):   # one host-side check instead of a sync per forward
+            for i in range(max(1, num_chunks)):
+                if num_chunks == 0:
+                    start, end = 0, remaining_size
+                else:
+                    start = 0 if i == 0 else self.chunk_size * i + remaining_size
+                    end = self.chunk_size * (i + 1) + remaining_size
+                x_next = x[:, :, start:end]
+                sch.config.flow_shift = shift
+                sch.set_timesteps(num_inference_steps=sample_steps, device=noise.device)
+                for timestep in sch.timesteps:
+                    t = (timestep / time_rescale_factor).expand(batch_size)
+                    x_cur = x_next
+                    flow_pred = self(x_cur, t, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=False,
+                                     is_ar=True)
+                    if guidance_scale is not None:
+                        flow_uncond = self(x_cur, t, condition=neg_condition, cache_tag="neg", cur_start_frame=start,
+                                           store_kv=False, is_ar=True)
+                        flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
+                    x_next = sch.step(flow_pred, timestep, x_next, return_dict=False)[0]
+                x[:, :, start:end] = x_next
+                # rerun at t = 0 (or with context noise) to write this chunk's keys / values into the caches
+                x_cache = x_next
+                t_cache = torch.full((batch_size,), 0, device=x.device, dtype=x.dtype)
+                if context_noise > 0:
+                    t_cache = torch.full((batch_size,), context_noise, device=x.device, dtype=x.dtype)
+                    x_cache = self.noise_scheduler.forward_process(x_next, torch.randn_like(x_next), t_cache)
+                _ = self(x_cache, t_cache, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=True, is_ar=True)
                 if guidance_scale is not None:
-                    flow_uncond = self(x_cur, t, condition=neg_condition, cache_tag="neg", cur_start_frame=start,
-                                       store_kv=False, is_ar=True)
-                    flow_pred = flow_uncond + guidance_scale * (flow_pred - flow_uncond)
-                x_next = sch.step(flow_pred, timestep, x_next, return_dict=False)[0]
-            x[:, :, start:end] = x_next
-            # rerun at t = 0 (or with context noise) to write this chunk's keys / values into the caches
-            x_cache = x_next
-            t_cache = torch.full((batch_size,), 0, device=x.device, dtype=x.dtype)
-            if context_noise > 0:
-                t_cache = torch.full((batch_size,), context_noise, device=x.device, dtype=x.dtype)
-                x_cache = self.noise_scheduler.forward_process(x_next, torch.randn_like(x_next), t_cache)
-            _ = self(x_cache, t_cache, condition=condition, cache_tag="pos", cur_start_frame=start, store_kv=True, is_ar=True)
-            if guidance_scale is not None:
-                _ = self(x_cache, t_cache, condition=neg_condition, cache_tag="neg", cur_start_frame=start, store_kv=True,
-                         is_ar=True)
+                    _ = self(x_cache, t_cache, condition=neg_condition, cache_tag="neg", cur_start_frame=start, store_kv=True,
+                             is_ar=True)
         self.clear_caches()
         self.train(was_training)
         return x
