@@ -28,6 +28,8 @@ from typing import Any, Dict, List
 import torch
 import torch.nn.functional as F
 
+from .device import sdpa
+
 SDXL_BASE = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
                  down_attn=(False, True, True), transformer_layers=(1, 2, 10), num_heads=(5, 10, 20),
                  cross_attention_dim=2048, addition_time_embed_dim=256, pooled_dim=1280, norm_groups=32)
@@ -146,8 +148,8 @@ def timesteps_proj(t: torch.Tensor, dim: int) -> torch.Tensor:
     """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32."""
     half = dim // 2
     exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
-    emb = t[:, None].float() * torch.exp(exponent)[None, :]
-    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+    emb = t.cpu()[:, None].float() * torch.exp(exponent)[None, :]     # small table: always evaluated on the CPU
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1).to(t.device)
 
 
 def _w(sd, name, x):
@@ -184,7 +186,7 @@ def attention(sd, p, x, ctx, heads):
     q = _lin(sd, p + "to_q", x).view(B, N, heads, -1).transpose(1, 2)
     k = _lin(sd, p + "to_k", ctx).view(B, ctx.shape[1], heads, -1).transpose(1, 2)
     v = _lin(sd, p + "to_v", ctx).view(B, ctx.shape[1], heads, -1).transpose(1, 2)
-    o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+    o = sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
     return _lin(sd, p + "to_out.0", o)
 
 
@@ -254,12 +256,13 @@ def alphas_cumprod() -> torch.Tensor:
 def sdxl_forward(sd, cfg, x_t, t, text, pooled, fwd_pred_type="x0", dtype=torch.float32, resolution=1024):
     """StableDiffusionXL.forward (SDXL/network.py:334-416): eps prediction, 'sdxl' (alphas) schedule."""
     B = x_t.shape[0]
-    time_ids = torch.tensor([[resolution, resolution, 0, 0, resolution, resolution]], dtype=torch.float32).repeat(B, 1)
+    time_ids = torch.tensor([[resolution, resolution, 0, 0, resolution, resolution]], dtype=torch.float32,
+                            device=x_t.device).repeat(B, 1)
     eps = unet_forward(sd, cfg, x_t.to(dtype), (t.double() * 1000.0).to(t.dtype), text, pooled.to(dtype), time_ids)
     eps = eps.to(x_t.dtype)
     if fwd_pred_type == "eps":
         return eps
-    abar = alphas_cumprod().double()
+    abar = alphas_cumprod().double().to(x_t.device)
     idx = (1000 * t.double()).long().clamp(0, 999)
     a, s = abar[idx].sqrt().reshape(-1, 1, 1, 1), (1 - abar[idx]).sqrt().reshape(-1, 1, 1, 1)
     a = torch.where(a >= 0, a.clamp(min=1e-6), a.clamp(max=-1e-6))

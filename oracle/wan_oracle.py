@@ -49,6 +49,8 @@ from typing import Any, Dict, List, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
+from .device import sdpa
+
 WAN_1_3B = dict(dim=1536, heads=12, head_dim=128, ffn_dim=8960, layers=30, in_channels=16, out_channels=16,
                 text_dim=4096, freq_dim=256, patch=(1, 2, 2), eps=1e-6, rope_max_seq_len=1024)
 WAN_14B = dict(WAN_1_3B, dim=5120, heads=40, ffn_dim=13824, layers=40)
@@ -199,10 +201,10 @@ class KVCache:
     """external self / cross KV caches of one cache tag (network_causal.py:703-814): zero-initialised buffers
     [B, capacity, H, d] per block, plus the static cross-attention K/V."""
 
-    def __init__(self, cfg, batch: int, capacity_tokens: int, text_len: int, dtype: torch.dtype):
+    def __init__(self, cfg, batch: int, capacity_tokens: int, text_len: int, dtype: torch.dtype, device=None):
         h, d = cfg["heads"], cfg["head_dim"]
-        self.k = [torch.zeros(batch, capacity_tokens, h, d, dtype=dtype) for _ in range(cfg["layers"])]
-        self.v = [torch.zeros(batch, capacity_tokens, h, d, dtype=dtype) for _ in range(cfg["layers"])]
+        self.k = [torch.zeros(batch, capacity_tokens, h, d, dtype=dtype, device=device) for _ in range(cfg["layers"])]
+        self.v = [torch.zeros(batch, capacity_tokens, h, d, dtype=dtype, device=device) for _ in range(cfg["layers"])]
         self.cross: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None] * cfg["layers"]
 
 
@@ -237,7 +239,7 @@ def attention(sd, pre, cfg, hidden, enc=None, rotary=None, cache: Optional[KVCac
         if cache_start > 0:
             k = torch.cat([cache.k[layer][:, :cache_start], k], dim=1)
             v = torch.cat([cache.v[layer][:, :cache_start], v], dim=1)
-    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=mask)
+    o = sdpa(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), mask)
     o = o.transpose(1, 2).flatten(2, 3).type_as(q)
     return _linear(sd, pre + "to_out.0", o)
 
@@ -320,12 +322,16 @@ def transformer_forward(sd, cfg, x: torch.Tensor, timestep: torch.Tensor, text: 
     ppf, pph, ppw = Fr // pt, Hh // ph, Ww // pw
     D = cfg["dim"]
     p = "transformer."
-    rotary = rope_for_grid(cfg, ppf, pph, ppw, cur_start_frame)
+    rotary = tuple(r.to(x.device) for r in rope_for_grid(cfg, ppf, pph, ppw, cur_start_frame))
     hs = F.conv3d(x, sd[p + "patch_embedding.weight"].to(dt), sd[p + "patch_embedding.bias"].to(dt), stride=(pt, ph, pw))
     hs = hs.flatten(2).transpose(1, 2)
     per_frame = timestep.ndim == 2
     ts = timestep.flatten()
-    emb = sinusoidal_embedding_1d_wan(cfg["freq_dim"], ts) if official_sinusoidal else timesteps_diffusers(ts, cfg["freq_dim"])
+    # (the small sinusoid tables are always evaluated on the CPU, so a GPU evaluation of this oracle differs from the CPU
+    # one by float32 layer arithmetic only, not by a different libm)
+    ts_h = ts.cpu()
+    emb = (sinusoidal_embedding_1d_wan(cfg["freq_dim"], ts_h) if official_sinusoidal
+           else timesteps_diffusers(ts_h, cfg["freq_dim"])).to(x.device)
     if per_frame:
         emb = emb.unflatten(0, (B, -1))
     emb = emb.to(dt)
@@ -339,11 +345,11 @@ def transformer_forward(sd, cfg, x: torch.Tensor, timestep: torch.Tensor, text: 
     if r_timestep is not None:
         if p + "r_embedder.time_proj.weight" not in sd:
             raise ValueError("r_timestep provided but no r_embedder is present")
-        rt = r_timestep.flatten()
+        rt = r_timestep.flatten().cpu()
         if time_cond_type == "diff":
-            rt = ts - rt
+            rt = ts_h - rt
         remb_in = (sinusoidal_embedding_1d_wan(cfg["freq_dim"], rt) if official_sinusoidal
-                   else timesteps_diffusers(rt, cfg["freq_dim"]))
+                   else timesteps_diffusers(rt, cfg["freq_dim"])).to(x.device)
         if per_frame:
             remb_in = remb_in.unflatten(0, (B, -1))
         remb = _linear(sd, p + "r_embedder.time_embedder.linear_2",
@@ -412,12 +418,12 @@ def causal_wan_forward(sd, cfg, x_t, t, text, *, cache: Optional[KVCache] = None
     ts = (t.double() * 1000.0).to(t.dtype)
     if ts.ndim == 1:
         ts = ts.view(-1, 1)
-    timestep = torch.ones(B, Fr, dtype=ts.dtype) * ts
+    timestep = torch.ones(B, Fr, dtype=ts.dtype, device=ts.device) * ts
     mask = None
     use_cache = cache if Fr < total_num_frames else None
     if use_cache is None and not is_ar:
         _, ph, pw = cfg["patch"]
-        mask = block_causal_mask(Fr, (Hh // ph) * (Ww // pw), chunk_size)
+        mask = block_causal_mask(Fr, (Hh // ph) * (Ww // pw), chunk_size).to(x_t.device)
     out = transformer_forward(sd, cfg, x_t.to(dtype), timestep, text.to(dtype), official_sinusoidal=official_sinusoidal,
                               cache=use_cache, cur_start_frame=cur_start_frame, store_kv=store_kv, mask=mask)
     t_conv = t[:, None, :, None, None] if t.ndim == 2 else t
