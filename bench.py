@@ -111,7 +111,7 @@ def _randomize_zero_init_(net, seed: int) -> None:
                 p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
 
 
-REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_DIR = os.environ.get("FASTGEN_B200_REF_DIR", os.path.join(ROOT, "baseline", "_ref"))
 
 
 def _reference_package():
@@ -202,7 +202,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = "cifar" if args.workload == "cifar" else "in64"
-    sample = 64 if wl == "cifar" else 16
+    sample = args.ref_sample or (64 if wl == "cifar" else 16)
     t0 = time.perf_counter()
     cpu = _cpu_baseline(wl, sample, repeats=max(1, args.steps), warmup=min(args.warmup, 1))
     metric = "samples/sec, 1-step CIFAR-10 EDM DMD2 generator" if wl == "cifar" else METRIC
@@ -220,24 +220,58 @@ def run_reference(args):
     print(json.dumps(out))
 
 
-def run_ours(args):
-    import torch.distributed as dist
+class _Dist:
+    """one process per GPU: rank / device / (optional) NCCL process group, the barrier and the max-over-ranks timer"""
 
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        torch.cuda.synchronize()
+
+    def timed(self, fn, iters):
+        """K calls bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks"""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def close(self):
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.destroy_process_group()
+
+
+def measure_in64(ctx: "_Dist", B: int, K: int, W: int, compute: str = "bf16", e2e: bool = True):
+    """EDM ImageNet-64 2-step sampler at batch B per GPU: device-resident throughput, end-to-end throughput through
+    FastGenModel.generator_fn with HOST buffers, and a per-launch CUDA-event pass for the roofline.  compute="bf16x3" is
+    the fp32 path (three bf16 products per convolution + fp32 attention): the reference's precision default."""
     from fastgen_b200 import ops
     from fastgen_b200.edm import EDMPrecond
     from fastgen_b200.sampler import FastGenModel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, max(args.warmup, 0)
-
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     torch.manual_seed(0)
-    net = EDMPrecond(**IN64)
+    net = EDMPrecond(**IN64, compute=compute)
     _randomize_zero_init_(net, 0)
     net = net.to(dev).eval()
     torch.manual_seed(1 + rank)  # per-rank seeds, like set_random_seed(by_rank=True) in the reference scripts
@@ -250,62 +284,44 @@ def run_ours(args):
         return FastGenModel.generator_fn(net, n_, condition=l_, student_sample_steps=STEPS_PER_SAMPLE, t_list=T_LIST,
                                          student_sample_type="sde")
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    def timed(fn, iters):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
     for _ in range(W):
         gen(noise, labels)
-    # ---- device-resident throughput ----
     ops.launch_count_reset()
-    with ClockSampler(local) as clk:
-        ms = timed(lambda: gen(noise, labels), K)
-    launches = ops.launch_count()
-    value = world * B * K / (ms / 1000.0)
+    with ClockSampler(ctx.local) as clk:
+        ms = ctx.timed(lambda: gen(noise, labels), K)
+    res = {"value": world * B * K / (ms / 1000.0), "ms_per_step": ms / K, "gpu_launches": ops.launch_count(),
+           "clocks": clk.summary(), "batch_per_gpu": B}
 
-    # ---- end to end through the public API with HOST buffers (H2D of noise+labels, D2H of the images, per step) ----
-    def e2e_step():
-        n_d = noise_h.to(dev, non_blocking=True)
-        l_d = labels_h.to(dev, non_blocking=True)
-        out_h.copy_(gen(n_d, l_d), non_blocking=True)
+    if e2e:
+        def e2e_step():
+            n_d = noise_h.to(dev, non_blocking=True)
+            l_d = labels_h.to(dev, non_blocking=True)
+            out_h.copy_(gen(n_d, l_d), non_blocking=True)
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, K)
-    e2e_value = world * B * K / (ms_e2e / 1000.0)
+        e2e_step()
+        ms_e2e = ctx.timed(e2e_step, K)
+        res["e2e"] = {"value": world * B * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
+                      "h2d_bytes_per_step": noise_h.numel() * 4 + labels_h.numel() * 4,
+                      "d2h_bytes_per_step": out_h.numel() * 4}
 
     # ---- roofline pass: CUDA-event pair around every launch of the same K steps ----
     hbm, tf_sus, tf_burst, peak_src = _peaks()
     net.profile = {}
-    barrier()
+    ctx.barrier()
     for _ in range(K):
         gen(noise, labels)
-    barrier()
+    ctx.barrier()
     prof, net.profile = net.profile, None
     tot_ms = sum(d["ms"] for d in prof.values())
     conv = prof.get("fg_conv_gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     conv_tflops = conv["flops"] / (conv["ms"] / 1000.0) / 1e12 if conv["ms"] else 0.0
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
+    if os.path.exists(tr_path) and compute == "bf16" and B == BATCH:
         with open(tr_path) as f:
             traffic = json.load(f).get("fg_conv_gemm_bytes_per_launch")
-    roofline = {
+    att = [d for k, d in prof.items() if k.startswith("fg_attention") and d.get("ms")]
+    res["roofline"] = {
         "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear)", "bound": "tensor",
         "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus if tf_sus else None,
         "traffic": traffic,
@@ -314,46 +330,114 @@ def run_ours(args):
                         "because consumers hit the 126 MB L2",
         "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
         "how": "sum of algorithmic conv/linear FLOPs of all fg_conv_gemm launches / sum of their CUDA-event durations, "
-               f"separate measurement pass of the same {K} steps",
+               f"separate measurement pass of the same {K} steps"
+               + (" (bf16x3: the tensor pipe executes 3x the algorithmic FLOPs, `executed_tflops`)" if compute == "bf16x3" else ""),
         "launches_per_step": conv["launches"] / K, "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
         "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
         "per_kernel_ms_per_step": {k: round(d["ms"] / K, 3) for k, d in sorted(prof.items())},
-        "attention_tflops": (prof["fg_attention"]["flops"] / (prof["fg_attention"]["ms"] / 1000.0) / 1e12
-                             if prof.get("fg_attention", {}).get("ms") else None),
+        "attention_tflops": (sum(d["flops"] for d in att) / (sum(d["ms"] for d in att) / 1000.0) / 1e12) if att else None,
         "model_flops_utilisation": (world * B * K * STEPS_PER_SAMPLE * GFLOP_PER_SAMPLE_FORWARD * 1e9 /
                                     (ms / 1000.0) / 1e12) / (world * tf_sus),
     }
+    if compute == "bf16x3":
+        res["roofline"]["executed_tflops"] = 3.0 * conv_tflops
+    del net
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample ----
+
+class _Watchdog:
+    """The secondary measurements of `also` must never cost the headline line: if they overrun (a hung collective, a
+    box slower than planned) rank 0 prints the line it already has and every rank leaves with status 0."""
+
+    def __init__(self, seconds: float, on_expire):
+        self.timer = threading.Timer(seconds, self._fire)
+        self.timer.daemon = True
+        self.on_expire = on_expire
+
+    def _fire(self):
+        try:
+            self.on_expire()
+        finally:
+            sys.stdout.flush()
+            os._exit(0)
+
+    def __enter__(self):
+        self.timer.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.timer.cancel()
+
+
+def run_ours(args):
+    ctx = _Dist()
+    world, rank = ctx.world, ctx.rank
+    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    main = measure_in64(ctx, B, K, W)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sample = 4
-        sps, _ = cpu_port_samples_per_sec(sample, threads, repeats=1, warmup=0)
-        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"one 2-step generation of a batch of {sample} (same network, t_list, fp32) with the oracle "
-                         "(pinned CPU port of the reference)"}
+        cpu = _cpu_baseline("in64", 16, repeats=2, warmup=0)
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "t_list": T_LIST,
-                       "sample_type": "sde", "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "l2": "no explicit flush: per step the kernels stream ~0.6 GB of weights and >10 GB of "
-                             "activations, far beyond the 126 MB L2"},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": noise_h.numel() * 4 + labels_h.numel() * 4,
-                    "d2h_bytes_per_step": out_h.numel() * 4},
-            "gpu_launches": launches,
-            "clocks": clk.summary(),
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    line = {
+        "metric": METRIC, "value": main["value"], "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "t_list": T_LIST,
+                   "sample_type": "sde", "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "l2": "no explicit flush: per step the kernels stream ~0.6 GB of weights and >10 GB of "
+                         "activations, far beyond the 126 MB L2"},
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "roofline": main["roofline"],
+        "cpu_baseline": cpu, "also": {},
+    }
+    also = line["also"]
+
+    def emit():
+        if rank == 0:
+            print(json.dumps(line))
+            sys.stdout.flush()
+
+    if args.no_also:
+        emit()
+        ctx.close()
+        return
+
+    def expired():
+        also["watchdog"] = f"secondary measurements cut off after {args.also_budget_s} s; entries present are complete"
+        emit()
+
+    with _Watchdog(args.also_budget_s, expired):
+        # (1) the fp32 path (compute="bf16x3": what matches the reference at the reference's precision, <= 1e-4)
+        try:
+            r = measure_in64(ctx, B, max(2, K // 4), 1, compute="bf16x3", e2e=False)
+            also["in64_bf16x3"] = {"metric": METRIC + " (fp32 path: three-product convolutions + fp32 attention, parity <= 1e-4)",
+                                   "value": r["value"], "unit": "samples/s", "ms_per_step": r["ms_per_step"],
+                                   "batch_per_gpu": B, "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]}
+        except Exception as e:  # pragma: no cover
+            also["in64_bf16x3"] = {"error": repr(e)}
+        # (2) strong scaling of BASELINE configs[1] as it is worded ("batch 256, batch-sharded over 8 GPUs": 256 / N per GPU)
+        if world > 1 and BATCH % world == 0:
+            try:
+                r = measure_in64(ctx, BATCH // world, K, W, e2e=False)
+                also["in64_strong_scaling"] = {"metric": METRIC + f", global batch {BATCH} sharded over {world} GPUs",
+                                               "value": r["value"], "unit": "samples/s", "ms_per_step": r["ms_per_step"],
+                                               "batch_per_gpu": BATCH // world, "scaling": "strong",
+                                               "conv_tflops": r["roofline"]["achieved"],
+                                               "model_flops_utilisation": r["roofline"]["model_flops_utilisation"]}
+            except Exception as e:  # pragma: no cover
+                also["in64_strong_scaling"] = {"error": repr(e)}
+        # (3) north_star's scaling target: Wan 2.1 1.3B 4-step self-forcing under Ulysses sequence parallelism
+        try:
+            w = measure_wan(ctx, big=False, K=2, W=2)
+            if w is not None:
+                also["wan13b"] = {k: w[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e",
+                                                    "gpu_launches", "roofline")}
+        except Exception as e:  # pragma: no cover
+            also["wan13b"] = {"error": repr(e)}
+    emit()
+    ctx.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -368,22 +452,22 @@ WAN14B_TFLOP_PER_SAMPLE = 4 * 6523.3  # bidirectional 14B forwar
 
 
 def run_wan(args):
-    import torch.distributed as dist
+    ctx = _Dist()
+    line = measure_wan(ctx, big=args.workload == "wan14b", K=args.steps, W=max(args.warmup, 0))
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
+
+def measure_wan(ctx: "_Dist", big: bool, K: int, W: int):
+    """big: BASELINE configs[4] (bidirectional 14B, 720p, 4-step ode, Ulysses over all ranks); else configs[3] (1.3B
+    self-forcing, Ulysses groups of min(N, 4) ranks x N / 4 replicas).  Returns the JSON line (rank 0) or None."""
     from fastgen_b200.sampler import CausVidModel, FastGenModel
     from fastgen_b200.wan import CausalWan, Wan
 
-    big = args.workload == "wan14b"   # BASELINE configs[4]: bidirectional 14B, 720p, 4-step ode, Ulysses over all ranks
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dist = ctx.dist
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
     sp = world if big else min(world, 4)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, max(args.warmup, 0)
     frames = 21
     lh, lw = (90, 160) if big else (60, 104)
     torch.manual_seed(0)
@@ -417,25 +501,7 @@ def run_wan(args):
         return CausVidModel.generator_fn(net, n_, student_sample_steps=4, t_list=WAN_TL, condition=c_,
                                          student_sample_type="sde")
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    def timed(fn, iters):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    barrier, timed = ctx.barrier, ctx.timed
 
     from fastgen_b200 import ops
 
@@ -466,6 +532,7 @@ def run_wan(args):
     att_tf = att["flops"] / (att["ms"] / 1000.0) / 1e12 if att["ms"] else 0.0
     gemm_ms = sum(d["ms"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
     gemm_fl = sum(d["flops"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
+    line = None
     if rank == 0:
         line = {
             "metric": ("samples/sec, 4-step Wan 2.1 14B T2V 720p 81 frames" if big else
@@ -493,9 +560,9 @@ def run_wan(args):
                                                     / (world * tf_sus)},
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    del net
+    torch.cuda.empty_cache()
+    return line
 
 
 SDXL_TFLOP_PER_SAMPLE_FORWARD = 6.75  # counted from our own layer table (sum of 2*M*N*K of every GEMM/conv + 4*N*Nk*d
@@ -665,6 +732,20 @@ def run_cifar(args):
     ms_e2e = timed(e2e_step, iters)
     hbm, tf_sus, tf_burst, peak_src = _peaks()
     value = B * iters / (ms / 1000.0)
+    # roofline pass: every launch of 20 generations bracketed by CUDA events (eager launches: a graph has no per-node events)
+    graphs, net.use_cuda_graphs = net.use_cuda_graphs, False
+    gen(noise, labels)
+    net.profile = {}
+    torch.cuda.synchronize()
+    for _ in range(20):
+        gen(noise, labels)
+    torch.cuda.synchronize()
+    prof, net.profile = net.profile, None
+    net.use_cuda_graphs = graphs
+    tot_ms = sum(d["ms"] for d in prof.values())
+    conv = prof.get("fg_conv_gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    conv_tf = conv["flops"] / (conv["ms"] / 1000.0) / 1e12 if conv["ms"] else None
+    cpu = None if args.no_cpu_baseline else _cpu_baseline("cifar", B, repeats=2, warmup=0)
     line = {
         "metric": "samples/sec, 1-step CIFAR-10 EDM DMD2 generator", "value": value, "unit": "samples/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -676,10 +757,16 @@ def run_cifar(args):
         "e2e": {"value": B * iters / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / iters,
                 "h2d_bytes_per_step": 4 * (noise_h.numel() + labels_h.numel()), "d2h_bytes_per_step": 4 * out_h.numel()},
         "gpu_launches": launches, "launches_per_generation": launches / iters, "clocks": clk.summary(),
-        "roofline": {"kernel": "conv_gemm_kernel", "bound": "tensor", "achieved": None, "peak": tf_sus, "unit": "TFLOP/s",
-                     "frac": None, "traffic": None,
+        "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear)", "bound": "tensor", "achieved": conv_tf,
+                     "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst if conv_tf and tf_burst else None,
+                     "traffic": None, "peak_source": peak_src + ", burst bf16 (30 us kernels timed one by one)",
+                     "how": "sum of algorithmic conv/linear FLOPs of the fg_conv_gemm launches of 20 generations / sum of "
+                            "their CUDA-event durations (eager launches; the timed region replays them as one CUDA graph)",
+                     "launches_per_generation": conv["launches"] / 20, "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
+                     "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
+                     "per_kernel_ms_per_generation": {k: round(d["ms"] / 20, 4) for k, d in sorted(prof.items())},
                      "model_flops_utilisation": value * CIFAR_GFLOP_PER_SAMPLE_FORWARD * 1e9 / 1e12 / tf_sus},
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 
@@ -694,6 +781,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: batch of the bounded CPU sample (default 16 / 64)")
+    ap.add_argument("--no-also", action="store_true", help="in64: skip the secondary measurements (fp32 path, strong scaling, Wan 1.3B)")
+    ap.add_argument("--also-budget-s", type=float, default=420.0, help="in64: wall-clock cap of the secondary measurements")
     ap.add_argument("--no-graphs", action="store_true", help="cifar workload: launch every kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

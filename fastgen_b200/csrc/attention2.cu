@@ -30,7 +30,8 @@ struct Attn2Cfg {
   static constexpr int Q_TILE_BYTES = DC * 128 * 128;
   static constexpr int KV_TILE_BYTES = DC * kA2BKV * 128;
   static constexpr int STAGES = DP == 128 ? 2 : 4;
-  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + STAGES * 2 * KV_TILE_BYTES + 1024 + 256;
+  static constexpr int XCH_BYTES = 3 * 2 * 2 * 128 * 4;  // WG == 2: row max (two parities) and row sum of the column halves
+  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + STAGES * 2 * KV_TILE_BYTES + 1024 + 256 + XCH_BYTES;
   static constexpr int TMEM_S = 0;        // S0 at 0, S1 at 128 (P aliases the first 64 columns of each)
   static constexpr int TMEM_O = 256;      // O0 at 256, O1 at 256 + DP
   static constexpr int TMEM_COLS = 512;
@@ -114,8 +115,16 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 // own S/P columns and barriers.  While the softmax warpgroup of a query tile works on one half, the tensor pipe runs
 // O += P.V of the other half and the next S = Q.K^T into the columns that product has released, so the softmax does
 // not idle for the MMA round trip between key tiles (23 % of its time in the ncu capture of the full-tile pipeline).
-template <int DP, int POLY, int HALF>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
-__global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+//
+// WG (softmax warps per TMEM lane quarter and query tile): with WG == 1 only two softmax warps share a scheduler and the
+// inner loop is bound by dependent-issue latency (issue slots 37-40 % used, no pipe saturated: profiles/attn_r01.md).
+// WG == 2 runs 16 softmax warps (576 threads): the two warps of a lane quarter split the 128 keys of an S tile into
+// column halves (a warp may only touch its own 32 TMEM lanes, so the split has to be along the columns), exchange their
+// row maxima through shared memory once per key tile (64-thread named barrier per quarter pair), keep partial row sums
+// and share the O columns in the rare rescale and in the epilogue.
+template <int DP, int POLY, int HALF, int WG = 1>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+__global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+  static_assert(WG == 1 || (WG == 2 && HALF == 0), "two warps per lane quarter: full-tile pipeline only");
   using Cfg = Attn2Cfg<DP>;
   constexpr int BKV = kA2BKV;
   constexpr int S = Cfg::STAGES;
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
   uint64_t* p_full = s_full + 4;       // [2][2]
   uint64_t* pv_done = p_full + 4;      // [2][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [3][2 tiles][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_blocks = (p.Tq + 255) / 256;
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
       }
       for (int i = 0; i < 4; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[i], 4);
+        mbar_init(&p_full[i], 4 * WG);
         mbar_init(&pv_done[i], 1);
       }
       fence_barrier_init();
@@ -351,6 +361,161 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention2_kernel(const __grid_
         phase = nphase;
       }
       }  // !HALF
+    }
+  } else if constexpr (WG == 2) {
+    // ===================== softmax: two warps per lane quarter, each one column half of the S tile =====================
+    constexpr int HK = BKV / 2;              // keys per warp and key tile
+    constexpr int OC = DP / 2;               // O columns per warp (rescale, epilogue)
+    const int sw = warp - 2;
+    const int t = sw >> 3;                   // query tile
+    const int hh = (sw >> 2) & 1;            // column half
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const int tok = q0 + t * 128 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
+    const uint32_t o_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP + hh * OC);
+    const uint32_t pair_bar = 1u + static_cast<uint32_t>(t * 4 + q);
+    const int limit = causal_limit2(p, tok);
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY;  // running max in scaled (log2) units: identical in both warps of a pair
+    float l_run = 0.f;        // partial row sum over this warp's keys
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[2 * t], j & 1);
+      tc_fence_after();
+      uint32_t sv[HK];
+#pragma unroll
+      for (int c = 0; c < HK; c += 32) {
+        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c]);
+        tmem_ld_32x32(s_addr + hh * HK + c, chunk);
+      }
+      tmem_ld_wait();
+      const int seg = (jb + j) >= n0;
+      const int col0 = (seg ? jb + j - n0 : jb + j) * BKV + hh * HK;
+      int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
+      if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
+      if (kv_valid < HK) {  // ragged end of a segment / causal limit inside this half (rare)
+#pragma unroll
+        for (int c = 0; c < HK; ++c)
+          if (c >= kv_valid) sv[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < HK; c += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+      }
+      float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
+      // row max of the whole tile: exchange with the partner warp.  The barrier also orders this warp's S loads before
+      // the partner's P stores (P of keys 64..127 lands on columns 32..63, which hold S of keys 32..63).  Slots alternate
+      // with j, so a write two tiles later cannot overtake the partner's read (one barrier per tile in between).
+      float* xs = xch + ((j & 1) * 2 + t) * 256;
+      xs[hh * 128 + row] = mx;
+      named_bar_sync(pair_bar, 64);
+      mx = fmaxf(mx, xs[(hh ^ 1) * 128 + row]);
+      mx *= sc;  // scale > 0: max commutes with the scaling
+      if (j > 0) {
+        const bool need = mx > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {   // same rows, same values: both warps of the pair take the same branch
+          mbar_wait(&pv_done[2 * t], (j - 1) & 1);  // O stable until this tile's P is published
+          tc_fence_after();
+          const float m_new = need ? mx : m_run;
+          const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < OC; c += 32) {   // this warp's half of the O columns
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+      } else {
+        m_run = mx;
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
+      uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
+#pragma unroll
+      for (int c = 0; c < HK; c += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c + i]), __uint_as_float(sv[c + i + 1])), sc2, negm2);
+          float e0, e1;
+          if (((i >> 1) & 7) < POLY) {
+            exp2_poly2(x2, e0, e1);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
+          }
+          lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
+          pk[i >> 1] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x16(s_addr + ((hh * HK + c) >> 1), pk);  // P of key k lives at column k / 2 of this tile's S
+      }
+      float lsum0, lsum1;
+      unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
+      l_run += lsum0 + lsum1;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[2 * t]);
+    }
+    // ---- epilogue: row sum of both halves, then O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ----
+    float* xl = xch + (4 + t) * 256;
+    xl[hh * 128 + row] = l_run;
+    named_bar_sync(pair_bar, 64);
+    l_run += xl[(hh ^ 1) * 128 + row];
+    if (nkv) {
+      mbar_wait(&pv_done[2 * t], (nkv - 1) & 1);  // the last product issued for this tile
+      tc_fence_after();
+    }
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    uint8_t* so = sQ + t * Cfg::Q_TILE_BYTES;
+#pragma unroll 1
+    for (int c0 = 0; c0 < OC; c0 += 32) {
+      const int c = hh * OC + c0;   // column within the head
+      uint32_t o[32];
+      if (nkv) {
+        tmem_ld_32x32(o_addr + c0, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      uint8_t* rowp = so + (c >> 6) * (128 * 128) + row * 128;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        const int chunk = ((c & 63) + i) >> 3;
+        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(9 + t, 256);
+    if (hh == 0 && p.nsplit > 1 && tok < p.Tq)
+      p.part_ml[(static_cast<int64_t>(img * p.H + head) * p.Tq + tok) * p.nsplit + split] = make_float2(m_run, l_run);
+    if (hh == 0 && q == 0 && lane == 0 && q0 + t * 128 < p.Tq) {
+      for (int dc = 0; dc < Cfg::DC; ++dc) {
+        if (p.nsplit > 1)
+          tma_store_4d(&p.tmO, so + dc * 128 * 128, dc * 64, split, q0 + t * 128, img * p.H + head);
+        else if (dc * 64 < p.d)
+          tma_store_4d(&p.tmO, so + dc * 128 * 128, dc * 64, head, q0 + t * 128, img);
+      }
+      tma_store_commit();
+      tma_store_wait<0>();
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -665,13 +830,13 @@ size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256 + 128;
 }
 
-template <int DP, int POLY, int HALF = 0>
+template <int DP, int POLY, int HALF = 0, int WG = 1>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -731,7 +896,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
     if (r != FG_OK) return r;
   }
   const int grid = kp.B * kp.H * q_blocks * nsplit;
-  attention2_kernel<DP, POLY, HALF><<<grid, kA2Threads, Cfg::SMEM_BYTES, stream>>>(kp);
+  attention2_kernel<DP, POLY, HALF, WG><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("flash_attn");
   if (nsplit > 1) {
     const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
@@ -753,6 +918,18 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
   if (half && poly == 2) {
     if (p->d <= 64) return launch_attention2<64, 2, 1>(p, scale, stream);
     return launch_attention2<128, 2, 1>(p, scale, stream);
+  }
+  // softmax warps per lane quarter (FG_ATTN_WG=1 restores the round-1 kernel for A/B measurements)
+  static const int wg = getenv("FG_ATTN_WG") ? atoi(getenv("FG_ATTN_WG")) : 2;
+  if (wg == 2 && (poly == 2 || poly == 0 || poly == 4)) {
+    if (p->d <= 64) {
+      if (poly == 0) return launch_attention2<64, 0, 0, 2>(p, scale, stream);
+      if (poly == 4) return launch_attention2<64, 4, 0, 2>(p, scale, stream);
+      return launch_attention2<64, 2, 0, 2>(p, scale, stream);
+    }
+    if (poly == 0) return launch_attention2<128, 0, 0, 2>(p, scale, stream);
+    if (poly == 4) return launch_attention2<128, 4, 0, 2>(p, scale, stream);
+    return launch_attention2<128, 2, 0, 2>(p, scale, stream);
   }
   if (p->d <= 64) {
     if (poly == 0) return launch_attention2<64, 0>(p, scale, stream);

@@ -244,17 +244,18 @@ class _WanBase:
         self.use_cuda_graphs = True
         self.graph_launches = 0                        # kernel launches replayed through graphs (bench bookkeeping)
         self.sp_group = None                           # torch.distributed group for Ulysses sequence parallelism
-        # how the sequence-parallel exchange around the self-attention runs: "nccl" = pack kernel + all_to_all_single +
-        # unpack kernel (measured, profiles/wan*_scaling_r01.md); "peer" = fg_peer_put / fg_peer_wait over symmetric
-        # memory: pack and exchange are one kernel storing into the peers' buffers over NVLink, no NCCL call in the
-        # layer loop (opt-in: written after the round's GPU budget ended, layout checked on CPU only)
-        self.sp_exchange = os.environ.get("FASTGEN_B200_SP_EXCHANGE", "nccl")
+        # how the sequence-parallel exchange around the self-attention runs: "peer" (default) = fg_peer_put / fg_peer_wait
+        # over symmetric memory: pack and exchange are one kernel storing into the peers' buffers over NVLink, no NCCL call
+        # in the layer loop; "nccl" = pack kernel + all_to_all_single + unpack kernel.  Measured on 2 x B200, Wan 1.3B
+        # self-forcing sample: nccl 787 ms, peer 745 ms, peer + CUDA graphs 720 ms (profiles/wan_scaling_r02.md).  If the
+        # symmetric-memory rendezvous is unavailable the workspace falls back to "nccl" with a warning.
+        self.sp_exchange = os.environ.get("FASTGEN_B200_SP_EXCHANGE", "peer")
         if self.sp_exchange not in ("nccl", "peer"):
             raise ValueError(f"FASTGEN_B200_SP_EXCHANGE must be 'nccl' or 'peer', got {self.sp_exchange}")
-        self.peer_timeout_s = 20.0
-        # with the peer exchange no NCCL call is left in a launch list, so it could replay as a CUDA graph under sequence
-        # parallelism too (36 k launches per sample); off until the exchange itself has run on hardware
-        self.sp_graphs = os.environ.get("FASTGEN_B200_SP_GRAPHS") == "1"
+        self.peer_timeout_s = 60.0
+        # with the peer exchange no NCCL call is left in a launch list, so it replays as a CUDA graph under sequence
+        # parallelism too (36 k launches per sample)
+        self.sp_graphs = os.environ.get("FASTGEN_B200_SP_GRAPHS", "1") == "1"
 
     # ---- reference helpers ------------------------------------------------------------------------------
     @classmethod
@@ -447,13 +448,23 @@ class _WanBase:
         if self.transformer.r_embedder is not None:
             ws.update(emb_r=z(groups, cfg["freq_dim"]), re1=z(groups, D), remb=z(groups, D), remb_act=z(groups, D),
                       rtproj=z(groups, 6 * D, dt=f32))
+        if P > 1 and self.sp_exchange not in ("nccl", "peer"):
+            raise ValueError(f"sp_exchange must be 'nccl' or 'peer', got {self.sp_exchange}")
         if P > 1 and self.sp_exchange == "peer":
             # one-pass exchange: qkv_full and att are the DESTINATIONS the peers store into (symmetric memory)
-            ws.update(hs_full=z(rows, D), att_full=z(B, n, Dl), tok_out_l=z(lrows, kout))
-            ws.update(self._peer_buffers(B, n, D, Dl, P, dev, kout))
-        elif P > 1:
-            if self.sp_exchange != "nccl":
-                raise ValueError(f"sp_exchange must be 'nccl' or 'peer', got {self.sp_exchange}")
+            try:
+                peer = self._peer_buffers(B, n, D, Dl, P, dev, kout)
+                ws.update(hs_full=z(rows, D), att_full=z(B, n, Dl), tok_out_l=z(lrows, kout))
+                ws.update(peer)
+            except L.FastGenB200Error:
+                raise
+            except Exception as e:   # no symmetric memory on this platform / group: every rank sees the same failure
+                import warnings
+
+                warnings.warn(f"sequence-parallel peer exchange unavailable ({e!r}); using the NCCL all-to-all")
+                self.sp_exchange = "nccl"
+                self._plans = {}
+        if P > 1 and self.sp_exchange == "nccl":
             # Ulysses exchange buffers (per sample b: [P][n/P][3][H/P*d] for q,k,v and [P][n/P][H/P*d] for the output)
             ws.update(hs_full=z(rows, D), a2a_s=z(B, P, n // P, 3 * Dl), qkv_full=z(B, n, 3 * Dl), att_full=z(B, n, Dl),
                       a2a_r=z(B, P, n // P, Dl), tok_out_l=z(lrows, kout), tok_out_g=z(P, lrows, kout))
@@ -889,10 +900,30 @@ class _WanBase:
                 plan.graph.replay()
                 self.graph_launches += sum(1 for st in plan.steps if st[1] is not None)
                 plan.runs += 1
+                self._poll_peer_exchange(ws)
                 return ws["flow"]
         self._run_split(plan, ws, torch.cuda.current_stream().cuda_stream)
         plan.runs += 1
+        self._poll_peer_exchange(ws)
         return ws["flow"]
+
+    def _poll_peer_exchange(self, ws) -> None:
+        """One-pass exchange only: queue an asynchronous copy of the device-side timeout flags behind this forward and
+        look at the copy queued behind the PREVIOUS one (complete by now, or skipped without waiting).  A wait that gave up
+        -- the consumer then read stale data -- therefore raises at the next forward, not only at clear_caches() /
+        the end of sample(); no synchronisation is added."""
+        px = ws.get("peer")
+        if px is None:
+            return
+        ev = px.get("poll_event")
+        if ev is not None and ev.query() and bool(px["poll_host"].any()):
+            raise L.FastGenB200Error(f"sequence-parallel peer exchange timed out after {self.peer_timeout_s} s: a rank of "
+                                     "the group did not reach the matching put (outputs since then are invalid)")
+        if "poll_host" not in px:
+            px["poll_host"] = torch.zeros(3, dtype=torch.int64).pin_memory()
+        px["poll_host"].copy_(px["state"][:, 3], non_blocking=True)
+        px["poll_event"] = torch.cuda.Event()
+        px["poll_event"].record()
 
     def _run_split(self, plan: _Plan, ws, stream: int) -> None:
         D = self.cfg["dim"]

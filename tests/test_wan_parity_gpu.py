@@ -242,7 +242,9 @@ def test_wan_teacher_sampler_runs_on_the_gpu_and_tracks_the_oracle():
         sch.set_timesteps(4)
         lat = (noise.double() * (sch.timesteps[0] / 1000).double()).bfloat16()
         for ts in sch.timesteps:
-            tt = (ts / 1000).expand(2).bfloat16().double()
+            # t reaches the network in the latent dtype, like in the reference loop (Wan/network.py:957-958): the rescaled
+            # timestep 1000 t is then a bf16 number (spacing 4 near 1000), which the sinusoid embedding is sensitive to
+            tt = (ts / 1000).expand(2).bfloat16()
             fc = WO.wan_forward(sd, cfg, lat, tt, text, fwd_pred_type="flow", dtype=dtype).bfloat16()
             fu = WO.wan_forward(sd, cfg, lat, tt, neg, fwd_pred_type="flow", dtype=dtype).bfloat16()
             lat = sch.step(fu + 2.0 * (fc - fu), ts, lat)[0]
@@ -259,10 +261,10 @@ def test_wan_teacher_sampler_runs_on_the_gpu_and_tracks_the_oracle():
     sch.set_timesteps(4)
     lat = (noise.double() * (sch.timesteps[0] / 1000).double()).bfloat16()
     for ts in sch.timesteps:
-        tt = (ts / 1000).expand(2).bfloat16().double()
+        tt = (ts / 1000).expand(2).bfloat16()
         fc = WO.wan_forward(sd, cfg, lat, tt, text, fwd_pred_type="flow", dtype=torch.float32).bfloat16()
         fu = WO.wan_forward(sd, cfg, lat, tt, neg, fwd_pred_type="flow", dtype=torch.float32).bfloat16()
-        ours = net(lat.cuda(), tt.bfloat16().cuda(), condition=text.cuda())
+        ours = net(lat.cuda(), tt.cuda(), condition=text.cuda())
         assert _rel(ours.float(), fc.float()) < TOL, _rel(ours.float(), fc.float())
         lat = sch.step(fu + 2.0 * (fc - fu), ts, lat)[0]
 
