@@ -21,7 +21,6 @@
 
 namespace fg {
 
-constexpr int kA2Threads = 320;
 constexpr int kA2BKV = 128;
 
 template <int DP>
@@ -380,40 +379,55 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     const float sc = p.scale_log2;
     float m_run = -INFINITY;  // running max in scaled (log2) units: identical in both warps of a pair
     float l_run = 0.f;        // partial row sum over this warp's keys
+    // Register budget: 18 warps are allocated as 20, i.e. 96 registers per thread -- a whole 64-key half row (the WG == 1
+    // scheme scaled down) spills.  So the row is handled as two 32-key chunks in two passes: pass 1 takes the maximum of
+    // both chunks and keeps only the second one; after the exchange pass 2 re-reads the first chunk from tensor memory
+    // (nobody has written there yet: P of keys k lands on column k / 2, i.e. this warp's first chunk is only ever
+    // overwritten by its own P, and the partner's P -- columns 32..63 when it owns keys 64..127 -- falls on the SECOND
+    // chunk of the warp that owns keys 0..63, which that warp holds in registers since before the barrier).
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[2 * t], j & 1);
       tc_fence_after();
-      uint32_t sv[HK];
-#pragma unroll
-      for (int c = 0; c < HK; c += 32) {
-        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c]);
-        tmem_ld_32x32(s_addr + hh * HK + c, chunk);
-      }
+      const uint32_t sh_addr = s_addr + static_cast<uint32_t>(hh * HK);
+      uint32_t sa[32], sb[32];
+      tmem_ld_32x32(sh_addr, sa);
+      tmem_ld_32x32(sh_addr + 32, sb);
       tmem_ld_wait();
       const int seg = (jb + j) >= n0;
       const int col0 = (seg ? jb + j - n0 : jb + j) * BKV + hh * HK;
       int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
       if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
-      if (kv_valid < HK) {  // ragged end of a segment / causal limit inside this half (rare)
+      const bool ragged = kv_valid < HK;  // ragged end of a segment / causal limit inside this half (rare)
+      if (ragged) {
 #pragma unroll
-        for (int c = 0; c < HK; ++c)
-          if (c >= kv_valid) sv[c] = 0xff800000u;  // -inf
+        for (int c = 0; c < 32; ++c) {
+          if (c >= kv_valid) sa[c] = 0xff800000u;  // -inf
+          if (c + 32 >= kv_valid) sb[c] = 0xff800000u;
+        }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < HK; c += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
-        mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+      for (int c = 0; c < 32; c += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sa[c]), __uint_as_float(sa[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sa[c + 2]), __uint_as_float(sa[c + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sa[c + 4]), __uint_as_float(sa[c + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sa[c + 6]), __uint_as_float(sa[c + 7]));
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sb[c]), __uint_as_float(sb[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sb[c + 2]), __uint_as_float(sb[c + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sb[c + 4]), __uint_as_float(sb[c + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sb[c + 6]), __uint_as_float(sb[c + 7]));
       }
       float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
       // row max of the whole tile: exchange with the partner warp.  The barrier also orders this warp's S loads before
-      // the partner's P stores (P of keys 64..127 lands on columns 32..63, which hold S of keys 32..63).  Slots alternate
-      // with j, so a write two tiles later cannot overtake the partner's read (one barrier per tile in between).
+      // the partner's P stores.  Slots alternate with j, so a write two tiles later cannot overtake the partner's read
+      // (one barrier per tile in between).
       float* xs = xch + ((j & 1) * 2 + t) * 256;
       xs[hh * 128 + row] = mx;
       named_bar_sync(pair_bar, 64);
+      tmem_ld_32x32(sh_addr, sa);   // pass 2: the first chunk again (in flight during the max bookkeeping below)
       mx = fmaxf(mx, xs[(hh ^ 1) * 128 + row]);
       mx *= sc;  // scale > 0: max commutes with the scaling
       if (j > 0) {
@@ -425,14 +439,15 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
           const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
           m_run = m_new;
           l_run *= alpha;
+          tmem_ld_wait();
 #pragma unroll 1
-          for (int c = 0; c < OC; c += 32) {   // this warp's half of the O columns
-            uint32_t o[32];
-            tmem_ld_32x32(o_addr + c, o);
+          for (int c = 0; c < OC; c += 16) {   // this warp's half of the O columns
+            uint32_t o[16];
+            tmem_ld_32x16(o_addr + c, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(o_addr + c, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(o_addr + c, o);
           }
           tmem_st_wait();
         }
@@ -442,12 +457,19 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
       uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
+      tmem_ld_wait();
+      if (ragged) {
 #pragma unroll
-      for (int c = 0; c < HK; c += 32) {
+        for (int c = 0; c < 32; ++c)
+          if (c >= kv_valid) sa[c] = 0xff800000u;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t(&sv)[32] = ch ? sb : sa;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c + i]), __uint_as_float(sv[c + i + 1])), sc2, negm2);
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sc2, negm2);
           float e0, e1;
           if (((i >> 1) & 7) < POLY) {
             exp2_poly2(x2, e0, e1);
@@ -459,7 +481,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
           lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
-        tmem_st_32x16(s_addr + ((hh * HK + c) >> 1), pk);  // P of key k lives at column k / 2 of this tile's S
+        tmem_st_32x16(s_addr + ((hh * HK + ch * 32) >> 1), pk);  // P of key k lives at column k / 2 of this tile's S
       }
       float lsum0, lsum1;
       unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
@@ -919,8 +941,11 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
     if (p->d <= 64) return launch_attention2<64, 2, 1>(p, scale, stream);
     return launch_attention2<128, 2, 1>(p, scale, stream);
   }
-  // softmax warps per lane quarter (FG_ATTN_WG=1 restores the round-1 kernel for A/B measurements)
-  static const int wg = getenv("FG_ATTN_WG") ? atoi(getenv("FG_ATTN_WG")) : 2;
+  // softmax warps per lane quarter.  WG = 2 (FG_ATTN_WG=2; 16 softmax warps, column-split rows) is an experiment that is
+  // correct (same tests) but measured SLOWER on B200: 970 vs 1008 TFLOP/s on the Wan chunk-6 shape, 431 vs 494 at d = 64
+  // (profiles/attn_r02.md) -- at 96 registers per thread the second TMEM read of half of S, the per-tile pair barrier and
+  // the halved per-thread instruction-level parallelism cost more than the extra warps per scheduler hide.
+  static const int wg = getenv("FG_ATTN_WG") ? atoi(getenv("FG_ATTN_WG")) : 1;
   if (wg == 2 && (poly == 2 || poly == 0 || poly == 4)) {
     if (p->d <= 64) {
       if (poly == 0) return launch_attention2<64, 0, 0, 2>(p, scale, stream);
