@@ -19,7 +19,7 @@ FG_ACT_NONE, FG_ACT_GELU_TANH, FG_ACT_SILU, FG_ACT_GEGLU = 0, 1, 2, 3
 # every extern "C" symbol of include/fastgen_b200.h (checked by tests/test_abi.py)
 SYMBOLS = (
     "fg_last_error", "fg_version", "fg_launch_count", "fg_launch_count_reset",
-    "fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_flash_attn",
+    "fg_conv_gemm", "fg_conv_gemm_prepared_size", "fg_conv_gemm_prepare", "fg_conv_gemm_run", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_flash_attn",
     "fg_flash_attn_workspace_size",
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
     "fg_peer_put", "fg_peer_wait", "fg_sampler_vec",
@@ -143,6 +143,13 @@ def lib() -> C.CDLL:
     l.fg_launch_count_reset.restype = None
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     l.fg_conv_gemm.argtypes = [C.POINTER(ConvParams), vp]
+    l.fg_conv_gemm_prepared_size.argtypes = []
+    l.fg_conv_gemm_prepared_size.restype = C.c_int64
+    l.fg_conv_gemm_prepare.argtypes = [C.POINTER(ConvParams), vp, i64]
+    l.fg_conv_gemm_prepare.restype = C.c_int
+    l.fg_conv_gemm_run.argtypes = [vp, vp]
+    l.fg_conv_gemm_run.restype = C.c_int
+    l.fg_conv_gemm_run.__name__ = "fg_conv_gemm"      # launch lists profile by function name: same operator
     l.fg_gn_stats.argtypes = [vp, i32, i64, i32, i32, i32, i32, vp, vp]
     l.fg_gn_apply.argtypes = [C.POINTER(GnApplyParams), vp]
     l.fg_attention.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]

@@ -42,10 +42,10 @@ __host__ __device__ constexpr int epi_mode(bool out_bf16, int res) { return (out
 // FG_ACT_GEGLU: bf16 output of half the accumulator width, out[j] = v[2j] * gelu_erf(v[2j+1]), no residual
 constexpr int kEpiGeglu = 8 | 1;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG = 1>   // CG = 2: CTA pair (cta_group::2), each CTA stages half of the B tile
 struct ConvCfg {
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
-  static constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
+  static constexpr int B_BYTES = (BLOCK_N / CG) * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_SLAB_BYTES = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 B (TMA box)
   static constexpr int OUT_SLABS = 4;                   // ring: residual prefetch (TMA load) -> in-place add -> TMA store
@@ -318,9 +318,22 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
   }
 }
 
-template <int BLOCK_N, int EPI>
+// CG = 2: a cluster of two CTAs owns two consecutive M tiles of one N tile.  Work items ("items") are tiles for CG = 1 and
+// tile pairs for CG = 2; item -> this CTA's tile index goes through item_tile().  An odd M-tile count leaves the second
+// CTA of the last pair a tile past the end: its TMA boxes are entirely out of bounds (zero-filled loads, clipped stores),
+// its statistics and plain accesses are masked by `img < N`.
+template <int CG>
+__device__ __forceinline__ int item_tile(const ConvKParams& p, int item, int cta_rank) {
+  if constexpr (CG == 1) return item;
+  return (2 * (item / p.tiles_n) + cta_rank) * p.tiles_n + item % p.tiles_n;
+}
+
+template <int BLOCK_N, int EPI, int CG = 1>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, CG>;
+  static_assert(CG == 1 || (EPI != kEpiGeneric && BLOCK_N >= 128), "CTA pairs: TMA-store epilogues, tiles >= 128 wide");
+  const int cr = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // rank in the pair; 0 = leader (issues the MMAs)
+  const int item0 = static_cast<int>(blockIdx.x) / CG, item_step = static_cast<int>(gridDim.x) / CG;
   constexpr bool kTmaStore = EPI != kEpiGeneric;
   constexpr bool kOutBf16 = kTmaStore && (EPI & 1);
   constexpr int kRes = kTmaStore ? ((EPI >> 1) & 3) : kResNone;
@@ -357,17 +370,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], 4 * CG);   // CG = 2: the leader's barrier collects the epilogue warps of both CTAs
       }
       for (int i = 0; i < Cfg::OUT_SLABS; ++i) mbar_init(&res_full[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);   // collective over the pair: the same warp of both CTAs
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers exist before anything signals them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -376,8 +395,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles && !(p.dbg & 4); tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      for (int item = item0; item < p.total_tiles && !(p.dbg & 4); item += item_step) {
+        const TileCoord t = decode_tile(p, item_tile<CG>(p, item, cr), BLOCK_N);
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           const int kch = p.seg_kchunks[s];
@@ -388,9 +407,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               mbar_wait(&empty[stage], phase ^ 1u);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               uint8_t* sb = sa + Cfg::A_BYTES;
-              mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-              tma_load_4d(sa, &p.tmA[s], &full[stage], kc * kBlockK, t.w0 + dx, t.h0 + dy, t.img0);
-              tma_load_3d(sb, &p.tmW[s], &full[stage], kc * kBlockK, tap, t.co0);
+              if constexpr (CG == 2) {
+                // both CTAs' bytes are counted on the leader's barrier; this CTA stages its A rows and its half of B
+                if (cr == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                const uint32_t lead_full = mapa_u32(&full[stage], 0);
+                tma_load_4d_2sm(sa, &p.tmA[s], lead_full, kc * kBlockK, t.w0 + dx, t.h0 + dy, t.img0);
+                tma_load_3d_2sm(sb, &p.tmW[s], lead_full, kc * kBlockK, tap, t.co0 + cr * (BLOCK_N / 2));
+              } else {
+                mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                tma_load_4d(sa, &p.tmA[s], &full[stage], kc * kBlockK, t.w0 + dx, t.h0 + dy, t.img0);
+                tma_load_3d(sb, &p.tmW[s], &full[stage], kc * kBlockK, tap, t.co0);
+              }
               if (++stage == Cfg::STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -402,13 +429,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    if (lane == 0 && cr == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int item = item0; item < p.total_tiles; item += item_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -419,16 +446,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                         (it | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              umma_bf16_ss2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                            (it | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                           (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire (CG = 2: in both CTAs -- each producer waits on its own barrier)
+          if constexpr (CG == 2) umma_commit2(&empty[stage], 3);
+          else umma_commit(&empty[stage]);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
+        if constexpr (CG == 2) umma_commit2(&tfull[acc], 3);  // accumulator ready for the epilogue warps of both CTAs
+        else umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -451,13 +485,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint8_t* res_up = out_slabs + (Cfg::OUT_SLABS - 1) * Cfg::OUT_SLAB_BYTES;
     uint32_t slab_idx = 0;
     uint32_t ld_idx = 0;  // store thread only: next residual slab to request, its tile and channel offset
-    int ld_tile = blockIdx.x, ld_c0 = 0;
+    int ld_item = item0, ld_c0 = 0;
     const uint32_t wkey = row & 7;
     // residual row inside a quarter-size UP2 box
     const int rs_up = (il * (p.BH >> 1) + (hl >> 1)) * (p.BW >> 1) + (wl >> 1);
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+    const uint32_t lead_tempty[2] = {CG == 2 ? mapa_u32(&tempty[0], 0) : 0u, CG == 2 ? mapa_u32(&tempty[1], 0) : 0u};
+    for (int item = item0; item < p.total_tiles; item += item_step) {
+      const TileCoord t = decode_tile(p, item_tile<CG>(p, item, cr), BLOCK_N);
       const int img = t.img0 + il, h = t.h0 + hl, w = t.w0 + wl;
       const bool valid = img < p.N;
       mbar_wait(&tfull[acc], acc_phase);
@@ -476,8 +511,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             // slab_idx + kResAhead lands in (last stored from two slabs ago) is free again
             tma_store_wait_read<1>();
             if constexpr (kRes != kResNone) {
-              while (ld_idx <= slab_idx + kResAhead && ld_tile < p.total_tiles) {
-                const TileCoord lt = decode_tile(p, ld_tile, BLOCK_N);
+              while (ld_idx <= slab_idx + kResAhead && ld_item < p.total_tiles) {
+                const TileCoord lt = decode_tile(p, item_tile<CG>(p, ld_item, cr), BLOCK_N);
                 const uint32_t lrb = ld_idx % Cfg::OUT_SLABS;
                 if constexpr (kRes == kResSame) {
                   mbar_arrive_expect_tx(&res_full[lrb], Cfg::OUT_SLAB_BYTES);
@@ -492,7 +527,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 ld_c0 += kSlabCols;
                 if (ld_c0 >= BLOCK_N || lt.co0 + ld_c0 >= p.Cout) {
                   ld_c0 = 0;
-                  ld_tile += gridDim.x;
+                  ld_item += item_step;
                 }
               }
             }
@@ -633,7 +668,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(lead_tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -641,20 +679,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // neither CTA leaves (or frees tensor memory) while the pair is still in use
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CG = 1>
 static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, CG>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -662,55 +702,103 @@ static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) 
     }
     configured.set(cfg_dev);
   }
-  const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-  conv_gemm_kernel<BLOCK_N, EPI><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  if constexpr (CG == 2) {
+    // kp.total_tiles counts tile PAIRS: one cluster of two CTAs (the two SMs of a TPC) per pair, persistent over pairs
+    const int clusters = kp.total_tiles < num_sms / 2 ? kp.total_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(kConvThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, EPI, CG>, kp);
+    if (e != cudaSuccess) {
+      set_error("conv_gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return FG_ERR_CUDA;
+    }
+  } else {
+    const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
+    conv_gemm_kernel<BLOCK_N, EPI, CG><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  }
   FG_CHECK_LAUNCH("conv_gemm");
   return FG_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG = 1>
 static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_t stream) {
   if constexpr (BLOCK_N >= 64) {
     switch (epi) {
-      case epi_mode(false, kResNone): return launch_conv<BLOCK_N, epi_mode(false, kResNone)>(kp, num_sms, stream);
-      case epi_mode(true, kResNone): return launch_conv<BLOCK_N, epi_mode(true, kResNone)>(kp, num_sms, stream);
-      case epi_mode(false, kResSame): return launch_conv<BLOCK_N, epi_mode(false, kResSame)>(kp, num_sms, stream);
-      case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame)>(kp, num_sms, stream);
-      case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2)>(kp, num_sms, stream);
-      case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2)>(kp, num_sms, stream);
+      case epi_mode(false, kResNone): return launch_conv<BLOCK_N, epi_mode(false, kResNone), CG>(kp, num_sms, stream);
+      case epi_mode(true, kResNone): return launch_conv<BLOCK_N, epi_mode(true, kResNone), CG>(kp, num_sms, stream);
+      case epi_mode(false, kResSame): return launch_conv<BLOCK_N, epi_mode(false, kResSame), CG>(kp, num_sms, stream);
+      case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame), CG>(kp, num_sms, stream);
+      case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2), CG>(kp, num_sms, stream);
+      case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2), CG>(kp, num_sms, stream);
       case kEpiGeglu:
-        if constexpr (BLOCK_N % 128 == 0) return launch_conv<BLOCK_N, kEpiGeglu>(kp, num_sms, stream);
+        if constexpr (BLOCK_N % 128 == 0) return launch_conv<BLOCK_N, kEpiGeglu, CG>(kp, num_sms, stream);
         break;
       default: break;
     }
   }
-  return launch_conv<BLOCK_N, kEpiGeneric>(kp, num_sms, stream);
+  if constexpr (CG == 2) {
+    set_error("conv_gemm: the CTA-pair kernels need a TMA-store epilogue");
+    return FG_ERR_UNSUPPORTED;
+  } else {
+    return launch_conv<BLOCK_N, kEpiGeneric>(kp, num_sms, stream);
+  }
 }
 
-// Tile width: the candidate that minimises (waves of tiles over the SMs) x (tile cost ~ width), i.e. padding waste in
-// N and wave quantisation are weighed together; ties go to the wider tile (fewer A re-reads from L2).
-static int pick_block_n(int cout, int m_tiles, int num_sms, bool geglu) {
+// Tile choice.  Cost of a candidate (tile width bn, CTAs per MMA cg) = waves of work items over the SMs (pairs of SMs)
+// x clocks per 64-deep K stage, the larger of
+//   * the tensor pipe: 2 bn clocks (an M = 128 (x cg) by bn by 16 MMA takes bn / 8 clocks per SM), and
+//   * the L2 -> SM port of 64 B/clk/SM feeding the stage: (16 KB of A + bn / cg * 128 B of B) / 64.
+// Measured on B200 (profiles/conv_2cta_r02.md): one-CTA tiles run at 50 % (bn = 128) and 67-69 % (bn = 256) of the tensor
+// pipe exactly as the port predicts; a CTA pair halves the B bytes per CTA (the peer's half is read over the pair link),
+// so a 256-wide pair tile is no longer port-bound.  Ties go to the wider tile / the pair.
+struct TileChoice {
+  int bn, cg;
+};
+static TileChoice pick_tile(int cout, int m_tiles, int k_iters, int num_sms, bool geglu, bool pair_ok) {
+  static const int forced = getenv("FG_CONV_BN") ? atoi(getenv("FG_CONV_BN")) : 0;  // tuning experiments only
+  static const int forced_cg = getenv("FG_CONV_CG") ? atoi(getenv("FG_CONV_CG")) : 0;
   if (!geglu) {
-    if (cout <= 16) return 16;
-    if (cout <= 64) return 64;
+    if (cout <= 16) return {16, 1};
+    if (cout <= 64) return {64, 1};
   }
-  if (cout <= 128) return 128;
-  int best = 128;
+  // a short K loop is epilogue-bound, and the accumulator hand-back of a pair couples the epilogues of two SMs: measured
+  // 586 vs 711 TFLOP/s (K = 384, N = 1152) and 471 vs 523 (K = 384, N = 384) for pair vs single CTA, against 1291 vs 1236
+  // at K = 3456 and 1182 vs 1130 at K = 1728 (profiles/conv_2cta_r02.md)
+  static const int min_k_iters = getenv("FG_CONV_CG_MIN_K") ? atoi(getenv("FG_CONV_CG_MIN_K")) : 16;
+  if (forced_cg == 1 || m_tiles < 2 || (forced_cg != 2 && k_iters < min_k_iters)) pair_ok = false;
+  TileChoice best = {128, 1};
   int64_t best_cost = INT64_MAX;
   const int cands[3] = {128, 192, 256};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (geglu && bn % 128) continue;  // a GEGLU slab is 128 accumulator columns
-    const int64_t tiles = static_cast<int64_t>(m_tiles) * ((cout + bn - 1) / bn);
-    const int64_t waves = (tiles + num_sms - 1) / num_sms;
-    // time of a tile ~ (bn + fixed per-tile cost) / efficiency: a 128-wide tile reads as many shared-memory bytes per
-    // MMA clock as the 128 B/clk port delivers (A 16 KB + B 16 KB per 256 clocks), wider tiles have headroom --
-    // measured 620-820 TFLOP/s on 128-wide tiles against 1200-1300 on 256-wide ones (profiles/sdxl_r01.md)
-    const int eff = bn == 128 ? 80 : bn == 192 ? 92 : 100;
-    const int64_t cost = waves * (bn + 16) * 100 / eff;
-    if (cost <= best_cost) {
-      best_cost = cost;
-      best = bn;
+  for (int cg = 1; cg <= (pair_ok ? 2 : 1); ++cg) {
+    if (forced_cg == 2 && pair_ok && cg == 1) continue;
+    for (int i = 0; i < 3; ++i) {
+      const int bn = cands[i];
+      if (geglu && bn % 128) continue;  // a GEGLU slab is 128 accumulator columns
+      if (forced && bn != forced && cout > 64 && !(geglu && forced % 128)) continue;
+      if (cout <= 128 && bn > 128) continue;
+      const int n_tiles = (cout + bn - 1) / bn;
+      const int64_t items = static_cast<int64_t>((m_tiles + cg - 1) / cg) * n_tiles;
+      const int64_t slots = num_sms / cg;
+      const int64_t waves = (items + slots - 1) / slots;
+      const int mma_clk = 2 * bn;
+      const int port_clk = (16384 + bn / cg * 128) / 64;
+      const int stage_clk = mma_clk > port_clk ? mma_clk : port_clk;
+      // + the part of the per-tile tail that the next tile's main loop cannot hide (two accumulator stages overlap them:
+      // only a K loop shorter than the epilogue shows it)
+      const int64_t epi_clk = 12 * bn;
+      const int64_t main_clk = static_cast<int64_t>(k_iters) * stage_clk;
+      const int64_t cost = waves * (main_clk > epi_clk ? main_clk : epi_clk) + main_clk / 8;
+      if (cost < best_cost || (cost == best_cost && (bn > best.bn || cg > best.cg))) {
+        best_cost = cost;
+        best = {bn, cg};
+      }
     }
   }
   return best;
@@ -721,9 +809,71 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace fg
 
+namespace fg {
+// What fg_conv_gemm_prepare leaves in the caller's blob: the kernel parameter block (tile geometry, the 2 nseg + 2 encoded
+// TMA descriptors, epilogue pointers) and the kernel choice.  fg_conv_gemm_run only launches it.
+struct alignas(64) ConvPrepared {
+  uint64_t magic;
+  int32_t block_n, cg, epi, num_sms, device;
+  ConvKParams kp;
+};
+constexpr uint64_t kConvPreparedMagic = 0x46474350524550ull;  // "FGCPREP"
+
+static int conv_launch_prepared(const ConvPrepared& pp, cudaStream_t stream) {
+  if (pp.cg == 2) {
+    switch (pp.block_n) {
+      case 128: return dispatch_epi<128, 2>(pp.kp, pp.epi, pp.num_sms, stream);
+      case 192: return dispatch_epi<192, 2>(pp.kp, pp.epi, pp.num_sms, stream);
+      case 256: return dispatch_epi<256, 2>(pp.kp, pp.epi, pp.num_sms, stream);
+    }
+    set_error("conv_gemm: no CTA-pair kernel for block_n=%d", pp.block_n);
+    return FG_ERR_UNSUPPORTED;
+  }
+  switch (pp.block_n) {
+    case 16: return dispatch_epi<16>(pp.kp, pp.epi, pp.num_sms, stream);
+    case 64: return dispatch_epi<64>(pp.kp, pp.epi, pp.num_sms, stream);
+    case 128: return dispatch_epi<128>(pp.kp, pp.epi, pp.num_sms, stream);
+    case 192: return dispatch_epi<192>(pp.kp, pp.epi, pp.num_sms, stream);
+    case 256: return dispatch_epi<256>(pp.kp, pp.epi, pp.num_sms, stream);
+  }
+  set_error("conv_gemm: no kernel for block_n=%d", pp.block_n);
+  return FG_ERR_UNSUPPORTED;
+}
+static int conv_prepare(const fg_conv_params* p, ConvPrepared& pp);
+}  // namespace fg
+
+extern "C" int64_t fg_conv_gemm_prepared_size(void) { return static_cast<int64_t>(sizeof(fg::ConvPrepared)); }
+
+extern "C" int fg_conv_gemm_prepare(const fg_conv_params* p, void* blob, int64_t blob_bytes) {
+  using namespace fg;
+  FG_CHECK_ARG(blob != nullptr && blob_bytes >= static_cast<int64_t>(sizeof(ConvPrepared)) &&
+                   (reinterpret_cast<uintptr_t>(blob) & 63u) == 0,
+               "conv_gemm_prepare: the blob must be 64-byte aligned and hold fg_conv_gemm_prepared_size() = %lld bytes",
+               (long long)sizeof(ConvPrepared));
+  ConvPrepared* pp = static_cast<ConvPrepared*>(blob);
+  pp->magic = 0;
+  const int r = conv_prepare(p, *pp);
+  if (r == FG_OK) pp->magic = kConvPreparedMagic;
+  return r;
+}
+
+extern "C" int fg_conv_gemm_run(const void* blob, fg_stream_t stream_) {
+  using namespace fg;
+  const ConvPrepared* pp = static_cast<const ConvPrepared*>(blob);
+  FG_CHECK_ARG(pp != nullptr && (reinterpret_cast<uintptr_t>(blob) & 63u) == 0 && pp->magic == kConvPreparedMagic,
+               "conv_gemm_run: not a blob filled by fg_conv_gemm_prepare");
+  return conv_launch_prepared(*pp, static_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   using namespace fg;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ConvPrepared pp;
+  const int r = conv_prepare(p, pp);
+  if (r != FG_OK) return r;
+  return conv_launch_prepared(pp, static_cast<cudaStream_t>(stream_));
+}
+
+static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   FG_CHECK_ARG(p != nullptr, "conv_gemm: null params");
   FG_CHECK_ARG(p->n > 0 && p->h > 0 && p->w > 0 && p->cout > 0, "conv_gemm: empty problem n=%d h=%d w=%d cout=%d",
                p->n, p->h, p->w, p->cout);
@@ -740,7 +890,7 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   if (p->gate)
     FG_CHECK_ARG(p->gate_rows > 0 && p->gate_ld >= p->cout, "conv_gemm: gate needs gate_rows > 0 and gate_ld >= cout");
 
-  ConvKParams kp;
+  ConvKParams& kp = pp.kp;
   memset(&kp, 0, sizeof(kp));
   kp.N = p->n, kp.H = p->h, kp.W = p->w, kp.Cout = p->cout;
   {
@@ -768,9 +918,22 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();  // no device (CPU-only argument check)
   const int num_sms = device_sm_count(dev);
-  const int block_n = pick_block_n(p->cout, kp.tiles_w * kp.tiles_h * kp.tiles_img, num_sms, geglu);
+  const int res_mode_eff = p->res ? p->res_mode : FG_RES_NONE;
+  kp.vec = (p->cout % 4 == 0) && (p->out_ld % 4 == 0) && aligned16(p->out) && (!p->bias || aligned16(p->bias)) &&
+           (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
+           (!p->gate || (aligned16(p->gate) && p->gate_ld % 4 == 0)) &&
+           (res_mode_eff == FG_RES_NONE || (aligned16(p->res) && p->res_ld % 4 == 0));
+  static const bool allow_tma_store = !(getenv("FG_CONV_TMA_STORE") && getenv("FG_CONV_TMA_STORE")[0] == '0');
+  // TMA-store epilogue whenever the output rows are 16-byte addressable and the tile is at least one slab wide
+  const bool tma_store_ok = allow_tma_store && kp.vec && (p->out_ld * (p->out_dtype == FG_F32 ? 4 : 2)) % 16 == 0;
+  const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_img;
+  int k_iters_total = 0;
+  for (int s = 0; s < p->nseg; ++s)
+    if (p->seg[s].cin > 0) k_iters_total += p->seg[s].taps * ((p->seg[s].cin + kBlockK - 1) / kBlockK);
+  const TileChoice tc = pick_tile(p->cout, m_tiles, k_iters_total, num_sms, geglu, /*pair_ok=*/tma_store_ok);
+  const int block_n = tc.bn, cg = tc.cg;
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
-  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_img * kp.tiles_n;
+  kp.total_tiles = ((m_tiles + cg - 1) / cg) * kp.tiles_n;   // work items: tiles, or tile pairs of a CTA pair
 
   kp.nseg = p->nseg;
   kp.k_iters = 0;
@@ -797,7 +960,7 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     {
       const uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)sg.taps, (uint64_t)p->cout};
       const uint64_t strides[3] = {2, (uint64_t)sg.cin * 2, (uint64_t)sg.cin * sg.taps * 2};
-      const uint32_t box[3] = {(uint32_t)kBlockK, 1u, (uint32_t)block_n};
+      const uint32_t box[3] = {(uint32_t)kBlockK, 1u, (uint32_t)(block_n / cg)};   // a CTA of a pair stages half the tile
       int r = encode_tmap_bf16(&kp.tmW[s], sg.w, 3, dims, strides, box);
       if (r != FG_OK) return r;
     }
@@ -837,18 +1000,11 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
     if (kp.res_mode == FG_RES_UP2)
       FG_CHECK_ARG(p->h % 2 == 0 && p->w % 2 == 0, "conv_gemm: FG_RES_UP2 needs even h,w");
   }
-  kp.vec = (p->cout % 4 == 0) && (p->out_ld % 4 == 0) && aligned16(p->out) && (!p->bias || aligned16(p->bias)) &&
-           (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
-           (!p->gate || (aligned16(p->gate) && p->gate_ld % 4 == 0)) &&
-           (kp.res_mode == FG_RES_NONE || (aligned16(p->res) && p->res_ld % 4 == 0));
-
-  // TMA-store epilogue whenever the output rows are 16-byte addressable and the tile is at least one slab wide;
-  // the residual rides the same slab ring when it has the output's element type (FG_RES_SAME / FG_RES_UP2)
+  // the residual rides the slab ring of the TMA-store epilogue when it has the output's element type (FG_RES_SAME / UP2)
   int epi = kEpiGeneric;
   {
     const int esz = p->out_dtype == FG_F32 ? 4 : 2;
-    static const bool allow_tma_store = !(getenv("FG_CONV_TMA_STORE") && getenv("FG_CONV_TMA_STORE")[0] == '0');
-    if (allow_tma_store && kp.vec && block_n >= 64 && (p->out_ld * esz) % 16 == 0) {
+    if (tma_store_ok && block_n >= 64) {
       const uint64_t dims[4] = {(uint64_t)out_cols, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
       const uint64_t ldb = (uint64_t)p->out_ld * esz;
       const uint64_t strides[4] = {(uint64_t)esz, ldb, ldb * p->w, ldb * p->w * p->h};
@@ -876,13 +1032,6 @@ extern "C" int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream_) {
   if (geglu) FG_CHECK_ARG(epi == kEpiGeglu, "conv_gemm: FG_ACT_GEGLU needs the TMA-store epilogue (16-byte aligned bf16 output rows)");
   if (kp.stats) FG_CHECK_ARG(epi != kEpiGeneric, "conv_gemm: fused GroupNorm statistics need the TMA-store epilogue (cout %% 4 == 0, cout > 16, 16-byte aligned rows)");
 
-  switch (block_n) {
-    case 16: return dispatch_epi<16>(kp, epi, num_sms, stream);
-    case 64: return dispatch_epi<64>(kp, epi, num_sms, stream);
-    case 128: return dispatch_epi<128>(kp, epi, num_sms, stream);
-    case 192: return dispatch_epi<192>(kp, epi, num_sms, stream);
-    case 256: return dispatch_epi<256>(kp, epi, num_sms, stream);
-  }
-  set_error("conv_gemm: no kernel for block_n=%d", block_n);
-  return FG_ERR_UNSUPPORTED;
+  pp.block_n = block_n, pp.cg = cg, pp.epi = epi, pp.num_sms = num_sms, pp.device = dev;
+  return FG_OK;
 }

@@ -235,8 +235,9 @@ class DiT(FastGenNetwork):
 
         def gemm(a, k, wt, r, cout, out, out_ld, desc, **kw):
             prm = ops.conv_gemm_params([ops.Seg(a, a.stride(0), wt, k, 1)], r, 1, 1, cout, out, out_ld, **kw)
-            plan.keep.append((prm, a, wt, out, kw))
-            plan.add(lib.fg_conv_gemm, C.byref(prm), desc=desc, flops=2.0 * r * k * cout)
+            fn, args, pkeep = ops.conv_gemm_launch(prm)
+            plan.keep.append((prm, pkeep, a, wt, out, kw))
+            plan.add(fn, *args, desc=desc, flops=2.0 * r * k * cout)
 
         def ln(x, y, scale, shift, desc):
             prm = ops.ln_mod_params(x, D, rows, D, 1e-6, y, D, scale=scale, shift=shift, mod_ld=ws["mod"].shape[1],

@@ -363,7 +363,9 @@ class _Plan:
         res = kw.get("res")
         nbytes = n * h * w * (sum(2 * s.cin for s in segs if s.alg) + cout * out.element_size()
                               + (cout * res.element_size() if res is not None else 0))
-        self._launch(L.lib().fg_conv_gemm, C.byref(p), flops=flops, nbytes=nbytes,
+        fn, args, keep = ops.conv_gemm_launch(p)
+        self.keep.append(keep)
+        self._launch(fn, *args, flops=flops, nbytes=nbytes,
                      desc=f"conv {h}x{w} K={ktot} N={cout} out={str(out.dtype)[6:]} res={kw.get('res_mode', 0)}")
 
     def new_stats(self) -> torch.Tensor:

@@ -130,6 +130,31 @@ def attention(qkv: torch.Tensor, qkv_ld: int, n: int, tokens: int, heads: int, d
             "fg_attention")
 
 
+class PreparedConv:
+    """A validated, tile-selected, descriptor-encoded fg_conv_gemm launch (``fg_conv_gemm_prepare``): ``fn(*args, stream)``
+    replays it.  Holds the 64-byte aligned host blob the library filled; the caller keeps the tensors alive."""
+
+    __slots__ = ("buf", "ptr", "fn", "args")
+
+    def __init__(self, p: "L.ConvParams"):
+        lib = L.lib()
+        size = int(lib.fg_conv_gemm_prepared_size())
+        self.buf = C.create_string_buffer(size + 64)
+        self.ptr = (C.addressof(self.buf) + 63) & ~63
+        L.check(lib.fg_conv_gemm_prepare(C.byref(p), self.ptr, size), "fg_conv_gemm")
+        self.fn, self.args = lib.fg_conv_gemm_run, (self.ptr,)
+
+
+def conv_gemm_launch(p: "L.ConvParams"):
+    """(fn, args, keep) of a launch-list entry for the convolution ``p``: the prepared form on a CUDA machine; the plain
+    ``fg_conv_gemm(params)`` call where there is no device to encode TMA descriptors for (host-side plan validation in the
+    CPU tests, which expects the call itself to fail with FG_ERR_CUDA)."""
+    if torch.cuda.is_available():
+        pc = PreparedConv(p)
+        return pc.fn, pc.args, pc
+    return L.lib().fg_conv_gemm, (C.byref(p),), p
+
+
 def sampler_vec(enable: Optional[bool] = None) -> bool:
     """Select (True / False) or query (None) the vectorised forms of the sampler-step kernels; returns the previous
     setting.  Default on (FASTGEN_B200_SAMPLER_VEC=0 turns them off): see ``fg_sampler_vec``."""

@@ -384,8 +384,9 @@ class StableDiffusionXL(FastGenNetwork):
                     ent["kv"][q] = kv
                     p = ops.conv_gemm_params([ops.Seg(ent["text"], X, pk[q + ".kv2.w"], X, 1)], B * Lt, 1, 1, 2 * a.dim,
                                              kv, 2 * a.dim)
-                    plan.keep.append(p)
-                    plan.add(L.lib().fg_conv_gemm, C.byref(p), desc="kv2", flops=2.0 * B * Lt * X * 2 * a.dim)
+                    fn, args, pkeep = ops.conv_gemm_launch(p)
+                    plan.keep.append((p, pkeep))
+                    plan.add(fn, *args, desc="kv2", flops=2.0 * B * Lt * X * 2 * a.dim)
             ent["plan"] = plan
             self._ctx = ent
             self._plans = {}     # forward plans point into the previous buffers
@@ -499,9 +500,9 @@ class StableDiffusionXL(FastGenNetwork):
 
         def conv(segs, n, h, w, cout, out, out_ld, desc, **kw):
             p = ops.conv_gemm_params(segs, n, h, w, cout, out, out_ld, **kw)
-            keep.append((p, segs, out, kw))
-            plan.add(lib.fg_conv_gemm, C.byref(p), desc=desc,
-                     flops=2.0 * n * h * w * cout * sum(s.cin * s.taps for s in segs))
+            fn, args, pkeep = ops.conv_gemm_launch(p)
+            keep.append((p, pkeep, segs, out, kw))
+            plan.add(fn, *args, desc=desc, flops=2.0 * n * h * w * cout * sum(s.cin * s.taps for s in segs))
 
         def gemm(a, k, wt, rows, cout, out, out_ld, desc, **kw):
             conv([ops.Seg(a, a.stride(0), wt, k, 1)], rows, 1, 1, cout, out, out_ld, desc, **kw)

@@ -539,8 +539,9 @@ class _WanBase:
     def _gemm(self, plan: _Plan, a: torch.Tensor, k: int, wt: torch.Tensor, rows: int, cout: int, out: torch.Tensor,
               out_ld: int, desc: str, **kw):
         p = ops.conv_gemm_params([ops.Seg(a, a.stride(0), wt, k, 1)], rows, 1, 1, cout, out, out_ld, **kw)
-        plan.keep.append((p, a, wt, out, kw))
-        plan.add(L.lib().fg_conv_gemm, C.byref(p), desc=desc, flops=2.0 * rows * k * cout)
+        fn, args, keep = ops.conv_gemm_launch(p)
+        plan.keep.append((p, keep, a, wt, out, kw))
+        plan.add(fn, *args, desc=desc, flops=2.0 * rows * k * cout)
 
     def _ln(self, plan: _Plan, x, rows, y, desc, **kw):
         D = self.cfg["dim"]

@@ -96,6 +96,16 @@ typedef struct {
 
 int fg_conv_gemm(const fg_conv_params* p, fg_stream_t stream);
 
+/* The same operator split into "validate + choose the tile + encode the TMA descriptors" and "launch", for callers that
+ * replay a fixed launch list (every network forward here is one: the reference re-dispatches F.conv2d / F.linear per call,
+ * fastgen/networks/EDM/network.py:93-126): fg_conv_gemm re-encodes up to 2 nseg + 2 CUtensorMaps on EVERY call, the
+ * prepared form does it once per plan entry.  `blob` is caller-owned host memory, 64-byte aligned, of at least
+ * fg_conv_gemm_prepared_size() bytes; it stays valid for as long as the tensors named in `p` keep their addresses, on
+ * the device that was current in fg_conv_gemm_prepare.  No allocation, no hidden state. */
+int64_t fg_conv_gemm_prepared_size(void);
+int fg_conv_gemm_prepare(const fg_conv_params* p, void* blob, int64_t blob_bytes);
+int fg_conv_gemm_run(const void* blob, fg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * GroupNorm (+ per-sample scale/shift, + SiLU, + 2x resample) -- replaces torch group_norm + silu +
  * addcmul + the depthwise resample convs (fastgen/networks/EDM/network.py:141-149, 114-121, 276-283).
