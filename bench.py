@@ -428,14 +428,36 @@ def run_ours(args):
                                                "model_flops_utilisation": r["roofline"]["model_flops_utilisation"]}
             except Exception as e:  # pragma: no cover
                 also["in64_strong_scaling"] = {"error": repr(e)}
-        # (3) north_star's scaling target: Wan 2.1 1.3B 4-step self-forcing under Ulysses sequence parallelism
+        keys = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline")
+        # (3) north_star's scaling target: Wan 2.1 1.3B 4-step self-forcing under Ulysses sequence parallelism (configs[3])
         try:
             w = measure_wan(ctx, big=False, K=2, W=2)
             if w is not None:
-                also["wan13b"] = {k: w[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e",
-                                                    "gpu_launches", "roofline")}
+                also["wan13b"] = {k: w[k] for k in keys if k in w}
         except Exception as e:  # pragma: no cover
             also["wan13b"] = {"error": repr(e)}
+        # (4) configs[0]: CIFAR-10 one-step generator, batch 64 -- one GPU by definition (rank 0; the others wait)
+        try:
+            if rank == 0:
+                c = measure_cifar(64, 3, 3, cpu=(world == 1 and not args.no_cpu_baseline), device=ctx.local)
+                also["cifar"] = {k: c[k] for k in keys if k in c}
+            ctx.barrier()
+        except Exception as e:  # pragma: no cover
+            also["cifar"] = {"error": repr(e)}
+        # (5) configs[2]: SDXL 4-step, batch 16 per GPU, batch-sharded (weak scaling like the headline)
+        try:
+            x = measure_sdxl(ctx, 16, 2, 1)
+            if x is not None:
+                also["sdxl"] = {k: x[k] for k in keys if k in x}
+        except Exception as e:  # pragma: no cover
+            also["sdxl"] = {"error": repr(e)}
+        # (6) configs[4]: Wan 14B 720p 4-step, Ulysses over all N ranks (one sample timed after one warm-up sample)
+        try:
+            w = measure_wan(ctx, big=True, K=1, W=1, profile=False, e2e=False)
+            if w is not None:
+                also["wan14b"] = {k: w[k] for k in keys if k in w}
+        except Exception as e:  # pragma: no cover
+            also["wan14b"] = {"error": repr(e)}
     emit()
     ctx.close()
 
@@ -459,7 +481,7 @@ def run_wan(args):
     ctx.close()
 
 
-def measure_wan(ctx: "_Dist", big: bool, K: int, W: int):
+def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e2e: bool = True):
     """big: BASELINE configs[4] (bidirectional 14B, 720p, 4-step ode, Ulysses over all ranks); else configs[3] (1.3B
     self-forcing, Ulysses groups of min(N, 4) ranks x N / 4 replicas).  Returns the JSON line (rank 0) or None."""
     from fastgen_b200.sampler import CausVidModel, FastGenModel
@@ -520,13 +542,15 @@ def measure_wan(ctx: "_Dist", big: bool, K: int, W: int):
 
     if not big:
         e2e_step()   # (the 14B sample takes ~30 GPU-seconds: its plans are warm already, skip the extra untimed pass)
-    ms_e2e = timed(e2e_step, K)
+    ms_e2e = timed(e2e_step, K) if e2e else None
     hbm, tf_sus, tf_burst, peak_src = _peaks()
-    net.profile = {}
-    barrier()
-    gen(noise, text)
-    barrier()
-    prof, net.profile = net.profile, None
+    prof = {}
+    if profile:
+        net.profile = {}
+        barrier()
+        gen(noise, text)
+        barrier()
+        prof, net.profile = net.profile, None
     tot_ms = sum(d["ms"] for d in prof.values())
     att = prof.get("fg_flash_attn:self_attn", {"launches": 0, "ms": 0.0, "flops": 0.0})
     att_tf = att["flops"] / (att["ms"] / 1000.0) / 1e12 if att["ms"] else 0.0
@@ -547,8 +571,9 @@ def measure_wan(ctx: "_Dist", big: bool, K: int, W: int):
                        "parallelism": f"Ulysses sequence parallel x{sp}, {replicas} replica(s)",
                        "l2": ("inputs exceed L2: 28 GB of bf16 weights and 75 600-token activations streamed per forward" if big
                               else "inputs exceed L2: 2.8 GB of weights + up to 6 GB of KV cache streamed per sample")},
-            "e2e": {"value": replicas * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": noise_h.numel() * 2 + text_h.numel() * 2, "d2h_bytes_per_step": out_h.numel() * 2},
+            "e2e": ({"value": replicas * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
+                     "h2d_bytes_per_step": noise_h.numel() * 2 + text_h.numel() * 2, "d2h_bytes_per_step": out_h.numel() * 2}
+                    if e2e else None),
             "gpu_launches": launches, "clocks": clk.summary(),
             "roofline": {"kernel": "attention2_kernel (tcgen05 flash attention, self-attention over the KV cache)",
                          "bound": "tensor", "achieved": att_tf, "peak": tf_sus, "unit": "TFLOP/s",
@@ -570,22 +595,20 @@ SDXL_TFLOP_PER_SAMPLE_FORWARD = 6.75  # counted from our own layer table (sum of
 
 
 def run_sdxl(args):
-    """BASELINE configs[2]: SDXL 1024x1024 (128x128 latent) DMD2 4-step UNet generation, batch 16 per GPU, bf16."""
-    import torch.distributed as dist
+    ctx = _Dist()
+    line = measure_sdxl(ctx, args.batch if args.batch != BATCH else 16, args.steps, max(args.warmup, 0))
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
+
+def measure_sdxl(ctx: "_Dist", B: int, K: int, W: int):
+    """BASELINE configs[2]: SDXL 1024x1024 (128x128 latent) DMD2 4-step UNet generation, batch 16 per GPU, bf16."""
     from fastgen_b200 import ops
     from fastgen_b200.sampler import FastGenModel
     from fastgen_b200.sdxl import StableDiffusionXL
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, max(args.warmup, 0)
-    B = args.batch if args.batch != BATCH else 16
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
     torch.manual_seed(0)
     with torch.device(dev):
         net = StableDiffusionXL()
@@ -600,27 +623,8 @@ def run_sdxl(args):
     def gen(n_, c_):
         return FastGenModel.generator_fn(net, n_, student_sample_steps=4, condition=c_, student_sample_type="sde")
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    def timed(fn, iters):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    for _ in range(W):
+    barrier, timed = ctx.barrier, ctx.timed
+    for _ in range(max(W, 1)):
         out = gen(noise, [text, pooled])
     assert torch.isfinite(out.float()).all(), "non-finite samples"
     ops.launch_count_reset()
@@ -646,6 +650,7 @@ def run_sdxl(args):
     gemm_fl = sum(d["flops"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
     gemm_n = sum(d["launches"] for k, d in prof.items() if k.startswith("fg_conv_gemm"))
     gemm_tf = gemm_fl / (gemm_ms / 1000.0) / 1e12 if gemm_ms else 0.0
+    line = None
     if rank == 0:
         line = {
             "metric": "samples/sec, 4-step DMD2 SDXL 1024x1024 UNet generation", "value": value, "unit": "samples/s",
@@ -670,9 +675,9 @@ def run_sdxl(args):
                          "model_flops_utilisation": (value * 4 * SDXL_TFLOP_PER_SAMPLE_FORWARD) / (world * tf_sus)},
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    del net
+    torch.cuda.empty_cache()
+    return line
 
 
 CIFAR = dict(img_resolution=32, img_channels=3, label_dim=10, sigma_shift=0.0, sigma_data=0.5, model_type="SongUNet",
@@ -683,20 +688,23 @@ CIFAR_GFLOP_PER_SAMPLE_FORWARD = 42.38
 
 
 def run_cifar(args):
+    print(json.dumps(measure_cifar(args.batch if args.batch != BATCH else 64, args.steps, max(args.warmup, 0),
+                                   graphs=not args.no_graphs, cpu=not args.no_cpu_baseline)))
+
+
+def measure_cifar(B: int, K: int, W: int, graphs: bool = True, cpu: bool = True, device: int = 0):
     """BASELINE configs[0]: EDM CIFAR-10 32x32 DMD2 one-step generator, batch 64 (the reference's CPU-runnable case)."""
     from fastgen_b200 import ops
     from fastgen_b200.edm import EDMPrecond
     from fastgen_b200.sampler import FastGenModel
 
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    K, W = args.steps, max(args.warmup, 0)
-    B = args.batch if args.batch != BATCH else 64
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
     torch.manual_seed(0)
     net = EDMPrecond(**CIFAR)
     _randomize_zero_init_(net, 0)
     net = net.to(dev).eval()
-    net.use_cuda_graphs = not args.no_graphs   # 174 launches of 10-30 us: replay them as one CUDA graph
+    net.use_cuda_graphs = graphs   # 174 launches of 10-30 us: replay them as one CUDA graph
     torch.manual_seed(1)
     noise_h = torch.randn(B, 3, 32, 32).pin_memory()
     labels_h = torch.eye(10)[torch.randint(10, (B,))].pin_memory()
@@ -721,7 +729,7 @@ def run_cifar(args):
     iters = K * 20     # a step is ~3 ms: time 20 generations per "step" so that the events see a long region
     ops.launch_count_reset()
     net.graph_launches = 0
-    with ClockSampler(0) as clk:
+    with ClockSampler(device) as clk:
         ms = timed(lambda: gen(noise, labels), iters)
     launches = ops.launch_count() + net.graph_launches   # direct launches + launches replayed through the CUDA graph
 
@@ -745,7 +753,7 @@ def run_cifar(args):
     tot_ms = sum(d["ms"] for d in prof.values())
     conv = prof.get("fg_conv_gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     conv_tf = conv["flops"] / (conv["ms"] / 1000.0) / 1e12 if conv["ms"] else None
-    cpu = None if args.no_cpu_baseline else _cpu_baseline("cifar", B, repeats=2, warmup=0)
+    cpu_base = _cpu_baseline("cifar", B, repeats=2, warmup=0) if cpu else None
     line = {
         "metric": "samples/sec, 1-step CIFAR-10 EDM DMD2 generator", "value": value, "unit": "samples/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -766,9 +774,11 @@ def run_cifar(args):
                      "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
                      "per_kernel_ms_per_generation": {k: round(d["ms"] / 20, 4) for k, d in sorted(prof.items())},
                      "model_flops_utilisation": value * CIFAR_GFLOP_PER_SAMPLE_FORWARD * 1e9 / 1e12 / tf_sus},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu_base,
     }
-    print(json.dumps(line))
+    del net
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -783,7 +793,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: batch of the bounded CPU sample (default 16 / 64)")
     ap.add_argument("--no-also", action="store_true", help="in64: skip the secondary measurements (fp32 path, strong scaling, Wan 1.3B)")
-    ap.add_argument("--also-budget-s", type=float, default=420.0, help="in64: wall-clock cap of the secondary measurements")
+    ap.add_argument("--also-budget-s", type=float, default=600.0, help="in64: wall-clock cap of the secondary measurements")
     ap.add_argument("--no-graphs", action="store_true", help="cifar workload: launch every kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
