@@ -436,6 +436,14 @@ def run_ours(args):
                 also["wan13b"] = {k: w[k] for k in keys if k in w}
         except Exception as e:  # pragma: no cover
             also["wan13b"] = {"error": repr(e)}
+        # (3b) the same with two samples per sequence-parallel group (SURVEY 8d lists B = 1, 2, 8 for this config): the
+        # throughput setting -- 2 340-row shards at P = 4 instead of 1 170, and half as many exchanges per sample
+        try:
+            w = measure_wan(ctx, big=False, K=2, W=2, profile=False, e2e=False, batch=2)
+            if w is not None:
+                also["wan13b_batch2"] = {k: w[k] for k in keys if k in w}
+        except Exception as e:  # pragma: no cover
+            also["wan13b_batch2"] = {"error": repr(e)}
         # (4) configs[0]: CIFAR-10 one-step generator, batch 64 -- one GPU by definition (rank 0; the others wait)
         try:
             if rank == 0:
@@ -475,13 +483,13 @@ WAN14B_TFLOP_PER_SAMPLE = 4 * 6523.3  # bidirectional 14B forwar
 
 def run_wan(args):
     ctx = _Dist()
-    line = measure_wan(ctx, big=args.workload == "wan14b", K=args.steps, W=max(args.warmup, 0))
+    line = measure_wan(ctx, big=args.workload == "wan14b", K=args.steps, W=max(args.warmup, 0), batch=args.wan_batch)
     if ctx.rank == 0:
         print(json.dumps(line))
     ctx.close()
 
 
-def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e2e: bool = True):
+def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e2e: bool = True, batch: int = 1):
     """big: BASELINE configs[4] (bidirectional 14B, 720p, 4-step ode, Ulysses over all ranks); else configs[3] (1.3B
     self-forcing, Ulysses groups of min(N, 4) ranks x N / 4 replicas).  Returns the JSON line (rank 0) or None."""
     from fastgen_b200.sampler import CausVidModel, FastGenModel
@@ -511,9 +519,9 @@ def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e
         groups = [dist.new_group(list(range(g * sp, (g + 1) * sp))) for g in range(world // sp)]
         net.sp_group = groups[replica]
     torch.manual_seed(1 + replica)  # ranks of one sequence-parallel group draw identical noise
-    noise_h = torch.randn(1, 16, frames, lh, lw).bfloat16().pin_memory()
-    text_h = torch.randn(1, 512, 4096).bfloat16().pin_memory()
-    out_h = torch.empty(1, 16, frames, lh, lw, dtype=torch.bfloat16).pin_memory()
+    noise_h = torch.randn(batch, 16, frames, lh, lw).bfloat16().pin_memory()
+    text_h = torch.randn(batch, 512, 4096).bfloat16().pin_memory()
+    out_h = torch.empty(batch, 16, frames, lh, lw, dtype=torch.bfloat16).pin_memory()
     noise, text = noise_h.to(dev), text_h.to(dev)
 
     def gen(n_, c_):
@@ -534,7 +542,7 @@ def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e
     with ClockSampler(local) as clk:
         ms = timed(lambda: gen(noise, text), K)
     launches = ops.launch_count() + net.graph_launches   # direct launches + launches replayed through CUDA graphs
-    replicas = world // sp
+    replicas = (world // sp) * batch     # samples in flight: data-parallel groups x samples per group
     value = replicas * K / (ms / 1000.0)
 
     def e2e_step():
@@ -566,9 +574,9 @@ def measure_wan(ctx: "_Dist", big: bool, K: int, W: int, profile: bool = True, e
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": ("Wan 2.1 14B T2V 720p 81-frame 4-step (ode), batch 1, Ulysses sequence parallel (BASELINE configs[4])"
                                     if big else
-                                    "Wan 2.1 1.3B T2V 480p 81-frame 4-step self-forcing, batch 1 per group (BASELINE configs[3])"),
-                       "latent": [1, 16, frames, lh, lw], "t_list": WAN_TL, "chunk_size": None if big else 3,
-                       "parallelism": f"Ulysses sequence parallel x{sp}, {replicas} replica(s)",
+                                    f"Wan 2.1 1.3B T2V 480p 81-frame 4-step self-forcing, batch {batch} per group (BASELINE configs[3])"),
+                       "latent": [batch, 16, frames, lh, lw], "t_list": WAN_TL, "chunk_size": None if big else 3,
+                       "parallelism": f"Ulysses sequence parallel x{sp}, {world // sp} group(s) x batch {batch}",
                        "l2": ("inputs exceed L2: 28 GB of bf16 weights and 75 600-token activations streamed per forward" if big
                               else "inputs exceed L2: 2.8 GB of weights + up to 6 GB of KV cache streamed per sample")},
             "e2e": ({"value": replicas * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
@@ -792,6 +800,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: batch of the bounded CPU sample (default 16 / 64)")
+    ap.add_argument("--wan-batch", type=int, default=1, help="wan workload: samples per sequence-parallel group")
     ap.add_argument("--no-also", action="store_true", help="in64: skip the secondary measurements (fp32 path, strong scaling, Wan 1.3B)")
     ap.add_argument("--also-budget-s", type=float, default=600.0, help="in64: wall-clock cap of the secondary measurements")
     ap.add_argument("--no-graphs", action="store_true", help="cifar workload: launch every kernel instead of replaying a CUDA graph")

@@ -92,6 +92,7 @@ class PeerPutParams(C.Structure):
         ("n", C.c_int32 * 4), ("src_strides", C.c_int64 * 4), ("dst_strides", C.c_int64 * 4),
         ("src_peer_stride", C.c_int64), ("dst_offset", C.c_int64), ("item_bytes", C.c_int32),
         ("flags", C.c_void_p * FG_MAX_PEERS), ("state", C.c_void_p),
+        ("wait_flags", C.c_void_p), ("wait_timeout_ns", C.c_int64),
     ]
 
 

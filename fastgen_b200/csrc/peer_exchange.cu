@@ -36,7 +36,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k) {
+// spin (one thread per peer) until every local flag has reached the next wait epoch; a timeout sets state[3]
+__device__ __forceinline__ void peer_wait_body(const unsigned long long* flags, int peers, unsigned long long* state,
+                                               long long timeout_ns, unsigned long long* epoch_smem) {
+  if (threadIdx.x == 0) {
+    *epoch_smem = state[2] + 1ull;
+    state[2] = *epoch_smem;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < peers) {
+    const unsigned long long e = *epoch_smem;
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < e) {
+      __nanosleep(32);
+      if (timeout_ns > 0 && static_cast<long long>(globaltimer_ns() - t0) > timeout_ns) {
+        state[3] = 1ull;  // the host raises on it (next forward / end of the sample); the consumer reads stale data
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k, const unsigned long long* wait_flags,
+                                                                long long wait_timeout_ns) {
+  __shared__ unsigned long long epoch;
+  __shared__ int is_last;
   peer_put_copy(k, blockIdx.y, blockIdx.x * static_cast<int64_t>(kPeerThreads) + threadIdx.x,
                 static_cast<int64_t>(gridDim.x) * kPeerThreads, [](const Vec16* p) {
                   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
@@ -46,7 +71,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(k.state + 1), 1u);
-    if (done == k.total_ctas - 1) {  // every other CTA fenced before it counted itself
+    is_last = done == k.total_ctas - 1;
+    if (is_last) {  // every other CTA fenced before it counted itself
       __threadfence_system();
       *reinterpret_cast<unsigned*>(k.state + 1) = 0u;
       const unsigned long long e = k.state[0] + 1ull;
@@ -54,28 +80,18 @@ __global__ void __launch_bounds__(kPeerThreads) peer_put_kernel(const PeerPutK k
       for (int p = 0; p < k.peers; ++p) st_release_sys(k.flags[p] + k.rank, e);
     }
   }
+  if (wait_flags == nullptr) return;
+  // fused wait: the CTA that published this rank's flags stays and waits for everybody else's, so the kernel's end means
+  // "the exchange is complete here" and no separate one-CTA wait launch sits between the put and the consumer
+  __syncthreads();
+  if (!is_last) return;
+  peer_wait_body(wait_flags, k.peers, k.state, wait_timeout_ns, &epoch);
 }
 
 __global__ void peer_wait_kernel(const unsigned long long* __restrict__ flags, int peers, unsigned long long* state,
                                  long long timeout_ns) {
   __shared__ unsigned long long epoch;
-  if (threadIdx.x == 0) {
-    epoch = state[2] + 1ull;
-    state[2] = epoch;
-  }
-  __syncthreads();
-  if (static_cast<int>(threadIdx.x) < peers) {
-    const unsigned long long e = epoch;
-    const uint64_t t0 = globaltimer_ns();
-    while (ld_acquire_sys(flags + threadIdx.x) < e) {
-      __nanosleep(64);
-      if (timeout_ns > 0 && static_cast<long long>(globaltimer_ns() - t0) > timeout_ns) {
-        state[3] = 1ull;  // the host raises on it after the next synchronisation; the consumer reads stale data, nothing hangs
-        break;
-      }
-    }
-  }
-  __threadfence_system();
+  peer_wait_body(flags, peers, state, timeout_ns, &epoch);
 }
 
 }  // namespace fg
@@ -110,14 +126,18 @@ extern "C" int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream_) {
     k.dst[q] = reinterpret_cast<Vec16*>(static_cast<char*>(p->dst[q]) + p->dst_offset);
     k.flags[q] = reinterpret_cast<unsigned long long*>(p->flags[q]);
   }
-  const int64_t vecs = items * k.vec;
-  // enough CTAs per destination to fill the machine with all destinations in flight, 4 vectors per thread at least
-  int64_t bx = (vecs + 4ll * kPeerThreads - 1) / (4ll * kPeerThreads);
-  const int64_t cap = (148ll * 8 + p->peers - 1) / p->peers;
+  FG_CHECK_ARG(items > 0 && items < (1ll << 31), "peer_put: too many items");
+  if (p->wait_flags)
+    FG_CHECK_ARG((reinterpret_cast<uintptr_t>(p->wait_flags) & 7) == 0, "peer_put: wait_flags must be 8-byte aligned");
+  // one warp per item, two items in flight per warp: enough CTAs per destination that all destinations together fill the
+  // machine (8 warps per CTA), at least two items per warp
+  int64_t bx = (items + 2 * (kPeerThreads / 32) - 1) / (2 * (kPeerThreads / 32));
+  const int64_t cap = (148ll * 4 + p->peers - 1) / p->peers;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   k.total_ctas = static_cast<unsigned>(bx * p->peers);
-  peer_put_kernel<<<dim3(static_cast<unsigned>(bx), p->peers), kPeerThreads, 0, static_cast<cudaStream_t>(stream_)>>>(k);
+  peer_put_kernel<<<dim3(static_cast<unsigned>(bx), p->peers), kPeerThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      k, reinterpret_cast<const unsigned long long*>(p->wait_flags), p->wait_timeout_ns);
   FG_CHECK_LAUNCH("peer_put");
   return FG_OK;
 }

@@ -12,6 +12,12 @@
 #define FG_PEER_HD inline
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define FG_PEER_UNROLL _Pragma("unroll")
+#else
+#define FG_PEER_UNROLL
+#endif
+
 #ifndef FG_MAX_PEERS
 #define FG_MAX_PEERS 8
 #endif
@@ -35,22 +41,53 @@ struct PeerPutK {
   unsigned total_ctas;
 };
 
+// One warp per item (an item = `vec` consecutive 16-byte vectors, e.g. one head slice of one token row): the 4-D index is
+// decomposed once per item with 32-bit arithmetic (the first version did four 64-bit divisions per 16 bytes), the lanes
+// stride over the item's vectors, and a warp keeps TWO items in flight (all loads issued before the first store) so that
+// the NVLink stores of one item overlap the local loads of the next.  `nthreads` must be a multiple of 32.
 template <typename LoadFn>
 FG_PEER_HD void peer_put_copy(const PeerPutK& k, int dst, int64_t tid, int64_t nthreads, LoadFn load) {
   const Vec16* src = k.src + dst * k.src_peer_stride;
   Vec16* out = k.dst[dst];
-  const int64_t total = static_cast<int64_t>(k.n[0]) * k.n[1] * k.n[2] * k.n[3] * k.vec;
-  for (int64_t i = tid; i < total; i += nthreads) {
-    const int v = static_cast<int>(i % k.vec);
-    int64_t item = i / k.vec;
-    const int i3 = static_cast<int>(item % k.n[3]);
-    item /= k.n[3];
-    const int i2 = static_cast<int>(item % k.n[2]);
-    item /= k.n[2];
-    const int i1 = static_cast<int>(item % k.n[1]);
-    const int i0 = static_cast<int>(item / k.n[1]);
-    out[i0 * k.ds[0] + i1 * k.ds[1] + i2 * k.ds[2] + i3 * k.ds[3] + v] =
-        load(src + i0 * k.ss[0] + i1 * k.ss[1] + i2 * k.ss[2] + i3 * k.ss[3] + v);
+  const uint32_t items = static_cast<uint32_t>(k.n[0]) * k.n[1] * k.n[2] * k.n[3];
+  const uint32_t warps = static_cast<uint32_t>(nthreads >> 5), warp = static_cast<uint32_t>(tid >> 5);
+  const int lane = static_cast<int>(tid & 31);
+  const uint32_t n3 = k.n[3], n2 = k.n[2], n1 = k.n[1];
+  auto offsets = [&](uint32_t item, int64_t& so, int64_t& dof) {
+    const uint32_t i3 = item % n3;
+    item /= n3;
+    const uint32_t i2 = item % n2;
+    item /= n2;
+    const uint32_t i1 = item % n1, i0 = item / n1;
+    so = i0 * k.ss[0] + i1 * k.ss[1] + i2 * k.ss[2] + i3 * k.ss[3];
+    dof = i0 * k.ds[0] + i1 * k.ds[1] + i2 * k.ds[2] + i3 * k.ds[3];
+  };
+  constexpr int kMaxPerLane = 4;   // vectors of one item a lane holds at once (items of up to 2 KB in one go)
+  for (uint32_t a = warp; a < items; a += 2 * warps) {
+    const uint32_t b = a + warps;
+    const bool two = b < items;
+    int64_t sa, da, sb = 0, db = 0;
+    offsets(a, sa, da);
+    if (two) offsets(b, sb, db);
+    for (int v0 = 0; v0 < k.vec; v0 += 32 * kMaxPerLane) {
+      Vec16 ra[kMaxPerLane], rb[kMaxPerLane];
+FG_PEER_UNROLL
+      for (int u = 0; u < kMaxPerLane; ++u) {
+        const int v = v0 + u * 32 + lane;
+        if (v < k.vec) {
+          ra[u] = load(src + sa + v);
+          if (two) rb[u] = load(src + sb + v);
+        }
+      }
+FG_PEER_UNROLL
+      for (int u = 0; u < kMaxPerLane; ++u) {
+        const int v = v0 + u * 32 + lane;
+        if (v < k.vec) {
+          out[da + v] = ra[u];
+          if (two) out[db + v] = rb[u];
+        }
+      }
+    }
   }
 }
 

@@ -400,7 +400,7 @@ def strided_copy(src, dst, n, src_strides, dst_strides, item_elems) -> None:
 
 
 def peer_put_params(src: torch.Tensor, desc, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], rank: int,
-                    state: torch.Tensor) -> "L.PeerPutParams":
+                    state: torch.Tensor, wait: bool = False, timeout_ns: int = 0) -> "L.PeerPutParams":
     """``fg_peer_put`` parameters from a ``parallel.peer_put_*_desc`` descriptor (strides / offsets in elements of
     ``src``'s dtype).  ``dst_ptrs[q]`` / ``flag_ptrs[q]``: device-mapped addresses of rank q's destination buffer and of
     its flag array for this channel (symmetric memory); ``state``: this channel's 4 local int64 words."""
@@ -420,6 +420,8 @@ def peer_put_params(src: torch.Tensor, desc, dst_ptrs: Sequence[int], flag_ptrs:
         p.n[i], p.src_strides[i], p.dst_strides[i] = desc["n"][i], desc["ss"][i] * es, desc["ds"][i] * es
     p.src_peer_stride, p.dst_offset, p.item_bytes = desc["src_peer_stride"] * es, desc["dst_off"] * es, desc["item"] * es
     p.state = state.data_ptr()
+    if wait:    # fused wait on this rank's own flags of the channel: put + wait are one launch
+        p.wait_flags, p.wait_timeout_ns = flag_ptrs[rank], timeout_ns
     return p
 
 

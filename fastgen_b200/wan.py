@@ -730,11 +730,11 @@ class _WanBase:
                 px, full, attf = ws["peer"], ws["qkv_full"], ws["att_full"]
                 tmo = int(self.peer_timeout_s * 1e9)
                 # qkv[b][r][j][dst][Dl] -> rank dst's full[b][rank*n_l + r][j][Dl], then wait for everybody's slices
+                # (put and wait are one launch: the CTA that publishes this rank's flags waits for the peers')
                 p = ops.peer_put_params(qkv, PL.peer_put_qkv_desc(B, n, P, rank, D, Dl), px["full_ptrs"], px["flag_ptrs"][0],
-                                        rank, px["state"][0])
+                                        rank, px["state"][0], wait=True, timeout_ns=tmo)
                 plan.keep.append(p)
                 plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_qkv")
-                plan.add(lib.fg_peer_wait, px["flag_ptrs"][0][rank], P, px["state"][0].data_ptr(), tmo, desc="peer_wait_qkv")
                 if kv is not None and store_kv:
                     self._copy(plan, full[:, :, Dl:], kv["k"][i][:, cache_start:], [B, n, 1, 1], [n * 3 * Dl, 3 * Dl, 0, 0],
                                [cap * Dl, Dl, 0, 0], Dl, "k_append")
@@ -748,10 +748,9 @@ class _WanBase:
                 plan.add(lib.fg_flash_attn, C.byref(p), desc="self_attn", flops=4.0 * B * n * kv_tot * Dl)
                 # att_full[b][dst*n_l + r][Dl] -> rank dst's att[b][r][rank*Dl ...]: exchange + unpack in one pass
                 p = ops.peer_put_params(attf, PL.peer_put_out_desc(B, n, P, rank, D, Dl), px["att_ptrs"], px["flag_ptrs"][1],
-                                        rank, px["state"][1])
+                                        rank, px["state"][1], wait=True, timeout_ns=tmo)
                 plan.keep.append(p)
                 plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_out")
-                plan.add(lib.fg_peer_wait, px["flag_ptrs"][1][rank], P, px["state"][1].data_ptr(), tmo, desc="peer_wait_out")
             else:
                 send, full, attf, recv = ws["a2a_s"], ws["qkv_full"], ws["att_full"], ws["a2a_r"]
                 # pack: qkv[b][r][j][dst][Dl] -> send[b][dst][r][j][Dl]   (one launch per sample keeps it 4-D)
@@ -805,11 +804,10 @@ class _WanBase:
                 # all-gather as a put of this rank's rows into slot `rank` of every rank's tok_out_g (third channel)
                 px = ws["peer"]
                 p = ops.peer_put_params(ws["tok_out_l"], PL.peer_gather_desc(lrows, kout, rank), px["gat_ptrs"],
-                                        px["flag_ptrs"][2], rank, px["state"][2])
+                                        px["flag_ptrs"][2], rank, px["state"][2], wait=True,
+                                        timeout_ns=int(self.peer_timeout_s * 1e9))
                 plan.keep.append(p)
                 plan.add(lib.fg_peer_put, C.byref(p), desc="peer_put_gather")
-                plan.add(lib.fg_peer_wait, px["flag_ptrs"][2][rank], P, px["state"][2].data_ptr(),
-                         int(self.peer_timeout_s * 1e9), desc="peer_wait_gather")
             else:
                 plan.add_py(lambda: dist.all_gather_into_tensor(ws["tok_out_g"], ws["tok_out_l"], group=group), "gather_out")
             # gathered[src][(b, f)][i] -> natural token order [(b, f)][src * fs_l + i]

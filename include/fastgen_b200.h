@@ -276,6 +276,8 @@ typedef struct {
   int32_t item_bytes;       /* multiple of 16 */
   uint64_t* flags[FG_MAX_PEERS];
   uint64_t* state;
+  const uint64_t* wait_flags; /* optional: this rank's own flag array of the channel -- the put then also WAITS (like      */
+  int64_t wait_timeout_ns;    /* fg_peer_wait) before the kernel ends: the exchange is one launch instead of two           */
 } fg_peer_put_params;
 
 int fg_peer_put(const fg_peer_put_params* p, fg_stream_t stream);

@@ -9,6 +9,7 @@ extern "C" int emu_peer_put(const void* src, void* const* dst, int peers, const 
                             int64_t threads_per_dst) {
   // same conversions as the fg_peer_put launcher (bytes -> 16-byte units)
   if (item_bytes % 16 || src_peer_stride % 16 || dst_offset % 16) return -1;
+  if (threads_per_dst <= 0 || threads_per_dst % 32) return -1;   // the copy is warp-granular (one warp per item)
   fg::PeerPutK k;
   k.src = static_cast<const fg::Vec16*>(src);
   k.vec = item_bytes / 16, k.peers = peers, k.rank = 0, k.total_ctas = 0, k.state = nullptr;

@@ -163,7 +163,7 @@ def test_peer_put_kernel_copy_loop_on_the_host_equals_the_descriptor_reference()
                               desc["src_peer_stride"] * es, desc["dst_off"] * es, desc["item"] * es, threads)
         assert st == 0
 
-    for P, threads in ((2, 7), (4, 1000), (8, 64)):
+    for P, threads in ((2, 32), (4, 992), (8, 64)):     # whole warps: the copy is one warp per item
         torch.manual_seed(P)
         B, Fr, fs, H, d = 2, 3, 16, 8, 8
         D = H * d

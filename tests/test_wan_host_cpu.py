@@ -106,16 +106,16 @@ def test_wan14b_peer_exchange_launch_list_validates_on_the_host(monkeypatch):
     statuses.clear()
     dry_run(plan)
     descs = [s[1] for s in statuses]
-    assert descs.count("peer_put_qkv") == descs.count("peer_wait_qkv") == 2
-    assert descs.count("peer_put_out") == descs.count("peer_wait_out") == 2
+    # (put and wait are one launch: fg_peer_put with wait_flags set)
+    assert descs.count("peer_put_qkv") == 2 and descs.count("peer_put_out") == 2 and "peer_wait_qkv" not in descs
     assert "a2a_pack" not in descs and "a2a_unpack" not in descs and "a2a_qkv" not in descs and "a2a_out" not in descs
     # no torch.distributed call is left anywhere in the launch list: the final gather is a put + wait as well
     assert not any(s[0] == "collective" for s in statuses)
     j = descs.index("peer_put_gather")
-    assert descs[j - 1:j + 4] == ["proj_out", "peer_put_gather", "peer_wait_gather", "unshard", "unpatchify"]
+    assert descs[j - 1:j + 3] == ["proj_out", "peer_put_gather", "unshard", "unpatchify"]
     # put -> wait -> attention -> put -> wait -> output projection, in that order inside a block
     i = descs.index("peer_put_qkv")
-    assert descs[i:i + 6] == ["peer_put_qkv", "peer_wait_qkv", "self_attn", "peer_put_out", "peer_wait_out", "o1"]
+    assert descs[i:i + 4] == ["peer_put_qkv", "self_attn", "peer_put_out", "o1"]
     invalid = [s for s in statuses if s[2] == -1]
     assert not invalid, invalid[:5]
     assert all(s[2] != 0 for s in statuses if s[0] != "collective"), "a launch succeeded without a GPU?"
