@@ -60,41 +60,14 @@ struct Num<float> {
   static FG_HD float from_float(float v) { return v; }
   static FG_HD double to_double(float v) { return static_cast<double>(v); }
 };
-// bf16 -> fp64 is exact; for normal numbers and zero it is a re-biased exponent and a shifted mantissa, i.e. three
-// integer instructions on the high word instead of a trip through the 64-bit conversion unit (which, with two widenings
-// and one narrowing per element, was what bounded the bf16 form of coef_vec_kernel: 5.1 TB/s at the asymptote).
-FG_HD double bf16_bits_to_double(uint32_t b) {
-  const uint32_t e = (b >> 7) & 0xFFu;
-  if (e - 1u < 254u || (b & 0x7FFFu) == 0u) {
-    const uint32_t hi = ((b & 0x8000u) << 16) | (e ? ((e + 896u) << 20) | ((b & 0x7Fu) << 13) : 0u);
-#if defined(__CUDA_ARCH__)
-    return __hiloint2double(static_cast<int>(hi), 0);
-#else
-    const uint64_t u = static_cast<uint64_t>(hi) << 32;
-    double d;
-    memcpy(&d, &u, sizeof(d));
-    return d;
-#endif
-  }
-  const uint32_t w = b << 16;  // subnormal, inf, nan: the conversion unit
-  float f;
-#if defined(__CUDA_ARCH__)
-  f = __uint_as_float(w);
-#else
-  memcpy(&f, &w, sizeof(f));
-#endif
-  return static_cast<double>(f);
-}
 template <>
 struct Num<__nv_bfloat16> {
   static FG_HD __nv_bfloat16 from_double(double v) { return __float2bfloat16_rn(d2f(v)); }  // torch: via float
   static FG_HD float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
   static FG_HD __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
-  static FG_HD double to_double(__nv_bfloat16 v) {
-    uint16_t b;
-    memcpy(&b, &v, sizeof(b));
-    return bf16_bits_to_double(b);
-  }
+  // (an integer re-bias of exponent and mantissa instead of the two conversions was tried: 2.3 TB/s against 5.1 TB/s --
+  // the special-case branch costs more than the conversion unit saves)
+  static FG_HD double to_double(__nv_bfloat16 v) { return static_cast<double>(__bfloat162float(v)); }
 };
 template <>
 struct Num<double> {
@@ -220,16 +193,21 @@ FG_UNROLL
   return r;
 }
 
-// Two vectors per thread and iteration (v and v + nthreads: both coalesced), all four loads issued before the arithmetic.
+// fp32 / fp64 (4 or 2 elements per 16-byte vector): two vectors per thread and iteration (v and v + nthreads: both
+// coalesced), all four loads issued before the arithmetic -- 6.07 TB/s at the 1.6 GB asymptote (0.93 of the copy rate).
+// bf16 (8 elements per vector, each through the fp64 pipe) keeps one vector per iteration: with two, the sixteen fp64
+// temporaries per thread cost more occupancy than the extra loads in flight gain (3.5 against 5.1 TB/s measured).
 template <typename T, int MODE>
 FG_HD void coef_vec_body(const T* a, const T* b, int64_t total, int64_t outer, int64_t mid, int64_t inner, const double* c0,
                          const double* c1, T* out, int64_t tid, int64_t nthreads) {
   constexpr int N = 16 / sizeof(T);
+  constexpr bool kTwo = sizeof(T) >= 4;
   const int64_t vecs = total / N;
   const bool has_b = MODE == 1 || b != nullptr;
-  for (int64_t v = tid; v < vecs; v += 2 * nthreads) {
+  const int64_t step = kTwo ? 2 * nthreads : nthreads;
+  for (int64_t v = tid; v < vecs; v += step) {
     const int64_t i0 = v * N, v1 = v + nthreads;
-    const bool two = v1 < vecs;
+    const bool two = kTwo && v1 < vecs;
     const int64_t i1 = two ? v1 * N : i0;
     const Pack<T, N> a0 = load_pack<T, N>(a + i0);
     Pack<T, N> a1 = a0, b0 = a0, b1 = a0;
@@ -239,11 +217,13 @@ FG_HD void coef_vec_body(const T* a, const T* b, int64_t total, int64_t outer, i
       if (two) b1 = load_pack<T, N>(b + i1);
     }
     const int64_t k_0 = (i0 / outer) * mid + (i0 / inner) % mid;
-    const int64_t k_1 = (i1 / outer) * mid + (i1 / inner) % mid;
     const double k00 = c0[k_0], k01 = has_b ? c1[k_0] : 0.0;
-    const double k10 = c0[k_1], k11 = has_b ? c1[k_1] : 0.0;
     store_pack<T, N>(out + i0, coef_vec_eval<T, MODE>(a0, b0, has_b, k00, k01));
-    if (two) store_pack<T, N>(out + i1, coef_vec_eval<T, MODE>(a1, b1, has_b, k10, k11));
+    if (two) {
+      const int64_t k_1 = (i1 / outer) * mid + (i1 / inner) % mid;
+      const double k10 = c0[k_1], k11 = has_b ? c1[k_1] : 0.0;
+      store_pack<T, N>(out + i1, coef_vec_eval<T, MODE>(a1, b1, has_b, k10, k11));
+    }
   }
 }
 

@@ -117,14 +117,50 @@ x = torch.randn(16, 64, 64, 640, device=dev)
 yb = torch.empty(16, 128, 128, 640, device=dev, dtype=torch.bfloat16)
 report("cast_resample up2 SDXL b16 64x64x640 fp32 -> 128x128 bf16", 16 * 64 * 64 * 640 * (4 + 8),
        lambda: ops.cast_resample(x, 640, 16, 64, 64, 640, yb, 640, up2=True))
-# vectorised sampler-step kernels (opt-in until run on hardware; `--vec` measures them next to the scalar forms)
+# the sampler-step rows above run the vector kernels (the default since round 2); `--scalar` adds the scalar forms the
+# launcher keeps for unaligned / odd shapes, `--graph` the BASELINE-size calls replayed inside a captured CUDA graph
 import sys  # noqa: E402
 
-if "--vec" in sys.argv:
-    ops.sampler_vec(True)
-    step("[vec] IN-64 b256 [256,3,64,64] fp32", 256, 3, 64, 64, torch.float32)
-    step("[vec] [4096,3,64,64] fp32 (asymptote)", 4096, 3, 64, 64, torch.float32)
-    step("[vec] SDXL b16 [16,4,128,128] bf16", 16, 4, 128, 128, torch.bfloat16)
-    axpby("[vec] Wan 720p [1,16,21,90,160] bf16 (10 MB)", (1, 16, 21, 90, 160), torch.bfloat16)
-    axpby("[vec] [64,16,21,60,104] bf16 (asymptote)", (64, 16, 21, 60, 104), torch.bfloat16)
+axpby("[64,16,21,60,104] fp32 (asymptote)", (64, 16, 21, 60, 104), torch.float32)
+if "--scalar" in sys.argv:
     ops.sampler_vec(False)
+    step("[scalar] [4096,3,64,64] fp32 (asymptote)", 4096, 3, 64, 64, torch.float32)
+    axpby("[scalar] [64,16,21,60,104] bf16 (asymptote)", (64, 16, 21, 60, 104), torch.bfloat16)
+    ops.sampler_vec(True)
+if "--graph" in sys.argv:
+    # the BASELINE latents are 4-63 MB: a single eager call is launch latency.  Inside a graph (how the Wan / CIFAR launch
+    # lists run them) 20 back-to-back calls on rotating buffers show the kernel time itself.
+    def graphed(tag, shape, dtype, bufs=8):
+        xs = [torch.randn(shape, device=dev).to(dtype) for _ in range(bufs)]
+        es = [torch.randn(shape, device=dev).to(dtype) for _ in range(bufs)]
+        a = torch.rand(shape[0], device=dev, dtype=torch.float64)
+        b = torch.rand(shape[0], device=dev, dtype=torch.float64)
+        outs = [torch.empty_like(xs[0]) for _ in range(bufs)]
+        def call(i):
+            ops.axpby(xs[i % bufs], a, es[i % bufs], b, out=outs[i % bufs])
+
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            call(0)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s_):
+                for i in range(20):
+                    call(i)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(10):
+                g.replay()
+            e1.record(s_)
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 200 * 1e3
+        nbytes = xs[0].numel() * xs[0].element_size() * 3
+        print(f"axpby (forward_process) in a CUDA graph, {tag:40s} {nbytes / 1e6:8.1f} MB {us:8.1f} us {nbytes / us / 1e3:8.0f} GB/s  "
+              f"{nbytes / us / 1e3 / PEAK:.2f} of measured peak", flush=True)
+
+    graphed("Wan 480p [1,16,21,60,104] bf16", (1, 16, 21, 60, 104), torch.bfloat16)
+    graphed("Wan 720p [1,16,21,90,160] bf16", (1, 16, 21, 90, 160), torch.bfloat16)
+    graphed("SDXL b16 [16,4,128,128] bf16", (16, 4, 128, 128), torch.bfloat16)
+    graphed("IN-64 b256 [256,3,64,64] fp32", (256, 3, 64, 64), torch.float32)
