@@ -205,9 +205,11 @@ def test_full_size_network_matches_oracle(cfg, batch, steps, tl):
 
 def test_batch_independence_at_bench_batch():
     """size-independent property at a bench-sized batch (the oracle would need minutes there): sample i of a large
-    batch equals the same sample run in a batch of 2 -- no cross-sample coupling, no tile-boundary effects.  Not
-    bit-for-bit: GroupNorm partial sums are merged with fp64 atomics, and a last-bit change upstream flips bf16
-    roundings downstream, so the bound is the bf16 noise floor."""
+    batch equals the same sample run in a batch of 2 -- no cross-sample coupling, no tile-boundary effects -- and the
+    network is a deterministic function of its inputs.  Measured on B200 (profiles/determinism_probe.py, 8 repeats, bf16
+    and bf16x3): BIT-IDENTICAL in both respects.  GroupNorm partial sums are merged with fp64 atomics whose order varies,
+    i.e. at the 1e-16 level before the statistics are rounded to fp32; the bound leaves room for one such flip
+    (a flipped bf16 rounding of one activation: ~1e-7 of the output) instead of asserting bit equality."""
     torch.manual_seed(2)
     net, _ = _net(IN64, 0, "bf16")
     B = 64
@@ -218,10 +220,10 @@ def test_batch_independence_at_bench_batch():
     assert torch.isfinite(big).all()
     for lo in (0, 10, 62):
         small = net(x[lo:lo + 2].clone(), t[:2], condition=lab[lo:lo + 2], fwd_pred_type="x0")
-        assert _rel(big[lo:lo + 2], small) < 1e-2
+        assert _rel(big[lo:lo + 2], small) < 1e-5
     # and the network is a deterministic function of its inputs run to run
     again = net(x, t, condition=lab, fwd_pred_type="x0")
-    assert _rel(again, big) < 1e-2
+    assert _rel(again, big) < 1e-5
 
 
 @pytest.mark.parametrize("compute,tol", [("bf16", 1e-2), ("bf16x3", 2e-3)])
