@@ -79,7 +79,7 @@ class FlashAttnParams(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32), ("tq", C.c_int32),
         ("scale", C.c_float), ("mask_first", C.c_int32), ("mask_chunk", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("kv_len0_per_sample", C.c_void_p),
     ]
 
 

@@ -51,6 +51,7 @@ struct AttnKParams {
   int32_t kv_len[2];
   int32_t mask_first, mask_chunk;  // block-causal mask (tokens of the first chunk / of every later chunk); 0 = none
   float scale_log2;                // log2(e) * scale
+  const int32_t* kv_len0_per_sample;  // optional [B]: per-sample key count of segment 0 (prefix attention mask)
   __nv_bfloat16* out;
   int64_t out_ld, out_bs;
 };
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   // key tiles: segment 0 then segment 1; under the block-causal mask (single segment) the tile loop stops at the
   // limit of the last query row of this tile
   int len0 = p.kv_len[0];
+  if (p.kv_len0_per_sample) len0 = max(0, min(len0, p.kv_len0_per_sample[img]));
   if (p.mask_chunk) len0 = min(len0, causal_limit(p, min(q0 + kQRows, p.Tq) - 1));
   const int n0 = (len0 + BKV - 1) / BKV;
   const int n1 = (p.kv_len[1] + BKV - 1) / BKV;
@@ -378,6 +380,10 @@ extern "C" int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream_)
   }
   kp.mask_first = p->mask_chunk > 0 ? p->mask_first : 0;
   kp.mask_chunk = p->mask_chunk;
+  kp.kv_len0_per_sample = p->kv_len0_per_sample;
+  if (p->kv_len0_per_sample)
+    FG_CHECK_ARG((reinterpret_cast<uintptr_t>(p->kv_len0_per_sample) & 3) == 0 && p->mask_chunk == 0,
+                 "flash_attn: kv_len0_per_sample must be 4-byte aligned and is not combined with the block-causal mask");
   const float scale = p->scale > 0.f ? p->scale : 1.0f / sqrtf(static_cast<float>(p->d));
   {
     // long sequences: two query tiles per CTA, P in tensor memory (attention2.cu)

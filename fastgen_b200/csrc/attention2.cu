@@ -51,6 +51,7 @@ struct Attn2KParams {
   // that attn2_merge_kernel combines.  nsplit == 1: the final output is written directly.
   int32_t nsplit;
   float2* part_ml;  // [B*H][Tq][nsplit]
+  const int32_t* kv_len0_per_sample;  // optional [B]: per-sample key count of segment 0 (prefix attention mask)
 };
 
 __device__ __forceinline__ int causal_limit2(const Attn2KParams& p, int tok) {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
   const int img = blockIdx.x / (p.nsplit * q_blocks * p.H);
   const int q0 = qb * 256;
   int len0 = p.kv_len[0];
+  if (p.kv_len0_per_sample) len0 = max(0, min(len0, p.kv_len0_per_sample[img]));
   if (p.mask_chunk) len0 = min(len0, causal_limit2(p, min(q0 + 256, p.Tq) - 1));
   const int n0 = (len0 + BKV - 1) / BKV;
   const int n1 = (p.kv_len[1] + BKV - 1) / BKV;
@@ -873,6 +875,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
   kp.mask_first = p->mask_chunk > 0 ? p->mask_first : 0;
   kp.mask_chunk = p->mask_chunk;
   kp.scale_log2 = 1.4426950408889634f * scale;
+  kp.kv_len0_per_sample = p->kv_len0_per_sample;
   const uint32_t box[4] = {64, 1, 128, 1};
   const int q_blocks = (kp.Tq + 255) / 256;
   // split the key range over several CTAs when the (sample, head, query block) grid alone leaves SMs idle or ends in

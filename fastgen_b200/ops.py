@@ -273,7 +273,8 @@ def launch_count_reset() -> None:
 def flash_attn_params(q: torch.Tensor, q_ld: int, q_bs: int, segs: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int, int]],
                       batch: int, heads: int, d: int, tq: int, out: torch.Tensor, out_ld: int, out_bs: int,
                       scale: float = 0.0, mask_first: int = 0, mask_chunk: int = 0,
-                      workspace: Optional[torch.Tensor] = None) -> "L.FlashAttnParams":
+                      workspace: Optional[torch.Tensor] = None,
+                      kv_len0_per_sample: Optional[torch.Tensor] = None) -> "L.FlashAttnParams":
     """``segs``: up to two key/value segments ``(k, v, ld, batch_stride, length)`` (cache prefix, current chunk)."""
     if not 1 <= len(segs) <= 2:
         raise ValueError("flash_attn: one or two key/value segments")
@@ -290,6 +291,11 @@ def flash_attn_params(q: torch.Tensor, q_ld: int, q_bs: int, segs: Sequence[Tupl
     if workspace is not None:
         _need_cuda(workspace)
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    if kv_len0_per_sample is not None:   # int32 [batch] on the device: a prefix attention mask over segment 0
+        _need_cuda(kv_len0_per_sample)
+        if kv_len0_per_sample.dtype != torch.int32 or kv_len0_per_sample.numel() != batch or not kv_len0_per_sample.is_contiguous():
+            raise ValueError("flash_attn: kv_len0_per_sample must be a contiguous int32 tensor of `batch` elements")
+        p.kv_len0_per_sample = kv_len0_per_sample.data_ptr()
     return p
 
 

@@ -43,7 +43,7 @@ from .network import FastGenNetwork, tensor_identity
 from .noise_schedule import NET_PRED_TYPES
 from .wan import _Plan
 
-__all__ = ["StableDiffusionXL", "SDXL_BASE"]
+__all__ = ["StableDiffusionXL", "StableDiffusion15", "SDXL_BASE", "SD15_BASE"]
 
 # tests/test_sdxl_host_cpu.py sets this to build the launch list against host memory, so that the argument validation
 # of every C-ABI call can be exercised on a CPU-only host; such a plan cannot execute (every launch fails).
@@ -54,6 +54,14 @@ SDXL_BASE: Dict[str, Any] = dict(
     in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
     down_attn=(False, True, True), transformer_layers=(1, 2, 10), num_heads=(5, 10, 20),
     cross_attention_dim=2048, addition_time_embed_dim=256, pooled_dim=1280, norm_groups=32)
+
+# runwayml/stable-diffusion-v1-5, unet/config.json: four levels, attention on the first three, ONE transformer layer each,
+# `attention_head_dim = 8` read by diffusers as 8 HEADS per level (head widths 40 / 80 / 160 / 160), 768-wide CLIP text
+# states, 1x1-convolution proj_in / proj_out (`use_linear_projection = False`), no additional embedding.
+SD15_BASE: Dict[str, Any] = dict(
+    in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+    down_attn=(True, True, True, False), transformer_layers=(1, 1, 1, 1), num_heads=(8, 8, 8, 8),
+    cross_attention_dim=768, addition_time_embed_dim=None, pooled_dim=0, norm_groups=32, use_linear_projection=False)
 
 
 def layout(cfg: Mapping[str, Any]) -> Dict[str, Any]:
@@ -74,7 +82,8 @@ def layout(cfg: Mapping[str, Any]) -> Dict[str, Any]:
                        heads=cfg["num_heads"][::-1][i], up=i < len(rev) - 1, c=c))
         prev = c
     return dict(down=down, up=up, mid_c=boc[-1], mid_tl=cfg["transformer_layers"][-1], mid_heads=cfg["num_heads"][-1],
-                temb=4 * boc[0], proj_in=cfg["pooled_dim"] + 6 * cfg["addition_time_embed_dim"])
+                temb=4 * boc[0],
+                proj_in=(cfg["pooled_dim"] + 6 * cfg["addition_time_embed_dim"]) if cfg.get("addition_time_embed_dim") else 0)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -129,12 +138,14 @@ class _BasicTransformerBlock(nn.Module):
 
 
 class _Transformer2D(nn.Module):
-    def __init__(self, dim: int, layers: int, heads: int, cross_dim: int, groups: int):
+    def __init__(self, dim: int, layers: int, heads: int, cross_dim: int, groups: int, linear: bool = True):
         super().__init__()
         self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
-        self.proj_in = nn.Linear(dim, dim)
+        # use_linear_projection: SDXL projects tokens with nn.Linear, SD 1.5 the feature map with a 1x1 convolution --
+        # the same arithmetic, different parameter shapes ([C, C] vs [C, C, 1, 1]) in the state dict
+        self.proj_in = nn.Linear(dim, dim) if linear else nn.Conv2d(dim, dim, 1)
         self.transformer_blocks = nn.ModuleList([_BasicTransformerBlock(dim, cross_dim) for _ in range(layers)])
-        self.proj_out = nn.Linear(dim, dim)
+        self.proj_out = nn.Linear(dim, dim) if linear else nn.Conv2d(dim, dim, 1)
         self.dim, self.heads = dim, heads
 
 
@@ -157,25 +168,27 @@ class _UNet(nn.Module):
         boc, G, T, X = cfg["block_out_channels"], cfg["norm_groups"], lay["temb"], cfg["cross_attention_dim"]
         self.conv_in = nn.Conv2d(cfg["in_channels"], boc[0], 3, padding=1)
         self.time_embedding = _TimestepEmbedding(boc[0], T)
-        self.add_embedding = _TimestepEmbedding(lay["proj_in"], T)
+        if lay["proj_in"]:
+            self.add_embedding = _TimestepEmbedding(lay["proj_in"], T)
+        lin = bool(cfg.get("use_linear_projection", True))
         self.down_blocks, self.up_blocks = nn.ModuleList(), nn.ModuleList()
         for d in lay["down"]:
             blk = _UNetBlock()
             blk.resnets.extend(_Resnet(ci, co, T, G) for ci, co in d["res"])
             if d["attn"]:
-                blk.attentions = nn.ModuleList(_Transformer2D(d["c"], d["tl"], d["heads"], X, G) for _ in d["res"])
+                blk.attentions = nn.ModuleList(_Transformer2D(d["c"], d["tl"], d["heads"], X, G, lin) for _ in d["res"])
             if d["down"]:
                 blk.downsamplers = nn.ModuleList([_Sampler2D(d["c"])])
             self.down_blocks.append(blk)
         mc = lay["mid_c"]
         self.mid_block = _UNetBlock()
         self.mid_block.resnets.extend([_Resnet(mc, mc, T, G), _Resnet(mc, mc, T, G)])
-        self.mid_block.attentions = nn.ModuleList([_Transformer2D(mc, lay["mid_tl"], lay["mid_heads"], X, G)])
+        self.mid_block.attentions = nn.ModuleList([_Transformer2D(mc, lay["mid_tl"], lay["mid_heads"], X, G, lin)])
         for u in lay["up"]:
             blk = _UNetBlock()
             blk.resnets.extend(_Resnet(rin + skip, co, T, G) for rin, skip, co in u["res"])
             if u["attn"]:
-                blk.attentions = nn.ModuleList(_Transformer2D(u["c"], u["tl"], u["heads"], X, G) for _ in u["res"])
+                blk.attentions = nn.ModuleList(_Transformer2D(u["c"], u["tl"], u["heads"], X, G, lin) for _ in u["res"])
             if u["up"]:
                 blk.upsamplers = nn.ModuleList([_Sampler2D(u["c"])])
             self.up_blocks.append(blk)
@@ -228,12 +241,13 @@ class StableDiffusionXL(FastGenNetwork):
             if c % self.cfg["norm_groups"] or c % 8:
                 raise ValueError("block_out_channels must be multiples of 8 and of norm_groups")
         for c, hds in zip(self.cfg["block_out_channels"], self.cfg["num_heads"]):
-            if c % hds or (c // hds) % 8 or c // hds > 128:
-                raise ValueError("attention head dim must be a multiple of 8 and <= 128")
+            if c % hds or (c // hds) % 8 or c // hds > 256:
+                raise ValueError("attention head dim must be a multiple of 8 and <= 256")
         # there is no hub here: `load_pretrained` is accepted for signature compatibility, weights arrive through
         # load_state_dict() with the diffusers key names (reference utils/checkpointer.py:88-108)
         self.unet = _UNet(self.cfg)
         self.add_time_ids = self.build_condition_input(1024)
+        self._has_add = bool(self.cfg.get("addition_time_embed_dim"))
         self.reset_parameters()
         self._packed: Optional[Dict[str, Any]] = None
         self._plans: Dict[Any, Any] = {}
@@ -312,7 +326,7 @@ class StableDiffusionXL(FastGenNetwork):
         b = lambda m: m.bias.detach().to(f32).contiguous()                          # noqa: E731
         pk: Dict[str, Any] = {}
         pk["conv_in.w"], pk["conv_in.b"] = conv_w(u.conv_in, 8), b(u.conv_in)
-        for nm, mod in (("te", u.time_embedding), ("ae", u.add_embedding)):
+        for nm, mod in (("te", u.time_embedding),) + ((("ae", u.add_embedding),) if self._has_add else ()):
             pk[nm + "1.w"], pk[nm + "1.b"] = w(mod.linear_1), b(mod.linear_1)
             pk[nm + "2.w"], pk[nm + "2.b"] = w(mod.linear_2), b(mod.linear_2)
         # the time projections of every ResnetBlock2D as ONE GEMM on SiLU(emb)
@@ -336,8 +350,9 @@ class StableDiffusionXL(FastGenNetwork):
         for key, a in self._transformers():
             k = "t." + key
             pk[k + ".norm"] = (a.norm.weight.detach().to(f32).contiguous(), b(a.norm))
-            pk[k + ".in.w"], pk[k + ".in.b"] = w(a.proj_in), b(a.proj_in)
-            pk[k + ".out.w"], pk[k + ".out.b"] = w(a.proj_out), b(a.proj_out)
+            w2 = lambda m: m.weight.detach().reshape(m.weight.shape[0], -1).to(bf).contiguous()   # noqa: E731  Linear | 1x1 conv
+            pk[k + ".in.w"], pk[k + ".in.b"] = w2(a.proj_in), b(a.proj_in)
+            pk[k + ".out.w"], pk[k + ".out.b"] = w2(a.proj_out), b(a.proj_out)
             for li, blk in enumerate(a.transformer_blocks):
                 q = f"{k}.{li}"
                 for n_ in ("norm1", "norm2", "norm3"):
@@ -367,8 +382,14 @@ class StableDiffusionXL(FastGenNetwork):
         self._packed, self._plans, self._ctx = pk, {}, None
 
     # ---- text keys / values of every cross-attention layer (static per prompt) ------------------------------
-    def _context(self, text: torch.Tensor) -> Dict[str, Any]:
+    def _context(self, text: torch.Tensor, mask: Optional[torch.Tensor] = None, masked: bool = False) -> Dict[str, Any]:
+        """text keys / values of every cross-attention layer, computed once per condition.  ``masked`` (SD 1.5): the
+        cross-attentions take per-sample key counts from ``ent["lens"]``, filled from the prefix ``encoder_attention_mask``
+        ``mask`` [B, L] of 0 / 1 (None: all keys)."""
         key = tensor_identity(text)
+        if key is not None and mask is not None:
+            mkey = tensor_identity(mask)
+            key = None if mkey is None else key + mkey
         B, Lt, X = text.shape
         if X != self.cfg["cross_attention_dim"]:
             raise ValueError(f"text embedding width {X} != cross_attention_dim {self.cfg['cross_attention_dim']}")
@@ -376,6 +397,8 @@ class StableDiffusionXL(FastGenNetwork):
         if ent is None or ent["batch"] != B or ent["len"] != Lt:
             dev, bf, pk = text.device, torch.bfloat16, self._packed
             ent = {"key": None, "batch": B, "len": Lt, "text": torch.empty(B * Lt, X, device=dev, dtype=bf), "kv": {}}
+            if masked:
+                ent["lens"] = torch.full((B,), Lt, device=dev, dtype=torch.int32)
             plan = _Plan()
             for tk, a in self._transformers():
                 for li in range(len(a.transformer_blocks)):
@@ -393,7 +416,22 @@ class StableDiffusionXL(FastGenNetwork):
         if key is None or ent["key"] != key:
             ent["text"].copy_(text.reshape(B * Lt, X))
             ent["plan"].run(torch.cuda.current_stream().cuda_stream, self.profile)
-            ent["key"], ent["keep"] = key, text
+            if masked:
+                if mask is None:
+                    ent["lens"].fill_(Lt)
+                else:
+                    if tuple(mask.shape) != (B, Lt):
+                        raise ValueError(f"encoder_attention_mask shape {tuple(mask.shape)} != {(B, Lt)}")
+                    m = mask.to(device=text.device) != 0
+                    lens = m.sum(dim=1)
+                    # the kernel takes key COUNTS: the mask must keep a prefix (what a tokenizer's padding mask is) and at
+                    # least one key per sample -- one host check per new condition
+                    prefix = bool((m[:, :-1] | ~m[:, 1:]).all().item()) if Lt > 1 else True
+                    if not prefix or int(lens.min().item()) < 1:
+                        raise NotImplementedError("encoder_attention_mask must keep a non-empty prefix of the text keys "
+                                                  "(a padding mask); general masks are not supported")
+                    ent["lens"].copy_(lens.to(torch.int32))
+            ent["key"], ent["keep"] = key, (text, mask)
         return ent
 
     # ---- the launch list -------------------------------------------------------------------------------------
@@ -523,9 +561,9 @@ class StableDiffusionXL(FastGenNetwork):
             keep.append((p, x, y))
             plan.add(lib.fg_ln_modulate, C.byref(p), desc=desc)
 
-        def attn(q, q_ld, k, v, kv_ld, kv_len, tq, heads, d, out, out_ld, desc):
+        def attn(q, q_ld, k, v, kv_ld, kv_len, tq, heads, d, out, out_ld, desc, lens=None):
             p = ops.flash_attn_params(q, q_ld, tq * q_ld, [(k, v, kv_ld, kv_len * kv_ld, kv_len)], B, heads, d, tq, out,
-                                      out_ld, tq * out_ld)
+                                      out_ld, tq * out_ld, kv_len0_per_sample=lens)
             wsz = ops.flash_attn_workspace_size(p)
             if wsz > 0:
                 ws_ = pool.get(("attn_ws", torch.uint8))
@@ -541,17 +579,20 @@ class StableDiffusionXL(FastGenNetwork):
         c0 = cfg["block_out_channels"][0]
         ws: Dict[str, torch.Tensor] = dict(
             x_in=new(B, cfg["in_channels"], H, W, dt=x_dtype), xin=new(B, H, W, 8, dt=bf), t_sin=new(B, c0, dt=bf),
-            add_in=new(B, lay["proj_in"], dt=bf), e1=new(B, T, dt=bf), emb_t=new(B, T), a1=new(B, T, dt=bf), emb=new(B, T),
+            add_in=new(B, max(lay["proj_in"], 8), dt=bf), e1=new(B, T, dt=bf), emb_t=new(B, T), a1=new(B, T, dt=bf), emb=new(B, T),
             emb_act=new(B, T, dt=bf), temb=new(B, pk["temb.w"].shape[0]), f_out=new(B, H, W, 4),
             eps=new(B, cfg["out_channels"], H, W, dt=x_dtype))
         keep.append(ws)
         plan.add(lib.fg_edm_input, ws["x_in"].data_ptr(), ops._DT[x_dtype], B, cfg["in_channels"], H * W, None,
                  ws["xin"].data_ptr(), None, 8, desc="nchw_to_nhwc")
         gemm(ws["t_sin"], c0, pk["te1.w"], B, T, ws["e1"], T, "time1", bias=pk["te1.b"], act=L.FG_ACT_SILU)
-        gemm(ws["e1"], T, pk["te2.w"], B, T, ws["emb_t"], T, "time2", bias=pk["te2.b"])
-        gemm(ws["add_in"], lay["proj_in"], pk["ae1.w"], B, T, ws["a1"], T, "add1", bias=pk["ae1.b"], act=L.FG_ACT_SILU)
-        gemm(ws["a1"], T, pk["ae2.w"], B, T, ws["emb"], T, "add2", bias=pk["ae2.b"], res=ws["emb_t"], res_ld=T,
-             res_mode=L.FG_RES_SAME)
+        if self._has_add:
+            gemm(ws["e1"], T, pk["te2.w"], B, T, ws["emb_t"], T, "time2", bias=pk["te2.b"])
+            gemm(ws["add_in"], lay["proj_in"], pk["ae1.w"], B, T, ws["a1"], T, "add1", bias=pk["ae1.b"], act=L.FG_ACT_SILU)
+            gemm(ws["a1"], T, pk["ae2.w"], B, T, ws["emb"], T, "add2", bias=pk["ae2.b"], res=ws["emb_t"], res_ld=T,
+                 res_mode=L.FG_RES_SAME)
+        else:   # SD 1.5: the time embedding alone
+            gemm(ws["e1"], T, pk["te2.w"], B, T, ws["emb"], T, "time2", bias=pk["te2.b"])
         plan.add(lib.fg_split_bf16, ws["emb"].data_ptr(), T, None, 0, B, T, 1, ws["emb_act"].data_ptr(), None, T, None, 0,
                  desc="silu_emb")
         tl = ws["temb"].shape[1]
@@ -600,7 +641,7 @@ class StableDiffusionXL(FastGenNetwork):
                 ln(hs, rows, c, pk[q + ".norm2"], nrm, "ln2")
                 gemm(nrm, c, pk[q + ".q2.w"], rows, c, qkv, 3 * c, "q2")
                 kv = ctx["kv"][q]
-                attn(qkv, 3 * c, kv, kv[:, c:], 2 * c, Lt, N, heads, d, att, c, "cross_attn")
+                attn(qkv, 3 * c, kv, kv[:, c:], 2 * c, Lt, N, heads, d, att, c, "cross_attn", lens=ctx.get("lens"))
                 gemm(att, c, pk[q + ".o2.w"], rows, c, hs, c, "attn2_out", bias=pk[q + ".o2.b"], res=hs, res_ld=c,
                      res_mode=L.FG_RES_SAME)
                 ln(hs, rows, c, pk[q + ".norm3"], nrm, "ln3")
@@ -774,7 +815,7 @@ class StableDiffusionXL(FastGenNetwork):
                 feature_indices: Optional[Set[int]] = None, return_logvar: bool = False,
                 fwd_pred_type: Optional[str] = None, **fwd_kwargs):
         if r is not None:
-            raise NotImplementedError("r is not yet supported for SDXL")
+            raise NotImplementedError(f"r is not yet supported for {'SDXL' if self._has_add else 'SD15'}")
         if feature_indices is None:
             feature_indices = {}
         if return_features_early and len(feature_indices) == 0:
@@ -798,9 +839,12 @@ class StableDiffusionXL(FastGenNetwork):
             B, Cc, H, W = x_t.shape
             if Cc != self.cfg["in_channels"]:
                 raise ValueError(f"x_t has {Cc} channels, the UNet takes {self.cfg['in_channels']}")
-            if text.shape[0] != B or pooled.shape[0] != B:
+            if text.shape[0] != B or (pooled is not None and pooled.shape[0] != B):
                 raise ValueError("condition batch size does not match x_t")
-            ctx = self._context(text)
+            if self._has_add:
+                ctx = self._context(text)
+            else:   # SD 1.5: condition = [encoder_hidden_states, encoder_attention_mask]
+                ctx = self._context(text, mask=pooled, masked=True)
             plan, ws = self._plan(B, H, W, x_t.dtype, ctx)
             dev = x_t.device
             timestep = self.noise_scheduler.rescale_t(torch.atleast_1d(t).to(dev))
@@ -808,9 +852,10 @@ class StableDiffusionXL(FastGenNetwork):
                 timestep = timestep.expand(B)
             ws["x_in"].copy_(x_t)
             ws["t_sin"].copy_(timestep_sinusoid(timestep, self.cfg["block_out_channels"][0]))
-            ids = self.add_time_ids.to(dev).repeat(B, 1)
-            te = timestep_sinusoid(ids.flatten(), self.cfg["addition_time_embed_dim"]).reshape(B, -1)
-            ws["add_in"].copy_(torch.cat([pooled.to(te.dtype), te], dim=-1))
+            if self._has_add:
+                ids = self.add_time_ids.to(dev).repeat(B, 1)
+                te = timestep_sinusoid(ids.flatten(), self.cfg["addition_time_embed_dim"]).reshape(B, -1)
+                ws["add_in"].copy_(torch.cat([pooled.to(te.dtype), te], dim=-1))
             plan.run(torch.cuda.current_stream().cuda_stream, self.profile)
             out = ws["eps"].clone()
             return self.noise_scheduler.convert_model_output(x_t, out, torch.atleast_1d(t).to(dev),
@@ -846,3 +891,21 @@ class StableDiffusionXL(FastGenNetwork):
                 x0_pred = sched.eps_to_x0(x, eps_pred, t_batch)
                 x = sched.forward_process(x0_pred, eps_pred, t_next.expand(B))
             return x
+
+
+class StableDiffusion15(StableDiffusionXL):
+    """B200 drop-in for ``fastgen.networks.SD15.network.StableDiffusion15`` (SD15/network.py:438-680): the same
+    ``UNet2DConditionModel`` driver (``classify_forward``, :46-341) at the SD 1.5 configuration -- four levels, 8 heads of
+    40 / 80 / 160 / 160, 1x1-convolution proj_in / proj_out, no additional embedding -- with
+    ``condition = [encoder_hidden_states [B, 77, 768], encoder_attention_mask [B, 77] | None]``.  The reference turns the
+    mask into an additive ``-10000`` bias on the cross-attention logits (:142-145), whose softmax weights underflow to
+    exactly 0; here a prefix mask (a tokenizer's padding mask) is passed to ``fg_flash_attn`` as per-sample key counts."""
+
+    MODEL_ID_15 = "runwayml/stable-diffusion-v1-5"
+    MODEL_ID_21 = "stabilityai/stable-diffusion-2-1"
+
+    def __init__(self, model_id: str = MODEL_ID_15, net_pred_type: str = "eps", schedule_type: str = "sd",
+                 load_pretrained: bool = True, unet_config: Optional[Mapping[str, Any]] = None, **model_kwargs):
+        super().__init__(model_id=model_id, net_pred_type=net_pred_type, schedule_type=schedule_type,
+                         load_pretrained=load_pretrained, unet_config=SD15_BASE if unet_config is None else unet_config,
+                         **model_kwargs)

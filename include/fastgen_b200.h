@@ -181,6 +181,10 @@ typedef struct {
   int64_t out_ld, out_bs;
   void* workspace;      /* optional scratch of fg_flash_attn_workspace_size() bytes: lets the library split the key  */
   int64_t workspace_bytes; /* range over several CTAs (partial results + merge) when the grid would leave SMs idle */
+  const int32_t* kv_len0_per_sample; /* optional device array [batch]: sample b attends to the first                    */
+                        /* min(kv_len[0], kv_len0_per_sample[b]) keys of segment 0 -- a prefix `encoder_attention_mask`   */
+                        /* (padding after the prompt's tokens) of the SD 1.5 UNet, fastgen/networks/SD15/network.py:142-145: */
+                        /* the reference adds -10000 to the masked logits, whose softmax weight underflows to exactly 0  */
 } fg_flash_attn_params;
 
 int fg_flash_attn(const fg_flash_attn_params* p, fg_stream_t stream);

@@ -33,8 +33,9 @@ def exact_fp32():
 
 def exact_sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
                max_score_bytes: int = 4 << 30) -> torch.Tensor:
-    """q [B, H, Tq, d], k / v [B, H, Tk, d]; attn_mask boolean [Tq, Tk] (True = attend) or None.  Scores, softmax and the
-    P V product in float32 whatever the input dtype; result in q.dtype."""
+    """q [B, H, Tq, d], k / v [B, H, Tk, d]; attn_mask: None, boolean [Tq, Tk] (True = attend), or a floating additive bias
+    broadcastable to [B, H, Tq, Tk] with a singleton query dim (the SD 1.5 `encoder_attention_mask` bias [B, 1, 1, Tk]).
+    Scores, softmax and the P V product in float32 whatever the input dtype; result in q.dtype."""
     B, H, Tq, d = q.shape
     Tk = k.shape[2]
     scale = 1.0 / math.sqrt(d)
@@ -44,7 +45,9 @@ def exact_sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, attn_mask: Opt
     for r0 in range(0, Tq, rows):
         r1 = min(Tq, r0 + rows)
         s = torch.matmul(q[:, :, r0:r1].float(), kf.transpose(-1, -2)) * scale
-        if attn_mask is not None:
+        if attn_mask is not None and attn_mask.is_floating_point():
+            s = s + attn_mask.to(device=s.device, dtype=s.dtype)
+        elif attn_mask is not None:
             s = s.masked_fill(~attn_mask[r0:r1].to(s.device), float("-inf"))
         out[:, :, r0:r1] = torch.matmul(torch.softmax(s, dim=-1), vf).to(q.dtype)
         del s

@@ -426,6 +426,32 @@ def sdxl_glue_fixture():
     print("wrote SDXL reference-glue fixture")
 
 
+def sd15_glue_fixture():
+    """Outputs of the UNMODIFIED reference `StableDiffusion15.forward` + `classify_forward` with an `encoder_attention_mask`
+    (SD15/network.py:602-678, 46-341: the mask becomes the additive bias (1 - mask) * -10000 handed to every block) on a
+    stand-in diffusers UNet at an SD 1.5-shaped configuration: no addition embedding, 1x1-conv proj_in / proj_out, four
+    levels, heads of 8 / 16 / 32 channels"""
+    from oracle import ref_sdxl_harness as H
+    from oracle import sdxl_oracle as XO
+
+    cfg = XO.tiny_sd15_config()
+    sd = XO.make_state_dict(cfg, 23)
+    g = torch.Generator().manual_seed(SEED + 53)
+    x = torch.randn(3, 4, 16, 16, generator=g)
+    text = torch.randn(3, 77, cfg["cross_attention_dim"], generator=g)
+    mask = torch.zeros(3, 77)
+    for b, n in enumerate((77, 9, 31)):
+        mask[b, :n] = 1
+    t = torch.tensor([0.999, 0.4, 0.05], dtype=torch.float64)
+    fx = dict(seed=np.int64(23), x=_np(x), text=_np(text), mask=_np(mask), t=_np(t))
+    with torch.no_grad():
+        for pred in ("eps", "x0"):
+            fx[f"masked_{pred}"] = _np(H.reference_sd15_forward(cfg, sd, x, t, text, mask, pred))
+        fx["nomask_eps"] = _np(H.reference_sd15_forward(cfg, sd, x, t, text, None, "eps"))
+    np.savez_compressed(os.path.join(OUT, "sd15_reference_glue.npz"), **fx)
+    print("wrote SD 1.5 reference-glue fixture")
+
+
 DIT_VARIANTS = {"d64": {}, "d72": dict(hidden_size=144, num_heads=2, depth=3), "sit": dict(use_sit_convention=True),
                 "r_diff": dict(r_timestep=True, time_cond_type="diff"), "r_abs": dict(r_timestep=True, time_cond_type="abs")}
 
@@ -649,6 +675,7 @@ if __name__ == "__main__":
     trig_fixture()
     wan_glue_fixture()
     sdxl_glue_fixture()
+    sd15_glue_fixture()
     dit_fixture()
     wan_sample_fixture()
     wan_remap_fixture()

@@ -50,7 +50,8 @@ class _DownBlock(nn.Module):
             hidden_states = XO.resnet(self.sd, f"{u}down_blocks.{self.i}.resnets.{j}.", hidden_states, temb, self.groups)
             if self.d["attn"]:
                 hidden_states = XO.transformer(self.sd, f"{u}down_blocks.{self.i}.attentions.{j}.", hidden_states,
-                                               encoder_hidden_states, self.d["tl"], self.d["heads"], self.groups)
+                                               encoder_hidden_states, self.d["tl"], self.d["heads"], self.groups,
+                                               kw.get("encoder_attention_mask"))
             out += (hidden_states,)
         if self.d["down"]:
             hidden_states = XO._conv(self.sd, f"{u}down_blocks.{self.i}.downsamplers.0.conv", hidden_states, stride=2, pad=1)
@@ -69,7 +70,7 @@ class _MidBlock(nn.Module):
         u = "unet."
         h = XO.resnet(self.sd, u + "mid_block.resnets.0.", hidden_states, temb, self.groups)
         h = XO.transformer(self.sd, u + "mid_block.attentions.0.", h, encoder_hidden_states, self.lay["mid_tl"],
-                           self.lay["mid_heads"], self.groups)
+                           self.lay["mid_heads"], self.groups, kw.get("encoder_attention_mask"))
         return XO.resnet(self.sd, u + "mid_block.resnets.1.", h, temb, self.groups)
 
 
@@ -89,7 +90,8 @@ class _UpBlock(nn.Module):
             hidden_states = XO.resnet(self.sd, f"{u}up_blocks.{self.i}.resnets.{j}.", hidden_states, temb, self.groups)
             if self.d["attn"]:
                 hidden_states = XO.transformer(self.sd, f"{u}up_blocks.{self.i}.attentions.{j}.", hidden_states,
-                                               encoder_hidden_states, self.d["tl"], self.d["heads"], self.groups)
+                                               encoder_hidden_states, self.d["tl"], self.d["heads"], self.groups,
+                                               kw.get("encoder_attention_mask"))
         if self.d["up"]:
             hidden_states = XO._conv(self.sd, f"{u}up_blocks.{self.i}.upsamplers.0.conv",
                                      F.interpolate(hidden_states, scale_factor=2.0, mode="nearest"))
@@ -104,7 +106,7 @@ class UNet2DConditionModel(nn.Module):
         lay, G, u = XO.layout(cfg), cfg["norm_groups"], "unet."
         self.sd, self.cfg = sd, cfg
         self.config = types.SimpleNamespace(center_input_sample=False, class_embeddings_concat=False,
-                                            addition_embed_type="text_time")
+                                            addition_embed_type="text_time" if cfg.get("addition_time_embed_dim") else None)
         self.num_upsamplers = len(cfg["block_out_channels"]) - 1
         self.time_embed_act = None
         self.time_embedding = _Fn(lambda t_emb, cond=None: XO._lin(sd, u + "time_embedding.linear_2",
@@ -129,7 +131,12 @@ class UNet2DConditionModel(nn.Module):
     def get_class_embed(self, sample, class_labels):
         return None
 
+    def enable_gradient_checkpointing(self):      # StableDiffusion15.forward calls it on every forward (SD15/network.py:643)
+        pass
+
     def get_aug_embed(self, emb, encoder_hidden_states, added_cond_kwargs):
+        if not self.cfg.get("addition_time_embed_dim"):   # diffusers: addition_embed_type None -> no additional embedding
+            return None
         text_embeds, time_ids = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
         te = XO.timesteps_proj(time_ids.flatten(), self.cfg["addition_time_embed_dim"]).reshape(text_embeds.shape[0], -1)
         add = torch.cat([text_embeds, te], dim=-1).to(emb.dtype)
@@ -181,3 +188,19 @@ def reference_sdxl_forward(cfg, sd, x_t, t, text, pooled, fwd_pred_type="x0"):
                                noise_scheduler=get_noise_schedule("alphas", alphas_cumprod=XO.alphas_cumprod()),
                                add_time_ids=m.StableDiffusionXL.build_condition_input(None, 1024))
     return m.StableDiffusionXL.forward(me, x_t, t, condition=[text, pooled], fwd_pred_type=fwd_pred_type)
+
+
+def reference_sd15_forward(cfg, sd, x_t, t, text, mask, fwd_pred_type="x0"):
+    """`StableDiffusion15.forward` (SD15/network.py:602-678, unbound, on a minimal stand-in for `self`) driving
+    `classify_forward` with `encoder_attention_mask` on the stand-in UNet at an SD 1.5-shaped configuration (no addition
+    embedding, 1x1-conv projections, four levels); the noise schedule is the reference's AlphasNoiseSchedule over the SD
+    scheduler's alphas_cumprod (the same scaled-linear betas as SDXL)"""
+    load_reference_sdxl()
+    m15 = importlib.import_module("fastgen.networks.SD15.network")
+    from fastgen.networks.noise_schedule import get_noise_schedule
+
+    unet = UNet2DConditionModel(cfg, sd)
+    unet.forward = types.MethodType(m15.classify_forward, unet)
+    me = types.SimpleNamespace(unet=unet, net_pred_type="eps",
+                               noise_scheduler=get_noise_schedule("alphas", alphas_cumprod=XO.alphas_cumprod()))
+    return m15.StableDiffusion15.forward(me, x_t, t, condition=[text, mask], fwd_pred_type=fwd_pred_type)

@@ -35,6 +35,24 @@ SDXL_BASE = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 12
                  cross_attention_dim=2048, addition_time_embed_dim=256, pooled_dim=1280, norm_groups=32)
 
 
+# runwayml/stable-diffusion-v1-5 unet/config.json (published; 859 520 964 parameters): attention_head_dim = 8 is read by
+# diffusers' UNet2DConditionModel as the NUMBER of heads, use_linear_projection = False (1x1-conv proj_in / proj_out),
+# no addition embedding
+SD15_BASE = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+                 down_attn=(True, True, True, False), transformer_layers=(1, 1, 1, 1), num_heads=(8, 8, 8, 8),
+                 cross_attention_dim=768, addition_time_embed_dim=None, pooled_dim=0, norm_groups=32,
+                 use_linear_projection=False)
+
+
+def tiny_sd15_config(**kw) -> Dict[str, Any]:
+    cfg = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256, 256), layers_per_block=1,
+               down_attn=(True, True, True, False), transformer_layers=(1, 1, 1, 1), num_heads=(8, 8, 8, 8),
+               cross_attention_dim=96, addition_time_embed_dim=None, pooled_dim=0, norm_groups=32,
+               use_linear_projection=False)
+    cfg.update(kw)
+    return cfg
+
+
 def tiny_config(**kw) -> Dict[str, Any]:
     cfg = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256), layers_per_block=2,
                down_attn=(False, True, True), transformer_layers=(1, 1, 2), num_heads=(1, 2, 4),
@@ -67,7 +85,8 @@ def layout(cfg) -> Dict[str, Any]:
                        heads=cfg["num_heads"][::-1][i], up=i < len(rev) - 1, c=c))
         prev = c
     return dict(down=down, up=up, mid_c=boc[-1], mid_tl=cfg["transformer_layers"][-1], mid_heads=cfg["num_heads"][-1],
-                temb=4 * boc[0], proj_in=cfg["pooled_dim"] + 6 * cfg["addition_time_embed_dim"])
+                temb=4 * boc[0],
+                proj_in=(cfg["pooled_dim"] + 6 * cfg["addition_time_embed_dim"]) if cfg.get("addition_time_embed_dim") else 0)
 
 
 def make_state_dict(cfg, seed: int) -> Dict[str, torch.Tensor]:
@@ -98,9 +117,17 @@ def make_state_dict(cfg, seed: int) -> Dict[str, torch.Tensor]:
         if cin != cout:
             conv(p + "conv_shortcut", cout, cin, 1)
 
+    linear_proj = bool(cfg.get("use_linear_projection", True))
+
+    def proj(name, c):
+        if linear_proj:
+            lin(name, c, c)
+        else:
+            conv(name, c, c, 1)
+
     def transformer(p, c, layers):
         norm(p + "norm", c)
-        lin(p + "proj_in", c, c)
+        proj(p + "proj_in", c)
         for k in range(layers):
             b = f"{p}transformer_blocks.{k}."
             for nm in ("norm1", "norm2", "norm3"):
@@ -112,14 +139,15 @@ def make_state_dict(cfg, seed: int) -> Dict[str, torch.Tensor]:
                 lin(b + a + ".to_out.0", c, c)
             lin(b + "ff.net.0.proj", 8 * c, c)
             lin(b + "ff.net.2", c, 4 * c)
-        lin(p + "proj_out", c, c)
+        proj(p + "proj_out", c)
 
     u = "unet."
     conv(u + "conv_in", cfg["block_out_channels"][0], cfg["in_channels"], 3)
     lin(u + "time_embedding.linear_1", T, cfg["block_out_channels"][0])
     lin(u + "time_embedding.linear_2", T, T)
-    lin(u + "add_embedding.linear_1", T, lay["proj_in"])
-    lin(u + "add_embedding.linear_2", T, T)
+    if lay["proj_in"]:
+        lin(u + "add_embedding.linear_1", T, lay["proj_in"])
+        lin(u + "add_embedding.linear_2", T, T)
     for i, d in enumerate(lay["down"]):
         for j, (ci, co) in enumerate(d["res"]):
             resnet(f"{u}down_blocks.{i}.resnets.{j}.", ci, co)
@@ -181,34 +209,48 @@ def resnet(sd, p, x, emb, groups):
     return x + h
 
 
-def attention(sd, p, x, ctx, heads):
+def attention(sd, p, x, ctx, heads, bias=None):
+    """diffusers Attention + AttnProcessor2_0; `bias` [B, 1, L]: the additive encoder_attention_mask of the cross-attention"""
     B, N, C = x.shape
     q = _lin(sd, p + "to_q", x).view(B, N, heads, -1).transpose(1, 2)
     k = _lin(sd, p + "to_k", ctx).view(B, ctx.shape[1], heads, -1).transpose(1, 2)
     v = _lin(sd, p + "to_v", ctx).view(B, ctx.shape[1], heads, -1).transpose(1, 2)
-    o = sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
+    if bias is None:
+        o = sdpa(q, k, v)
+    else:   # [B, 1, L] -> broadcast over heads and queries, added to the scaled logits
+        o = sdpa(q, k, v, bias[:, None, :, :].to(q.dtype))
+    o = o.transpose(1, 2).reshape(B, N, C)
     return _lin(sd, p + "to_out.0", o)
 
 
-def transformer(sd, p, x, ctx, layers, heads, groups):
+def transformer(sd, p, x, ctx, layers, heads, groups, bias=None):
     B, C, H, W = x.shape
     res = x
-    h = _gn(sd, p + "norm", x, groups, 1e-6).permute(0, 2, 3, 1).reshape(B, H * W, C)
-    h = _lin(sd, p + "proj_in", h)
+    linear_proj = sd[p + "proj_in.weight"].dim() == 2
+    h = _gn(sd, p + "norm", x, groups, 1e-6)
+    if linear_proj:
+        h = _lin(sd, p + "proj_in", h.permute(0, 2, 3, 1).reshape(B, H * W, C))
+    else:   # use_linear_projection = False: 1x1 convolution on the feature map, then tokens
+        h = _conv(sd, p + "proj_in", h, pad=0).permute(0, 2, 3, 1).reshape(B, H * W, C)
     for k in range(layers):
         b = f"{p}transformer_blocks.{k}."
         n = _ln(sd, b + "norm1", h)
         h = attention(sd, b + "attn1.", n, n, heads) + h
-        h = attention(sd, b + "attn2.", _ln(sd, b + "norm2", h), ctx, heads) + h
+        h = attention(sd, b + "attn2.", _ln(sd, b + "norm2", h), ctx, heads, bias) + h
         g = _lin(sd, b + "ff.net.0.proj", _ln(sd, b + "norm3", h))
         hid, gate = g.chunk(2, dim=-1)
         h = _lin(sd, b + "ff.net.2", hid * F.gelu(gate)) + h
-    h = _lin(sd, p + "proj_out", h).reshape(B, H, W, C).permute(0, 3, 1, 2)
+    if linear_proj:
+        h = _lin(sd, p + "proj_out", h).reshape(B, H, W, C).permute(0, 3, 1, 2)
+    else:
+        h = _conv(sd, p + "proj_out", h.reshape(B, H, W, C).permute(0, 3, 1, 2), pad=0)
     return h + res
 
 
-def unet_forward(sd, cfg, sample, timestep, text, pooled, time_ids) -> torch.Tensor:
-    """classify_forward (fastgen/networks/SD15/network.py:46-341) for the SDXL configuration."""
+def unet_forward(sd, cfg, sample, timestep, text, pooled, time_ids, encoder_attention_mask=None) -> torch.Tensor:
+    """classify_forward (fastgen/networks/SD15/network.py:46-341) for the SDXL configuration, and -- without the addition
+    embedding and with `encoder_attention_mask` [B, L] of 0 / 1 turned into the additive bias (1 - mask) * -10000 of
+    :142-145 -- for the SD 1.5 configuration."""
     lay = layout(cfg)
     G = cfg["norm_groups"]
     dt = sample.dtype
@@ -217,30 +259,34 @@ def unet_forward(sd, cfg, sample, timestep, text, pooled, time_ids) -> torch.Ten
     t_emb = timesteps_proj(timestep.expand(B) if timestep.ndim == 0 or timestep.numel() == 1 else timestep,
                            cfg["block_out_channels"][0]).to(dt)
     emb = _lin(sd, u + "time_embedding.linear_2", F.silu(_lin(sd, u + "time_embedding.linear_1", t_emb)))
-    te = timesteps_proj(time_ids.flatten(), cfg["addition_time_embed_dim"]).reshape(B, -1)
-    add = torch.cat([pooled, te.to(pooled.dtype)], dim=-1).to(dt)
-    emb = emb + _lin(sd, u + "add_embedding.linear_2", F.silu(_lin(sd, u + "add_embedding.linear_1", add)))
+    if cfg.get("addition_time_embed_dim"):
+        te = timesteps_proj(time_ids.flatten(), cfg["addition_time_embed_dim"]).reshape(B, -1)
+        add = torch.cat([pooled, te.to(pooled.dtype)], dim=-1).to(dt)
+        emb = emb + _lin(sd, u + "add_embedding.linear_2", F.silu(_lin(sd, u + "add_embedding.linear_1", add)))
     ctx = text.to(dt)
+    bias = None
+    if encoder_attention_mask is not None:
+        bias = ((1 - encoder_attention_mask.to(dt)) * -10000.0).unsqueeze(1)
     h = _conv(sd, u + "conv_in", sample)
     skips: List[torch.Tensor] = [h]
     for i, d in enumerate(lay["down"]):
         for j in range(len(d["res"])):
             h = resnet(sd, f"{u}down_blocks.{i}.resnets.{j}.", h, emb, G)
             if d["attn"]:
-                h = transformer(sd, f"{u}down_blocks.{i}.attentions.{j}.", h, ctx, d["tl"], d["heads"], G)
+                h = transformer(sd, f"{u}down_blocks.{i}.attentions.{j}.", h, ctx, d["tl"], d["heads"], G, bias)
             skips.append(h)
         if d["down"]:
             h = _conv(sd, f"{u}down_blocks.{i}.downsamplers.0.conv", h, stride=2, pad=1)
             skips.append(h)
     h = resnet(sd, u + "mid_block.resnets.0.", h, emb, G)
-    h = transformer(sd, u + "mid_block.attentions.0.", h, ctx, lay["mid_tl"], lay["mid_heads"], G)
+    h = transformer(sd, u + "mid_block.attentions.0.", h, ctx, lay["mid_tl"], lay["mid_heads"], G, bias)
     h = resnet(sd, u + "mid_block.resnets.1.", h, emb, G)
     for i, d in enumerate(lay["up"]):
         for j in range(len(d["res"])):
             h = torch.cat([h, skips.pop()], dim=1)
             h = resnet(sd, f"{u}up_blocks.{i}.resnets.{j}.", h, emb, G)
             if d["attn"]:
-                h = transformer(sd, f"{u}up_blocks.{i}.attentions.{j}.", h, ctx, d["tl"], d["heads"], G)
+                h = transformer(sd, f"{u}up_blocks.{i}.attentions.{j}.", h, ctx, d["tl"], d["heads"], G, bias)
         if d["up"]:
             h = _conv(sd, f"{u}up_blocks.{i}.upsamplers.0.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
     h = F.silu(_gn(sd, u + "conv_norm_out", h, G, 1e-5))
@@ -259,6 +305,21 @@ def sdxl_forward(sd, cfg, x_t, t, text, pooled, fwd_pred_type="x0", dtype=torch.
     time_ids = torch.tensor([[resolution, resolution, 0, 0, resolution, resolution]], dtype=torch.float32,
                             device=x_t.device).repeat(B, 1)
     eps = unet_forward(sd, cfg, x_t.to(dtype), (t.double() * 1000.0).to(t.dtype), text, pooled.to(dtype), time_ids)
+    eps = eps.to(x_t.dtype)
+    if fwd_pred_type == "eps":
+        return eps
+    abar = alphas_cumprod().double().to(x_t.device)
+    idx = (1000 * t.double()).long().clamp(0, 999)
+    a, s = abar[idx].sqrt().reshape(-1, 1, 1, 1), (1 - abar[idx]).sqrt().reshape(-1, 1, 1, 1)
+    a = torch.where(a >= 0, a.clamp(min=1e-6), a.clamp(max=-1e-6))
+    return ((x_t.double() - eps.double() * s) / a).to(x_t.dtype)
+
+
+def sd15_forward(sd, cfg, x_t, t, text, mask=None, fwd_pred_type="x0", dtype=torch.float32):
+    """StableDiffusion15.forward (SD15/network.py:602-678): eps prediction, 'sd' (alphas) schedule,
+    condition = [encoder_hidden_states, encoder_attention_mask]."""
+    eps = unet_forward(sd, cfg, x_t.to(dtype), (t.double() * 1000.0).to(t.dtype), text, None, None,
+                       encoder_attention_mask=mask)
     eps = eps.to(x_t.dtype)
     if fwd_pred_type == "eps":
         return eps

@@ -204,6 +204,35 @@ def test_sdxl_base_configuration_one_sample_eps_and_x0():
             assert e < max(1e-2, e16), (pred, e, e16)
 
 
+def test_sd15_base_configuration_with_padding_masks():
+    """SD 1.5 UNet at its published configuration (859.5 M parameters; heads of 40 / 80 / 160 channels), 2 samples at a
+    64 x 64 latent with different prompt lengths"""
+    from fastgen_b200.sdxl import StableDiffusion15
+
+    torch.manual_seed(0)
+    with torch.device(DEV):
+        net = StableDiffusion15()
+        for p in net.parameters():
+            p.data = p.data.bfloat16().float()
+    net = net.eval()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    ocfg = dict(XO.SD15_BASE)
+    g = torch.Generator(device=DEV).manual_seed(6)
+    x = torch.randn(2, 4, 64, 64, device=DEV, generator=g)
+    text = torch.randn(2, 77, 768, device=DEV, generator=g).bfloat16().float()
+    mask = torch.zeros(2, 77, device=DEV)
+    mask[0, :77], mask[1, :11] = 1, 1
+    t = torch.tensor([0.749, 0.3], dtype=torch.float64, device=DEV)
+    with torch.no_grad(), OD.exact_fp32():
+        out = net(x, t, condition=[text, mask], fwd_pred_type="eps")
+        ref = XO.sd15_forward(sd, ocfg, x, t, text, mask, fwd_pred_type="eps")
+        ref16 = XO.sd15_forward(sd, ocfg, x.bfloat16(), t, text.bfloat16(), mask.bfloat16(), fwd_pred_type="eps",
+                                dtype=torch.bfloat16)
+    e, e16 = _rel(out, ref), _rel(ref16.float(), ref)
+    print(f"sd15 base, 2 samples with masks, eps: rel-L2 ours {e:.3e}, reference bf16 arithmetic {e16:.3e}")
+    assert e < max(1e-2, e16), (e, e16)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # EDM networks at full width, fp32 path (compute="bf16x3": three-product convolutions + fp32 attention)
 # ---------------------------------------------------------------------------------------------------------------------

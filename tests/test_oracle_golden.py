@@ -280,6 +280,29 @@ def test_sdxl_oracle_matches_reference_glue():
             assert torch.equal(out, ref) or _rel(out, ref) < 2e-3, pred
 
 
+def test_sd15_oracle_matches_reference_glue():
+    """oracle/sdxl_oracle.py at an SD 1.5-shaped configuration against the UNMODIFIED reference `StableDiffusion15.forward` +
+    `classify_forward` with an `encoder_attention_mask` (SD15/network.py:602-678, 46-341) on the stand-in diffusers UNet
+    (tests/golden/sd15_reference_glue.npz): the mask -> additive-bias conversion reaching every cross-attention, no addition
+    embedding, 1x1-convolution projections, four levels, eps -> x0 through the reference's schedule"""
+    from oracle import sdxl_oracle as XO
+
+    g = _load("sd15_reference_glue.npz")
+    cfg = XO.tiny_sd15_config()
+    sd = XO.make_state_dict(cfg, int(g["seed"]))
+    x, text, mask, t = (torch.from_numpy(g[k]) for k in ("x", "text", "mask", "t"))
+    with torch.no_grad():
+        for pred in ("eps", "x0"):
+            out = XO.sd15_forward(sd, cfg, x, t, text, mask, fwd_pred_type=pred)
+            ref = torch.from_numpy(g[f"masked_{pred}"])
+            assert torch.equal(out, ref) or _rel(out, ref) < 1e-5, pred
+        out = XO.sd15_forward(sd, cfg, x, t, text, None, fwd_pred_type="eps")
+        assert torch.equal(out, torch.from_numpy(g["nomask_eps"])) or _rel(out, torch.from_numpy(g["nomask_eps"])) < 1e-5
+        # the mask matters: the padded samples change, the unpadded one does not
+        d = (torch.from_numpy(g["nomask_eps"]) - torch.from_numpy(g["masked_eps"])).flatten(1).abs().amax(1)
+        assert d[0] == 0 and d[1] > 1e-2 and d[2] > 1e-2
+
+
 def test_dit_oracle_matches_reference():
     """oracle/dit_oracle.py against the UNMODIFIED reference DiT (its own __init__, blocks, embedders, modulation, unpatchify,
     SiT convention, r embedder) run with stand-ins for timm's PatchEmbed / Attention / Mlp only

@@ -36,6 +36,27 @@ def test_sdxl_base_parameter_count_is_the_published_one():
     assert n == 2_567_463_684
 
 
+def test_sd15_parameter_count_and_keys():
+    """known answer: the SD 1.5 UNet2DConditionModel has 859,520,964 parameters; 1x1-conv projections, no add_embedding;
+    the oracle's state-dict factory produces exactly the module tree's keys"""
+    from fastgen_b200.sdxl import SD15_BASE, StableDiffusion15
+
+    with torch.device("meta"):
+        net = StableDiffusion15()
+    n = sum(p.numel() for name, p in net.unet.named_parameters() if not name.startswith("logvar_linear"))
+    assert n == 859_520_964
+    sd = net.state_dict()
+    assert sd["unet.down_blocks.0.attentions.0.proj_in.weight"].shape == (320, 320, 1, 1)
+    assert not any("add_embedding" in k for k in sd) and net.schedule_type == "sd" and net.net_pred_type == "eps"
+    assert {k: tuple(v) for k, v in SD15_BASE.items() if isinstance(v, tuple)} == \
+        {k: tuple(v) for k, v in XO.SD15_BASE.items() if isinstance(v, tuple)}
+    tiny = XO.tiny_sd15_config()
+    small = StableDiffusion15(unet_config=tiny)
+    want = set(XO.make_state_dict(tiny, 0).keys())
+    have = {k for k in small.state_dict().keys() if "logvar_linear" not in k}
+    assert want == have
+
+
 def test_scheduler_constants():
     from fastgen_b200.noise_schedule import get_noise_schedule
 

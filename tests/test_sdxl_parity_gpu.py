@@ -154,3 +154,43 @@ def test_sdxl_base_configuration_batch_independence():
     a, s = sched.alpha(t).reshape(-1, 1, 1, 1), sched.sigma(t).reshape(-1, 1, 1, 1)
     ref = ((x.double() - eps2.double() * s) / a).to(torch.bfloat16)
     assert torch.equal(x0, ref)
+
+
+def test_sd15_forward_with_encoder_attention_mask_matches_oracle():
+    """SD 1.5-shaped network (four levels, 8 heads per level, 1x1-conv projections, no addition embedding) with a prefix
+    `encoder_attention_mask`: the CUDA path (per-sample key counts in fg_flash_attn) against the oracle, which applies the
+    reference's additive -10000 bias and is pinned to the unmodified reference by tests/golden/sd15_reference_glue.npz"""
+    from fastgen_b200.sdxl import StableDiffusion15
+
+    cfg = XO.tiny_sd15_config()
+    sd = {k: v.bfloat16().float() for k, v in XO.make_state_dict(cfg, 3).items()}
+    net = StableDiffusion15(unet_config=cfg)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("unet.logvar_linear") for k in missing)
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    B, S = 3, 32
+    x = torch.randn(B, 4, S, S, generator=g)
+    text = torch.randn(B, 77, cfg["cross_attention_dim"], generator=g).bfloat16().float()
+    mask = torch.zeros(B, 77)
+    for b, n in enumerate((77, 5, 40)):
+        mask[b, :n] = 1
+    t = torch.tensor([0.999, 0.5, 0.1], dtype=torch.float64)
+    for pred in ("eps", "x0"):
+        out = net(x.cuda(), t.cuda(), condition=[text.cuda(), mask.cuda()], fwd_pred_type=pred)
+        ref = XO.sd15_forward(sd, cfg, x, t, text, mask, fwd_pred_type=pred)
+        assert out.shape == x.shape and _rel(out, ref) < 1e-2, (pred, _rel(out, ref))
+    # a new mask on the same text buffer is picked up (the key counts are refreshed per condition)
+    mask2 = torch.ones(B, 77)
+    out2 = net(x.cuda(), t.cuda(), condition=[text.cuda(), mask2.cuda()], fwd_pred_type="eps")
+    ref2 = XO.sd15_forward(sd, cfg, x, t, text, None, fwd_pred_type="eps")
+    assert _rel(out2, ref2) < 1e-2 and _rel(out2, XO.sd15_forward(sd, cfg, x, t, text, mask, fwd_pred_type="eps")) > 2e-2
+    out3 = net(x.cuda(), t.cuda(), condition=[text.cuda(), None], fwd_pred_type="eps")
+    assert _rel(out3, ref2) < 1e-2
+    # a mask that is not a prefix is refused, not silently mis-handled
+    bad = mask.clone()
+    bad[1, 20] = 1
+    with pytest.raises(NotImplementedError):
+        net(x.cuda(), t.cuda(), condition=[text.cuda(), bad.cuda()], fwd_pred_type="eps")
+    with pytest.raises(NotImplementedError):
+        net(x.cuda(), t.cuda(), condition=[text.cuda(), mask.cuda()], r=t.cuda())

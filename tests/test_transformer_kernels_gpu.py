@@ -285,3 +285,27 @@ def test_ln_affine_fp32_rows(rows, d):
     torch.cuda.synchronize()
     ref = F.layer_norm(x[:, :d], (d,), gamma, beta, 1e-5)
     assert _rel(y, ref) < 3e-3, _rel(y, ref)
+
+
+@pytest.mark.parametrize("tq,heads,d", [(300, 8, 40), (64, 8, 160), (1024, 8, 80)])
+def test_flash_attn_per_sample_key_lengths(tq, heads, d):
+    """a prefix `encoder_attention_mask` (SD 1.5: 77 text tokens, padding masked, fastgen/networks/SD15/network.py:142-145)
+    as per-sample key counts: equal to SDPA with the reference's additive -10000 bias on the masked keys"""
+    from fastgen_b200 import ops
+
+    torch.manual_seed(7)
+    b, lk = 3, 77
+    dm = heads * d
+    q = torch.randn(b, tq, dm, device=DEV).bfloat16()
+    kv = torch.randn(b, lk, 2 * dm, device=DEV).bfloat16()
+    lens = torch.tensor([77, 9, 31], dtype=torch.int32, device=DEV)
+    out = torch.empty(b, tq, dm, device=DEV, dtype=torch.bfloat16)
+    ops.flash_attn(q, dm, tq * dm, [(kv, kv[..., dm:], 2 * dm, lk * 2 * dm, lk)], b, heads, d, tq, out, dm, tq * dm,
+                   kv_len0_per_sample=lens)
+    torch.cuda.synchronize()
+    mask = (torch.arange(lk, device=DEV)[None, :] < lens[:, None]).float()          # [b, lk] of 0 / 1
+    bias = ((1 - mask) * -10000.0)[:, None, None, :]                                   # the reference's conversion
+    ref = F.scaled_dot_product_attention(q.float().view(b, tq, heads, d).transpose(1, 2),
+                                         kv[..., :dm].float().reshape(b, lk, heads, d).transpose(1, 2),
+                                         kv[..., dm:].float().reshape(b, lk, heads, d).transpose(1, 2), attn_mask=bias)
+    assert _rel(out, ref.transpose(1, 2).flatten(2)) < 1e-2
