@@ -19,6 +19,7 @@ def test_reference_arm_prints_the_contract_line(installed):
     if installed and not have:
         pytest.skip("baseline/_ref not installed here (python -c 'import __graft_entry__ as g; g.build()')")
     env = dict(os.environ)
+    env.pop("FASTGEN_B200_REF_DIR", None)
     if not installed:
         env["FASTGEN_B200_REF_DIR"] = "/nonexistent"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",

@@ -1,5 +1,5 @@
 """The vectorised sampler-step kernels (fg_edm_step / fg_axpby / fg_sub_div, csrc/sampler_vec.cuh) on hardware: equal to the
-scalar forms bit for bit and to fp64 torch.  First run on a B200 in round 2 (all green, profiles/r2_first_gpu_calls.md);
+scalar forms bit for bit and to fp64 torch.  First run on a B200 in round 2 (all green, profiles/r2_logs/r2_unverified.log);
 they are the default since."""
 import pytest
 import torch

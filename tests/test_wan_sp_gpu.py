@@ -99,8 +99,7 @@ def test_sequence_parallel_matches_single_gpu():
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_matches_single_gpu():
     """the one-pass exchange (fg_peer_put / fg_peer_wait over symmetric memory, no NCCL in the block) gives the same
-    chunks as the single-GPU path.  NOT yet run on hardware (written after round 1's GPU budget ended): first thing to
-    run in round 2 with `gpurun --gpus 2`, under a short timeout."""
+    chunks as the single-GPU path (green on 2 and 4 B200s, round 2: profiles/r2_logs/)."""
     world = 2
     with mp.Manager() as mgr:
         ret = mgr.dict()
@@ -114,7 +113,7 @@ def test_sequence_parallel_peer_exchange_matches_single_gpu():
 @pytest.mark.timeout(600)
 def test_sequence_parallel_peer_exchange_replays_as_cuda_graphs():
     """with the peer exchange a forward holds no torch.distributed call, so its launch list is captured into a CUDA graph
-    under sequence parallelism too.  NOT yet run on hardware; run after the test above is green."""
+    under sequence parallelism too (green on 2 and 4 B200s, round 2)."""
     world = 2
     with mp.Manager() as mgr:
         ret = mgr.dict()
