@@ -7,9 +7,10 @@
 //            N = cout (BLOCK_N per tile), K = sum over segments of taps * cin (64 per pipeline stage).
 // A 3x3 tap is the same TMA box shifted by (dx, dy); TMA's out-of-bounds zero fill IS the padding.
 //
-// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  Two TMEM accumulator stages let the epilogue of
-// tile i overlap the main loop of tile i+1.
+// Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp_idx % 4; the two warps of a quarter -- "twins" -- split the columns of
+// every output slab: with one epilogue warp per scheduler the tail of an epilogue-bound layer was dependency-latency bound,
+// profiles/conv_epilogue_r02.md).  Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Epilogue: a ring of four 16 KB slabs (128 rows x 128 B).  The residual of a slab is prefetched into the ring by
 // TMA two slabs ahead (FG_RES_SAME: into the slab itself, added in place; FG_RES_UP2: the quarter-size source box),
@@ -31,7 +32,7 @@ namespace fg {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;   // producer warp + MMA warp + 8 epilogue warps (two per TMEM lane quarter)
 
 // epilogue specialisations
 constexpr int kEpiGeneric = -1;  // no TMA store: direct (vector or scalar) global accesses, every feature at run time
@@ -257,14 +258,14 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint3
 // Specialised tail of the TMA-store path for 32 accumulator columns: everything except the residual that arrives
 // through shared memory and the final scale.  Branches are warp-uniform; the rare plain-load residual (FG_RES_DOWN2,
 // or a residual whose type differs from the output's) stays behind one of them.
-template <int RES>
-__device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t (&v)[32], int c_base, int img, int h,
-                                            int w, bool valid, float (&a)[32]) {
+template <int RES, int CH = 32>
+__device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t (&v)[CH], int c_base, int img, int h,
+                                            int w, bool valid, float (&a)[CH]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+  for (int j = 0; j < CH; ++j) a[j] = __uint_as_float(v[j]);
   if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < CH; j += 4) {
       if (c_base + j < p.Cout) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c_base + j));
         a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
@@ -274,7 +275,7 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
   if (p.rowvec && valid) {
     const float* rv = p.rowvec + img * p.rowvec_ld + c_base;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < CH; j += 4) {
       if (c_base + j < p.Cout) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
         a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
@@ -283,7 +284,7 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
   }
   if (p.act == FG_ACT_GELU_TANH) {  // (the switch is hoisted: one warp-uniform branch per 32 columns)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < CH; ++j) {
       const float x = a[j];
       const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
       const float hx = 0.5f * x;
@@ -291,13 +292,13 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
     }
   } else if (p.act == FG_ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = silu_f(a[j]);
+    for (int j = 0; j < CH; ++j) a[j] = silu_f(a[j]);
   }
   if (p.gate && valid) {
     const int64_t pix = (static_cast<int64_t>(img) * p.H + h) * p.W + w;
     const float* g = p.gate + (pix / p.gate_rows) * p.gate_ld + c_base;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < CH; j += 4) {
       if (c_base + j < p.Cout) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(g + j));
         a[j] *= b.x, a[j + 1] *= b.y, a[j + 2] *= b.z, a[j + 3] *= b.w;
@@ -308,7 +309,7 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
     if (p.res_mode != FG_RES_NONE && valid) {
       const ResAddr ra = res_addr(p, img, h, w);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {  // (unrolled: a dynamic index would push a[] into local memory)
+      for (int j = 0; j < CH; j += 4) {  // (unrolled: a dynamic index would push a[] into local memory)
         if (c_base + j < p.Cout) {
           const float4 b = res_load4(p, ra, c_base + j);
           a[j] += b.x, a[j + 1] += b.y, a[j + 2] += b.z, a[j + 3] += b.w;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4 * CG);   // CG = 2: the leader's barrier collects the epilogue warps of both CTAs
+        mbar_init(&tempty[i], 8 * CG);   // 8 epilogue warps; CG = 2: the leader's barrier collects those of both CTAs
       }
       for (int i = 0; i < Cfg::OUT_SLABS; ++i) mbar_init(&res_full[i], 1);
       fence_barrier_init();
@@ -470,6 +471,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;
+    const int twin = (warp - 2) >> 2;   // which half of every slab's columns this warp handles
     const int row = q * 32 + lane;
     const int wl = row % p.BW;
     const int hl = (row / p.BW) % p.BH;
@@ -545,8 +547,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           uint8_t* my_row = slab + row * 128;
           const float sc = p.out_scale;
+          if constexpr (!kOutBf16 && !kGeglu) {
+            // fp32 slab = 32 accumulator columns: each twin takes 16 of them (four 16-byte chunks of the slab row)
+            uint32_t v[16];
+            float a[16];
+            tmem_ld_32x16(taddr + c0 + twin * 16, v);
+            tmem_ld_wait();
+            tail_values<kRes, 16>(p, v, t.co0 + c0 + twin * 16, img, h, w, valid, a);
 #pragma unroll
-          for (int cc = 0; cc < kSlabCols; cc += 32) {
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = twin * 4 + j;
+              float4 o = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+              if constexpr (kRes != kResNone) {
+                const float4 r = *reinterpret_cast<const float4*>(rrow + ((chunk ^ rkey) << 4));
+                o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+              }
+              o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+              *reinterpret_cast<float4*>(my_row + ((chunk ^ wkey) << 4)) = o;
+            }
+          }
+#pragma unroll
+          for (int cc = twin * (kSlabCols / 2); cc < (twin + 1) * (kSlabCols / 2) && (kOutBf16 || kGeglu); cc += 32) {
             uint32_t v[32];
             float a[32];
             if (!(p.dbg & 2)) {
@@ -604,7 +625,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
           if (is_store_thread && !(p.dbg & 1)) {
             tma_store_4d(&p.tmOut, slab, kGeglu ? ((t.co0 + c0) >> 1) : (t.co0 + c0), t.w0, t.h0, t.img0);
             tma_store_commit();
@@ -612,21 +633,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if constexpr (!kOutBf16) {
             if (p.stats) {
               // GroupNorm statistics of the finished slab (the next consumer's fg_gn_stats pass disappears): thread
-              // (row block rb, column) sums 32 rows of one column out of shared memory, runs of lanes that fall into
-              // the same group are combined with a segmented shuffle reduction, one fp64 atomic pair per run.
+              // (row block rb, column, twin) sums 16 rows of one column out of shared memory (the twins halve the
+              // dependent load chain), runs of lanes that fall into the same group are combined with a segmented
+              // shuffle reduction, one fp64 atomic pair per run and twin.
               const int col = row & 31, rb = row >> 5;
               const int ch = t.co0 + c0 + col;
               const int simg = t.img0 + (rb * 32) / (p.BW * p.BH);
               float s1 = 0.f, s2 = 0.f;
               if (ch < p.Cout && simg < p.N) {
-                const uint8_t* base = slab + (rb * 32) * 128 + (col & 3) * 4;
+                const uint8_t* base = slab + (rb * 32 + twin * 16) * 128 + (col & 3) * 4;
                 const uint32_t cchunk = static_cast<uint32_t>(col >> 2);
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
+                float t1 = 0.f, t2 = 0.f;   // two independent chains
+#pragma unroll
+                for (int r = 0; r < 16; r += 2) {   // (twin * 16 + r) & 7 == r & 7: the swizzle key of the row
                   const float v = *reinterpret_cast<const float*>(base + r * 128 + ((cchunk ^ (r & 7)) << 4));
-                  s1 += v;
-                  s2 = fmaf(v, v, s2);
+                  const float u = *reinterpret_cast<const float*>(base + (r + 1) * 128 + ((cchunk ^ ((r + 1) & 7)) << 4));
+                  s1 += v, t1 += u;
+                  s2 = fmaf(v, v, s2), t2 = fmaf(u, u, t2);
                 }
+                s1 += t1, s2 += t2;
               }
               // the column sums feed up to two group layouts: this tensor's own next norm and, for a tensor that is also
               // a skip connection, the decoder norm that reads it at channel offset stats2_ch0 of a concatenation
@@ -654,17 +679,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
       } else if constexpr (BLOCK_N >= 32) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = twin * 32; c0 < BLOCK_N; c0 += 64) {   // the twins alternate 32-column chunks
           uint32_t v[32];
           tmem_ld_32x32(taddr + c0, v);
           tmem_ld_wait();
           if (valid && t.co0 + c0 < p.Cout) epilogue_chunk<32>(p, v, t.co0 + c0, img, h, w);
         }
       } else {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr, v);
-        tmem_ld_wait();
-        if (valid) epilogue_chunk<16>(p, v, t.co0, img, h, w);
+        if (twin == 0) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr, v);
+          tmem_ld_wait();
+          if (valid) epilogue_chunk<16>(p, v, t.co0, img, h, w);
+        }
       }
       tc_fence_before();
       __syncwarp();
