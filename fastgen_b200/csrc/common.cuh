@@ -261,6 +261,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// The same descriptor with an explicit stride between 8-row groups.  The 128B swizzle is a function of ABSOLUTE shared-
+// memory address bits (chunk index ^ bits [7,10) of the address), for TMA writes and tcgen05 operand reads alike, so a
+// descriptor may start at any 128-byte row of a TMA-written buffer and step over it with any SBO that is a multiple of
+// 128 -- measured exact on B200 with unaligned starts and SBO = 1280, base-offset field 0
+// (profiles/experiments/halo_umma_test.cu): what lets one halo tile serve the nine taps of a 3x3 convolution.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // instruction descriptor for kind::f16, A/B = bf16, D = fp32 (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |

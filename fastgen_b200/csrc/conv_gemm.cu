@@ -43,24 +43,37 @@ __host__ __device__ constexpr int epi_mode(bool out_bf16, int res) { return (out
 // FG_ACT_GEGLU: bf16 output of half the accumulator width, out[j] = v[2j] * gelu_erf(v[2j+1]), no residual
 constexpr int kEpiGeglu = 8 | 1;
 
-template <int BLOCK_N, int CG = 1>   // CG = 2: CTA pair (cta_group::2), each CTA stages half of the B tile
+// halo tiles (HALO): a tile is 16 rows x 8 pixels of one image; ONE TMA box of (16 + 2) x (8 + 2) pixel rows per 64-channel
+// K chunk serves all nine taps of a 3x3 segment (tap (dy, dx) = the same buffer read from row (1 + dy) * 10 + (1 + dx) with
+// a 10-row stride between the 8-pixel tile rows), so A traffic per tap drops from 16 KB to 2.5 KB
+constexpr int kHaloW = 8, kHaloH = 16;
+constexpr int kHaloRows = (kHaloH + 2) * (kHaloW + 2);       // 180 pixel rows of 128 bytes
+constexpr int kHaloTxBytes = kHaloRows * 128;                // bytes one halo box load delivers
+constexpr int kHaloSbo = (kHaloW + 2) * 128;                 // descriptor stride between 8-pixel tile rows
+
+template <int BLOCK_N, int CG = 1, bool HALO = false>   // CG = 2: CTA pair (cta_group::2), each CTA stages half of the B tile
 struct ConvCfg {
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
   static constexpr int B_BYTES = (BLOCK_N / CG) * kBlockK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int HALO_BYTES = ((kHaloTxBytes + 1023) / 1024) * 1024;
+  static constexpr int HALO_BUFS = 2;
+  static constexpr int A_REGION = HALO ? HALO_BUFS * HALO_BYTES : 0;      // halo ring in front of the B ring
+  static constexpr int STAGE_BYTES = HALO ? B_BYTES : A_BYTES + B_BYTES;  // HALO: a stage holds one tap's B tile
   static constexpr int OUT_SLAB_BYTES = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 B (TMA box)
   static constexpr int OUT_SLABS = 4;                   // ring: residual prefetch (TMA load) -> in-place add -> TMA store
   static constexpr int RES_UP_BYTES = OUT_SLAB_BYTES / 4;  // FG_RES_UP2: the (BW/2 x BH/2) source box of a slab
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - 256 - OUT_SLABS * OUT_SLAB_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - BAR_BYTES - OUT_SLABS * OUT_SLAB_BYTES - A_REGION) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > (HALO ? 10 : 8) ? (HALO ? 10 : 8) : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
                                    : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
   static constexpr int SMEM_BYTES =
-      STAGES * STAGE_BYTES + OUT_SLABS * OUT_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+      A_REGION + STAGES * STAGE_BYTES + OUT_SLABS * OUT_SLAB_BYTES + 1024 /*align slack*/ + BAR_BYTES /*barriers*/;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
 };
 
@@ -329,10 +342,11 @@ __device__ __forceinline__ int item_tile(const ConvKParams& p, int item, int cta
   return (2 * (item / p.tiles_n) + cta_rank) * p.tiles_n + item % p.tiles_n;
 }
 
-template <int BLOCK_N, int EPI, int CG = 1>
+template <int BLOCK_N, int EPI, int CG = 1, bool HALO = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BLOCK_N, CG>;
+  using Cfg = ConvCfg<BLOCK_N, CG, HALO>;
   static_assert(CG == 1 || (EPI != kEpiGeneric && BLOCK_N >= 128), "CTA pairs: TMA-store epilogues, tiles >= 128 wide");
+  static_assert(!HALO || CG == 2, "halo tiles are built for the CTA-pair kernels");
   const int cr = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // rank in the pair; 0 = leader (issues the MMAs)
   const int item0 = static_cast<int>(blockIdx.x) / CG, item_step = static_cast<int>(gridDim.x) / CG;
   constexpr bool kTmaStore = EPI != kEpiGeneric;
@@ -344,13 +358,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_slabs = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* ring = smem + Cfg::A_REGION;     // HALO: [halo buffers][B ring]; else [A | B] stages
+  uint8_t* out_slabs = ring + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(out_slabs + Cfg::OUT_SLABS * Cfg::OUT_SLAB_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* res_full = tempty + 2;  // [OUT_SLABS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::OUT_SLABS);
+  uint64_t* a_full = res_full + Cfg::OUT_SLABS;   // [HALO_BUFS] (HALO only)
+  uint64_t* a_empty = a_full + Cfg::HALO_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + Cfg::HALO_BUFS);
+  static_assert((2 * Cfg::STAGES + 4 + Cfg::OUT_SLABS + 2 * Cfg::HALO_BUFS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -374,6 +392,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         mbar_init(&tempty[i], 8 * CG);   // 8 epilogue warps; CG = 2: the leader's barrier collects those of both CTAs
       }
       for (int i = 0; i < Cfg::OUT_SLABS; ++i) mbar_init(&res_full[i], 1);
+      for (int i = 0; i < Cfg::HALO_BUFS; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -396,6 +418,40 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (HALO) {
+        int ab = 0;
+        uint32_t aphase = 0;
+        for (int item = item0; item < p.total_tiles; item += item_step) {
+          const TileCoord t = decode_tile(p, item_tile<CG>(p, item, cr), BLOCK_N);
+          for (int s = 0; s < p.nseg; ++s) {
+            const int taps = p.seg_taps[s];
+            const int kch = p.seg_kchunks[s];
+            for (int kc = 0; kc < kch; ++kc) {
+              // one halo box per 64-channel chunk (a 1x1 segment reads only its centre); both CTAs' boxes are counted on
+              // the leader's barrier
+              mbar_wait(&a_empty[ab], aphase ^ 1u);
+              // 3x3 segment: the (16 + 2) x (8 + 2) halo box; 1x1 segment (a shortcut projection riding along): the plain
+              // 16 x 8 tile box of its tensor map, read back with the standard 8-row stride
+              const int halo = taps == 9 ? 1 : 0;
+              if (cr == 0) mbar_arrive_expect_tx(&a_full[ab], 2 * (halo ? kHaloTxBytes : Cfg::A_BYTES));
+              tma_load_4d_2sm(smem + ab * Cfg::HALO_BYTES, &p.tmA[s], mapa_u32(&a_full[ab], 0), kc * kBlockK, t.w0 - halo,
+                              t.h0 - halo, t.img0);
+              ab ^= 1;
+              if (ab == 0) aphase ^= 1u;
+              for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                if (cr == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::B_BYTES);
+                tma_load_3d_2sm(ring + stage * Cfg::STAGE_BYTES, &p.tmW[s], mapa_u32(&full[stage], 0), kc * kBlockK, tap,
+                                t.co0 + cr * (BLOCK_N / 2));
+                if (++stage == Cfg::STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int item = item0; item < p.total_tiles && !(p.dbg & 4); item += item_step) {
         const TileCoord t = decode_tile(p, item_tile<CG>(p, item, cr), BLOCK_N);
         for (int s = 0; s < p.nseg; ++s) {
@@ -406,7 +462,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
             for (int kc = 0; kc < kch; ++kc) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
               uint8_t* sb = sa + Cfg::A_BYTES;
               if constexpr (CG == 2) {
                 // both CTAs' bytes are counted on the leader's barrier; this CTA stages its A rows and its half of B
@@ -436,14 +492,50 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      [[maybe_unused]] int hab = 0;
+      [[maybe_unused]] uint32_t haphase = 0;
       for (int item = item0; item < p.total_tiles; item += item_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        if constexpr (HALO) {
+          uint32_t started = 0;
+          for (int s = 0; s < p.nseg; ++s) {
+            const int taps = p.seg_taps[s];
+            const int kch = p.seg_kchunks[s];
+            for (int kc = 0; kc < kch; ++kc) {
+              mbar_wait(&a_full[hab], haphase);
+              tc_fence_after();
+              const uint32_t halo_addr = smem_u32(smem + hab * Cfg::HALO_BYTES);
+              for (int tap = 0; tap < taps; ++tap) {
+                // tap (dy, dx): the tile's pixel (y, x) sits at halo row (y + 1 + dy) * 10 + (x + 1 + dx)
+                const uint32_t row0 = taps == 9 ? static_cast<uint32_t>((tap / 3) * (kHaloW + 2) + tap % 3) : 0u;
+                const uint32_t sbo = taps == 9 ? kHaloSbo : 1024u;
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16_ss2(d_tmem, umma_desc_sw128_sbo(halo_addr + row0 * 128 + k * 32, sbo),
+                                umma_desc_sw128(b_addr + k * 32), idesc, (started | k) != 0 ? 1u : 0u);
+                }
+                started = 1;
+                umma_commit2(&empty[stage], 3);
+                if (++stage == Cfg::STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+              umma_commit2(&a_empty[hab], 3);   // the halo buffer is free once the last tap's MMAs retire (both CTAs)
+              hab ^= 1;
+              if (hab == 0) haphase ^= 1u;
+            }
+          }
+        } else
         for (int it = 0; it < p.k_iters && !(p.dbg & 4); ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
@@ -715,13 +807,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
 }
 
-template <int BLOCK_N, int EPI, int CG = 1>
+template <int BLOCK_N, int EPI, int CG = 1, bool HALO = false>
 static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N, CG>;
+  using Cfg = ConvCfg<BLOCK_N, CG, HALO>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI, CG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -741,31 +833,31 @@ static int launch_conv(const ConvKParams& kp, int num_sms, cudaStream_t stream) 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, EPI, CG>, kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, EPI, CG, HALO>, kp);
     if (e != cudaSuccess) {
       set_error("conv_gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return FG_ERR_CUDA;
     }
   } else {
     const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-    conv_gemm_kernel<BLOCK_N, EPI, CG><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+    conv_gemm_kernel<BLOCK_N, EPI, CG, HALO><<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(kp);
   }
   FG_CHECK_LAUNCH("conv_gemm");
   return FG_OK;
 }
 
-template <int BLOCK_N, int CG = 1>
+template <int BLOCK_N, int CG = 1, bool HALO = false>
 static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_t stream) {
   if constexpr (BLOCK_N >= 64) {
     switch (epi) {
-      case epi_mode(false, kResNone): return launch_conv<BLOCK_N, epi_mode(false, kResNone), CG>(kp, num_sms, stream);
-      case epi_mode(true, kResNone): return launch_conv<BLOCK_N, epi_mode(true, kResNone), CG>(kp, num_sms, stream);
-      case epi_mode(false, kResSame): return launch_conv<BLOCK_N, epi_mode(false, kResSame), CG>(kp, num_sms, stream);
-      case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame), CG>(kp, num_sms, stream);
-      case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2), CG>(kp, num_sms, stream);
-      case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2), CG>(kp, num_sms, stream);
+      case epi_mode(false, kResNone): return launch_conv<BLOCK_N, epi_mode(false, kResNone), CG, HALO>(kp, num_sms, stream);
+      case epi_mode(true, kResNone): return launch_conv<BLOCK_N, epi_mode(true, kResNone), CG, HALO>(kp, num_sms, stream);
+      case epi_mode(false, kResSame): return launch_conv<BLOCK_N, epi_mode(false, kResSame), CG, HALO>(kp, num_sms, stream);
+      case epi_mode(true, kResSame): return launch_conv<BLOCK_N, epi_mode(true, kResSame), CG, HALO>(kp, num_sms, stream);
+      case epi_mode(false, kResUp2): return launch_conv<BLOCK_N, epi_mode(false, kResUp2), CG, HALO>(kp, num_sms, stream);
+      case epi_mode(true, kResUp2): return launch_conv<BLOCK_N, epi_mode(true, kResUp2), CG, HALO>(kp, num_sms, stream);
       case kEpiGeglu:
-        if constexpr (BLOCK_N % 128 == 0) return launch_conv<BLOCK_N, kEpiGeglu, CG>(kp, num_sms, stream);
+        if constexpr (BLOCK_N % 128 == 0) return launch_conv<BLOCK_N, kEpiGeglu, CG, HALO>(kp, num_sms, stream);
         break;
       default: break;
     }
@@ -788,7 +880,7 @@ static int dispatch_epi(const ConvKParams& kp, int epi, int num_sms, cudaStream_
 struct TileChoice {
   int bn, cg;
 };
-static TileChoice pick_tile(int cout, int m_tiles, int k_iters, int num_sms, bool geglu, bool pair_ok) {
+static TileChoice pick_tile(int cout, int m_tiles, int k_iters, int num_sms, bool geglu, bool pair_ok, bool halo_ok) {
   static const int forced = getenv("FG_CONV_BN") ? atoi(getenv("FG_CONV_BN")) : 0;  // tuning experiments only
   static const int forced_cg = getenv("FG_CONV_CG") ? atoi(getenv("FG_CONV_CG")) : 0;
   if (!geglu) {
@@ -815,8 +907,13 @@ static TileChoice pick_tile(int cout, int m_tiles, int k_iters, int num_sms, boo
       const int64_t slots = num_sms / cg;
       const int64_t waves = (items + slots - 1) / slots;
       const int mma_clk = 2 * bn;
-      const int port_clk = (16384 + bn / cg * 128) / 64;
-      const int stage_clk = mma_clk > port_clk ? mma_clk : port_clk;
+      // halo tiles (pairs only): 23 KB of A per nine tap stages instead of 16 KB per stage
+      const int a_bytes = (halo_ok && cg == 2) ? kHaloTxBytes / 9 + 512 : 16384;
+      const int port_clk = (a_bytes + bn / cg * 128) / 64;
+      // + the fixed cost of a pipeline stage (barrier wait, descriptor set-up, commit): a 256-clock stage of a 128-wide
+      // tile pays it on every 64 channels -- measured 740-880 vs 1030-1150 TFLOP/s when the model first picked 128-wide
+      // pair tiles for the N = 384 layers
+      const int stage_clk = (mma_clk > port_clk ? mma_clk : port_clk) + 64;
       // + the part of the per-tile tail that the next tile's main loop cannot hide (two accumulator stages overlap them:
       // only a K loop shorter than the epilogue shows it)
       const int64_t epi_clk = 12 * bn;
@@ -841,12 +938,21 @@ namespace fg {
 // TMA descriptors, epilogue pointers) and the kernel choice.  fg_conv_gemm_run only launches it.
 struct alignas(64) ConvPrepared {
   uint64_t magic;
-  int32_t block_n, cg, epi, num_sms, device;
+  int32_t block_n, cg, halo, epi, num_sms, device;
   ConvKParams kp;
 };
 constexpr uint64_t kConvPreparedMagic = 0x46474350524550ull;  // "FGCPREP"
 
 static int conv_launch_prepared(const ConvPrepared& pp, cudaStream_t stream) {
+  if (pp.cg == 2 && pp.halo) {
+    switch (pp.block_n) {
+      case 128: return dispatch_epi<128, 2, true>(pp.kp, pp.epi, pp.num_sms, stream);
+      case 192: return dispatch_epi<192, 2, true>(pp.kp, pp.epi, pp.num_sms, stream);
+      case 256: return dispatch_epi<256, 2, true>(pp.kp, pp.epi, pp.num_sms, stream);
+    }
+    set_error("conv_gemm: no halo kernel for block_n=%d", pp.block_n);
+    return FG_ERR_UNSUPPORTED;
+  }
   if (pp.cg == 2) {
     switch (pp.block_n) {
       case 128: return dispatch_epi<128, 2>(pp.kp, pp.epi, pp.num_sms, stream);
@@ -957,8 +1063,21 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   int k_iters_total = 0;
   for (int s = 0; s < p->nseg; ++s)
     if (p->seg[s].cin > 0) k_iters_total += p->seg[s].taps * ((p->seg[s].cin + kBlockK - 1) / kBlockK);
-  const TileChoice tc = pick_tile(p->cout, m_tiles, k_iters_total, num_sms, geglu, /*pair_ok=*/tma_store_ok);
+  // halo tiles: every segment 3x3 or 1x1, at least one 3x3, the image tiles into 16 x 8 pixel blocks
+  static const bool allow_halo = !(getenv("FG_CONV_HALO") && getenv("FG_CONV_HALO")[0] == '0');
+  bool halo_ok = allow_halo && tma_store_ok && p->w % kHaloW == 0 && p->h % kHaloH == 0;
+  {
+    bool any9 = false;
+    for (int s = 0; s < p->nseg; ++s) any9 = any9 || p->seg[s].taps == 9;
+    halo_ok = halo_ok && any9;
+  }
+  const TileChoice tc = pick_tile(p->cout, m_tiles, k_iters_total, num_sms, geglu, /*pair_ok=*/tma_store_ok, halo_ok);
   const int block_n = tc.bn, cg = tc.cg;
+  const bool halo = halo_ok && cg == 2;
+  if (halo) {   // same tile count (128 pixels each), different shape: 16 rows x 8 pixels of one image
+    kp.BW = kHaloW, kp.BH = kHaloH, kp.BNI = 1;
+    kp.tiles_w = p->w / kp.BW, kp.tiles_h = p->h / kp.BH, kp.tiles_img = p->n;
+  }
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
   kp.total_tiles = ((m_tiles + cg - 1) / cg) * kp.tiles_n;   // work items: tiles, or tile pairs of a CTA pair
 
@@ -980,7 +1099,9 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
       const uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
       const uint64_t ldb = (uint64_t)sg.a_ld * 2;
       const uint64_t strides[4] = {2, ldb, ldb * p->w, ldb * p->w * p->h};
-      const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
+      const bool hbox = halo && sg.taps == 9;   // (a 1x1 segment of a halo launch keeps the plain tile box)
+      const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(hbox ? kHaloW + 2 : kp.BW), (uint32_t)(hbox ? kHaloH + 2 : kp.BH),
+                               (uint32_t)kp.BNI};
       int r = encode_tmap_bf16(&kp.tmA[s], sg.a, 4, dims, strides, box);
       if (r != FG_OK) return r;
     }
@@ -1059,6 +1180,6 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   if (geglu) FG_CHECK_ARG(epi == kEpiGeglu, "conv_gemm: FG_ACT_GEGLU needs the TMA-store epilogue (16-byte aligned bf16 output rows)");
   if (kp.stats) FG_CHECK_ARG(epi != kEpiGeneric, "conv_gemm: fused GroupNorm statistics need the TMA-store epilogue (cout %% 4 == 0, cout > 16, 16-byte aligned rows)");
 
-  pp.block_n = block_n, pp.cg = cg, pp.epi = epi, pp.num_sms = num_sms, pp.device = dev;
+  pp.block_n = block_n, pp.cg = cg, pp.halo = halo ? 1 : 0, pp.epi = epi, pp.num_sms = num_sms, pp.device = dev;
   return FG_OK;
 }
