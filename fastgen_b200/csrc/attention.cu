@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged issuer warp, one elected lane issues (see umma_bf16_ss_elect)
+      const uint32_t elected = elect_one_sync();
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kQRows, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kQRows, DP, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -159,9 +160,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         for (int dc = 0; dc < Cfg::DC; ++dc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + dc * kQRows * 128 + k * 32),
+            umma_bf16_ss_elect(elected, d_tmem, umma_desc_sw128(q_addr + dc * kQRows * 128 + k * 32),
                          umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk, (dc | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+        umma_commit_elect(elected, &s_full[s]);
       };
       mbar_wait(q_full, 0);
       if (nkv) issue_qk(0);
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         const uint32_t v_addr = smem_u32(sKV + s * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16_ss(tmem_base + Cfg::TMEM_O, umma_desc_sw128(p_addr + (kk >> 2) * kQRows * 128 + (kk & 3) * 32),
+          umma_bf16_ss_elect(elected, tmem_base + Cfg::TMEM_O, umma_desc_sw128(p_addr + (kk >> 2) * kQRows * 128 + (kk & 3) * 32),
                        umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv, (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
+        umma_commit_elect(elected, &kv_empty[s]);
+        umma_commit_elect(elected, pv_done);
       }
     }
   } else {

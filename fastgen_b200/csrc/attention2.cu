@@ -23,6 +23,17 @@ namespace fg {
 
 constexpr int kA2BKV = 128;
 
+#ifdef FG_ATTN_TIMING
+// Experiment build only (profiles/experiments/attn_phase_timing.py): clocks per softmax phase of one CTA, summed over its
+// key tiles -- [tile t][wait S, TMEM read, max (+ rescale), exp + P stores, store wait + publish, tiles].
+__device__ unsigned long long g_attn_timing[2][8];
+// [tile][key tile 2..5][P published, issuer saw it, issuer done issuing, next S seen by the softmax warp] (SM clock)
+__device__ long long g_attn_trace[2][4][4];
+#define FG_TSTAMP(var) const long long var = clock64()
+#else
+#define FG_TSTAMP(var)
+#endif
+
 template <int DP>
 struct Attn2Cfg {
   static constexpr int DC = DP / 64;
@@ -235,8 +246,10 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && nkv > 0) {
+    // ===================== MMA issuer =====================
+    // the whole warp runs the loop (converged: uniform operands, no per-MMA broadcast loop); one elected lane issues
+    if (nkv > 0) {
+      const uint32_t elected = elect_one_sync();
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DP, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -248,9 +261,9 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         for (int dc = 0; dc < Cfg::DC; ++dc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
+            umma_bf16_ss_elect(elected, d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
                          umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk, (dc | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[2 * t]);
+        umma_commit_elect(elected, &s_full[2 * t]);
       };
       auto issue_pv = [&](int t, int stage, int j) {
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
@@ -258,9 +271,9 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16_ts(o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv,
+          umma_bf16_ts_elect(elected, o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv,
                        (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&pv_done[2 * t]);
+        umma_commit_elect(elected, &pv_done[2 * t]);
       };
       // half-tile pipeline: per key tile j and half h, O_t += P_th.V_j[h] then S_th <- Q_t.K_{j+1}[h]^T for both tiles
       constexpr uint32_t idesc_qk_h = umma_idesc_bf16(128, 64, 0, 0);
@@ -272,9 +285,9 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         for (int dc = 0; dc < Cfg::DC; ++dc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
+            umma_bf16_ss_elect(elected, d_tmem, umma_desc_sw128(qa + dc * 128 * 128 + k * 32),
                          umma_desc_sw128(k_addr + dc * BKV * 128 + k * 32), idesc_qk_h, (dc | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[2 * t + h]);
+        umma_commit_elect(elected, &s_full[2 * t + h]);
       };
       auto issue_pv_h = [&](int t, int h, int stage, int j) {
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
@@ -282,9 +295,9 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128 + h * 64);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + (h * 4 + kk) * 2048, BKV * 128), idesc_pv,
+          umma_bf16_ts_elect(elected, o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + (h * 4 + kk) * 2048, BKV * 128), idesc_pv,
                        (j | h | kk) != 0 ? 1u : 0u);
-        umma_commit(&pv_done[2 * t + h]);
+        umma_commit_elect(elected, &pv_done[2 * t + h]);
       };
       if constexpr (HALF) {
         mbar_wait(q_full, 0);
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         issue_qk_h(1, 0, 0);
         issue_qk_h(0, 1, 0);
         issue_qk_h(1, 1, 0);
-        umma_commit(&kv_empty[0]);  // K_0 has no further reader
+        umma_commit_elect(elected, &kv_empty[0]);  // K_0 has no further reader
         int stage = 0;
         uint32_t phase = 0;
         for (int j = 0; j < nkv; ++j) {
@@ -313,14 +326,14 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
               mbar_wait(&p_full[2 * t + h], j & 1);
               tc_fence_after();
               issue_pv_h(t, h, stage, j);
-              if (h == 1 && t == 1) umma_commit(&v_empty[stage]);  // every reader of V_j has been issued
+              if (h == 1 && t == 1) umma_commit_elect(elected, &v_empty[stage]);  // every reader of V_j has been issued
               if (more) {
                 if (h == 0 && t == 0) {
                   mbar_wait(&kv_full[nstage], nphase);
                   tc_fence_after();
                 }
                 issue_qk_h(t, h, nstage);  // overwrites P_th: issued after the product that reads it
-                if (h == 1 && t == 1) umma_commit(&kv_empty[nstage]);  // every reader of K_{j+1} has been issued
+                if (h == 1 && t == 1) umma_commit_elect(elected, &kv_empty[nstage]);  // every reader of K_{j+1} has been issued
               }
             }
           }
@@ -346,18 +359,31 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         // query tile 0: O0 += P0.V_j, then S0 <- Q0.K_{j+1}^T (overwrites P0: issued after the product that reads it)
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
+#ifdef FG_ATTN_TIMING
+        const bool trc = blockIdx.x == gridDim.x / 2 && j >= 2 && j < 6;
+        if (trc) g_attn_trace[0][j - 2][1] = clock64();
+#endif
         issue_pv(0, stage, j);
         if (more) {
           mbar_wait(&kv_full[nstage], nphase);
           tc_fence_after();
           issue_qk(0, nstage);
         }
+#ifdef FG_ATTN_TIMING
+        if (trc) g_attn_trace[0][j - 2][2] = clock64();
+#endif
         // query tile 1
         mbar_wait(&p_full[2], j & 1);
         tc_fence_after();
+#ifdef FG_ATTN_TIMING
+        if (trc) g_attn_trace[1][j - 2][1] = clock64();
+#endif
         issue_pv(1, stage, j);
-        umma_commit(&kv_empty[stage]);  // every reader of K_j / V_j has been issued before this commit
+        umma_commit_elect(elected, &kv_empty[stage]);  // every reader of K_j / V_j has been issued before this commit
         if (more) issue_qk(1, nstage);
+#ifdef FG_ATTN_TIMING
+        if (trc) g_attn_trace[1][j - 2][2] = clock64();
+#endif
         stage = nstage;
         phase = nphase;
       }
@@ -642,9 +668,14 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         if (lane == 0) mbar_arrive(&p_full[2 * t + h]);
       }
     } else {
+#ifdef FG_ATTN_TIMING
+    long long tacc[5] = {0, 0, 0, 0, 0};
+#endif
     for (int j = 0; j < nkv; ++j) {
+      FG_TSTAMP(ts0);
       mbar_wait(&s_full[2 * t], j & 1);
       tc_fence_after();
+      FG_TSTAMP(ts1);
       uint32_t sv[BKV];
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) {
@@ -652,6 +683,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         tmem_ld_32x32(s_addr + c, chunk);
       }
       tmem_ld_wait();
+      FG_TSTAMP(ts2);
       const int seg = (jb + j) >= n0;
       const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
       int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
@@ -696,6 +728,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       } else {
         m_run = mx;
       }
+      FG_TSTAMP(ts3);
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
       uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};  // independent chains
@@ -723,11 +756,26 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       float lsum0, lsum1;
       unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
       l_run += lsum0 + lsum1;
+      FG_TSTAMP(ts4);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * t]);
+#ifdef FG_ATTN_TIMING
+      const long long ts5 = clock64();
+      tacc[0] += ts1 - ts0, tacc[1] += ts2 - ts1, tacc[2] += ts3 - ts2, tacc[3] += ts4 - ts3, tacc[4] += ts5 - ts4;
+      if (blockIdx.x == gridDim.x / 2 && q == 0 && lane == 0) {
+        if (j >= 2 && j < 6) g_attn_trace[t][j - 2][0] = ts5;
+        if (j >= 3 && j < 7) g_attn_trace[t][j - 3][3] = ts1;
+      }
+#endif
     }
+#ifdef FG_ATTN_TIMING
+    if (blockIdx.x == gridDim.x / 2 && q == 0 && lane == 0) {
+      for (int i = 0; i < 5; ++i) g_attn_timing[t][i] = tacc[i];
+      g_attn_timing[t][5] = nkv;
+    }
+#endif
     }  // !HALF
     // ---- epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ----
     if (nkv) {
@@ -935,7 +983,12 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
 
 // called by fg_flash_attn after argument validation
 int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
-  static const int poly = getenv("FG_ATTN_POLY") ? atoi(getenv("FG_ATTN_POLY")) : 2;  // (0|2|3|4: tuning experiments)
+  // share of the exponentials taken by the FMA-pipe polynomial (pairs out of 8; FG_ATTN_POLY=0|2|3|4 overrides).  Since
+  // the MMA issuer runs converged (profiles/attn_r02.md) the d = 128 kernel is bound by the tensor pipe and the fewest
+  // instructions win: all exponentials on the MUFU unit (+3..4 % over 2/8); at d = 64 the softmax warps are the bound
+  // and 2/8 is still the best split (535 vs 522 TFLOP/s at 0/8, 507 at 3/8 on the EDM 32x32 shape).
+  static const int poly_env = getenv("FG_ATTN_POLY") ? atoi(getenv("FG_ATTN_POLY")) : -1;
+  const int poly = poly_env >= 0 ? poly_env : (p->d <= 64 ? 2 : 0);
   // half-tile pipeline: opt-in experiment (FG_ATTN_HALF=1).  Measured on B200 it is SLOWER at d = 128 (816 vs 1017 TFLOP/s
   // on the Wan chunk-6 shape: the N = 64 S products run at half the tensor-pipe efficiency) and equal at d = 64, where
   // the softmax warps are bound by dependent-issue latency, not by the wait for S (profiles/attn_r01.md).
@@ -972,3 +1025,12 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
 }
 
 }  // namespace fg
+
+#ifdef FG_ATTN_TIMING
+extern "C" int fg_debug_attn_timing(unsigned long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fg::g_attn_timing, sizeof(fg::g_attn_timing)));
+}
+extern "C" int fg_debug_attn_trace(long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fg::g_attn_trace, sizeof(fg::g_attn_trace)));
+}
+#endif

@@ -166,6 +166,45 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same instructions for an issuer warp that stays CONVERGED: every lane executes the call with warp-uniform
+// operands and only the lane with `elected != 0` (elect_one_sync) issues.  Inside an `if (lane == 0)` region the compiler
+// cannot prove the descriptor registers uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// (~20 instructions and several R2UR latencies per MMA: ~90 clocks per issue on a scheduler shared with two softmax
+// warps, measured in profiles/attn_r02.md); with converged control flow the operands live in uniform registers.
+__device__ __forceinline__ void umma_bf16_ss_elect(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t elected, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(elected)
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -226,6 +265,29 @@ __device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t cta_mask) {
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+// converged-issuer forms (see umma_bf16_ss_elect)
+__device__ __forceinline__ void umma_bf16_ss2_elect(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2_elect(uint32_t elected, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(cta_mask), "r"(elected)
+      : "memory");
 }
 // TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier at cluster
 // address `bar_cluster` (the leader's)

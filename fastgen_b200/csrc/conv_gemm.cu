@@ -485,8 +485,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && cr == 0) {
+    // ===================== MMA issuer =====================
+    // the whole warp walks the loop (converged: descriptors stay in uniform registers, no per-MMA broadcast loop -- see
+    // umma_bf16_ss_elect), one elected lane issues
+    if (cr == 0) {
+      const uint32_t elected = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -516,17 +519,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 const uint32_t b_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                  umma_bf16_ss2(d_tmem, umma_desc_sw128_sbo(halo_addr + row0 * 128 + k * 32, sbo),
+                  umma_bf16_ss2_elect(elected, d_tmem, umma_desc_sw128_sbo(halo_addr + row0 * 128 + k * 32, sbo),
                                 umma_desc_sw128(b_addr + k * 32), idesc, (started | k) != 0 ? 1u : 0u);
                 }
                 started = 1;
-                umma_commit2(&empty[stage], 3);
+                umma_commit2_elect(elected, &empty[stage], 3);
                 if (++stage == Cfg::STAGES) {
                   stage = 0;
                   phase ^= 1u;
                 }
               }
-              umma_commit2(&a_empty[hab], 3);   // the halo buffer is free once the last tap's MMAs retire (both CTAs)
+              umma_commit2_elect(elected, &a_empty[hab], 3);   // the halo buffer is free once the last tap's MMAs retire (both CTAs)
               hab ^= 1;
               if (hab == 0) haphase ^= 1u;
             }
@@ -540,22 +543,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if constexpr (CG == 2)
-              umma_bf16_ss2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+              umma_bf16_ss2_elect(elected, d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                             (it | k) != 0 ? 1u : 0u);
             else
-              umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+              umma_bf16_ss_elect(elected, d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                            (it | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot once these MMAs retire (CG = 2: in both CTAs -- each producer waits on its own barrier)
-          if constexpr (CG == 2) umma_commit2(&empty[stage], 3);
-          else umma_commit(&empty[stage]);
+          if constexpr (CG == 2) umma_commit2_elect(elected, &empty[stage], 3);
+          else umma_commit_elect(elected, &empty[stage]);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if constexpr (CG == 2) umma_commit2(&tfull[acc], 3);  // accumulator ready for the epilogue warps of both CTAs
-        else umma_commit(&tfull[acc]);
+        if constexpr (CG == 2) umma_commit2_elect(elected, &tfull[acc], 3);  // accumulator ready for the epilogue warps of both CTAs
+        else umma_commit_elect(elected, &tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
