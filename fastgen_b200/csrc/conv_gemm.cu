@@ -77,6 +77,21 @@ struct ConvCfg {
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
 };
 
+#ifdef FG_CONV_TIMING
+// Experiment build only (profiles/experiments/conv_epilogue_timing.py): SM clocks per epilogue phase of CTA 0, summed over
+// its slabs, for the store thread (warp 2, lane 0) and for a plain epilogue thread (warp 7, lane 0) --
+// [who][wait accumulator, store-thread prologue, residual wait, TMEM read, tail values, smem writes + fence, barrier,
+//  store issue, statistics, slabs].
+__device__ unsigned long long g_conv_timing[2][12];
+#define FG_CT_DECL long long ct_prev = clock64(); unsigned long long ct_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define FG_CT(i) do { const long long ct_now = clock64(); ct_acc[i] += ct_now - ct_prev; ct_prev = ct_now; } while (0)
+#define FG_XDBG(bit) (p.dbg & (bit))   // FG_CONV_DBG bits of the experiment build: 16 no statistics atomics, 32 no shuffles, 64 no column sums, 128 no bias / row-vector loads
+#else
+#define FG_CT_DECL
+#define FG_CT(i)
+#define FG_XDBG(bit) false
+#endif
+
 struct ConvKParams {
   CUtensorMap tmA[FG_MAX_SEG];
   CUtensorMap tmW[FG_MAX_SEG];
@@ -88,6 +103,7 @@ struct ConvKParams {
   int32_t N, H, W, Cout;
   int32_t BW, BH, BNI;  // TMA box in pixels, BW*BH*BNI == 128
   int32_t tiles_w, tiles_h, tiles_img, tiles_n, total_tiles;
+  uint32_t magic_tiles_n, magic_tiles_w, magic_tiles_h;   // fast_div multipliers of decode_tile (0: divide)
   int32_t k_iters;
   int32_t vec;  // generic epilogue: every access may use 4-element vectors
   int32_t dbg;  // FG_CONV_DBG bit mask (profiling experiments only; results are wrong when non-zero)
@@ -110,21 +126,36 @@ struct ConvKParams {
   int32_t stats_groups, stats_cg, stats_ch0;
   double* stats2;  // second consumer of the same output (the decoder GroupNorm that reads it inside a skip concatenation)
   int32_t stats2_groups, stats2_cg, stats2_ch0;
+  // group index of a channel without an integer division: g = umulhi(ch0 + ch, magic), magic = ceil(2^32 / cg) (exact for
+  // channel numbers below 2^16); span = lanes a group can cover inside a warp (bounds the segmented shuffle reduction)
+  uint32_t stats_magic, stats2_magic;
+  int32_t stats_span, stats2_span;
+  // lean slab loop of the TMA-store epilogues: no activation / gate / plain-load residual / ragged last slab, so a slab is
+  // TMEM read -> + bias (requested one slab ahead) [+ row vector] [+ staged residual] -> scale -> shared memory
+  int32_t lean;
 };
 
 struct TileCoord {
   int w0, h0, img0, co0;
 };
 
+// x / d through one multiplication: magic = ceil(2^32 / d), exact while x * d < 2^32 (the host passes 0 -- plain division
+// -- when a launch cannot guarantee that, and for d == 1)
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t magic) {
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic)) : d == 1 ? x : x / d;
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile, int block_n) {
   TileCoord t;
-  const int n_tile = tile % p.tiles_n;
-  int m_tile = tile / p.tiles_n;
+  int m_tile = fast_div(tile, p.tiles_n, p.magic_tiles_n);
+  const int n_tile = tile - m_tile * p.tiles_n;
   t.co0 = n_tile * block_n;
-  t.w0 = (m_tile % p.tiles_w) * p.BW;
-  m_tile /= p.tiles_w;
-  t.h0 = (m_tile % p.tiles_h) * p.BH;
-  t.img0 = (m_tile / p.tiles_h) * p.BNI;
+  int q = fast_div(m_tile, p.tiles_w, p.magic_tiles_w);
+  t.w0 = (m_tile - q * p.tiles_w) * p.BW;
+  m_tile = q;
+  q = fast_div(m_tile, p.tiles_h, p.magic_tiles_h);
+  t.h0 = (m_tile - q * p.tiles_h) * p.BH;
+  t.img0 = q * p.BNI;
   return t;
 }
 
@@ -276,7 +307,7 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
                                             int w, bool valid, float (&a)[CH]) {
 #pragma unroll
   for (int j = 0; j < CH; ++j) a[j] = __uint_as_float(v[j]);
-  if (p.bias) {
+  if (p.bias && !FG_XDBG(128)) {
 #pragma unroll
     for (int j = 0; j < CH; j += 4) {
       if (c_base + j < p.Cout) {
@@ -285,7 +316,7 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
       }
     }
   }
-  if (p.rowvec && valid) {
+  if (p.rowvec && valid && !FG_XDBG(128)) {
     const float* rv = p.rowvec + img * p.rowvec_ld + c_base;
 #pragma unroll
     for (int j = 0; j < CH; j += 4) {
@@ -339,7 +370,8 @@ __device__ __forceinline__ void tail_values(const ConvKParams& p, const uint32_t
 template <int CG>
 __device__ __forceinline__ int item_tile(const ConvKParams& p, int item, int cta_rank) {
   if constexpr (CG == 1) return item;
-  return (2 * (item / p.tiles_n) + cta_rank) * p.tiles_n + item % p.tiles_n;
+  const int mp = fast_div(item, p.tiles_n, p.magic_tiles_n);
+  return (2 * mp + cta_rank) * p.tiles_n + (item - mp * p.tiles_n);
 }
 
 template <int BLOCK_N, int EPI, int CG = 1, bool HALO = false>
@@ -583,17 +615,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t slab_idx = 0;
     uint32_t ld_idx = 0;  // store thread only: next residual slab to request, its tile and channel offset
     int ld_item = item0, ld_c0 = 0;
+    TileCoord lt = {0, 0, 0, 0};   // decoded tile of ld_item
+    int lt_item = -1;
     const uint32_t wkey = row & 7;
     // residual row inside a quarter-size UP2 box
     const int rs_up = (il * (p.BH >> 1) + (hl >> 1)) * (p.BW >> 1) + (wl >> 1);
 
     const uint32_t lead_tempty[2] = {CG == 2 ? mapa_u32(&tempty[0], 0) : 0u, CG == 2 ? mapa_u32(&tempty[1], 0) : 0u};
+    const int stat_img = ((row >> 5) * 32) / (p.BW * p.BH);   // image (within the tile) of this thread's statistics rows
+    constexpr bool kCanLean = kTmaStore && !kGeglu && kRes != kResUp2;
+    constexpr int kLeanCols = kOutBf16 ? 32 : 16;             // accumulator columns per thread and slab
+    const bool lean = kCanLean && p.lean != 0;
+    float nb[kLeanCols];                                       // lean: bias of the next slab, requested one slab ahead
+    auto lean_bias = [&](int cbase) {
+#pragma unroll
+      for (int j = 0; j < kLeanCols; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+        nb[j] = b.x, nb[j + 1] = b.y, nb[j + 2] = b.z, nb[j + 3] = b.w;
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < kLeanCols; ++j) nb[j] = 0.f;
+    FG_CT_DECL;
     for (int item = item0; item < p.total_tiles; item += item_step) {
       const TileCoord t = decode_tile(p, item_tile<CG>(p, item, cr), BLOCK_N);
       const int img = t.img0 + il, h = t.h0 + hl, w = t.w0 + wl;
       const bool valid = img < p.N;
+      const float* rv_row = nullptr;   // lean: this row's slice of the per-image row vector (rows past the last image
+      if (lean) {                      // read the last image's: the TMA store clips them)
+        if (p.bias) lean_bias(t.co0 + twin * kLeanCols);
+        if (p.rowvec) rv_row = p.rowvec + static_cast<int64_t>(valid ? img : p.N - 1) * p.rowvec_ld;
+      }
+      FG_CT(11);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      FG_CT(0);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       if (p.dbg & 8) {
       } else if constexpr (kTmaStore) {
@@ -609,7 +665,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             tma_store_wait_read<1>();
             if constexpr (kRes != kResNone) {
               while (ld_idx <= slab_idx + kResAhead && ld_item < p.total_tiles) {
-                const TileCoord lt = decode_tile(p, item_tile<CG>(p, ld_item, cr), BLOCK_N);
+                if (ld_item != lt_item) {   // (the divisions of decode_tile once per tile, not once per slab)
+                  lt = decode_tile(p, item_tile<CG>(p, ld_item, cr), BLOCK_N);
+                  lt_item = ld_item;
+                }
                 const uint32_t lrb = ld_idx % Cfg::OUT_SLABS;
                 if constexpr (kRes == kResSame) {
                   mbar_arrive_expect_tx(&res_full[lrb], Cfg::OUT_SLAB_BYTES);
@@ -629,6 +688,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
             }
           }
+          FG_CT(1);
           const uint8_t* rrow = nullptr;
           uint32_t rkey = 0;
           if constexpr (kRes == kResSame) {
@@ -642,13 +702,71 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           uint8_t* my_row = slab + row * 128;
           const float sc = p.out_scale;
-          if constexpr (!kOutBf16 && !kGeglu) {
+          FG_CT(2);
+          if (lean) {
+            if constexpr (kCanLean) {
+              const int cb = t.co0 + c0 + twin * kLeanCols;   // first of this thread's columns
+              const uint32_t my_row_s = smem_u32(my_row);
+              const uint32_t rrow_s = kRes == kResSame ? smem_u32(rrow) : 0u;
+              float rv[kLeanCols];
+              if (rv_row) {
+#pragma unroll
+                for (int j = 0; j < kLeanCols; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(rv_row + cb + j));
+                  rv[j] = b.x, rv[j + 1] = b.y, rv[j + 2] = b.z, rv[j + 3] = b.w;
+                }
+              }
+              uint32_t v[kLeanCols];
+              if constexpr (kOutBf16) tmem_ld_32x32(taddr + c0 + twin * 32, v);
+              else tmem_ld_32x16(taddr + c0 + twin * 16, v);
+              tmem_ld_wait();
+              FG_CT(3);
+              float a[kLeanCols];
+#pragma unroll
+              for (int j = 0; j < kLeanCols; ++j) a[j] = __uint_as_float(v[j]) + nb[j];
+              if (rv_row) {
+#pragma unroll
+                for (int j = 0; j < kLeanCols; ++j) a[j] += rv[j];
+              }
+              // the next slab's bias: in flight during the stores, the barrier and the statistics of this one
+              if (p.bias && c0 + kSlabCols < BLOCK_N && t.co0 + c0 + kSlabCols < p.Cout) lean_bias(cb + kSlabCols);
+              FG_CT(4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t chunk = static_cast<uint32_t>(twin * 4 + j);   // 16-byte chunk of the 128-byte slab row
+                if constexpr (!kOutBf16) {
+                  float4 o = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                  if constexpr (kRes == kResSame) {
+                    const float4 r = lds_v4f(rrow_s + ((chunk ^ rkey) << 4));
+                    o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+                  }
+                  o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+                  sts_v4f(my_row_s + ((chunk ^ wkey) << 4), o);
+                } else {
+                  if constexpr (kRes == kResSame) {
+                    const uint4 r = lds_v4u(rrow_s + ((chunk ^ rkey) << 4));
+                    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
+                                 r3 = unpack_bf16x2(r.w);
+                    a[8 * j] += r0.x, a[8 * j + 1] += r0.y, a[8 * j + 2] += r1.x, a[8 * j + 3] += r1.y;
+                    a[8 * j + 4] += r2.x, a[8 * j + 5] += r2.y, a[8 * j + 6] += r3.x, a[8 * j + 7] += r3.y;
+                  }
+                  uint4 u;
+                  u.x = pack_bf16x2(a[8 * j] * sc, a[8 * j + 1] * sc), u.y = pack_bf16x2(a[8 * j + 2] * sc, a[8 * j + 3] * sc);
+                  u.z = pack_bf16x2(a[8 * j + 4] * sc, a[8 * j + 5] * sc);
+                  u.w = pack_bf16x2(a[8 * j + 6] * sc, a[8 * j + 7] * sc);
+                  sts_v4u(my_row_s + ((chunk ^ wkey) << 4), u);
+                }
+              }
+            }
+          } else if constexpr (!kOutBf16 && !kGeglu) {
             // fp32 slab = 32 accumulator columns: each twin takes 16 of them (four 16-byte chunks of the slab row)
             uint32_t v[16];
             float a[16];
             tmem_ld_32x16(taddr + c0 + twin * 16, v);
             tmem_ld_wait();
+            FG_CT(3);
             tail_values<kRes, 16>(p, v, t.co0 + c0 + twin * 16, img, h, w, valid, a);
+            FG_CT(4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int chunk = twin * 4 + j;
@@ -662,13 +780,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
 #pragma unroll
-          for (int cc = twin * (kSlabCols / 2); cc < (twin + 1) * (kSlabCols / 2) && (kOutBf16 || kGeglu); cc += 32) {
+          for (int cc = twin * (kSlabCols / 2); cc < (twin + 1) * (kSlabCols / 2) && (kOutBf16 || kGeglu) && !lean; cc += 32) {
             uint32_t v[32];
             float a[32];
             if (!(p.dbg & 2)) {
               tmem_ld_32x32(taddr + c0 + cc, v);
               tmem_ld_wait();
+              FG_CT(3);
               tail_values<kRes>(p, v, t.co0 + c0 + cc, img, h, w, valid, a);
+              FG_CT(4);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) a[j] = 1.0f;
@@ -719,58 +839,75 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
             }
           }
-          fence_proxy_async_smem();
+          if (!FG_XDBG(256)) fence_proxy_async_smem();
+          FG_CT(5);
           named_bar_sync(1, 256);
+          FG_CT(6);
           if (is_store_thread && !(p.dbg & 1)) {
             tma_store_4d(&p.tmOut, slab, kGeglu ? ((t.co0 + c0) >> 1) : (t.co0 + c0), t.w0, t.h0, t.img0);
             tma_store_commit();
           }
-          if constexpr (!kOutBf16) {
+          FG_CT(7);
+          if constexpr (!kGeglu) {
             if (p.stats) {
               // GroupNorm statistics of the finished slab (the next consumer's fg_gn_stats pass disappears): thread
               // (row block rb, column, twin) sums 16 rows of one column out of shared memory (the twins halve the
               // dependent load chain), runs of lanes that fall into the same group are combined with a segmented
-              // shuffle reduction, one fp64 atomic pair per run and twin.
+              // shuffle reduction, one fp64 atomic pair per run and twin.  A bf16 slab holds 64 columns: a thread then
+              // owns a PAIR of adjacent columns (one 4-byte word per row; the host checks that a pair never straddles
+              // two groups) and sums the rounded values, i.e. exactly what the consumer's fg_gn_apply will read.
               const int col = row & 31, rb = row >> 5;
-              const int ch = t.co0 + c0 + col;
-              const int simg = t.img0 + (rb * 32) / (p.BW * p.BH);
+              const int ch = t.co0 + c0 + col * (kOutBf16 ? 2 : 1);
+              const int simg = t.img0 + stat_img;
               float s1 = 0.f, s2 = 0.f;
-              if (ch < p.Cout && simg < p.N) {
-                const uint8_t* base = slab + (rb * 32 + twin * 16) * 128 + (col & 3) * 4;
+              if (ch < p.Cout && simg < p.N && !FG_XDBG(64)) {
+                const uint32_t base = smem_u32(slab) + (rb * 32 + twin * 16) * 128 + (col & 3) * 4;
                 const uint32_t cchunk = static_cast<uint32_t>(col >> 2);
                 float t1 = 0.f, t2 = 0.f;   // two independent chains
 #pragma unroll
                 for (int r = 0; r < 16; r += 2) {   // (twin * 16 + r) & 7 == r & 7: the swizzle key of the row
-                  const float v = *reinterpret_cast<const float*>(base + r * 128 + ((cchunk ^ (r & 7)) << 4));
-                  const float u = *reinterpret_cast<const float*>(base + (r + 1) * 128 + ((cchunk ^ ((r + 1) & 7)) << 4));
-                  s1 += v, t1 += u;
-                  s2 = fmaf(v, v, s2), t2 = fmaf(u, u, t2);
+                  if constexpr (kOutBf16) {
+                    const float2 v = unpack_bf16x2(lds_u(base + r * 128 + ((cchunk ^ (r & 7)) << 4)));
+                    const float2 u = unpack_bf16x2(lds_u(base + (r + 1) * 128 + ((cchunk ^ ((r + 1) & 7)) << 4)));
+                    s1 += v.x + v.y, t1 += u.x + u.y;
+                    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2)), t2 = fmaf(u.x, u.x, fmaf(u.y, u.y, t2));
+                  } else {
+                    const float v = lds_f(base + r * 128 + ((cchunk ^ (r & 7)) << 4));
+                    const float u = lds_f(base + (r + 1) * 128 + ((cchunk ^ ((r + 1) & 7)) << 4));
+                    s1 += v, t1 += u;
+                    s2 = fmaf(v, v, s2), t2 = fmaf(u, u, t2);
+                  }
                 }
                 s1 += t1, s2 += t2;
               }
               // the column sums feed up to two group layouts: this tensor's own next norm and, for a tensor that is also
               // a skip connection, the decoder norm that reads it at channel offset stats2_ch0 of a concatenation
-              auto reduce_groups = [&](double* base, int groups, int cg, int ch0) {
+              auto reduce_groups = [&](double* base, int groups, uint32_t magic, int span, int ch0) {
                 float r1 = s1, r2 = s2;
-                const int g = (ch < p.Cout) ? (ch0 + ch) / cg : -1 - col;  // invalid lanes: singleton runs
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
+                const int g = (ch < p.Cout) ? static_cast<int>(__umulhi(static_cast<uint32_t>(ch0 + ch), magic))
+                                            : -1 - col;  // invalid lanes: singleton runs
+#pragma unroll 1
+                for (int off = 1; off < span && !FG_XDBG(32); off <<= 1) {   // lanes >= span apart never share a group
                   const float o1 = __shfl_down_sync(0xffffffffu, r1, off);
                   const float o2 = __shfl_down_sync(0xffffffffu, r2, off);
                   const int og = __shfl_down_sync(0xffffffffu, g, off);
                   if (lane + off < 32 && og == g) r1 += o1, r2 += o2;
                 }
                 const int pg = __shfl_up_sync(0xffffffffu, g, 1);
-                if ((lane == 0 || pg != g) && g >= 0 && simg < p.N) {
+                if ((lane == 0 || pg != g) && g >= 0 && simg < p.N && !FG_XDBG(16)) {
                   double* dst = base + (static_cast<int64_t>(simg) * groups + g) * 2;
                   atomicAdd(dst, static_cast<double>(r1));
                   atomicAdd(dst + 1, static_cast<double>(r2));
                 }
               };
-              reduce_groups(p.stats, p.stats_groups, p.stats_cg, p.stats_ch0);
-              if (p.stats2) reduce_groups(p.stats2, p.stats2_groups, p.stats2_cg, p.stats2_ch0);
+              reduce_groups(p.stats, p.stats_groups, p.stats_magic, p.stats_span, p.stats_ch0);
+              if (p.stats2) reduce_groups(p.stats2, p.stats2_groups, p.stats2_magic, p.stats2_span, p.stats2_ch0);
             }
           }
+          FG_CT(8);
+#ifdef FG_CONV_TIMING
+          ++ct_acc[9];
+#endif
         }
       } else if constexpr (BLOCK_N >= 32) {
 #pragma unroll 1
@@ -798,6 +935,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       if (acc == 0) acc_phase ^= 1u;
     }
     if (kTmaStore && is_store_thread) tma_store_wait<0>();
+#ifdef FG_CONV_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 7)) {
+      for (int i = 0; i < 12; ++i) g_conv_timing[warp == 2 ? 0 : 1][i] = ct_acc[i];
+    }
+#endif
   }
 
   tc_fence_before();
@@ -1083,6 +1225,15 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   }
   kp.tiles_n = (p->cout + block_n - 1) / block_n;
   kp.total_tiles = ((m_tiles + cg - 1) / cg) * kp.tiles_n;   // work items: tiles, or tile pairs of a CTA pair
+  {
+    // decode_tile without integer divisions (largest dividend: a tile index of the padded tile grid)
+    const int64_t max_tile = static_cast<int64_t>(m_tiles + cg) * kp.tiles_n;
+    auto magic_of = [&](int d) -> uint32_t {
+      if (d <= 1 || max_tile * d >= (1ll << 32)) return 0u;
+      return static_cast<uint32_t>(((1ull << 32) + d - 1) / d);
+    };
+    kp.magic_tiles_n = magic_of(kp.tiles_n), kp.magic_tiles_w = magic_of(kp.tiles_w), kp.magic_tiles_h = magic_of(kp.tiles_h);
+  }
 
   kp.nseg = p->nseg;
   kp.k_iters = 0;
@@ -1134,14 +1285,27 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   kp.out_ld = p->out_ld;
   FG_CHECK_ARG(!p->stats2 || p->stats, "conv_gemm: stats2 without stats (use stats for a single consumer)");
   if (p->stats) {
-    FG_CHECK_ARG(p->out_dtype == FG_F32 && p->stats_groups > 0 && p->stats_cg > 0 && p->stats_ch0 >= 0,
-                 "conv_gemm: fused GroupNorm statistics need an fp32 output, stats_groups > 0, stats_cg > 0");
+    FG_CHECK_ARG(p->stats_groups > 0 && p->stats_cg > 0 && p->stats_ch0 >= 0,
+                 "conv_gemm: fused GroupNorm statistics need stats_groups > 0, stats_cg > 0, stats_ch0 >= 0");
+    // bf16 output: the epilogue sums pairs of adjacent columns, which must fall into one group
+    FG_CHECK_ARG(p->out_dtype == FG_F32 || (p->act != FG_ACT_GEGLU && p->stats_cg % 2 == 0 && p->stats_ch0 % 2 == 0 &&
+                                            (!p->stats2 || (p->stats2_cg % 2 == 0 && p->stats2_ch0 % 2 == 0))),
+                 "conv_gemm: fused GroupNorm statistics of a bf16 output need even group widths and channel offsets");
     FG_CHECK_ARG(kp.BW * kp.BH >= 32, "conv_gemm: fused GroupNorm statistics need images of at least 32 pixels");
     kp.stats = p->stats, kp.stats_groups = p->stats_groups, kp.stats_cg = p->stats_cg, kp.stats_ch0 = p->stats_ch0;
+    // group index by multiplication (see ConvKParams::stats_magic) and the lanes a group spans in the epilogue's warps
+    auto magic_of = [](int cg) { return static_cast<uint32_t>(((1ull << 32) + cg - 1) / cg); };
+    auto span_of = [&](int cg) { const int l = p->out_dtype == FG_F32 ? cg : cg / 2; return l > 32 ? 32 : l; };
+    FG_CHECK_ARG(p->stats_cg >= 2 && (!p->stats2 || p->stats2_cg >= 2), "conv_gemm: fused GroupNorm statistics need groups of at least 2 channels");
+    FG_CHECK_ARG(static_cast<int64_t>(p->stats_ch0 + p->cout) * p->stats_cg < (1ll << 32) &&
+                     (!p->stats2 || static_cast<int64_t>(p->stats2_ch0 + p->cout) * p->stats2_cg < (1ll << 32)),
+                 "conv_gemm: fused GroupNorm statistics: channel range too large");
+    kp.stats_magic = magic_of(p->stats_cg), kp.stats_span = span_of(p->stats_cg);
     if (p->stats2) {
       FG_CHECK_ARG(p->stats2_groups > 0 && p->stats2_cg > 0 && p->stats2_ch0 >= 0,
                    "conv_gemm: stats2 needs stats2_groups > 0, stats2_cg > 0, stats2_ch0 >= 0");
       kp.stats2 = p->stats2, kp.stats2_groups = p->stats2_groups, kp.stats2_cg = p->stats2_cg, kp.stats2_ch0 = p->stats2_ch0;
+      kp.stats2_magic = magic_of(p->stats2_cg), kp.stats2_span = span_of(p->stats2_cg);
     }
   }
   FG_CHECK_ARG(kp.res_mode >= FG_RES_NONE && kp.res_mode <= FG_RES_DOWN2, "conv_gemm: bad res_mode %d", kp.res_mode);
@@ -1178,6 +1342,10 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
         res_kind = up ? kResUp2 : kResSame;
       }
       epi = geglu ? kEpiGeglu : epi_mode(p->out_dtype == FG_BF16, res_kind);
+      static const bool allow_lean = !(getenv("FG_CONV_LEAN") && getenv("FG_CONV_LEAN")[0] == '0');
+      kp.lean = allow_lean && !geglu && p->act == FG_ACT_NONE && !p->gate && res_kind != kResUp2 &&
+                (kp.res_mode == FG_RES_NONE || res_kind == kResSame) && p->cout % (128 / esz) == 0 &&
+                (!p->bias || aligned16(p->bias)) && (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0));
     }
   }
   if (geglu) FG_CHECK_ARG(epi == kEpiGeglu, "conv_gemm: FG_ACT_GEGLU needs the TMA-store epilogue (16-byte aligned bf16 output rows)");
@@ -1186,3 +1354,9 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
   pp.block_n = block_n, pp.cg = cg, pp.halo = halo ? 1 : 0, pp.epi = epi, pp.num_sms = num_sms, pp.device = dev;
   return FG_OK;
 }
+
+#ifdef FG_CONV_TIMING
+extern "C" int fg_debug_conv_timing(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, fg::g_conv_timing, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -275,6 +275,7 @@ class _Plan:
         self.net, self.n = net, n
         self.dev = next(net.parameters()).device
         self.x3 = net.compute == "bf16x3"
+        self.h1_bf16 = (not self.x3) and bool(net.bf16_h1)
         self.attn_f32 = self.x3 and net.x3_attention == "f32"   # fp32 CUDA-core attention on the fp32-parity path
         self._warned_widths: Set[int] = set()
         self.steps: List[Tuple[Any, tuple]] = []
@@ -322,7 +323,9 @@ class _Plan:
         last = list(m.dec.values())
         c_last = [b for b in last if isinstance(b, _Block)][-1].out_channels
         req("h0", n * R * R * c_last)
-        f32_roles = ("h1", "mid", "qkv_f32")
+        # h1 (conv0's output) is read by norm1 only: on the bf16 path it is stored as bf16 (statistics of the rounded values
+        # from the producer's epilogue), which takes a third off norm1's HBM traffic and half off conv0's stores
+        f32_roles = ("mid", "qkv_f32") if self.h1_bf16 else ("h1", "mid", "qkv_f32")
         self._scratch_buf: Dict[str, torch.Tensor] = {}
         for name, numel in need.items():
             dt = torch.float32 if name in f32_roles else torch.bfloat16
@@ -375,10 +378,12 @@ class _Plan:
         assert i < self.stats_arena.shape[0], "planner bug: statistics arena too small"
         return self.stats_arena[i]
 
-    def fused_stats(self, h: int, w: int, cout: int, out_ld: int, norm: "_GroupNorm", c_norm: int):
+    def fused_stats(self, h: int, w: int, cout: int, out_ld: int, norm: "_GroupNorm", c_norm: int, bf16_out: bool = False):
         """kwargs that make a conv accumulate the GroupNorm statistics `norm` needs of its output, or None when the
         producer cannot (tiny images, narrow or unaligned outputs): the consumer then runs fg_gn_stats itself."""
         if not self.net.fuse_gn_stats or h * w < 32 or cout % 4 or cout <= 16 or out_ld % 4 or cout != c_norm:
+            return None
+        if bf16_out and ((c_norm // norm.num_groups) % 2 or out_ld % 8):   # the epilogue sums column pairs of a bf16 slab
             return None
         slot = self.new_stats()
         return dict(stats=slot, stats_groups=norm.num_groups, stats_cg=c_norm // norm.num_groups, stats_ch0=0)
@@ -651,7 +656,7 @@ class _Plan:
         kw = {}
         if not b.adaptive_scale:
             kw = dict(rowvec=aff, rowvec_ld=self.affine.shape[1])
-        st1 = self.fused_stats(ho, wo, cout, cout, b.norm1, cout)
+        st1 = self.fused_stats(ho, wo, cout, cout, b.norm1, cout, bf16_out=self.h1_bf16)
         self.conv(self.segs3(h0, h0_lo, cin, w0["hi"], w0.get("lo"), cin, 9), n, ho, wo, cout, h1, cout, bias=w0["bias"],
                   **kw, **(st1 or {}))
         s1 = st1["stats"] if st1 else None
@@ -759,6 +764,7 @@ class EDMPrecond(FastGenNetwork):
         self.sigma_data, self.sigma_shift, self.drop_precond = sigma_data, sigma_shift, drop_precond
         self.compute = compute
         self.fuse_gn_stats = True   # GroupNorm statistics accumulated by the conv that writes the tensor
+        self.bf16_h1 = os.environ.get("FASTGEN_B200_BF16_H1", "1") != "0"   # conv0 -> norm1 tensor in bf16 (compute="bf16")
         # attention of the "bf16x3" path: "bf16" = the tensor-core kernel (q, k, v, softmax weights rounded to bf16:
         # ~1e-3 of the fp32 reference), "f32" = fg_attention_f32 (CUDA cores; profiles/x3_emulation.py predicts ~1e-5)
         if _X3_ATTENTION_DEFAULT not in ("f32", "bf16"):

@@ -197,8 +197,10 @@ def test_linear_activation_gate_residual(rows, k, n, out_dtype, act, gate_rows, 
     (6, 64, 64, 32, 384, 9, 32, 0, 384, True),
     (16, 16, 16, 64, 320, 1, 32, 64, 576, False),    # channels [64, 384) of a wider normalised tensor, ragged N tile
 ])
-def test_conv_gemm_fused_groupnorm_statistics(n, h, w, cin, cout, taps, groups, ch0, ctot, res):
-    """the conv epilogue accumulates per (image, group) sum / sum of squares of its fp32 output"""
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_conv_gemm_fused_groupnorm_statistics(n, h, w, cin, cout, taps, groups, ch0, ctot, res, out_dtype):
+    """the conv epilogue accumulates per (image, group) sum / sum of squares of its output (fp32, or the ROUNDED values of
+    a bf16 output -- what the consumer's fg_gn_apply reads -- summed as pairs of adjacent columns)"""
     from fastgen_b200 import ops
 
     torch.manual_seed(9)
@@ -209,9 +211,9 @@ def test_conv_gemm_fused_groupnorm_statistics(n, h, w, cin, cout, taps, groups, 
     bias = torch.randn(cout, device=dev)
     kw = {}
     if res:
-        r = torch.randn(n, h, w, cout, device=dev)
+        r = torch.randn(n, h, w, cout, device=dev).to(out_dtype)
         kw = dict(res=r, res_ld=cout, res_mode=1)
-    out = torch.empty(n, h, w, cout, device=dev)
+    out = torch.empty(n, h, w, cout, device=dev, dtype=out_dtype)
     stats = torch.zeros(n, groups, 2, device=dev, dtype=torch.float64)
     cg = ctot // groups
     ops.conv_gemm([ops.Seg(_nhwc(x), cin, wt.permute(0, 2, 3, 1).contiguous(), cin, taps)], n, h, w, cout, out, cout,
