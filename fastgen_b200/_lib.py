@@ -55,6 +55,7 @@ class GnApplyParams(C.Structure):
         ("silu", C.c_int32), ("resample", C.c_int32),
         ("y", C.c_void_p), ("y_ld", C.c_int64), ("y_lo", C.c_void_p),
         ("raw", C.c_void_p), ("raw_ld", C.c_int64), ("raw_lo", C.c_void_p),
+        ("raw_f32", C.c_void_p), ("raw_f32_ld", C.c_int64),
     ]
 
 

@@ -41,7 +41,10 @@ struct Attn2Cfg {
   static constexpr int KV_TILE_BYTES = DC * kA2BKV * 128;
   static constexpr int STAGES = DP == 128 ? 2 : 4;
   static constexpr int XCH_BYTES = 3 * 2 * 2 * 128 * 4;  // WG == 2: row max (two parities) and row sum of the column halves
-  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + STAGES * 2 * KV_TILE_BYTES + 1024 + 256 + XCH_BYTES;
+  // BX > 0 (row sum taken by the P.V product): a 16-key slice of a "ones atom" -- 16 rows x 128 B, 1.0 in column 0 --
+  // that every P.V MMA reads as V's columns [64, 80) through its descriptor's leading-dimension offset
+  static constexpr int ONES_BYTES = 2048;
+  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + STAGES * 2 * KV_TILE_BYTES + ONES_BYTES + 1024 + 256 + XCH_BYTES;
   static constexpr int TMEM_S = 0;        // S0 at 0, S1 at 128 (P aliases the first 64 columns of each)
   static constexpr int TMEM_O = 256;      // O0 at 256, O1 at 256 + DP
   static constexpr int TMEM_COLS = 512;
@@ -101,6 +104,14 @@ __device__ __forceinline__ float exp2_mufu(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair in ONE MUFU issue: the arguments are rounded to bf16 first and the result arrives packed as bf16x2 -- the
+// format P is stored in (profiles/attn_r01.md: what that rounding costs in accuracy)
+__device__ __forceinline__ uint32_t exp2_bf16x2(float x0, float x1) {
+  uint32_t xb, y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb) : "f"(x1), "f"(x0));
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(xb));
+  return y;
+}
 // 2^x for a pair, on the FMA pipe: x = n + f with f in [-0.5, 0.5] (adding 1.5 * 2^23 rounds to the nearest integer
 // and leaves n in the low mantissa bits), 2^f by a degree-3 polynomial (max relative error 1.8e-4; the result is
 // rounded to bf16 anyway), 2^n by adding n << 23 to the exponent field -- (bits(x + magic) << 23) is exactly n << 23.
@@ -133,17 +144,35 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 // column halves (a warp may only touch its own 32 TMEM lanes, so the split has to be along the columns), exchange their
 // row maxima through shared memory once per key tile (64-thread named barrier per quarter pair), keep partial row sums
 // and share the O columns in the rare rescale and in the epilogue.
-template <int DP, int POLY, int HALF, int WG = 1>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+//
+// BX (d <= 64 only; pairs out of every 8 whose exponential is the packed bf16 MUFU form): the softmax warps of the d = 64
+// problems are bound by their own instruction stream (profiles/attn_phase_timing_r02.txt: 1 850 of the 3 270 clocks of a key
+// tile are the exp + pack loop), so (a) those pairs cost FFMA2 + CVT + MUFU for two keys and (b) the row sum leaves the
+// warps altogether: V gets a 65th column of ones (read from a constant shared-memory slice through the descriptor's
+// leading-dimension offset, N = 80), so column 64 of the O accumulator IS the row sum of the bf16-rounded weights -- the
+// same weights the numerator uses -- and the lazy rescale covers it like any other O column.
+//
+// PP (ping-pong): the softmax warps of the two query tiles that share a scheduler (warps w and w + 4) pass a token through
+// a pair of 64-thread named barriers so that their exp loops never overlap: the 16 / clk MUFU unit is what the two loops
+// compete for, and a warp that has it to itself finishes in half the time while its partner waits for S, reads it and
+// takes the row max.
+template <int DP, int POLY, int HALF, int WG = 1, int BX = 0, int PP = 0>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
 __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+  static_assert(PP == 0 || (HALF == 0 && WG == 1), "ping-pong: full tiles, WG = 1");
   static_assert(WG == 1 || (WG == 2 && HALF == 0), "two warps per lane quarter: full-tile pipeline only");
+  static_assert(BX == 0 || (DP == 64 && HALF == 0 && WG == 1 && POLY + BX <= 8 && BX >= -1), "ones column: d <= 64, full tiles, WG = 1");
   using Cfg = Attn2Cfg<DP>;
+  constexpr bool ONES = BX != 0;           // BX = -1: the ones column alone (every exponential in fp32)
+  constexpr int OW = DP + (ONES ? 16 : 0);   // accumulator columns per query tile (O, then the row sum)
+  static_assert(Cfg::TMEM_O + 2 * OW <= 512, "TMEM budget");
   constexpr int BKV = kA2BKV;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                               // tile t at t * Q_TILE_BYTES
   uint8_t* sKV = sQ + 2 * Cfg::Q_TILE_BYTES;        // stage s: K at s*2*KV_TILE_BYTES, V right after
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + S * 2 * Cfg::KV_TILE_BYTES);
+  uint8_t* sOnes = sKV + S * 2 * Cfg::KV_TILE_BYTES;   // 1024-aligned like every tile in front of it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::ONES_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;        // [S]
   uint64_t* kv_empty = kv_full + S;    // [S]
@@ -201,6 +230,15 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  if constexpr (ONES) {
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // one 16-byte chunk each: row r holds 1.0 (bf16) in logical column 0,
+      const int i = threadIdx.x - 64, r = i >> 3, ch = i & 7;   // i.e. in chunk (0 ^ (r & 7)) of the 128B-swizzled row
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (ch == (r & 7)) u.x = 0x3f80u;
+      *reinterpret_cast<uint4*>(sOnes + i * 16) = u;
+      fence_proxy_async_smem();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -251,7 +289,8 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     if (nkv > 0) {
       const uint32_t elected = elect_one_sync();
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DP, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, OW, 0, 1);  // B (= V [+ the ones column]) is MN-major
+      const uint32_t ones_addr = smem_u32(sOnes);
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int t, int stage) {
         const uint32_t k_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES);
@@ -267,12 +306,15 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       };
       auto issue_pv = [&](int t, int stage, int j) {
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
-        const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP);
+        const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_O + t * OW);
         const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16_ts_elect(elected, o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, BKV * 128), idesc_pv,
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          // second 64-column chunk of B: the next d chunk of V (d = 128) | the ones slice, the same 16 rows for every kk
+          const uint32_t lbo = ONES ? ones_addr - (v_addr + kk * 2048) : static_cast<uint32_t>(BKV * 128);
+          umma_bf16_ts_elect(elected, o_tmem, p_tmem + kk * 8, umma_desc_sw128(v_addr + kk * 2048, lbo), idesc_pv,
                        (j | kk) != 0 ? 1u : 0u);
+        }
         umma_commit_elect(elected, &pv_done[2 * t]);
       };
       // half-tile pipeline: per key tile j and half h, O_t += P_th.V_j[h] then S_th <- Q_t.K_{j+1}[h]^T for both tiles
@@ -575,7 +617,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     const int tok = q0 + t * 128 + row;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
-    const uint32_t o_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + t * DP);
+    const uint32_t o_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + t * OW);
     const int limit = causal_limit2(p, tok);
     const float sc = p.scale_log2;
     float m_run = -INFINITY;  // running max in scaled (log2) units
@@ -723,12 +765,24 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32(o_addr + c, o);
           }
+          if constexpr (ONES) {   // the row sum lives in column DP of the accumulator
+            uint32_t o[16];
+            tmem_ld_32x16(o_addr + DP, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(o_addr + DP, o);
+          }
           tmem_st_wait();
         }
       } else {
         m_run = mx;
       }
       FG_TSTAMP(ts3);
+      if constexpr (PP) {   // wait for the exp token of this scheduler's warp pair (tile 0 holds it first)
+        if (t == 1 && j == 0) named_bar_arrive(3 + q, 64);
+        named_bar_sync(3 + 4 * t + q, 64);
+      }
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
       uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};  // independent chains
@@ -740,6 +794,12 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c + i]), __uint_as_float(sv[c + i + 1])), sc2, negm2);
+          if (BX > 0 && ((i >> 1) & 7) >= 8 - BX) {   // packed bf16 exponential: two keys per MUFU issue, no F2FP
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            pk[i >> 1] = exp2_bf16x2(x0, x1);
+            continue;
+          }
           float e0, e1;
           if (((i >> 1) & 7) < POLY) {
             exp2_poly2(x2, e0, e1);
@@ -748,15 +808,20 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
             unpack2(x2, x0, x1);
             e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
           }
-          lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
+          if constexpr (!ONES) lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
         tmem_st_32x16(s_addr + (c >> 1), pk);
       }
-      float lsum0, lsum1;
-      unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
-      l_run += lsum0 + lsum1;
+      if constexpr (!ONES) {
+        float lsum0, lsum1;
+        unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
+        l_run += lsum0 + lsum1;
+      }
       FG_TSTAMP(ts4);
+      if constexpr (PP) {   // hand the token to the partner (which needs it for its tile j, or j + 1 if this is tile 1)
+        if (t == 0 || j + 1 < nkv) named_bar_arrive(3 + 4 * (t ^ 1) + q, 64);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -781,6 +846,14 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     if (nkv) {
       mbar_wait(&pv_done[2 * t + HALF], (nkv - 1) & 1);  // the last product issued for this tile
       tc_fence_after();
+    }
+    if constexpr (ONES) {
+      if (nkv) {   // column DP of the accumulator: sum of the bf16 weights the numerator was built from
+        uint32_t o[16];
+        tmem_ld_32x16(o_addr + DP, o);
+        tmem_ld_wait();
+        l_run = __uint_as_float(o[0]);
+      }
     }
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
     uint8_t* so = sQ + t * Cfg::Q_TILE_BYTES;
@@ -902,13 +975,13 @@ size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256 + 128;
 }
 
-template <int DP, int POLY, int HALF = 0, int WG = 1>
+template <int DP, int POLY, int HALF = 0, int WG = 1, int BX = 0, int PP = 0>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG, BX, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -969,7 +1042,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
     if (r != FG_OK) return r;
   }
   const int grid = kp.B * kp.H * q_blocks * nsplit;
-  attention2_kernel<DP, POLY, HALF, WG><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
+  attention2_kernel<DP, POLY, HALF, WG, BX, PP><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("flash_attn");
   if (nsplit > 1) {
     const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
@@ -1011,6 +1084,27 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
     if (poly == 0) return launch_attention2<128, 0, 0, 2>(p, scale, stream);
     if (poly == 4) return launch_attention2<128, 4, 0, 2>(p, scale, stream);
     return launch_attention2<128, 2, 0, 2>(p, scale, stream);
+  }
+  // d <= 64: row sum through a ones column of V and packed bf16 exponentials (see attention2_kernel).  FG_ATTN_BX = -1
+  // (ones column alone) | 0 (off) | 2 | 4 | 8 eighths of the exponentials in the packed form
+  static const int bx_env = getenv("FG_ATTN_BX") ? atoi(getenv("FG_ATTN_BX")) : 0;
+  static const int pp_env = getenv("FG_ATTN_PP") ? atoi(getenv("FG_ATTN_PP")) : 0;
+  if (p->d <= 64 && pp_env) {
+    if (bx_env == -1) return launch_attention2<64, 2, 0, 1, -1, 1>(p, scale, stream);
+    if (poly == 0) return launch_attention2<64, 0, 0, 1, 0, 1>(p, scale, stream);
+    if (poly == 4) return launch_attention2<64, 4, 0, 1, 0, 1>(p, scale, stream);
+    return launch_attention2<64, 2, 0, 1, 0, 1>(p, scale, stream);
+  }
+  if (p->d > 64 && pp_env) {
+    if (poly == 2) return launch_attention2<128, 2, 0, 1, 0, 1>(p, scale, stream);
+    return launch_attention2<128, 0, 0, 1, 0, 1>(p, scale, stream);
+  }
+  if (p->d <= 64 && bx_env != 0) {
+    if (bx_env == -1) return launch_attention2<64, 2, 0, 1, -1>(p, scale, stream);
+    if (bx_env == 2) return launch_attention2<64, 2, 0, 1, 2>(p, scale, stream);
+    if (bx_env == 4) return launch_attention2<64, 2, 0, 1, 4>(p, scale, stream);
+    if (bx_env == 40) return launch_attention2<64, 0, 0, 1, 4>(p, scale, stream);
+    if (bx_env == 8) return launch_attention2<64, 0, 0, 1, 8>(p, scale, stream);
   }
   if (p->d <= 64) {
     if (poly == 0) return launch_attention2<64, 0>(p, scale, stream);

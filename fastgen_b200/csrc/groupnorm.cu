@@ -119,6 +119,8 @@ struct GnApplyK {
   __nv_bfloat16* raw;
   int64_t raw_ld;
   __nv_bfloat16* raw_lo;
+  float* raw_f32;    // FG_RES_DOWN2 only: the 2x2 mean of x itself in fp32 (the block's resampled identity skip)
+  int64_t raw_f32_ld;
   int pix_per_slab;  // in OUTPUT pixels for DOWN2, input pixels otherwise
   int vpp;           // 4-channel vectors per pass over the channels (= threads per pixel row)
 };
@@ -252,6 +254,8 @@ __global__ void __launch_bounds__(kGnApplyMaxThreads, 4) gn_apply_kernel(const G
           split4(acc, lo);
           store4_bf16(p.y_lo + o * p.y_ld + co, lo);
         }
+        if (p.raw_f32)
+          *reinterpret_cast<float4*>(p.raw_f32 + o * p.raw_f32_ld + co) = make_float4(racc[0], racc[1], racc[2], racc[3]);
         if (p.raw) {
           store4_bf16(p.raw + o * p.raw_ld + co, racc);
           if (LO && p.raw_lo) {
@@ -296,6 +300,22 @@ __global__ void __launch_bounds__(kGnApplyMaxThreads, 4) gn_apply_kernel(const G
     };
 
     int pix = p0 + prow;
+    if constexpr (sizeof(T) == 2 && !LO) {
+      // bf16 input: 8-byte loads, so eight of them in flight per thread keep as many bytes on the way as the four 16-byte
+      // loads of the fp32 form (with four, the bf16-input launches ran at the fp32 launches' time: latency-, not byte-bound)
+      for (; pix + 7 * ppi < p1; pix += 8 * ppi) {
+        uint2 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          r[u] = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(pix + u * ppi) * p.x_ld + co));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float2 f0 = unpack_bf16x2(r[u].x), f1 = unpack_bf16x2(r[u].y);
+          const float v[4] = {f0.x, f0.y, f1.x, f1.y};
+          emit(pix + u * ppi, v);
+        }
+      }
+    }
     for (; pix + 3 * ppi < p1; pix += 4 * ppi) {
       float v0[4], v1[4], v2[4], v3[4];
       load4<T>(xb + static_cast<int64_t>(pix) * p.x_ld + co, v0);
@@ -428,6 +448,11 @@ extern "C" int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream_) {
   k.scale = p->scale, k.shift = p->shift, k.mod_ld = p->mod_ld, k.silu = p->silu, k.resample = p->resample;
   k.y = static_cast<__nv_bfloat16*>(p->y), k.y_ld = p->y_ld, k.y_lo = static_cast<__nv_bfloat16*>(p->y_lo);
   k.raw = static_cast<__nv_bfloat16*>(p->raw), k.raw_ld = p->raw_ld, k.raw_lo = static_cast<__nv_bfloat16*>(p->raw_lo);
+  if (p->raw_f32)
+    FG_CHECK_ARG(p->resample == FG_RES_DOWN2 && p->raw_f32_ld % 4 == 0 && p->raw_f32_ld >= p->c &&
+                     (reinterpret_cast<uintptr_t>(p->raw_f32) & 15u) == 0,
+                 "gn_apply: raw_f32 needs FG_RES_DOWN2, 16-byte aligned rows, raw_f32_ld >= c");
+  k.raw_f32 = static_cast<float*>(p->raw_f32), k.raw_f32_ld = p->raw_f32_ld;
   const int pixels = p->resample == FG_RES_DOWN2 ? (p->h / 2) * (p->w / 2) : p->h * p->w;
   const int slabs = pick_slab_apply(p->n, pixels, p->c, &k.pix_per_slab);
   const dim3 grid(slabs, p->n);

@@ -310,6 +310,8 @@ class _Plan:
                 req("h0", px * b.in_channels)
                 if b.skip is not None and b.skip.kernel == 1:
                     req("raw", px * b.in_channels)
+                elif b.skip is not None and b.down:
+                    req("xds", px * b.in_channels)
                 req("h1", px * b.out_channels)
                 req("h2", px * b.out_channels)
                 if b.num_heads:
@@ -325,7 +327,7 @@ class _Plan:
         req("h0", n * R * R * c_last)
         # h1 (conv0's output) is read by norm1 only: on the bf16 path it is stored as bf16 (statistics of the rounded values
         # from the producer's epilogue), which takes a third off norm1's HBM traffic and half off conv0's stores
-        f32_roles = ("mid", "qkv_f32") if self.h1_bf16 else ("h1", "mid", "qkv_f32")
+        f32_roles = ("mid", "qkv_f32", "xds") if self.h1_bf16 else ("h1", "mid", "qkv_f32", "xds")
         self._scratch_buf: Dict[str, torch.Tensor] = {}
         for name, numel in need.items():
             dt = torch.float32 if name in f32_roles else torch.bfloat16
@@ -389,7 +391,8 @@ class _Plan:
         return dict(stats=slot, stats_groups=norm.num_groups, stats_cg=c_norm // norm.num_groups, stats_ch0=0)
 
     def gn(self, x: _Act, norm: _GroupNorm, pk: Dict[str, torch.Tensor], y: torch.Tensor, silu: bool, resample: int = 0,
-           scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None, stats: Optional[torch.Tensor] = None):
+           scale=None, shift=None, mod_ld=0, y_lo=None, raw=None, raw_lo=None, stats: Optional[torch.Tensor] = None,
+           raw_f32=None):
         n, h, w, c = x.n, x.h, x.w, x.c
         groups = norm.num_groups
         xv = x.t
@@ -399,8 +402,8 @@ class _Plan:
                          stats.data_ptr(), desc=f"gn_stats {h}x{w} c={c}", nbytes=n * h * w * c * xv.element_size())
         p = ops.gn_apply_params(xv, x.ld, n, h, w, c, groups, stats, norm.eps, pk["gamma"], pk["beta"], y, c,
                                 scale=scale, shift=shift, mod_ld=mod_ld, silu=silu, resample=resample, y_lo=y_lo,
-                                raw=raw, raw_ld=c, raw_lo=raw_lo)
-        self.keep.append((p, xv, y, y_lo, raw, raw_lo, scale, shift, stats))
+                                raw=raw, raw_ld=c, raw_lo=raw_lo, raw_f32=raw_f32, raw_f32_ld=c)
+        self.keep.append((p, xv, y, y_lo, raw, raw_lo, scale, shift, stats, raw_f32))
         outs = 1 + (y_lo is not None) + (raw is not None) + (raw_lo is not None)
         opix = h * w * (4 if resample == L.FG_RES_UP2 else 1) // (4 if resample == L.FG_RES_DOWN2 else 1)
         self._launch(L.lib().fg_gn_apply, C.byref(p), desc=f"gn_apply {h}x{w} c={c} outs={outs} rs={resample}",
@@ -646,8 +649,14 @@ class _Plan:
         h0_lo = self._scratch("h0_lo", [n, ho, wo, cin]) if self.x3 else None
         raw = self._scratch("raw", [n, ho, wo, cin]) if skip_conv else None
         raw_lo = self._scratch("raw_lo", [n, ho, wo, cin]) if (skip_conv and self.x3) else None
+        # a down block without a skip projection adds the 2x2 mean of x: norm0's pass (which reads x anyway) leaves it in fp32,
+        # so that conv1 takes it as a same-size residual through its TMA-staged slab ring (plain loads of four pixels per
+        # output in the epilogue ran the three such convolutions of the IN-64 network at 200-460 TFLOP/s)
+        xds = None
+        if b.down and b.skip is not None and not skip_conv:
+            xds = self._scratch("xds", [n, ho, wo, cin])
         self.gn(x, b.norm0, pk[key + ".norm0"], h0, silu=True, resample=resample, y_lo=h0_lo, raw=raw, raw_lo=raw_lo,
-                stats=x_stats)
+                stats=x_stats, raw_f32=xds)
         # conv0 (+ bias, + additive embedding)
         aff_off = pk[key + ".affine_off"]
         aff = self.affine[:, aff_off:]
@@ -681,6 +690,8 @@ class _Plan:
         else:
             mode = L.FG_RES_SAME if b.skip is None else resample
             rkw = dict(res=x.t, res_ld=x.ld, res_mode=mode)
+            if xds is not None:
+                rkw = dict(res=xds, res_ld=cin, res_mode=L.FG_RES_SAME)
         mid = dst if not b.num_heads else _Act(self._scratch("mid", [n, ho, wo, cout]), 0, cout)
         st2 = self.fused_stats(ho, wo, cout, mid.ld, b.norm2, cout) if b.num_heads else out_stats
         self.conv(segs, n, ho, wo, cout, mid.t, mid.ld, bias=bias, out_scale=float(b.skip_scale), **rkw, **(st2 or {}))

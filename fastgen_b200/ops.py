@@ -104,8 +104,9 @@ def gn_apply_params(
     silu: bool = True, resample: int = L.FG_RES_NONE,
     y_lo: Optional[torch.Tensor] = None,
     raw: Optional[torch.Tensor] = None, raw_ld: int = 0, raw_lo: Optional[torch.Tensor] = None,
+    raw_f32: Optional[torch.Tensor] = None, raw_f32_ld: int = 0,
 ) -> "L.GnApplyParams":
-    _need_cuda(x, stats, gamma, beta, y, scale, shift, y_lo, raw, raw_lo)
+    _need_cuda(x, stats, gamma, beta, y, scale, shift, y_lo, raw, raw_lo, raw_f32)
     p = L.GnApplyParams()
     p.x, p.x_dtype, p.x_ld = x.data_ptr(), _DT[x.dtype], x_ld
     p.n, p.h, p.w, p.c, p.groups = n, h, w, c, groups
@@ -115,6 +116,7 @@ def gn_apply_params(
     p.silu, p.resample = int(silu), resample
     p.y, p.y_ld, p.y_lo = y.data_ptr(), y_ld, _ptr(y_lo)
     p.raw, p.raw_ld, p.raw_lo = _ptr(raw), raw_ld, _ptr(raw_lo)
+    p.raw_f32, p.raw_f32_ld = _ptr(raw_f32), raw_f32_ld
     return p
 
 

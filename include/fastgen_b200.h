@@ -134,6 +134,8 @@ typedef struct {
   void* raw;            /* optional bf16 copy of x itself under the same resample (skip 1x1 operand) or NULL */
   int64_t raw_ld;
   void* raw_lo;         /* optional low part of raw or NULL */
+  void* raw_f32;        /* FG_RES_DOWN2 only, optional: the 2x2 mean of x itself in fp32 -- the resampled identity skip of a   */
+  int64_t raw_f32_ld;   /* down block (EDM/network.py:114-121, 286-288), which the conv behind then adds as FG_RES_SAME     */
 } fg_gn_apply_params;
 
 int fg_gn_apply(const fg_gn_apply_params* p, fg_stream_t stream);
