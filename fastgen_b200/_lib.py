@@ -24,6 +24,7 @@ SYMBOLS = (
     "fg_ln_modulate", "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_strided_copy", "fg_geglu", "fg_cast_resample", "fg_bcast_add",
     "fg_peer_put", "fg_peer_wait", "fg_sampler_vec",
     "fg_edm_input", "fg_edm_step", "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_zero",
+    "fg_latent_affine", "fg_clamp", "fg_zero_tail_rows",
 )
 
 
@@ -176,12 +177,15 @@ def lib() -> C.CDLL:
     l.fg_axpby.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
     l.fg_sub_div.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]
     l.fg_zero.argtypes = [vp, i64, vp]
+    l.fg_latent_affine.argtypes = [vp, i32, vp, i32, vp, vp, i64, i32, i64, i32, vp]
+    l.fg_clamp.argtypes = [vp, i32, i64, C.c_float, C.c_float, vp]
+    l.fg_zero_tail_rows.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, vp, i32, vp]
     l.fg_pos_embedding.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp]
     l.fg_split_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]
     for name in ("fg_conv_gemm", "fg_gn_stats", "fg_gn_apply", "fg_attention", "fg_attention_f32", "fg_edm_input", "fg_edm_step",
                  "fg_axpby", "fg_sub_div", "fg_pos_embedding", "fg_split_bf16", "fg_flash_attn", "fg_ln_modulate",
                  "fg_qk_norm_rope", "fg_patchify", "fg_unpatchify", "fg_bcast_add", "fg_strided_copy", "fg_zero", "fg_geglu", "fg_cast_resample",
-                 "fg_peer_put", "fg_peer_wait"):
+                 "fg_peer_put", "fg_peer_wait", "fg_latent_affine", "fg_clamp", "fg_zero_tail_rows"):
         getattr(l, name).restype = C.c_int
     _lib = l
     return l

@@ -447,3 +447,45 @@ def cast_resample(x: torch.Tensor, x_ld: int, n: int, h: int, w: int, c: int, y:
     assert y.dtype == torch.bfloat16
     L.check(L.lib().fg_cast_resample(x.data_ptr(), _DT[x.dtype], x_ld, n, h, w, c, L.FG_RES_UP2 if up2 else L.FG_RES_NONE,
                                      y.data_ptr(), y_ld, _stream()), "fg_cast_resample")
+
+
+def latent_affine(x: torch.Tensor, a: torch.Tensor, b: Optional[torch.Tensor], mode: int, out_dtype: torch.dtype,
+                  channel_dim: int = 1) -> torch.Tensor:
+    """``fg_latent_affine`` on a contiguous [B, C, ...] latent: mode 0 ``x / a + b``, 1 ``(x - b) * a``, 2 ``x * a``
+    (per channel; every op rounded to x's dtype like the reference's eager ops), result in ``out_dtype``."""
+    _need_cuda(x, a, b)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    assert a.dtype == torch.float32 and (b is None or b.dtype == torch.float32)
+    c = a.numel()
+    outer = 1
+    for s_ in x.shape[:channel_dim]:
+        outer *= s_
+    if c == 1:
+        outer, inner = 1, x.numel()
+    else:
+        assert x.shape[channel_dim] == c, (x.shape, c)
+        inner = x.numel() // (outer * c)
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    L.check(L.lib().fg_latent_affine(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[out_dtype], a.data_ptr(), _ptr(b),
+                                     outer, c, inner, mode, _stream()), "fg_latent_affine")
+    return out
+
+
+def clamp_(x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
+    """in-place ``x.clip_(lo, hi)`` as one launch"""
+    _need_cuda(x)
+    assert x.is_contiguous()
+    L.check(L.lib().fg_clamp(x.data_ptr(), _DT[x.dtype], x.numel(), lo, hi, _stream()), "fg_clamp")
+    return x
+
+
+def zero_tail_rows(x: torch.Tensor, lens: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """out[s, t] = x[s, t] for t < lens[s], 0 behind: [B, L, D] -> contiguous [B, L, D] in ``out_dtype``"""
+    _need_cuda(x, lens)
+    assert x.dim() == 3 and x.stride(2) == 1 and lens.dtype == torch.int64 and lens.numel() == x.shape[0]
+    b, rows, d = x.shape
+    out = torch.empty(b, rows, d, device=x.device, dtype=out_dtype)
+    L.check(L.lib().fg_zero_tail_rows(x.data_ptr(), _DT[x.dtype], x.stride(1), x.stride(0), lens.data_ptr(), b, rows, d,
+                                      out.data_ptr(), _DT[out_dtype], _stream()), "fg_zero_tail_rows")
+    return out

@@ -350,6 +350,27 @@ int fg_sampler_vec(int enable);
 /* cudaMemsetAsync(ptr, 0, bytes) as a plan step (statistics arenas) */
 int fg_zero(void* ptr, int64_t bytes, fg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Hand-off either side of the sampler: the arithmetic the reference's VAE / text-encoder WRAPPERS do
+ * around the external networks, one streaming pass each, rounded like the reference's eager ops (bit-identical).
+ * ---------------------------------------------------------------------------------------------------- */
+/* x, out: [outer][c][inner] (fp32 | bf16); a, b: [c] fp32 holding values already rounded to x's dtype.
+ * mode 0: (x / a) + b   -- WanVideoEncoder.decode: a = 1 / std, b = mean (fastgen/networks/Wan/network.py:515-528)
+ * mode 1: (x - b) * a   -- WanVideoEncoder.encode (:496-513)
+ * mode 2: x * a         -- SDXLImageEncoder.encode / .decode: the VAE scaling factor or its reciprocal, c = 1
+ *                          (fastgen/networks/SDXL/network.py:141-149)
+ * every op rounds to x's dtype, the result is cast to out's dtype (the reference's .to(vae.dtype)). */
+int fg_latent_affine(const void* x, int32_t x_dtype, void* out, int32_t out_dtype, const float* a, const float* b,
+                     int64_t outer, int32_t c, int64_t inner, int32_t mode, fg_stream_t stream);
+/* x <- min(max(x, lo), hi) in place, NaN kept: the .clip_(-1.0, 1.0) behind both VAE decoders (Wan/network.py:527,
+ * SDXL/network.py:147) */
+int fg_clamp(void* x, int32_t dtype, int64_t total, float lo, float hi, fg_stream_t stream);
+/* out[s, t, :] = t < len[s] ? x[s, t, :] : 0 for x [b][rows][d] (row stride x_ld, batch stride x_bs, elements), out
+ * contiguous: WanTextEncoder.encode's "u[:v] padded with zeros to 512 rows" + the cast to `precision`
+ * (Wan/network.py:463-470).  len: device int64 [b]. */
+int fg_zero_tail_rows(const void* x, int32_t x_dtype, int64_t x_ld, int64_t x_bs, const int64_t* len, int32_t b,
+                      int32_t rows, int32_t d, void* out, int32_t out_dtype, fg_stream_t stream);
+
 /* small helpers used by the embedding path */
 /* PositionalEmbedding (:306-319): out[n, :] = [cos(t*f) | sin(t*f)] (optionally swapped), fp32 */
 int fg_pos_embedding(const float* t, int32_t n, int32_t channels, int32_t max_positions, int32_t endpoint,

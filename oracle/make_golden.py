@@ -661,6 +661,56 @@ def wan_remap_fixture():
     print("wan_original_key_remap.json", {k: len(v["dst"]) for k, v in fx.items()})
 
 
+def handoff_fixture():
+    """tests/golden/handoff_reference.npz: the UNMODIFIED reference wrappers WanTextEncoder / WanVideoEncoder
+    (fastgen/networks/Wan/network.py:431-539) and SDXLTextEncoder / SDXLImageEncoder (SDXL/network.py:46-156), built with
+    __new__ (their constructors download checkpoints) around the stand-in networks of oracle/ref_handoff_harness.py."""
+    from oracle import ref_handoff_harness as H
+    from oracle.ref_sdxl_harness import load_reference_sdxl
+    from oracle.ref_wan_harness import load_reference_wan
+
+    wan, _ = load_reference_wan()
+    sdxl = load_reference_sdxl()
+    out = {}
+    g = torch.Generator().manual_seed(SEED + 77)
+    # --- Wan text encoder: real transformers UMT5 (toy size), prompt cleaning, truncation to the token count, zero padding
+    te = wan.WanTextEncoder.__new__(wan.WanTextEncoder)
+    te.text_encoder, te.tokenizer = H.toy_umt5(), H.ToyTokenizer(97)
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        out[f"wan_text_{name}"] = _np(te.encode(H.PROMPTS, precision=dt))
+    out["wan_text_single_f32"] = _np(te.encode(H.PROMPTS[1]))
+    # --- Wan VAE wrapper: latent (de)normalisation, dtype hand-over, clip
+    ve = wan.WanVideoEncoder.__new__(wan.WanVideoEncoder)
+    ve.vae = H.ToyWanVAE().eval().requires_grad_(False)
+    lat32 = torch.randn(2, 16, 3, 6, 10, generator=g) * 1.3
+    lat16 = lat32.bfloat16()
+    video = torch.randn(1, 3, 5, 16, 24, generator=g)
+    out["wan_latent_f32"], out["wan_latent_bf16"], out["wan_video"] = _np(lat32), _np(lat16), _np(video)
+    out["wan_decode_f32"] = _np(ve.decode(lat32))
+    out["wan_decode_bf16"] = _np(ve.decode(lat16))          # bf16 latent, fp32 VAE: coefficients and ops round in bf16
+    out["wan_encode_sample"] = _np(ve.encode(video, mode="sample"))
+    out["wan_encode_argmax"] = _np(ve.encode(video.bfloat16(), mode="argmax"))
+    # --- SDXL text encoders: real transformers CLIP pair (toy size)
+    st = sdxl.SDXLTextEncoder.__new__(sdxl.SDXLTextEncoder)
+    st.text_encoder_one, st.text_encoder_two = H.toy_clip_pair()
+    st.tokenizer_one, st.tokenizer_two = H.ToyTokenizer(97), H.ToyTokenizer(97)
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        pe, pooled = st.encode(H.PROMPTS, precision=dt)
+        out[f"sdxl_text_{name}"], out[f"sdxl_pooled_{name}"] = _np(pe), _np(pooled)
+    # --- SDXL VAE wrapper
+    ie = sdxl.SDXLImageEncoder.__new__(sdxl.SDXLImageEncoder)
+    ie.vae = H.ToySDVAE().eval().requires_grad_(False)
+    slat = torch.randn(2, 4, 8, 8, generator=g) * 2.0
+    img = torch.randn(2, 3, 32, 32, generator=g)
+    out["sdxl_latent"], out["sdxl_image"] = _np(slat), _np(img)
+    out["sdxl_decode_f32"] = _np(ie.decode(slat))
+    out["sdxl_encode_f32"] = _np(ie.encode(img))
+    ie.vae = H.ToySDVAE().eval().requires_grad_(False).bfloat16()
+    out["sdxl_decode_bf16"] = _np(ie.decode(slat.bfloat16()))
+    np.savez_compressed(os.path.join(OUT, "handoff_reference.npz"), **out)
+    print("handoff_reference.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -680,3 +730,4 @@ if __name__ == "__main__":
     wan_sample_fixture()
     wan_remap_fixture()
     dit_remap_fixture()
+    handoff_fixture()

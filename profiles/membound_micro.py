@@ -164,3 +164,37 @@ if "--graph" in sys.argv:
     graphed("Wan 720p [1,16,21,90,160] bf16", (1, 16, 21, 90, 160), torch.bfloat16)
     graphed("SDXL b16 [16,4,128,128] bf16", (16, 4, 128, 128), torch.bfloat16)
     graphed("IN-64 b256 [256,3,64,64] fp32", (256, 3, 64, 64), torch.float32)
+
+
+def handoff_lines():
+    """SURVEY.md 8f-2 hand-off kernels at the Wan 480p sizes: latent (de)normalisation of a [1,16,21,60,104] latent and the
+    clamp of the decoded [1,3,81,480,832] fp32 video (algorithmic bytes: read + write once)"""
+    import torch
+    from fastgen_b200 import ops
+
+    def timed(f, nbytes, tag, iters=20):
+        f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"{tag:54s} {ms * 1e3:9.1f} us {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
+
+    a = torch.rand(16, device="cuda") + 0.5
+    b = torch.randn(16, device="cuda")
+    for bsz in (1, 8):
+        lat = torch.randn(bsz, 16, 21, 60, 104, device="cuda").bfloat16()
+        timed(lambda: ops.latent_affine(lat, a, b, 0, torch.float32), lat.numel() * 6, f"latent_affine decode bf16->f32 B={bsz} (Wan 480p)")
+    vid = torch.randn(1, 3, 81, 480, 832, device="cuda") * 1.2
+    timed(lambda: ops.clamp_(vid, -1.0, 1.0), vid.numel() * 8, "clamp_ fp32 [1,3,81,480,832] (decoded video)")
+    h = torch.randn(8, 512, 4096, device="cuda")
+    lens = torch.randint(5, 300, (8,), device="cuda")
+    timed(lambda: ops.zero_tail_rows(h, lens, torch.bfloat16), h.numel() * 6, "zero_tail_rows f32->bf16 [8,512,4096] (prompt embeds)")
+
+
+if __name__ == "__main__" and "--handoff" in sys.argv:
+    handoff_lines()
