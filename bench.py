@@ -326,7 +326,7 @@ def measure_in64(ctx: "_Dist", B: int, K: int, W: int, compute: str = "bf16", e2
         "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus if tf_sus else None,
         "traffic": traffic,
         "traffic_note": "DRAM read+write bytes per fg_conv_gemm launch (ncu, profiles/traffic.json); algorithmic bytes per "
-                        "launch at batch 256 = 610 MB of activations + ~5 MB of weights (DESIGN.md): the excess is < 0 "
+                        "launch at batch 256 = 558 MB of activations (conv0 -> norm1 tensors in bf16; 610 MB with fp32 ones) + ~5 MB of weights (DESIGN.md): the excess is < 0 "
                         "because consumers hit the 126 MB L2",
         "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
         "how": "sum of algorithmic conv/linear FLOPs of all fg_conv_gemm launches / sum of their CUDA-event durations, "
