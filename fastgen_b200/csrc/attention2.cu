@@ -156,8 +156,14 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 // a pair of 64-thread named barriers so that their exp loops never overlap: the 16 / clk MUFU unit is what the two loops
 // compete for, and a warp that has it to itself finishes in half the time while its partner waits for S, reads it and
 // takes the row max.
-template <int DP, int POLY, int HALF, int WG = 1, int BX = 0, int PP = 0>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+//
+// TP (two passes over S): the one-pass loop keeps all 128 scores of a row in registers from the TMEM read to the last
+// exponential (~170 live registers, small spills, little room for the scheduler to overlap independent pairs).  TP reads S
+// from tensor memory twice in 32-column chunks -- once for the row max, once for the exponentials -- double-buffered, so
+// the loops run at ~70 live registers; a TMEM read is ~40 clocks per chunk and overlaps the arithmetic of the previous one.
+template <int DP, int POLY, int HALF, int WG = 1, int BX = 0, int PP = 0, int TP = 0>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
 __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+  static_assert(TP == 0 || (HALF == 0 && WG == 1), "two-pass softmax: full tiles, WG = 1");
   static_assert(PP == 0 || (HALF == 0 && WG == 1), "ping-pong: full tiles, WG = 1");
   static_assert(WG == 1 || (WG == 2 && HALF == 0), "two warps per lane quarter: full-tile pipeline only");
   static_assert(BX == 0 || (DP == 64 && HALF == 0 && WG == 1 && POLY + BX <= 8 && BX >= -1), "ones column: d <= 64, full tiles, WG = 1");
@@ -718,6 +724,118 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       mbar_wait(&s_full[2 * t], j & 1);
       tc_fence_after();
       FG_TSTAMP(ts1);
+      if constexpr (TP) {
+        const int seg = (jb + j) >= n0;
+        const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
+        int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
+        if (p.mask_chunk) kv_valid = min(kv_valid, limit - col0);
+        const bool ragged = kv_valid < BKV;   // ragged end of a segment / causal limit inside this tile (rare)
+        // ---- pass 1: row max, 32 columns at a time, the next chunk's TMEM read in flight ----
+        uint32_t ca[32], cb[32];
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        auto max_chunk = [&](uint32_t (&sv)[32], int c) {
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i >= kv_valid) sv[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+          }
+        };
+        tmem_ld_32x32(s_addr, ca);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 32, cb);
+        max_chunk(ca, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 64, ca);
+        max_chunk(cb, 32);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 96, cb);
+        max_chunk(ca, 64);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr, ca);        // pass 2, first chunk: in flight during the max bookkeeping
+        max_chunk(cb, 96);
+        FG_TSTAMP(ts2);
+        float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
+        mx *= sc;  // scale > 0: max commutes with the scaling
+        if (j > 0) {
+          const bool need = mx > m_run + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(&pv_done[2 * t], (j - 1) & 1);  // O stable until this tile's P is published
+            tc_fence_after();
+            const float m_new = need ? mx : m_run;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+            m_run = m_new;
+            l_run *= alpha;
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < OW; c += 16) {
+              uint32_t o[16];
+              tmem_ld_32x16(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(o_addr + c, o);
+            }
+            tmem_st_wait();
+          }
+        } else {
+          m_run = mx;
+        }
+        FG_TSTAMP(ts3);
+        if constexpr (PP) {
+          if (t == 1 && j == 0) named_bar_arrive(3 + q, 64);
+          named_bar_sync(3 + 4 * t + q, 64);
+        }
+        const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+        const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
+        uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        // ---- pass 2: P = exp2(s * scale - m) as bf16 over the S columns (P of chunk c lands in columns already consumed) ----
+        auto exp_chunk = [&](uint32_t (&sv)[32], int c) {
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i >= kv_valid) sv[i] = 0xff800000u;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sc2, negm2);
+            float e0, e1;
+            if (((i >> 1) & 7) < POLY) {
+              exp2_poly2(x2, e0, e1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              e0 = exp2_mufu(x0), e1 = exp2_mufu(x1);
+            }
+            if constexpr (!ONES) lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x16(s_addr + (c >> 1), pk);
+        };
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 32, cb);
+        exp_chunk(ca, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 64, ca);
+        exp_chunk(cb, 32);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 96, cb);
+        exp_chunk(ca, 64);
+        tmem_ld_wait();
+        exp_chunk(cb, 96);
+        if constexpr (!ONES) {
+          float lsum0, lsum1;
+          unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
+          l_run += lsum0 + lsum1;
+        }
+      } else {
       uint32_t sv[BKV];
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) {
@@ -817,6 +935,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         float lsum0, lsum1;
         unpack2(fadd2(fadd2(lsum2[0], lsum2[1]), fadd2(lsum2[2], lsum2[3])), lsum0, lsum1);
         l_run += lsum0 + lsum1;
+      }
       }
       FG_TSTAMP(ts4);
       if constexpr (PP) {   // hand the token to the partner (which needs it for its tile j, or j + 1 if this is tile 1)
@@ -975,13 +1094,13 @@ size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256 + 128;
 }
 
-template <int DP, int POLY, int HALF = 0, int WG = 1, int BX = 0, int PP = 0>
+template <int DP, int POLY, int HALF = 0, int WG = 1, int BX = 0, int PP = 0, int TP = 0>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG, BX, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -1042,7 +1161,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
     if (r != FG_OK) return r;
   }
   const int grid = kp.B * kp.H * q_blocks * nsplit;
-  attention2_kernel<DP, POLY, HALF, WG, BX, PP><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
+  attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("flash_attn");
   if (nsplit > 1) {
     const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
@@ -1088,6 +1207,16 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
   // d <= 64: row sum through a ones column of V and packed bf16 exponentials (see attention2_kernel).  FG_ATTN_BX = -1
   // (ones column alone) | 0 (off) | 2 | 4 | 8 eighths of the exponentials in the packed form
   static const int bx_env = getenv("FG_ATTN_BX") ? atoi(getenv("FG_ATTN_BX")) : 0;
+  static const int tp_env = getenv("FG_ATTN_TP") ? atoi(getenv("FG_ATTN_TP")) : 0;
+  if (tp_env) {
+    if (p->d <= 64) {
+      if (poly == 0) return launch_attention2<64, 0, 0, 1, 0, 0, 1>(p, scale, stream);
+      if (poly == 4) return launch_attention2<64, 4, 0, 1, 0, 0, 1>(p, scale, stream);
+      return launch_attention2<64, 2, 0, 1, 0, 0, 1>(p, scale, stream);
+    }
+    if (poly == 2) return launch_attention2<128, 2, 0, 1, 0, 0, 1>(p, scale, stream);
+    return launch_attention2<128, 0, 0, 1, 0, 0, 1>(p, scale, stream);
+  }
   static const int pp_env = getenv("FG_ATTN_PP") ? atoi(getenv("FG_ATTN_PP")) : 0;
   if (p->d <= 64 && pp_env) {
     if (bx_env == -1) return launch_attention2<64, 2, 0, 1, -1, 1>(p, scale, stream);
