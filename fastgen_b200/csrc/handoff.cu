@@ -107,24 +107,51 @@ __global__ void __launch_bounds__(kHoThreads) clamp_kernel(T* __restrict__ x, in
   }
 }
 
-// out[b, t, :] = t < len[b] ? cast(x[b, t, :]) : 0  -- "u[:v] then pad with zeros to max_length" of WanTextEncoder.encode
-template <typename TI, typename TO>
+// out[b, t, :] = t < len[b] ? cast(x[b, t, :]) : 0  -- "u[:v] then pad with zeros to max_length" of WanTextEncoder.encode.
+// VEC: four elements per thread and iteration (rows of a multiple of 4 elements, 16-byte aligned input rows); rows behind a
+// prompt's last token are written without being read.
+template <typename TI, typename TO, bool VEC>
 __global__ void __launch_bounds__(kHoThreads) zero_tail_rows_kernel(const TI* __restrict__ x, int64_t x_ld, int64_t x_bs,
                                                                     const int64_t* __restrict__ len, int b, int rows, int d,
                                                                     TO* __restrict__ out) {
-  const int64_t total = static_cast<int64_t>(b) * rows * d;
+  constexpr int V = VEC ? 4 : 1;
+  const int dv = d / V;
+  const int64_t total = static_cast<int64_t>(b) * rows * dv;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kHoThreads) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * kHoThreads) {
-    const int col = static_cast<int>(i % d);
-    const int64_t r = i / d;
+    const int col = static_cast<int>(i % dv) * V;
+    const int64_t r = i / dv;
     const int t = static_cast<int>(r % rows), s = static_cast<int>(r / rows);
-    float v = 0.f;
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = 0.f;
     if (t < len[s]) {
-      if constexpr (sizeof(TI) == 2) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[s * x_bs + t * x_ld + col]);
-      else v = reinterpret_cast<const float*>(x)[s * x_bs + t * x_ld + col];
+      const TI* src = x + s * x_bs + t * x_ld + col;
+      if constexpr (VEC && sizeof(TI) == 4) {
+        const float4 u = *reinterpret_cast<const float4*>(src);
+        v[0] = u.x, v[1] = u.y, v[2] = u.z, v[3] = u.w;
+      } else if constexpr (VEC) {
+        const uint2 u = *reinterpret_cast<const uint2*>(src);
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+        v[0] = f0.x, v[1] = f0.y, v[2] = f1.x, v[3] = f1.y;
+      } else if constexpr (sizeof(TI) == 2) {
+        v[0] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src));
+      } else {
+        v[0] = *reinterpret_cast<const float*>(src);
+      }
     }
-    if constexpr (sizeof(TO) == 2) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(out)[i] = v;
+    TO* dst = out + r * d + col;
+    if constexpr (VEC && sizeof(TO) == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (VEC) {
+      uint2 u;
+      u.x = pack_bf16x2(v[0], v[1]), u.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(dst) = u;
+    } else if constexpr (sizeof(TO) == 2) {
+      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[0]);
+    } else {
+      *reinterpret_cast<float*>(dst) = v[0];
+    }
   }
 }
 
@@ -188,9 +215,19 @@ extern "C" int fg_zero_tail_rows(const void* x, int32_t x_dtype, int64_t x_ld, i
   FG_CHECK_ARG(x && out && len && b > 0 && rows > 0 && d > 0 && x_ld >= d, "zero_tail_rows: bad arguments");
   FG_CHECK_ARG((x_dtype == FG_F32 || x_dtype == FG_BF16) && (out_dtype == FG_F32 || out_dtype == FG_BF16),
                "zero_tail_rows: bad dtype");
-  const int grid = ho_grid(static_cast<int64_t>(b) * rows * d);
-#define FG_ZT(TI, TO) zero_tail_rows_kernel<TI, TO><<<grid, kHoThreads, 0, stream>>>( \
-      static_cast<const TI*>(x), x_ld, x_bs, len, b, rows, d, static_cast<TO*>(out))
+  const int esz = x_dtype == FG_F32 ? 4 : 2;
+  const bool vec = d % 4 == 0 && x_ld % 4 == 0 && x_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & (4 * esz - 1)) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const int grid = ho_grid(static_cast<int64_t>(b) * rows * (vec ? d / 4 : d));
+#define FG_ZT(TI, TO)                                                                                                  \
+  do {                                                                                                                 \
+    if (vec)                                                                                                           \
+      zero_tail_rows_kernel<TI, TO, true><<<grid, kHoThreads, 0, stream>>>(static_cast<const TI*>(x), x_ld, x_bs, len, b, \
+                                                                           rows, d, static_cast<TO*>(out));            \
+    else                                                                                                               \
+      zero_tail_rows_kernel<TI, TO, false><<<grid, kHoThreads, 0, stream>>>(static_cast<const TI*>(x), x_ld, x_bs, len, \
+                                                                            b, rows, d, static_cast<TO*>(out));        \
+  } while (0)
   if (x_dtype == FG_F32 && out_dtype == FG_F32) FG_ZT(float, float);
   else if (x_dtype == FG_F32) FG_ZT(float, __nv_bfloat16);
   else if (out_dtype == FG_F32) FG_ZT(__nv_bfloat16, float);
