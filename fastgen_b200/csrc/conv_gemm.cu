@@ -133,6 +133,7 @@ struct ConvKParams {
   // lean slab loop of the TMA-store epilogues: no activation / gate / plain-load residual / ragged last slab, so a slab is
   // TMEM read -> + bias (requested one slab ahead) [+ row vector] [+ staged residual] -> scale -> shared memory
   int32_t lean;
+  uint32_t magic_gate_rows;   // fast_div multiplier of gate_rows (lean path; 0: divide)
 };
 
 struct TileCoord {
@@ -645,6 +646,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       if (lean) {                      // read the last image's: the TMA store clips them)
         if (p.bias) lean_bias(t.co0 + twin * kLeanCols);
         if (p.rowvec) rv_row = p.rowvec + static_cast<int64_t>(valid ? img : p.N - 1) * p.rowvec_ld;
+        // ... or of the multiplicative AdaLN gate (one gate row per gate_rows consecutive pixels); a launch has one or the other
+        if (p.gate) {
+          const int pix = valid ? (img * p.H + h) * p.W + w : 0;
+          rv_row = p.gate + static_cast<int64_t>(fast_div(pix, p.gate_rows, p.magic_gate_rows)) * p.gate_ld;
+        }
       }
       FG_CT(11);
       mbar_wait(&tfull[acc], acc_phase);
@@ -725,8 +731,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < kLeanCols; ++j) a[j] = __uint_as_float(v[j]) + nb[j];
               if (rv_row) {
+                if (p.gate) {
 #pragma unroll
-                for (int j = 0; j < kLeanCols; ++j) a[j] += rv[j];
+                  for (int j = 0; j < kLeanCols; ++j) a[j] *= rv[j];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < kLeanCols; ++j) a[j] += rv[j];
+                }
               }
               // the next slab's bias: in flight during the stores, the barrier and the statistics of this one
               if (p.bias && c0 + kSlabCols < BLOCK_N && t.co0 + c0 + kSlabCols < p.Cout) lean_bias(cb + kSlabCols);
@@ -1343,9 +1354,15 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
       }
       epi = geglu ? kEpiGeglu : epi_mode(p->out_dtype == FG_BF16, res_kind);
       static const bool allow_lean = !(getenv("FG_CONV_LEAN") && getenv("FG_CONV_LEAN")[0] == '0');
-      kp.lean = allow_lean && !geglu && p->act == FG_ACT_NONE && !p->gate && res_kind != kResUp2 &&
+      const int64_t pixels = static_cast<int64_t>(p->n) * p->h * p->w;
+      kp.lean = allow_lean && !geglu && p->act == FG_ACT_NONE && res_kind != kResUp2 &&
                 (kp.res_mode == FG_RES_NONE || res_kind == kResSame) && p->cout % (128 / esz) == 0 &&
-                (!p->bias || aligned16(p->bias)) && (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0));
+                (!p->bias || aligned16(p->bias)) && (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
+                (!p->gate || (!p->rowvec && aligned16(p->gate) && p->gate_ld % 4 == 0 && p->gate_rows > 0 &&
+                              pixels < (1ll << 31)));
+      kp.magic_gate_rows = 0;
+      if (p->gate && p->gate_rows > 1 && pixels * p->gate_rows < (1ll << 32))
+        kp.magic_gate_rows = static_cast<uint32_t>(((1ull << 32) + p->gate_rows - 1) / p->gate_rows);
     }
   }
   if (geglu) FG_CHECK_ARG(epi == kEpiGeglu, "conv_gemm: FG_ACT_GEGLU needs the TMA-store epilogue (16-byte aligned bf16 output rows)");
