@@ -730,14 +730,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               float a[kLeanCols];
 #pragma unroll
               for (int j = 0; j < kLeanCols; ++j) a[j] = __uint_as_float(v[j]) + nb[j];
-              if (rv_row) {
-                if (p.gate) {
+              if (rv_row && !p.gate) {
 #pragma unroll
-                  for (int j = 0; j < kLeanCols; ++j) a[j] *= rv[j];
-                } else {
+                for (int j = 0; j < kLeanCols; ++j) a[j] += rv[j];
+              }
+              if (p.act == FG_ACT_GELU_TANH) {   // (warp-uniform; same arithmetic as tail_values)
 #pragma unroll
-                  for (int j = 0; j < kLeanCols; ++j) a[j] += rv[j];
+                for (int j = 0; j < kLeanCols; ++j) {
+                  const float x = a[j];
+                  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+                  const float hx = 0.5f * x;
+                  a[j] = fmaf(hx, tanh_fast(u), hx);
                 }
+              } else if (p.act == FG_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < kLeanCols; ++j) a[j] = silu_f(a[j]);
+              }
+              if (rv_row && p.gate) {
+#pragma unroll
+                for (int j = 0; j < kLeanCols; ++j) a[j] *= rv[j];
               }
               // the next slab's bias: in flight during the stores, the barrier and the statistics of this one
               if (p.bias && c0 + kSlabCols < BLOCK_N && t.co0 + c0 + kSlabCols < p.Cout) lean_bias(cb + kSlabCols);
@@ -1355,7 +1366,7 @@ static int fg::conv_prepare(const fg_conv_params* p, ConvPrepared& pp) {
       epi = geglu ? kEpiGeglu : epi_mode(p->out_dtype == FG_BF16, res_kind);
       static const bool allow_lean = !(getenv("FG_CONV_LEAN") && getenv("FG_CONV_LEAN")[0] == '0');
       const int64_t pixels = static_cast<int64_t>(p->n) * p->h * p->w;
-      kp.lean = allow_lean && !geglu && p->act == FG_ACT_NONE && res_kind != kResUp2 &&
+      kp.lean = allow_lean && !geglu && res_kind != kResUp2 &&
                 (kp.res_mode == FG_RES_NONE || res_kind == kResSame) && p->cout % (128 / esz) == 0 &&
                 (!p->bias || aligned16(p->bias)) && (!p->rowvec || (aligned16(p->rowvec) && p->rowvec_ld % 4 == 0)) &&
                 (!p->gate || (!p->rowvec && aligned16(p->gate) && p->gate_ld % 4 == 0 && p->gate_rows > 0 &&
