@@ -30,8 +30,10 @@ __device__ unsigned long long g_attn_timing[2][8];
 // [tile][key tile 2..5][P published, issuer saw it, issuer done issuing, next S seen by the softmax warp] (SM clock)
 __device__ long long g_attn_trace[2][4][4];
 #define FG_TSTAMP(var) const long long var = clock64()
+#define FG_TSET(var) var = clock64()
 #else
 #define FG_TSTAMP(var)
+#define FG_TSET(var)
 #endif
 
 template <int DP>
@@ -724,6 +726,9 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       mbar_wait(&s_full[2 * t], j & 1);
       tc_fence_after();
       FG_TSTAMP(ts1);
+#ifdef FG_ATTN_TIMING
+      long long ts2 = 0, ts3 = 0;
+#endif
       if constexpr (TP) {
         const int seg = (jb + j) >= n0;
         const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         tmem_ld_wait();
         tmem_ld_32x32(s_addr, ca);        // pass 2, first chunk: in flight during the max bookkeeping
         max_chunk(cb, 96);
-        FG_TSTAMP(ts2);
+        FG_TSET(ts2);
         float mx = fmax3(fmaxf(mx0, mx1), mx2, mx3);
         mx *= sc;  // scale > 0: max commutes with the scaling
         if (j > 0) {
@@ -787,7 +792,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         } else {
           m_run = mx;
         }
-        FG_TSTAMP(ts3);
+        FG_TSET(ts3);
         if constexpr (PP) {
           if (t == 1 && j == 0) named_bar_arrive(3 + q, 64);
           named_bar_sync(3 + 4 * t + q, 64);
@@ -843,7 +848,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         tmem_ld_32x32(s_addr + c, chunk);
       }
       tmem_ld_wait();
-      FG_TSTAMP(ts2);
+      FG_TSET(ts2);
       const int seg = (jb + j) >= n0;
       const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
       int kv_valid = (seg ? p.kv_len[1] : len0) - col0;
@@ -896,7 +901,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       } else {
         m_run = mx;
       }
-      FG_TSTAMP(ts3);
+      FG_TSET(ts3);
       if constexpr (PP) {   // wait for the exp token of this scheduler's warp pair (tile 0 holds it first)
         if (t == 1 && j == 0) named_bar_arrive(3 + q, 64);
         named_bar_sync(3 + 4 * t + q, 64);
