@@ -163,8 +163,17 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 // exponential (~170 live registers, small spills, little room for the scheduler to overlap independent pairs).  TP reads S
 // from tensor memory twice in 32-column chunks -- once for the row max, once for the exponentials -- double-buffered, so
 // the loops run at ~70 live registers; a TMEM read is ~40 clocks per chunk and overlaps the arithmetic of the previous one.
-template <int DP, int POLY, int HALF, int WG = 1, int BX = 0, int PP = 0, int TP = 0>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
+//
+// SEP (d <= 64: P in tensor-memory columns of its own).  With P written over S, S of key tile j + 1 can only be computed
+// after P.V of tile j has consumed P, so every softmax warp waits an MMA round trip (~720 of the ~3 270 clocks of a key tile
+// at d = 64: profiles/attn_phase_timing_r02.txt) between publishing P_j and seeing S_{j+1}.  At d <= 64 tensor memory has
+// room for S0 S1 | O0 O1 | P0 P1 (128 + 128 + 64 + 64 + 64 + 64 = 512 columns): the softmax warps hand S back as soon as
+// they have READ it (s_free), the issuer computes S_{j+1} under the softmax of tile j, and P.V_j follows when P_j is
+// published -- the next S is already there.
+template <int DP, int POLY, int HALF, int WG = 1, int BX = 0, int PP = 0, int TP = 0, int SEP = 0>  // POLY: pairs out of every 8 whose exponential runs on the FMA pipe
 __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __grid_constant__ Attn2KParams p) {
+  static_assert(SEP == 0 || (DP == 64 && HALF == 0 && WG == 1 && BX == 0 && TP == 0), "separate P columns: d <= 64, one-pass loop");
+  constexpr int TMEM_P = 384;   // SEP: P of query tile t at TMEM_P + 64 t
   static_assert(TP == 0 || (HALF == 0 && WG == 1), "two-pass softmax: full tiles, WG = 1");
   static_assert(PP == 0 || (HALF == 0 && WG == 1), "ping-pong: full tiles, WG = 1");
   static_assert(WG == 1 || (WG == 2 && HALF == 0), "two warps per lane quarter: full-tile pipeline only");
@@ -189,7 +198,8 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
   uint64_t* s_full = v_empty + S;      // [2 tiles][2 halves] (index t * 2 + h; the full-tile pipeline uses h = 0)
   uint64_t* p_full = s_full + 4;       // [2][2]
   uint64_t* pv_done = p_full + 4;      // [2][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+  uint64_t* s_free = pv_done + 4;      // [2 tiles] SEP: the softmax warps have read S (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [3][2 tiles][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,6 +242,8 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         mbar_init(&p_full[i], 4 * WG);
         mbar_init(&pv_done[i], 1);
       }
+      mbar_init(&s_free[0], 4);
+      mbar_init(&s_free[1], 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
       auto issue_pv = [&](int t, int stage, int j) {
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * Cfg::KV_TILE_BYTES + Cfg::KV_TILE_BYTES);
         const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_O + t * OW);
-        const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
+        const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(SEP ? TMEM_P + t * 64 : Cfg::TMEM_S + t * 128);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           // second 64-column chunk of B: the next d chunk of V (d = 128) | the ones slice, the same 16 rows for every kk
@@ -406,6 +418,28 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
           nphase ^= 1u;
         }
         const bool more = j + 1 < nkv;
+        if constexpr (SEP) {
+          // S_{j+1} of both tiles as soon as their softmax warps have read S_j; the P.V products when P_j is published
+          if (more) {
+            mbar_wait(&kv_full[nstage], nphase);
+            mbar_wait(&s_free[0], j & 1);
+            tc_fence_after();
+            issue_qk(0, nstage);
+            mbar_wait(&s_free[1], j & 1);
+            tc_fence_after();
+            issue_qk(1, nstage);
+          }
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(0, stage, j);
+          mbar_wait(&p_full[2], j & 1);
+          tc_fence_after();
+          issue_pv(1, stage, j);
+          umma_commit_elect(elected, &kv_empty[stage]);
+          stage = nstage;
+          phase = nphase;
+          continue;
+        }
         // query tile 0: O0 += P0.V_j, then S0 <- Q0.K_{j+1}^T (overwrites P0: issued after the product that reads it)
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
@@ -626,6 +660,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_S + t * 128);
     const uint32_t o_addr = tmem_base + lane_base + static_cast<uint32_t>(Cfg::TMEM_O + t * OW);
+    const uint32_t p_addr = tmem_base + lane_base + static_cast<uint32_t>(TMEM_P + t * 64);   // SEP only
     const int limit = causal_limit2(p, tok);
     const float sc = p.scale_log2;
     float m_run = -INFINITY;  // running max in scaled (log2) units
@@ -848,6 +883,11 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         tmem_ld_32x32(s_addr + c, chunk);
       }
       tmem_ld_wait();
+      if constexpr (SEP) {   // S is in registers: hand its columns back, the issuer computes S of the next key tile now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+      }
       FG_TSET(ts2);
       const int seg = (jb + j) >= n0;
       const int col0 = (seg ? jb + j - n0 : jb + j) * BKV;
@@ -906,6 +946,12 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
         if (t == 1 && j == 0) named_bar_arrive(3 + q, 64);
         named_bar_sync(3 + 4 * t + q, 64);
       }
+      if constexpr (SEP) {
+        if (j > 0) {   // P_{j-1} must have been consumed by its P.V product before P_j overwrites it (long done by now)
+          mbar_wait(&pv_done[2 * t], (j - 1) & 1);
+          tc_fence_after();
+        }
+      }
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t sc2 = pack2(sc, sc), negm2 = pack2(neg_m, neg_m);
       uint64_t lsum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};  // independent chains
@@ -934,7 +980,7 @@ __global__ void __launch_bounds__(64 + 256 * WG, 1) attention2_kernel(const __gr
           if constexpr (!ONES) lsum2[(i >> 1) & 3] = fadd2(lsum2[(i >> 1) & 3], pack2(e0, e1));
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
-        tmem_st_32x16(s_addr + (c >> 1), pk);
+        tmem_st_32x16((SEP ? p_addr : s_addr) + (c >> 1), pk);
       }
       if constexpr (!ONES) {
         float lsum0, lsum1;
@@ -1099,13 +1145,13 @@ size_t flash_attn_v2_workspace(const fg_flash_attn_params* p) {
   return rows * 8 * (static_cast<size_t>(dp) * 2 + 8) + 256 + 128;
 }
 
-template <int DP, int POLY, int HALF = 0, int WG = 1, int BX = 0, int PP = 0, int TP = 0>
+template <int DP, int POLY, int HALF = 0, int WG = 1, int BX = 0, int PP = 0, int TP = 0, int SEP = 0>
 static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DP>;
   static PerDeviceFlag configured;
   const int cfg_dev = current_device();
   if (!configured.test(cfg_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP, SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("flash_attn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -1166,7 +1212,7 @@ static int launch_attention2(const fg_flash_attn_params* p, float scale, cudaStr
     if (r != FG_OK) return r;
   }
   const int grid = kp.B * kp.H * q_blocks * nsplit;
-  attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
+  attention2_kernel<DP, POLY, HALF, WG, BX, PP, TP, SEP><<<grid, 64 + 256 * WG, Cfg::SMEM_BYTES, stream>>>(kp);
   FG_CHECK_LAUNCH("flash_attn");
   if (nsplit > 1) {
     const int64_t rows = static_cast<int64_t>(kp.B) * kp.H * kp.Tq;
@@ -1212,6 +1258,18 @@ int flash_attn_v2(const fg_flash_attn_params* p, float scale, cudaStream_t strea
   // d <= 64: row sum through a ones column of V and packed bf16 exponentials (see attention2_kernel).  FG_ATTN_BX = -1
   // (ones column alone) | 0 (off) | 2 | 4 | 8 eighths of the exponentials in the packed form
   static const int bx_env = getenv("FG_ATTN_BX") ? atoi(getenv("FG_ATTN_BX")) : 0;
+  // d <= 64: P in its own tensor-memory columns, S of the next key tile computed under the softmax (see attention2_kernel)
+  // Default at d <= 64 since the end of round 2 (FG_ATTN_SEP=0 restores the aliased layout): 516 -> 551 TFLOP/s on the EDM
+  // 32x32 shape with every exponential on the MUFU unit (the polynomial share no longer pays once S never has to be waited
+  // for: 519 with 2 of 8, 438 with 4 of 8 -- profiles/attn_separate_p_r02.txt).
+  static const int sep_env = getenv("FG_ATTN_SEP") ? atoi(getenv("FG_ATTN_SEP")) : 1;
+  static const bool other_experiment = getenv("FG_ATTN_TP") || getenv("FG_ATTN_PP") || getenv("FG_ATTN_BX") ||
+                                       getenv("FG_ATTN_WG") || getenv("FG_ATTN_HALF");
+  if (sep_env && p->d <= 64 && !other_experiment) {
+    if (poly_env == 2) return launch_attention2<64, 2, 0, 1, 0, 0, 0, 1>(p, scale, stream);
+    if (poly_env == 4) return launch_attention2<64, 4, 0, 1, 0, 0, 0, 1>(p, scale, stream);
+    return launch_attention2<64, 0, 0, 1, 0, 0, 0, 1>(p, scale, stream);
+  }
   static const int tp_env = getenv("FG_ATTN_TP") ? atoi(getenv("FG_ATTN_TP")) : 0;
   if (tp_env) {
     if (p->d <= 64) {
